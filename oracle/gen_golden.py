@@ -1,0 +1,265 @@
+"""TEST INFRASTRUCTURE ONLY — generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference/smrt).
+
+Run in the authoring container only (the reference does not exist on the GPU box):
+
+    python oracle/gen_golden.py [case ...]
+
+For every case it (1) builds snowpacks and a sensor with the reference's own builders, (2) runs the reference
+``make_model(em, "dort").run(sensor, snowpacks, parallel_computation="none")``, (3) packs the very same objects with
+``smrt_b200.pack.pack_simulations`` and (4) writes the packed inputs + the reference outputs to one ``.npz``.
+The synthetic ensembles are SURVEY.md §8(d)'s generators (same seeds).  xarray is replaced by oracle/xarray_shim.
+"""
+
+import json
+import os
+import sys
+import time
+import warnings
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, "xarray_shim"))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+
+import numpy as np  # noqa: E402
+
+from smrt import PSU, make_ice_column, make_model, make_snowpack, sensor_list  # noqa: E402
+from smrt.core.error import SMRTWarning  # noqa: E402
+from smrt.interface.transparent import Transparent  # noqa: E402
+
+from smrt_b200.pack import pack_simulations  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+AMSRE_FREQS = [6.925e9, 10.65e9, 18.7e9, 23.8e9, 36.5e9, 89e9]
+
+
+def snow(rng, L, kind):
+    """SURVEY.md §8(d) generators"""
+    th = np.concatenate((rng.uniform(0.05, 0.5, L - 1), [1000.0]))
+    if kind == "exponential":
+        rho = rng.uniform(150, 450, L)
+        T = rng.uniform(240, 272, L)
+        pc = rng.uniform(5e-5, 3e-4, L)
+        return make_snowpack(th, "exponential", density=rho, temperature=T, corr_length=pc)
+    rho = rng.uniform(200, 400, L)
+    T = rng.uniform(240, 270, L)
+    a = rng.uniform(1e-4, 3e-4, L)
+    return make_snowpack(th, "sticky_hard_spheres", density=rho, temperature=T, radius=a, stickiness=0.2)
+
+
+def seaice(rng, L=30):
+    H = rng.uniform(1, 3)
+    dT = rng.uniform(10, 30)
+    ss = rng.uniform(0.5, 1.5)
+    por = rng.uniform(0.02, 0.12)
+    pc = rng.uniform(0.5e-3, 1.5e-3)
+    return make_ice_column("multiyear", thickness=np.full(L, H / L), temperature=np.linspace(273.15 - dT, 273.15 - 1.8, L),
+                           microstructure_model="exponential", brine_inclusion_shape="spheres",
+                           salinity=np.linspace(2, 10, L) * PSU * ss, porosity=por, corr_length=pc,
+                           add_water_substrate="ocean")
+
+
+def simulations_of(sensor, snowpacks):
+    """frequency outermost, snowpack innermost — reference smrt/core/model.py:485-502"""
+    freqs = np.atleast_1d(sensor.frequency)
+    sims = []
+    if len(freqs) > 1:
+        for sub in sensor.iterate("frequency"):
+            sims += [(sub, sp) for sp in snowpacks]
+    else:
+        sims = [(sensor, sp) for sp in snowpacks]
+    return sims
+
+
+def run_case(name, emmodel, sensor, snowpacks, rtsolver_options=None, emmodel_options=None):
+    rtsolver_options = rtsolver_options or {}
+    t0 = time.time()
+    m = make_model(emmodel, "dort", rtsolver_options=rtsolver_options, emmodel_options=emmodel_options)
+    sims = simulations_of(sensor, snowpacks)
+    batch = pack_simulations(sims, emmodel, emmodel_options)
+    values, ks, ka, eps, angles = [], [], [], [], []
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", SMRTWarning)
+        for sen, sp in sims:
+            res = m.run(sen, sp, parallel_computation="none")
+            values.append(np.asarray(res.data.values, dtype=float))
+            ks.append(np.asarray(res.other_data["ks"].values, dtype=float))
+            ka.append(np.asarray(res.other_data["ka"].values, dtype=float))
+            eps.append(np.asarray(res.other_data["effective_permittivity"].values, dtype=complex))
+            angles.append(np.asarray(res.other_data["stream_angles"].values, dtype=float))
+    L = batch.L
+
+    def pad(rows, n, dt):
+        out = np.full((len(rows), n), np.nan, dtype=dt)
+        for i, r in enumerate(rows):
+            out[i, :len(r)] = r
+        return out
+
+    nmax = max(len(a) for a in angles)
+    out = {f"in_{k}": v for k, v in batch.save_fields().items()}
+    out.update(ref_values=np.stack(values), ref_ks=pad(ks, L, float), ref_ka=pad(ka, L, float),
+               ref_eps_eff=pad(eps, L, complex), ref_stream_angles=pad(angles, nmax, float),
+               ref_n_air=np.array([len(a) for a in angles]),
+               rtsolver_options=np.array(json.dumps(rtsolver_options)), emmodel=np.array(str(emmodel)))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(f"{name}: B={batch.B} L={L} values{np.stack(values).shape} in {time.time() - t0:.1f}s  first={np.stack(values)[0].ravel()[:4]}")
+
+
+def two_layer_iba():
+    return make_snowpack(thickness=[0.1, 100], microstructure_model="exponential", density=[200, 400],
+                         temperature=[250.0, 250.0], corr_length=[5e-5, 5e-5])
+
+
+def two_layer_shs():
+    return make_snowpack([0.1, 1000], "sticky_hard_spheres", density=[200, 400], temperature=[250.0, 250.0],
+                         radius=[2e-4, 2e-4], stickiness=[0.1, 0.1])
+
+
+CASES = {}
+
+
+def case(fn):
+    CASES[fn.__name__] = fn
+    return fn
+
+
+@case
+def cfg1_iba_onelayer():
+    sp = make_snowpack([100], "exponential", density=[320], temperature=[270], corr_length=[5e-5])
+    run_case("cfg1_iba_onelayer", "iba", sensor_list.amsre("37V"), [sp])
+
+
+@case
+def ref_iba_2layer_passive():  # reference test/test_integration_iba.py:33-49
+    run_case("ref_iba_2layer_passive", "iba", sensor_list.amsre("37V"), [two_layer_iba()])
+
+
+@case
+def ref_iba_2layer_active():  # reference test/test_integration_iba.py:52-69
+    run_case("ref_iba_2layer_active", "iba", sensor_list.active(frequency=19e9, theta_inc=55), [two_layer_iba()])
+
+
+@case
+def ref_dmrt_qcacp_2layer_passive():  # reference test/test_dmrtdort.py:41-76
+    run_case("ref_dmrt_qcacp_2layer_passive", "dmrt_qcacp_shortrange", sensor_list.amsre(["19", "37"]),
+             [two_layer_shs()])
+
+
+@case
+def ref_dmrt_less_refringent_active():  # reference test/test_dmrtdort.py:99-108
+    sp = make_snowpack([0.2, 0.3], "sticky_hard_spheres", density=[290.0, 250.0], radius=1e-4, stickiness=0.2)
+    run_case("ref_dmrt_less_refringent_active", "dmrt_qcacp_shortrange", sensor_list.active(10e9, 45), [sp])
+
+
+@case
+def ref_sea_ice_128streams():  # reference test/test_iba_sea_ice.py:30-68
+    layer = 9
+    thickness = np.array([1.5 / layer] * layer)
+    temperature = np.linspace(273.15 - 20.0, 273.15 - 1.8, layer)
+    salinity = np.linspace(2.0, 10.0, layer) * PSU
+    sps = []
+    for ice_type, porosity, pex in (("firstyear", 0, 500e-6), ("multiyear", 0.08, 1000e-6)):
+        sps.append(make_ice_column(ice_type=ice_type, thickness=thickness, temperature=temperature,
+                                   microstructure_model="exponential", brine_inclusion_shape="spheres",
+                                   salinity=salinity, porosity=porosity, corr_length=np.array([pex] * layer),
+                                   add_water_substrate="ocean"))
+    run_case("ref_sea_ice_128streams", "iba", sensor_list.passive(1.4e9, 40.0), sps, dict(n_max_stream=128))
+
+
+@case
+def nonscattering_transparent():  # reference rtsolver/test_rtsolver.py:16-51, 104-113
+    sps = [make_snowpack([100], "homogeneous", density=[300], temperature=[250], interface=[Transparent]),
+           make_snowpack([0.5, 1000], "homogeneous", density=[300, 250], temperature=2 * [250],
+                         interface=2 * [Transparent])]
+    run_case("nonscattering_transparent", "nonscattering", sensor_list.passive(37e9, [0, 5, 30, 40]), sps)
+
+
+@case
+def nonscattering_active():  # reference rtsolver/test_rtsolver.py:64-101
+    sps = [make_snowpack([0.5, 1000], "homogeneous", density=[250, 300], temperature=2 * [250],
+                         interface=2 * [Transparent]),
+           make_snowpack([0.5, 1000], "homogeneous", density=[300, 250], temperature=2 * [250])]
+    run_case("nonscattering_active", "nonscattering", sensor_list.active(13e9, 45), sps)
+
+
+@case
+def iba_multiangle_passive():
+    rng = np.random.default_rng(11)
+    sps = [snow(rng, 5, "exponential") for _ in range(3)]
+    run_case("iba_multiangle_passive", "iba", sensor_list.passive([10.65e9, 36.5e9], [0, 10, 25, 40, 55, 70, 85]),
+             sps, dict(n_max_stream=16))
+
+
+@case
+def iba_options_passive():
+    rng = np.random.default_rng(12)
+    sps = [snow(rng, 8, "exponential") for _ in range(2)]
+    run_case("iba_options_prune_rj", "iba", sensor_list.passive(36.5e9, [40, 55]), sps,
+             dict(n_max_stream=16, prune_deep_snowpack=6, rayleigh_jeans_approximation=True))
+
+
+@case
+def iba_shs_active_multiangle():
+    rng = np.random.default_rng(13)
+    sps = []
+    for _ in range(2):
+        th = np.concatenate((rng.uniform(0.05, 0.5, 3), [1000.0]))
+        sps.append(make_snowpack(th, "sticky_hard_spheres", density=rng.uniform(200, 400, 4),
+                                 temperature=rng.uniform(240, 270, 4), radius=rng.uniform(1e-4, 3e-4, 4),
+                                 stickiness=0.3))
+    run_case("iba_shs_active_multiangle", "iba", sensor_list.active(13.5e9, [20, 35, 50]), sps, dict(n_max_stream=16))
+
+
+@case
+def iba_exp_substrate_passive():
+    from smrt.substrate.flat import Flat as FlatSub
+
+    rng = np.random.default_rng(14)
+    sps = []
+    for _ in range(2):
+        L = 4
+        sub = FlatSub(temperature=265.0, permittivity_model=complex(rng.uniform(4, 20), rng.uniform(0.5, 5)))
+        sps.append(make_snowpack(rng.uniform(0.05, 0.5, L), "exponential", density=rng.uniform(150, 450, L),
+                                 temperature=rng.uniform(240, 272, L), corr_length=rng.uniform(5e-5, 3e-4, L),
+                                 substrate=sub))
+    run_case("iba_exp_substrate_passive", "iba", sensor_list.passive([18.7e9, 36.5e9], 55), sps, dict(n_max_stream=16))
+
+
+@case
+def cfg2_first4():
+    rng = np.random.default_rng(2)
+    sps = [snow(rng, 20, "exponential") for _ in range(4)]
+    run_case("cfg2_first4", "iba", sensor_list.amsre(), sps, dict(n_max_stream=32))
+
+
+@case
+def cfg3_first4():
+    rng = np.random.default_rng(3)
+    sps = [snow(rng, 10, "shs") for _ in range(4)]
+    run_case("cfg3_first4", "dmrt_qca_shortrange", sensor_list.active([5.4e9, 9.6e9, 13.5e9], 40), sps,
+             dict(n_max_stream=16, m_max=2))
+
+
+@case
+def cfg4_first1():
+    rng = np.random.default_rng(4)
+    sps = [snow(rng, 50, "exponential")]
+    freqs = [1.4135e9, 5.4e9, 6.925e9, 7.3e9, 9.6e9, 10.65e9, 13.5e9, 18.7e9, 23.8e9, 31.4e9, 36.5e9, 89.0e9]
+    run_case("cfg4_first1", "iba", sensor_list.passive(freqs, 55), sps, dict(n_max_stream=64))
+
+
+@case
+def cfg5_first6():
+    rng = np.random.default_rng(5)
+    sps = [seaice(rng) for _ in range(6)]
+    run_case("cfg5_first6", "iba", sensor_list.passive(1.4e9, 40), sps, dict(n_max_stream=32))
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLDEN, exist_ok=True)
+    names = sys.argv[1:] or list(CASES)
+    for n in names:
+        CASES[n]()
