@@ -1,0 +1,162 @@
+/* smrt_dort_b200.h — C ABI of the B200-native DORT hot path (libsmrt_dort_b200.so).
+ *
+ * The reference (smrt-model/smrt, pure Python) has NO FFI: the hot path sits behind two Python plugin seams
+ *   - the rtsolver seam  DORT(**options).solve(snowpack, emmodels, sensor, atmosphere)   smrt/rtsolver/dort.py:148-161,189
+ *     called once per simulation by Model.run_single_simulation                          smrt/core/model.py:584-619
+ *   - the runner seam    runner(function, argument_list) -> list[Result]                 smrt/core/model.py:395-398
+ * This header is what a binding for that path binds (ctypes stub in INTEGRATION.md): one *batched* call that replaces
+ * the per-simulation chain  IBA/DMRT.__init__ -> compute_stream -> compute_interface_properties ->
+ * EigenValueSolver.solve -> dort_modem_banded -> sum_modes -> interpolate_intensity  for B problems at once.
+ *
+ * Conventions
+ *   - plain C symbols, no C++ types, no exceptions across the boundary
+ *   - every function returns int: 0 = ok, < 0 = API misuse / CUDA error; smrtb200_last_error() gives the message
+ *     (thread-local)
+ *   - the caller owns every buffer; the library owns only the opaque plan (workspace + streams)
+ *   - *_device entry points take DEVICE pointers and are asynchronous on the given cudaStream_t (passed as void*)
+ *   - *_host entry points take HOST pointers, stage through pinned memory and return when the results are in the
+ *     output buffers
+ *   - per-problem numerical failures never abort the batch: they are reported in status[b]
+ *   - all floating point data is IEEE fp64; complex numbers are (re, im) pairs of doubles
+ */
+#ifndef SMRT_DORT_B200_H
+#define SMRT_DORT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMRTB200_ABI_VERSION 1
+
+/* sensor mode (reference smrt/core/sensor.py:331-339) */
+#define SMRTB200_MODE_PASSIVE 0
+#define SMRTB200_MODE_ACTIVE 1
+
+/* electromagnetic model of a layer */
+#define SMRTB200_EM_IBA 0            /* smrt/emmodel/iba.py:53 */
+#define SMRTB200_EM_DMRT_QCA_SR 1    /* smrt/emmodel/dmrt_qca_shortrange.py:55 */
+#define SMRTB200_EM_NONSCATTERING 2  /* smrt/emmodel/nonscattering.py:17 */
+#define SMRTB200_EM_DMRT_QCACP_SR 3  /* smrt/emmodel/dmrt_qcacp_shortrange.py:55 */
+
+/* microstructure model (FT of the autocorrelation function) */
+#define SMRTB200_MS_EXPONENTIAL 0 /* p0 = corr_length                smrt/microstructure_model/exponential.py:53-58 */
+#define SMRTB200_MS_SHS 1         /* p0 = radius, p1 = stickiness    smrt/microstructure_model/sticky_hard_spheres.py:63-167 */
+#define SMRTB200_MS_HOMOGENEOUS 2 /* no scatterers (non-scattering layers only) */
+
+/* interface above a layer */
+#define SMRTB200_IF_FLAT 0        /* Fresnel, smrt/interface/flat.py:11-75 + smrt/core/fresnel.py:99-146,417-474 */
+#define SMRTB200_IF_TRANSPARENT 1 /* smrt/interface/transparent.py:7-49 */
+
+/* substrate */
+#define SMRTB200_SUB_NONE 0
+#define SMRTB200_SUB_FLAT 1 /* flat half-space of permittivity substrate_eps at substrate_temperature, smrt/substrate/flat.py:15-17 */
+
+/* phase_normalization option (smrt/rtsolver/dort.py:94-103, 782-819) */
+#define SMRTB200_NORM_OFF 0
+#define SMRTB200_NORM_ON 1     /* True / "auto": normalise, error if the correction exceeds 30 % */
+#define SMRTB200_NORM_FORCED 2 /* "forced" */
+
+/* status[b]: low 4 bits = error code, bit 4 = warning flag */
+#define SMRTB200_OK 0
+#define SMRTB200_ERR_NORMALIZATION 1 /* SMRTError of dort.py:792-801 */
+#define SMRTB200_ERR_EIGEN 2         /* SMRTError of dort.py:826,844,852,1068-1085 (layer matrix not diagonalisable with real positive spectrum) */
+#define SMRTB200_ERR_SINGULAR 3      /* singular boundary block (scipy.linalg.solve_banded would raise, dort.py:469) */
+#define SMRTB200_ERR_INPUT 4         /* invalid per-problem input (fewer than 2 streams in a layer, bad enum, SHS t has no solution ...) */
+#define SMRTB200_ERR_MASK 15
+#define SMRTB200_WARN_SHALLOW 16     /* smrt_warn of dort.py:460-467: optically shallow snowpack without substrate */
+
+typedef struct smrtb200_plan smrtb200_plan; /* opaque */
+
+typedef struct {
+  int abi_version;     /* SMRTB200_ABI_VERSION */
+  int device;          /* CUDA device ordinal */
+  int mode;            /* SMRTB200_MODE_* */
+  int n_max_stream;    /* DORT option n_max_stream (dort.py:150), 2..256 */
+  int m_max;           /* DORT option m_max (dort.py:151); ignored (0) in passive mode; 0..3 */
+  int max_layers;      /* L: row stride of every [B, L] array */
+  int max_batch;       /* largest B of one solve call (host staging is sized for it) */
+  int n_theta;         /* number of viewing angles (passive) */
+  int n_inc;           /* number of incidence angles (active; theta == theta_inc for backscatter), <= 8 */
+  int normalization;   /* SMRTB200_NORM_* */
+  int rayleigh_jeans;  /* 1 = Rayleigh-Jeans approximation: B(T) = T (dort.py:160, rtsolver_utils.py:411-419) */
+  double prune_deep_snowpack; /* optical depth beyond which layers are dropped (dort.py:117-120, 444-452); <= 0: off */
+  int chunk;           /* problems processed per kernel wave; 0 = automatic */
+  int reserved;
+} smrtb200_options;
+
+/* One batch of B independent (snowpack x frequency) problems.  Arrays marked [B, L] have row stride max_layers. */
+typedef struct {
+  int B;
+  /* inputs */
+  const double* frequency;            /* [B] Hz */
+  const int* nlayer;                  /* [B] 1..L */
+  const double* thickness;            /* [B, L] m */
+  const double* temperature;          /* [B, L] K */
+  const double* frac_volume;          /* [B, L] */
+  const double* eps_bg;               /* [B, L, 2] background permittivity  layer.permittivity(0, f)  smrt/core/layer.py:120-156 */
+  const double* eps_sc;               /* [B, L, 2] scatterer permittivity   layer.permittivity(1, f) */
+  const int* emmodel;                 /* [B, L] SMRTB200_EM_* */
+  const int* ms_kind;                 /* [B, L] SMRTB200_MS_* */
+  const double* ms_p0;                /* [B, L] */
+  const double* ms_p1;                /* [B, L] */
+  const int* interface_kind;          /* [B, L] interface ABOVE layer l, SMRTB200_IF_* */
+  const int* dense_snow_correction;   /* [B, L] 1 = emmodel option dense_snow_correction="auto" (iba.py:95-96) */
+  const int* substrate_kind;          /* [B] SMRTB200_SUB_* */
+  const double* substrate_eps;        /* [B, 2] */
+  const double* substrate_temperature;/* [B] K; <= 0 means "no temperature" (dort.py:429-441) */
+  const double* theta;                /* [n_theta] rad, viewing angles (passive) */
+  const double* theta_inc;            /* [n_inc] rad, incidence angles (active) */
+  double phi;                         /* rad, relative azimuth (active; pi = backscatter) */
+  /* outputs */
+  double* values;        /* passive: [B, 2, n_theta] brightness temperature (V, H), K
+                            active : [B, 3, 3, n_inc] intensity laid out exactly as the reference's Result
+                                     (polarization_inc-label, polarization-label, theta_inc), rtsolver_utils.py:309-332;
+                                     sigma0 = 4 pi cos(theta) * value (smrt/core/result.py:485) */
+  double* ks;            /* [B, L] scattering coefficient   (Result.other_data["ks"], rtsolver_utils.py:373-398) */
+  double* ka;            /* [B, L] absorption coefficient */
+  double* eps_eff;       /* [B, L, 2] effective permittivity */
+  int* n_streams_out;    /* [B] number of valid entries in stream_angles */
+  double* stream_angles; /* [B, n_max_stream] degrees; passive: all air streams, active: the incident streams */
+  double* optical_depth; /* [B] sum over the layers kept of min|beta| * thickness (dort.py:444) */
+  int* status;           /* [B] SMRTB200_OK / SMRTB200_ERR_* | SMRTB200_WARN_* */
+} smrtb200_batch;
+
+/* Library / device information. */
+int smrtb200_abi_version(void);
+const char* smrtb200_last_error(void);
+int smrtb200_device_count(int* count);
+
+/* Plan lifetime.  A plan owns the device workspace, two CUDA streams and the pinned staging buffers. */
+int smrtb200_plan_create(const smrtb200_options* options, smrtb200_plan** plan);
+int smrtb200_plan_destroy(smrtb200_plan* plan);
+/* bytes of device workspace held by the plan */
+int smrtb200_plan_workspace_bytes(const smrtb200_plan* plan, unsigned long long* bytes);
+/* number of kernels launched by the plan since creation (bench.py reports it as gpu_launches) */
+int smrtb200_plan_launch_count(const smrtb200_plan* plan, unsigned long long* launches);
+
+/* Solve with DEVICE pointers; asynchronous on `cuda_stream` (a cudaStream_t; NULL = default stream).
+ * Replaces, for every b in [0, B): DORT.solve of smrt/rtsolver/dort.py:189-261 including the emmodel construction of
+ * smrt/core/model.py:529-582. */
+int smrtb200_solve_batch_device(smrtb200_plan* plan, const smrtb200_batch* batch, void* cuda_stream);
+
+/* Solve with HOST pointers (pageable or pinned): H2D copies, kernels and D2H copies, then synchronises. */
+int smrtb200_solve_batch_host(smrtb200_plan* plan, const smrtb200_batch* batch);
+
+/* Synchronise `cuda_stream` (the stream given to smrtb200_solve_batch_device) and collect the CUDA-event timings of
+ * the last solve.  smrtb200_solve_batch_host does this itself. */
+int smrtb200_plan_sync_timing(smrtb200_plan* plan, void* cuda_stream);
+
+/* Time of the last solve on the device, from CUDA events recorded on the launching streams around the kernels
+ * (ms; H2D/D2H excluded): total (first launch to last completion), and the summed durations of the per-layer eigen
+ * kernel launches and of the boundary kernel launches (one launch of each per chunk; n_chunks = number of launches). */
+int smrtb200_plan_last_timing(const smrtb200_plan* plan, float* total_ms, float* eigen_kernel_ms,
+                              float* boundary_kernel_ms, int* n_chunks);
+
+/* Micro-benchmark used by bench.py to obtain the FP64 roofline denominator on the box (MEASURED_PEAKS.json has no
+ * FP64 entry): runs an unrolled DFMA kernel for ~`ms` milliseconds and returns the achieved TFLOP/s. */
+int smrtb200_measure_fp64_peak(int device, float ms, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMRT_DORT_B200_H */

@@ -1,0 +1,869 @@
+// dort_kernels.cuh — the three kernels of the B200 DORT path.
+//
+//   optics_kernel    one THREAD per (problem, layer): effective permittivity, ks (65-point Romberg), ka, IBA coefficient
+//   eigen_kernel     one CTA per (problem, layer) work item (persistent grid, atomic work counter): stream angles,
+//                    Fourier modes of the phase matrix on the layer's streams, symmetrised half-rank eigenproblem by
+//                    two concurrent Cholesky factorisations + one-sided Jacobi, eigenvectors written to the layer
+//                    workspace in HBM (k, F, G with Eu = [F | G], Ed = D [G | F], beta = [k, -k])
+//   boundary_kernel  one CTA per problem (persistent grid): Fresnel coefficients, bottom-up elimination of the
+//                    block-tridiagonal boundary system with h x h blocks, emerging intensity, mode summation,
+//                    inverse Planck, interpolation to the sensor angles
+//
+// Algebra and reference citations: DESIGN.md §3-§5; NumPy model of exactly this algorithm: oracle/b200_algorithm.py.
+#pragma once
+#include "dort_device.cuh"
+#include "dort_linalg.cuh"
+
+#define SMRT_MAX_MODES 4      // m = 0 .. 3
+#define SMRT_MAX_INC 16       // incident streams (<= 2 per incidence angle, n_inc <= 8)
+#define SMRT_AUX_STRIDE 4     // per (problem, layer): iba_coeff, kk, f_eff, spare
+#define SMRT_NT 256           // threads per CTA of the eigen and boundary kernels
+
+struct KArgs {
+  int B, L;  // problems in this launch (all pointers are already offset to its first problem), row stride
+  int mode, n, m_max, n_theta, n_inc, normalization, rayleigh_jeans, K;
+  double prune_tau, phi;
+  // inputs
+  const double* frequency;
+  const int* nlayer;
+  const double *thickness, *temperature, *frac_volume, *eps_bg, *eps_sc;
+  const int *emmodel, *ms_kind;
+  const double *ms_p0, *ms_p1;
+  const int *interface_kind, *dense_corr, *substrate_kind;
+  const double *substrate_eps, *substrate_temperature, *theta, *theta_inc;
+  // outputs
+  double *values, *ks, *ka, *eps_eff;
+  int* n_streams_out;
+  double *stream_angles, *optical_depth;
+  int* status;
+  // workspace
+  const double* gl_mu;  // [n] positive Gauss-Legendre nodes of order 2n, descending
+  double* aux;          // [B, L, SMRT_AUX_STRIDE]
+  double* eig;          // [B, L, eig_stride]
+  double* kmin;         // [B, L, SMRT_MAX_MODES]
+  int* scat_flag;       // [B, L]
+  int* counters;        // [2]: eigen / boundary work counters
+  double* scratch;      // [gridDim.x, scratch_stride] when use_global_scratch
+  long long eig_stride, scratch_stride;
+  int use_global_scratch;
+  int eig_off[SMRT_MAX_MODES];  // offset of mode m inside one (problem, layer) eigen record
+};
+
+// layout of one mode record: k[hmax_even] | F[h*h] | G[h*h]  (F, G compact column-major with ld = h)
+SMRT_HD int smrt_npol(int m) { return m == 0 ? 2 : 3; }
+SMRT_HD long long smrt_even(long long x) { return (x + 1) & ~1LL; }
+
+#ifdef __CUDACC__
+#define SMRT_DYN_SMEM(ptr)                                        \
+  extern __shared__ __align__(16) unsigned char smrt_smem_raw[]; \
+  double* ptr = reinterpret_cast<double*>(smrt_smem_raw)
+#else
+#define SMRT_DYN_SMEM(ptr) double* ptr = reinterpret_cast<double*>(simt::dynamic_smem(0))
+#endif
+
+// --------------------------------------------------------------------------------------------------------------------
+// kernel 1: layer optics
+// --------------------------------------------------------------------------------------------------------------------
+SMRT_GLOBAL void __launch_bounds__(128) optics_kernel(KArgs A) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= A.B * A.L) return;
+  int b = idx / A.L, l = idx % A.L;
+  if (l >= A.nlayer[b]) return;  // status[] is zeroed by the host before the launch
+  cplx e0 = c_make(A.eps_bg[2 * idx], A.eps_bg[2 * idx + 1]);
+  cplx es = c_make(A.eps_sc[2 * idx], A.eps_sc[2 * idx + 1]);
+  MicroParams mp;
+  LayerOptics o = layer_optics(A.frequency[b], A.frac_volume[idx], e0, es, A.emmodel[idx], A.ms_kind[idx],
+                               A.ms_p0[idx], A.ms_p1[idx], A.dense_corr[idx], &mp);
+  A.eps_eff[2 * idx] = o.eps_eff.re;
+  A.eps_eff[2 * idx + 1] = o.eps_eff.im;
+  A.ks[idx] = o.ks;
+  A.ka[idx] = o.ka;
+  double* aux = A.aux + (size_t)idx * SMRT_AUX_STRIDE;
+  aux[0] = o.iba_coeff;
+  aux[1] = o.kk;
+  aux[2] = o.f;
+  aux[3] = 0.0;
+  if (o.status != ST_OK) atomicOr(&A.status[b], o.status);
+}
+
+// Re sqrt(eps_star / eps_medium): the refraction index ratio that maps the most refringent layer's nodes to a medium
+SMRT_DEV double real_index_of(cplx eps_star, cplx eps_medium) { return c_sqrt(c_div(eps_star, eps_medium)).re; }
+
+SMRT_DEV void set_error(int* status, int b, int code) {
+  // keep the first error code (low 4 bits); warnings are OR-ed separately
+  int old = status[b];
+  if ((old & 15) == 0) atomicOr(&status[b], code);
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// kernel 2: per-layer eigenproblem
+// --------------------------------------------------------------------------------------------------------------------
+// shared-memory vector region (doubles): mu[n] w[n] norm0[2n] g[hmax] sdiag[hmax] dk[hmax] sigma[hmax] ctab[2K] stab[2K]
+SMRT_HD size_t eigen_vec_doubles(int n, int hmax, int K) { return (size_t)4 * n + 4 * hmax + 4 * K + 8; }
+SMRT_HD size_t eigen_mat_doubles(int hmax) { return (size_t)3 * hmax * (hmax + 1); }
+
+SMRT_GLOBAL void __launch_bounds__(SMRT_NT) eigen_kernel(KArgs A) {
+  SMRT_DYN_SMEM(smem);
+  SMRT_SHARED int s_item;
+  SMRT_SHARED int s_ctrl[8];
+  const int tid = threadIdx.x;
+  const int NT = blockDim.x;
+  const int n = A.n;
+  const int nmodes = A.m_max + 1;
+  const int hmax = smrt_npol(A.m_max) * n;
+  const int K = A.K;
+
+  double* mu = smem;
+  double* w = mu + n;
+  double* norm0 = w + n;
+  double* gvec = norm0 + 2 * n;
+  double* sdiag = gvec + hmax;
+  double* dk = sdiag + hmax;
+  double* sigma = dk + hmax;
+  double* ctab = sigma + hmax;
+  double* stab = ctab + 2 * K;
+  double* mats = A.use_global_scratch ? (A.scratch + (size_t)blockIdx.x * A.scratch_stride)
+                                      : (smem + eigen_vec_doubles(n, hmax, K));
+  const size_t matsz = (size_t)hmax * (hmax + 1);
+  double* A1 = mats;
+  double* A2 = mats + matsz;
+  double* A3 = mats + 2 * matsz;
+
+  for (int j = tid; j < 2 * K; j += NT) {
+    double s, c;
+    sincospi((double)j / (double)K, &s, &c);
+    ctab[j] = c;
+    stab[j] = s;
+  }
+  __syncthreads();
+
+  const int nitems = A.B * A.L;
+  for (;;) {
+    if (tid == 0) s_item = atomicAdd(&A.counters[0], 1);
+    __syncthreads();
+    const int item = s_item;
+    __syncthreads();
+    if (item >= nitems) break;
+    const int b = item / A.L, l = item % A.L;
+    const int nl = A.nlayer[b];
+    if (l >= nl) continue;
+    const size_t bl = (size_t)b * A.L + l;
+    const double* eps_b = A.eps_eff + (size_t)b * A.L * 2;
+    const double ks = A.ks[bl], ke = A.ks[bl] + A.ka[bl];
+    const int emmodel = A.emmodel[bl];
+
+    // streams of this layer -------------------------------------------------------------------- streams.py:136-223
+    const int kstar = most_refringent_layer(eps_b, nl);
+    const cplx eps_star = c_make(eps_b[2 * kstar], eps_b[2 * kstar + 1]);
+    const double rindex = real_index_of(eps_star, c_make(eps_b[2 * l], eps_b[2 * l + 1]));
+    const int n_l = stream_count(rindex, A.gl_mu, n);
+    double* kmin = A.kmin + bl * SMRT_MAX_MODES;
+    if (n_l < 2) {
+      if (tid == 0) {
+        set_error(A.status, b, ST_INPUT);
+        A.scat_flag[bl] = 0;
+        for (int m = 0; m < nmodes; ++m) kmin[m] = 0.0;
+      }
+      continue;
+    }
+    for (int j = tid; j < n_l; j += NT) mu[j] = stream_mu(rindex, A.gl_mu, j);
+    __syncthreads();
+    for (int j = tid; j < n_l; j += NT) w[j] = stream_weight(mu, n_l, j);
+    __syncthreads();
+
+    const bool scattering = (ks != 0.0) && (emmodel != EM_NONSCATTERING);
+    if (!scattering) {  // dort.py:716-717, 765-780: trivial solution, nothing to store
+      if (tid == 0) {
+        A.scat_flag[bl] = 0;
+        for (int m = 0; m < nmodes; ++m) kmin[m] = ke / mu[0];
+      }
+      __syncthreads();
+      continue;
+    }
+
+    const double* aux = A.aux + bl * SMRT_AUX_STRIDE;
+    const double iba_coeff = aux[0], kk = aux[1];
+    MicroParams mp = micro_prepare(A.ms_kind[bl], aux[2], A.ms_p0[bl], A.ms_p1[bl]);
+    double* rec = A.eig + bl * A.eig_stride;
+    bool failed = false;
+
+    for (int m = 0; m < nmodes && !failed; ++m) {
+      const int npol = smrt_npol(m);
+      const int h = npol * n_l;
+      const int ld = (h & 1) ? h : h + 1;
+      const double coef = (m == 0) ? 0.5 : 0.25;
+
+      // phase matrix Fourier mode m on (mu_s > 0) x (mu_i > 0 | mu_i < 0): A1 <- P++, A2 <- (P+-) D
+      for (int pidx = tid; pidx < n_l * n_l; pidx += NT) {
+        int js = pidx % n_l, ji = pidx / n_l;
+        double pp[9], pm[9];
+        if (emmodel == EM_IBA) {
+          iba_phase_mode(m, K, ctab, stab, mu[js], mu[ji], iba_coeff, kk, mp, pp);
+          iba_phase_mode(m, K, ctab, stab, mu[js], -mu[ji], iba_coeff, kk, mp, pm);
+        } else {
+          rayleigh_phase_mode(m, mu[js], mu[ji], ks, pp);
+          rayleigh_phase_mode(m, mu[js], -mu[ji], ks, pm);
+        }
+        for (int ps = 0; ps < npol; ++ps)
+          for (int pi = 0; pi < npol; ++pi) {
+            int a = js * npol + ps, c = ji * npol + pi;
+            SMRT_AT(A1, ld, a, c) = pp[ps * npol + pi];
+            SMRT_AT(A2, ld, a, c) = (pi == 2) ? -pm[ps * npol + pi] : pm[ps * npol + pi];
+          }
+      }
+      if (tid == 0) s_ctrl[2] = 0;
+      __syncthreads();
+
+      // row normalisation (dort.py:782-819) and the symmetrising scales
+      for (int a = tid; a < h; a += NT) {
+        int j = a / npol, p = a % npol;
+        double norm = 1.0;
+        if (A.normalization != 0) {
+          if (m == 0) {
+            double rs = 0.0;
+            for (int c = 0; c < h; ++c) rs += (SMRT_AT(A1, ld, a, c) + SMRT_AT(A2, ld, a, c)) * w[c / npol];
+            // A row sum = -coef * rs ; norm_0 = -ks / rowsum
+            norm = ks / (coef * rs);
+            norm0[a] = norm;
+            if (A.normalization == 1 && !(fabs(norm - 1.0) <= 0.3)) s_ctrl[2] = 1;
+          } else {
+            norm = (p < 2) ? norm0[2 * j + p] : sqrt(norm0[2 * j] * norm0[2 * j + 1]);
+          }
+        } else if (m == 0) {
+          norm0[a] = 1.0;
+        }
+        double q = (p == 2) ? 2.0 : 1.0;
+        double cw = coef * w[j];
+        gvec[a] = sqrt(norm * q * cw / mu[j]);
+        sdiag[a] = sqrt(norm * q / (mu[j] * cw));
+        dk[a] = ke / mu[j];
+      }
+      __syncthreads();
+      if (s_ctrl[2]) {
+        if (tid == 0) set_error(A.status, b, ST_NORMALIZATION);
+        failed = true;
+        break;
+      }
+      // X- = diag(ke/mu) - g Ps++ g + g Ps+-' g   (A1),   X+ = diag(ke/mu) - g Ps++ g - g Ps+-' g   (A2)
+      for (int e = tid; e < h * h; e += NT) {
+        int a = e % h, c = e / h;
+        double q = ((a % npol) == 2) ? 2.0 : 1.0;
+        double sc = gvec[a] * gvec[c] / q;
+        double x1 = sc * SMRT_AT(A1, ld, a, c), x2 = sc * SMRT_AT(A2, ld, a, c);
+        double d = (a == c) ? dk[a] : 0.0;
+        SMRT_AT(A1, ld, a, c) = d - x1 + x2;
+        SMRT_AT(A2, ld, a, c) = d - x1 - x2;
+      }
+      __syncthreads();
+
+      // two concurrent Cholesky factorisations: X- = L L^T (A1), X+ = C C^T (A2)
+      {
+        Team tm;
+        int half = NT / 2;
+        tm.size = half;
+        int which = tid / half;
+        tm.rank = tid % half;
+        tm.bar_id = 1 + which;
+        int bad = team_cholesky(tm, which == 0 ? A1 : A2, ld, h, &s_ctrl[4 + which]);
+        (void)bad;
+      }
+      __syncthreads();
+      if (s_ctrl[4] | s_ctrl[5]) {
+        if (tid == 0) set_error(A.status, b, ST_EIGEN);
+        failed = true;
+        break;
+      }
+
+      // M = C^T L  -> A3
+      {
+        Team tm = block_team();
+        team_gemm(
+            tm, h, h, h, [&](int i, int k) { return (k >= i) ? SMRT_AT(A2, ld, k, i) : 0.0; },
+            [&](int k, int j) { return (k >= j) ? SMRT_AT(A1, ld, k, j) : 0.0; },
+            [&](int i, int j, double acc) { SMRT_AT(A3, ld, i, j) = acc; });
+      }
+      __syncthreads();
+
+      // singular values / right rotations by one-sided Jacobi: A3 <- W = U Sigma
+      block_jacobi_svd(A3, ld, h, s_ctrl);
+      __syncthreads();
+      for (int j = tid; j < h; j += NT) {
+        double s2 = 0.0;
+        for (int i = 0; i < h; ++i) s2 = fma(SMRT_AT(A3, ld, i, j), SMRT_AT(A3, ld, i, j), s2);
+        sigma[j] = sqrt(s2);
+      }
+      __syncthreads();
+
+      // E~- = -C U = -C W Sigma^-1  -> A1
+      {
+        Team tm = block_team();
+        team_gemm(
+            tm, h, h, h, [&](int i, int k) { return (k <= i) ? SMRT_AT(A2, ld, i, k) : 0.0; },
+            [&](int k, int j) { return SMRT_AT(A3, ld, k, j); },
+            [&](int i, int j, double acc) { SMRT_AT(A1, ld, i, j) = -acc / sigma[j]; });
+      }
+      __syncthreads();
+
+      // E~+ = C^-T W: back substitution with the upper-triangular C^T, in place on the columns of A3
+      {
+        int tpc = 32;
+        while (tpc > 1 && h * tpc > NT) tpc >>= 1;
+        const int ngroups = NT / tpc;
+        const int grp = tid / tpc, lane = tid % tpc;
+        const unsigned gmask = (tpc == 32) ? 0xffffffffu : (((1u << tpc) - 1u) << ((tid & 31) & ~(tpc - 1)));
+        for (int c = grp; c < h; c += ngroups) {
+          double* x = A3 + (size_t)c * ld;
+          for (int j = h - 1; j >= 0; --j) {
+            if (lane == 0) x[j] = x[j] / SMRT_AT(A2, ld, j, j);
+            __syncwarp(gmask);
+            double xj = x[j];
+            for (int i = lane; i < j; i += tpc) x[i] = fma(-SMRT_AT(A2, ld, j, i), xj, x[i]);
+            __syncwarp(gmask);
+          }
+        }
+      }
+      __syncthreads();
+
+      // store k, F = s (E~+ - E~-) / 2, G = s (E~+ + E~-) / 2
+      {
+        double* rk = rec + A.eig_off[m];
+        double* rF = rk + smrt_even(smrt_npol(m) * n);
+        double* rG = rF + smrt_even((long long)h * h);
+        for (int j = tid; j < h; j += NT) rk[j] = sigma[j];
+        for (int e = tid; e < h * h; e += NT) {
+          int a = e % h, j = e / h;
+          double ep = SMRT_AT(A3, ld, a, j), em = SMRT_AT(A1, ld, a, j);
+          double s = 0.5 * sdiag[a];
+          rF[e] = s * (ep - em);
+          rG[e] = s * (ep + em);
+        }
+        if (tid < 32) {
+          double mn = 1e300;
+          for (int j = tid; j < h; j += 32) mn = fmin(mn, sigma[j]);
+          for (int off = 16; off > 0; off >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off, 32));
+          if (tid == 0) kmin[m] = mn;
+        }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) A.scat_flag[bl] = failed ? 0 : 1;
+    __syncthreads();
+  }
+}
+
+// --------------------------------------------------------------------------------------------------------------------
+// kernel 3: boundary system, mode summation, output stage
+// --------------------------------------------------------------------------------------------------------------------
+// vector region (doubles): mu[n] outmu[n] outw[n] kvec[hmax] tvec[hmax] Rt Tt Rb Tb Ttprev [hmax each] Rair Tair [hmax]
+//                          acc[9 * SMRT_MAX_INC] coh[4 * SMRT_MAX_INC] ; ints: perm1[hmax] perm2[hmax] inc[SMRT_MAX_INC]
+SMRT_HD size_t boundary_vec_doubles(int n, int hmax) {
+  return (size_t)3 * n + 9 * hmax + 13 * SMRT_MAX_INC + hmax /* two int arrays */ + SMRT_MAX_INC + 16;
+}
+SMRT_HD size_t boundary_mat_doubles(int hmax, int nrhs_max) {
+  return (size_t)2 * hmax * hmax + 3 * (size_t)hmax * (hmax + 1) + 3 * (size_t)hmax * nrhs_max + 16;
+}
+
+struct BoundaryCtx {
+  // per problem
+  int b, nl, n_air, n_incs, npol_out;
+  double freq;
+  cplx eps_star;
+};
+
+SMRT_GLOBAL void __launch_bounds__(SMRT_NT) boundary_kernel(KArgs A) {
+  SMRT_DYN_SMEM(smem);
+  SMRT_SHARED int s_item;
+  SMRT_SHARED int s_ctrl[8];
+  SMRT_SHARED double s_tau;
+  SMRT_SHARED int s_lend;
+  const int tid = threadIdx.x;
+  const int NT = blockDim.x;
+  const int n = A.n;
+  const int hmax = smrt_npol(A.m_max) * n;
+  const int nrhs_max = (A.mode == 0) ? 1 : 3 * 2 * A.n_inc;
+
+  double* mu = smem;
+  double* outmu = mu + n;
+  double* outw = outmu + n;
+  double* kvec = outw + n;
+  double* tvec = kvec + hmax;
+  double* Rt = tvec + hmax;
+  double* Tt = Rt + hmax;
+  double* Rb = Tt + hmax;
+  double* Tb = Rb + hmax;
+  double* Ttprev = Tb + hmax;
+  double* Rair = Ttprev + hmax;
+  double* Tair = Rair + hmax;
+  double* acc_act = Tair + hmax;                  // [3][3][SMRT_MAX_INC]
+  double* coh_act = acc_act + 9 * SMRT_MAX_INC;   // [2][2][SMRT_MAX_INC]
+  int* perm1 = reinterpret_cast<int*>(coh_act + 4 * SMRT_MAX_INC);
+  int* perm2 = perm1 + hmax;
+  int* inc = perm2 + hmax;
+  double* mats = A.use_global_scratch ? (A.scratch + (size_t)blockIdx.x * A.scratch_stride)
+                                      : (smem + boundary_vec_doubles(n, hmax));
+  const size_t szc = (size_t)hmax * hmax, szp = (size_t)hmax * (hmax + 1), szr = (size_t)hmax * nrhs_max;
+  double* BF = mats;
+  double* BG = BF + szc;
+  double* BR = BG + szc;
+  double* B1 = BR + szp;
+  double* B2 = B1 + szp;
+  double* btop = B2 + szp;
+  double* bbot = btop + szr;
+  double* svec = bbot + szr;
+
+  for (;;) {
+    if (tid == 0) s_item = atomicAdd(&A.counters[1], 1);
+    __syncthreads();
+    const int b = s_item;
+    __syncthreads();
+    if (b >= A.B) break;
+    const int nl = A.nlayer[b];
+    const size_t bL = (size_t)b * A.L;
+    const double freq = A.frequency[b];
+    const int n_out = (A.mode == 0) ? 2 * A.n_theta : 9 * A.n_inc;
+    double* out = A.values + (size_t)b * n_out;
+    if (nl <= 0 || (A.status[b] & 15) != 0) {
+      for (int i = tid; i < n_out; i += NT) out[i] = (nl <= 0) ? 0.0 : nan("");
+      if (tid == 0) {
+        A.n_streams_out[b] = 0;
+        A.optical_depth[b] = 0.0;
+      }
+      continue;
+    }
+    const double* eps_b = A.eps_eff + bL * 2;
+    const int kstar = most_refringent_layer(eps_b, nl);
+    const cplx eps_star = c_make(eps_b[2 * kstar], eps_b[2 * kstar + 1]);
+    const cplx eps0 = c_make(eps_b[0], eps_b[1]);
+    // air streams ----------------------------------------------------------------------------- streams.py:156, 212-218
+    const double rindex_air = c_sqrt(eps_star).re;
+    const int n_air = stream_count(rindex_air, A.gl_mu, n);
+    for (int j = tid; j < n_air; j += NT) outmu[j] = stream_mu(rindex_air, A.gl_mu, j);
+    __syncthreads();
+    if (n_air < 2) {
+      for (int i = tid; i < n_out; i += NT) out[i] = nan("");
+      if (tid == 0) {
+        set_error(A.status, b, ST_INPUT);
+        A.n_streams_out[b] = 0;
+        A.optical_depth[b] = 0.0;
+      }
+      __syncthreads();
+      continue;
+    }
+    for (int j = tid; j < n_air; j += NT) outw[j] = stream_weight(outmu, n_air, j);
+    // incident streams (active) --------------------------------------------------------- rtsolver_utils.py:91-107
+    if (tid == 0) {
+      int cnt = 0;
+      if (A.mode == 1) {
+        for (int t = 0; t < A.n_inc; ++t) {
+          double mu_inc = cos(A.theta_inc[t]);
+          int i0 = 0;
+          while (i0 < n_air && outmu[i0] > mu_inc) ++i0;  // searchsorted(-outmu, -mu_inc), left
+          int cand[2], nc = 0;
+          if (i0 == 0)
+            cand[nc++] = 0;
+          else if (i0 == n_air)
+            cand[nc++] = n_air - 1;
+          else {
+            cand[nc++] = i0 - 1;
+            cand[nc++] = i0;
+          }
+          for (int c = 0; c < nc; ++c) {
+            bool found = false;
+            for (int e = 0; e < cnt; ++e) found = found || (inc[e] == cand[c]);
+            if (!found && cnt < SMRT_MAX_INC) inc[cnt++] = cand[c];
+          }
+        }
+        // sort ascending (insertion sort, cnt <= 16)
+        for (int i = 1; i < cnt; ++i) {
+          int v = inc[i], j = i - 1;
+          while (j >= 0 && inc[j] > v) {
+            inc[j + 1] = inc[j];
+            --j;
+          }
+          inc[j + 1] = v;
+        }
+      }
+      s_ctrl[3] = cnt;
+    }
+    __syncthreads();
+    const int n_incs = s_ctrl[3];
+    for (int i = tid; i < 9 * SMRT_MAX_INC; i += NT) acc_act[i] = 0.0;
+    for (int i = tid; i < 4 * SMRT_MAX_INC; i += NT) coh_act[i] = 0.0;
+    __syncthreads();
+
+    const int nruns = (A.mode == 0) ? 1 : (A.m_max + 2);  // active: coherent pass + modes 0..m_max
+    bool failed = false;
+    double tau_report = 0.0;
+    bool shallow = false;
+
+    for (int run = 0; run < nruns && !failed; ++run) {
+      const bool coherent = (A.mode == 1 && run == 0);
+      const int m = (A.mode == 0) ? 0 : (run == 0 ? 0 : run - 1);
+      const int npol = smrt_npol(m);
+      const int nrhs = (A.mode == 0) ? 1 : npol * n_incs;
+
+      // optical depth, top-down, and the last layer kept ------------------------------------------ dort.py:444-452
+      if (tid == 0) {
+        double tau = 0.0;
+        int lend = nl - 1;
+        for (int l = 0; l < nl; ++l) {
+          double kmn;
+          if (!coherent && A.scat_flag[bL + l]) {
+            kmn = A.kmin[(bL + l) * SMRT_MAX_MODES + m];
+          } else {
+            double ri = real_index_of(eps_star, c_make(eps_b[2 * l], eps_b[2 * l + 1]));
+            kmn = (A.ks[bL + l] + A.ka[bL + l]) / stream_mu(ri, A.gl_mu, 0);
+          }
+          tau += kmn * A.thickness[bL + l];
+          if (A.prune_tau > 0.0 && tau > A.prune_tau) {
+            lend = l;
+            break;
+          }
+        }
+        s_tau = tau;
+        s_lend = lend;
+      }
+      __syncthreads();
+      const int l_end = s_lend;
+      if (run == ((A.mode == 0) ? 0 : 1)) tau_report = s_tau;  // the mode-0 (scattering) run
+      if (A.substrate_kind[b] == SUB_NONE && s_tau < 5.0) shallow = true;
+
+      int h_prev = 0, ldr_prev = 1;
+      bool have_prev = false;
+      bool r_transposed = false;
+
+      for (int l = l_end; l >= 0 && !failed; --l) {
+        const cplx eps_l = c_make(eps_b[2 * l], eps_b[2 * l + 1]);
+        const double rindex = real_index_of(eps_star, eps_l);
+        const int n_l = stream_count(rindex, A.gl_mu, n);
+        const int h = npol * n_l;
+        const int ldp = (h & 1) ? h : h + 1;
+        const double thick = A.thickness[bL + l];
+        const double ke = A.ks[bL + l] + A.ka[bL + l];
+        const bool scat = (!coherent) && (A.scat_flag[bL + l] != 0);
+        for (int j = tid; j < n_l; j += NT) mu[j] = stream_mu(rindex, A.gl_mu, j);
+        __syncthreads();
+
+        // eigen data: (k, F, G) from the workspace, or the trivial solution F = I, G = 0, k = ke / mu
+        if (scat) {
+          const double* rk = A.eig + (bL + l) * A.eig_stride + A.eig_off[m];
+          const double* rF = rk + smrt_even(smrt_npol(m) * n);
+          const double* rG = rF + smrt_even((long long)h * h);
+          for (int e = tid; e < h * h; e += NT) {
+            BF[e] = rF[e];
+            BG[e] = rG[e];
+          }
+          for (int a = tid; a < h; a += NT) kvec[a] = rk[a];
+        } else {
+          for (int e = tid; e < h * h; e += NT) {
+            BF[e] = ((e % h) == (e / h)) ? 1.0 : 0.0;
+            BG[e] = 0.0;
+          }
+          for (int a = tid; a < h; a += NT) kvec[a] = ke / mu[a / npol];
+        }
+        // interface coefficients on this layer's streams ------------------------ rtsolver_utils.py:473-644 (flat only)
+        for (int j = tid; j < n_l; j += NT) {
+          cplx eps_up = (l > 0) ? c_make(eps_b[2 * (l - 1)], eps_b[2 * (l - 1) + 1]) : c_make(1.0, 0.0);
+          FresnelRT ft = fresnel_power(A.interface_kind[bL + l], eps_l, eps_up, mu[j]);
+          FresnelRT fb;
+          if (l < nl - 1) {
+            fb = fresnel_power(A.interface_kind[bL + l + 1], eps_l, c_make(eps_b[2 * (l + 1)], eps_b[2 * (l + 1) + 1]),
+                               mu[j]);
+          } else if (A.substrate_kind[b] == SUB_FLAT) {
+            fb = fresnel_power(IF_FLAT, eps_l, c_make(A.substrate_eps[2 * b], A.substrate_eps[2 * b + 1]), mu[j]);
+          } else {
+            fb.R[0] = fb.R[1] = fb.R[2] = 0.0;
+            fb.T[0] = fb.T[1] = fb.T[2] = 0.0;
+          }
+          for (int p = 0; p < npol; ++p) {
+            Rt[j * npol + p] = ft.R[p];
+            Tt[j * npol + p] = ft.T[p];
+            Rb[j * npol + p] = fb.R[p];
+            Tb[j * npol + p] = fb.T[p];
+          }
+        }
+        __syncthreads();
+        for (int a = tid; a < h; a += NT) tvec[a] = exp(-kvec[a] * thick);
+
+        // right-hand sides ---------------------------------------------------------------------- dort.py:375-441
+        const int r = have_prev ? (h < h_prev ? h : h_prev) : 0;
+        {
+          const bool thermal = (A.mode == 0 && m == 0);
+          const double Tl = A.temperature[bL + l];
+          const double Bl = (thermal && Tl > 0.0) ? planck_function(freq, Tl, A.rayleigh_jeans) : 0.0;
+          for (int e = tid; e < h * nrhs; e += NT) {
+            int a = e % h, c = e / h;
+            int j = a / npol, p = a % npol;
+            double vt = 0.0, vb = 0.0;
+            if (thermal) {
+              if (Tl > 0.0) {
+                vt -= (1.0 - Rt[a]) * Bl;
+                vb -= (1.0 - Rb[a]) * Bl;
+              }
+              if (l > 0) {  // emission of the layer above transmitted into this layer (its own streams, truncated)
+                double Tup = A.temperature[bL + l - 1];
+                cplx eps_up = c_make(eps_b[2 * (l - 1)], eps_b[2 * (l - 1) + 1]);
+                double ri_up = real_index_of(eps_star, eps_up);
+                int n_up = stream_count(ri_up, A.gl_mu, n);
+                if (Tup > 0.0 && j < n_up) {
+                  FresnelRT fu = fresnel_power(A.interface_kind[bL + l], eps_up, eps_l, stream_mu(ri_up, A.gl_mu, j));
+                  vt += fu.T[p] * planck_function(freq, Tup, A.rayleigh_jeans);
+                }
+              }
+              if (l < l_end && a < r) {
+                double Tdn = A.temperature[bL + l + 1];
+                if (Tdn > 0.0) vb += Ttprev[a] * planck_function(freq, Tdn, A.rayleigh_jeans);
+              }
+              if (l == nl - 1 && A.substrate_kind[b] != SUB_NONE) {
+                vb += Tb[a] * planck_function(freq, A.substrate_temperature[b], A.rayleigh_jeans);
+              }
+            }
+            if (l < l_end && a < r) vb += Ttprev[a] * SMRT_AT(svec, h_prev, a, c);
+            SMRT_AT(btop, h, a, c) = vt;
+            SMRT_AT(bbot, h, a, c) = vb;
+          }
+        }
+        __syncthreads();
+        if (l == 0 && A.mode == 1) {
+          // incident beams (rtsolver_utils.py:109-135) through the air-snow interface: b_top += T_air I_down
+          for (int c = tid; c < nrhs; c += NT) {
+            int jinc = c / npol, ipol = c % npol;
+            int i = inc[jinc];
+            if (i < n_l) {  // rows beyond the layer's streams are truncated (dort.py:391-395)
+              double power = 1.0 / (2.0 * SMRT_PI * outw[i]);
+              if (m > 0) power *= 2.0;
+              FresnelRT fa = fresnel_power(A.interface_kind[bL], c_make(1.0, 0.0), eps0, outmu[i]);
+              SMRT_AT(btop, h, i * npol + ipol, c) += fa.T[ipol] * power;
+            }
+          }
+        }
+        __syncthreads();
+
+        // A21 = F - Rb' D G  -> B1 ;  A22 = (G - Rb' D F) t  -> B2, with Rb' = diag(Rb) + Tt(l+1) R(l+1) Tb(l) truncated
+        {
+          Team tm = block_team();
+          const double* Rm = BR;
+          const int ldr = ldr_prev;
+          const bool rt = r_transposed;
+          auto aop = [&](int i, int k) {
+            if (i >= r) return 0.0;
+            double rv = rt ? SMRT_AT(Rm, ldr, k, i) : SMRT_AT(Rm, ldr, i, k);
+            double dsgn = ((k % npol) == 2) ? -1.0 : 1.0;
+            return Ttprev[i] * rv * (Tb[k] * dsgn);
+          };
+          team_gemm(
+              tm, h, h, r, aop, [&](int k, int j) { return SMRT_AT(BG, h, k, j); },
+              [&](int i, int j, double acc) {
+                double dsgn = ((i % npol) == 2) ? -1.0 : 1.0;
+                SMRT_AT(B1, ldp, i, j) = SMRT_AT(BF, h, i, j) - Rb[i] * dsgn * SMRT_AT(BG, h, i, j) - acc;
+              });
+          team_gemm(
+              tm, h, h, r, aop, [&](int k, int j) { return SMRT_AT(BF, h, k, j); },
+              [&](int i, int j, double acc) {
+                double dsgn = ((i % npol) == 2) ? -1.0 : 1.0;
+                SMRT_AT(B2, ldp, i, j) =
+                    (SMRT_AT(BG, h, i, j) - Rb[i] * dsgn * SMRT_AT(BF, h, i, j) - acc) * tvec[j];
+              });
+        }
+        __syncthreads();
+        if (block_lu(B1, ldp, h, perm1, s_ctrl)) {
+          failed = true;
+          break;
+        }
+        block_lu_solve(B1, ldp, h, perm1, B2, ldp, h, 0);     // Y22 = A21^-1 A22
+        block_lu_solve(B1, ldp, h, perm1, bbot, h, nrhs, 0);  // Yr  = A21^-1 b_bot
+
+        // Schur complement S = A12 - A11 Y22 -> BR ;  b_top' = b_top - A11 Yr
+        {
+          Team tm = block_team();
+          auto a11 = [&](int i, int k) {
+            double dsgn = ((i % npol) == 2) ? -1.0 : 1.0;
+            return (dsgn * SMRT_AT(BG, h, i, k) - Rt[i] * SMRT_AT(BF, h, i, k)) * tvec[k];
+          };
+          team_gemm(
+              tm, h, h, h, a11, [&](int k, int j) { return SMRT_AT(B2, ldp, k, j); },
+              [&](int i, int j, double acc) {
+                double dsgn = ((i % npol) == 2) ? -1.0 : 1.0;
+                SMRT_AT(BR, ldp, i, j) = dsgn * SMRT_AT(BF, h, i, j) - Rt[i] * SMRT_AT(BG, h, i, j) - acc;
+              });
+          team_gemm(
+              tm, h, nrhs, h, a11, [&](int k, int c) { return SMRT_AT(bbot, h, k, c); },
+              [&](int i, int c, double acc) { SMRT_AT(btop, h, i, c) -= acc; });
+        }
+        __syncthreads();
+        if (block_lu(BR, ldp, h, perm2, s_ctrl)) {
+          failed = true;
+          break;
+        }
+        block_lu_solve(BR, ldp, h, perm2, btop, h, nrhs, 0);  // z- = S^-1 b_top'
+        // z+ = Yr - Y22 z-  (in place in bbot), then s = F t z+ + G z-
+        {
+          Team tm = block_team();
+          team_gemm(
+              tm, h, nrhs, h, [&](int i, int k) { return SMRT_AT(B2, ldp, i, k); },
+              [&](int k, int c) { return SMRT_AT(btop, h, k, c); },
+              [&](int i, int c, double acc) { SMRT_AT(bbot, h, i, c) -= acc; });
+          __syncthreads();
+          team_gemm(
+              tm, h, nrhs, 2 * h,
+              [&](int i, int k) { return (k < h) ? SMRT_AT(BF, h, i, k) * tvec[k] : SMRT_AT(BG, h, i, k - h); },
+              [&](int k, int c) { return (k < h) ? SMRT_AT(bbot, h, k, c) : SMRT_AT(btop, h, k - h, c); },
+              [&](int i, int c, double acc) { SMRT_AT(svec, h, i, c) = acc; });
+        }
+        __syncthreads();
+
+        if (l > 0) {
+          // reflection operator of the stack seen from the layer above: R = (G - F t Y22) S^-1, kept transposed in B1
+          Team tm = block_team();
+          team_gemm(
+              tm, h, h, h, [&](int i, int k) { return SMRT_AT(BF, h, i, k) * tvec[k]; },
+              [&](int k, int j) { return SMRT_AT(B2, ldp, k, j); },
+              [&](int i, int j, double acc) { SMRT_AT(B1, ldp, j, i) = SMRT_AT(BG, h, i, j) - acc; });
+          __syncthreads();
+          block_lu_solve(BR, ldp, h, perm2, B1, ldp, h, 1);  // S^T R^T = K^T
+          double* tmp = BR;
+          BR = B1;
+          B1 = tmp;
+          r_transposed = true;
+          ldr_prev = ldp;
+          for (int a = tid; a < h; a += NT) Ttprev[a] = Tt[a];
+          h_prev = h;
+          have_prev = true;
+          __syncthreads();
+        }
+      }  // layers
+      if (failed) break;
+
+      // emerging intensity ---------------------------------------------------------------------------- dort.py:472-488
+      // layer 0 quantities are still live: mu (layer 0), Tt (snow -> air), svec (h0 x nrhs)
+      {
+        const cplx eps_l0 = eps0;
+        const double rindex0 = real_index_of(eps_star, eps_l0);
+        const int n_0 = stream_count(rindex0, A.gl_mu, n);
+        const int h0 = npol * n_0;
+        const double T0 = A.temperature[bL];
+        const double B0 = (A.mode == 0 && m == 0 && T0 > 0.0) ? planck_function(freq, T0, A.rayleigh_jeans) : 0.0;
+        if (A.mode == 0) {
+          // passive: I0up = T_top0 (I1up + B0) on the first npol*n_air rows; Tb(theta) by inverse Planck + interpolation
+          for (int a = tid; a < 2 * n_air; a += NT) {
+            double v = (a < h0) ? Tt[a] * (svec[a] + B0) : 0.0;
+            btop[a] = inverse_planck_function(freq, v, A.rayleigh_jeans);  // reuse btop: Tb per (stream, pol)
+          }
+          __syncthreads();
+          for (int e = tid; e < 2 * A.n_theta; e += NT) {
+            int p = e / A.n_theta, t = e % A.n_theta;
+            double umu = cos(A.theta[t]);
+            // rtsolver_utils.py:179-239: linear in mu with extrapolation; node mu = 1 inserted when needed
+            bool ins = false;
+            for (int tt = 0; tt < A.n_theta; ++tt) ins = ins || (cos(A.theta[tt]) > outmu[0]);
+            int nn = n_air + (ins ? 1 : 0);
+            auto xn = [&](int i) { return ins ? (i == 0 ? 1.0 : outmu[i - 1]) : outmu[i]; };
+            auto yn = [&](int i) {
+              if (ins) {
+                if (i == 0) return 0.5 * (btop[0] + btop[1]);
+                return btop[(i - 1) * 2 + p];
+              }
+              return btop[i * 2 + p];
+            };
+            // nodes are descending; find the segment [lo, lo+1] in ASCENDING order semantics of scipy interp1d
+            // ascending index k = nn-1-i ; idx = searchsorted(x_asc, umu) clipped to [1, nn-1]
+            int cnt = 0;  // number of nodes with x < umu
+            for (int i = 0; i < nn; ++i) cnt += (xn(i) < umu) ? 1 : 0;
+            int idx = cnt < 1 ? 1 : (cnt > nn - 1 ? nn - 1 : cnt);
+            int ilo = nn - 1 - (idx - 1), ihi = nn - 1 - idx;  // descending-array indices of x_lo < x_hi
+            double xlo = xn(ilo), xhi = xn(ihi), ylo = yn(ilo), yhi = yn(ihi);
+            double slope = (yhi - ylo) / (xhi - xlo);
+            out[p * A.n_theta + t] = slope * (umu - xlo) + ylo;
+          }
+          if (tid == 0) {
+            A.n_streams_out[b] = n_air;
+          }
+          for (int j = tid; j < n; j += NT)
+            A.stream_angles[(size_t)b * n + j] = (j < n_air) ? acos(outmu[j]) * (180.0 / SMRT_PI) : nan("");
+        } else {
+          // active: keep only the backscatter element (stream inc[j], beam j) of every (pol_out, pol_in) pair
+          for (int e = tid; e < npol * npol * n_incs; e += NT) {
+            int jinc = e / (npol * npol), rem = e % (npol * npol);
+            int ps = rem / npol, pi = rem % npol;
+            int i = inc[jinc];
+            int row = i * npol + ps, col = jinc * npol + pi;
+            double power = 1.0 / (2.0 * SMRT_PI * outw[i]);
+            if (m > 0) power *= 2.0;
+            FresnelRT fa = fresnel_power(A.interface_kind[bL], c_make(1.0, 0.0), eps0, outmu[i]);
+            double idn = (ps == pi) ? power : 0.0;
+            double i1 = (row < h0) ? SMRT_AT(svec, h0, row, col) : 0.0;
+            double v = fa.R[ps] * idn + ((row < h0) ? Tt[row] * i1 : 0.0);
+            if (coherent) {
+              coh_act[(ps * 2 + pi) * SMRT_MAX_INC + jinc] = v;
+            } else {
+              if (ps < 2 && pi < 2) v -= coh_act[(ps * 2 + pi) * SMRT_MAX_INC + jinc] * (m > 0 ? 2.0 : 1.0);
+              double f;
+              if (m == 0)
+                f = 1.0;
+              else
+                f = (ps < 2) ? cos(m * A.phi) : sin(m * A.phi);
+              acc_act[(ps * 3 + pi) * SMRT_MAX_INC + jinc] += f * v;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }  // runs
+
+    if (failed) {
+      for (int i = tid; i < n_out; i += NT) out[i] = nan("");
+      if (tid == 0) {
+        set_error(A.status, b, ST_SINGULAR);
+        A.n_streams_out[b] = 0;
+        A.optical_depth[b] = tau_report;
+      }
+      __syncthreads();
+      continue;
+    }
+    if (A.mode == 1) {
+      // interpolation over the incident streams ------------------------------------------- rtsolver_utils.py:179-239
+      for (int e = tid; e < 9 * A.n_inc; e += NT) {
+        int ps = e / (3 * A.n_inc), pi = (e / A.n_inc) % 3, t = e % A.n_inc;
+        double umu = cos(A.theta_inc[t]);
+        bool ins = false;
+        for (int tt = 0; tt < A.n_inc; ++tt) ins = ins || (cos(A.theta_inc[tt]) > outmu[inc[0]]);
+        int nn = n_incs + (ins ? 1 : 0);
+        auto val = [&](int a, int c, int j) { return acc_act[(a * 3 + c) * SMRT_MAX_INC + j]; };
+        auto xn = [&](int i) { return ins ? (i == 0 ? 1.0 : outmu[inc[i - 1]]) : outmu[inc[i]]; };
+        auto yn = [&](int i) {
+          if (ins) {
+            if (i == 0) {  // inserted nadir node: co/cross-pol means of the steepest stream
+              double copol = 0.5 * (val(0, 0, 0) + val(1, 1, 0));
+              double cross = 0.5 * (val(1, 0, 0) + val(0, 1, 0));
+              if (ps < 2 && pi < 2) return (ps == pi) ? copol : cross;
+              return val(ps, pi, 0);
+            }
+            return val(ps, pi, i - 1);
+          }
+          return val(ps, pi, i);
+        };
+        double res;
+        if (nn == 1) {
+          res = yn(0);
+        } else {
+          int cnt = 0;
+          for (int i = 0; i < nn; ++i) cnt += (xn(i) < umu) ? 1 : 0;
+          int idx = cnt < 1 ? 1 : (cnt > nn - 1 ? nn - 1 : cnt);
+          int ilo = nn - 1 - (idx - 1), ihi = nn - 1 - idx;
+          double xlo = xn(ilo), xhi = xn(ihi), ylo = yn(ilo), yhi = yn(ihi);
+          double slope = (yhi - ylo) / (xhi - xlo);
+          res = slope * (umu - xlo) + ylo;
+        }
+        out[(ps * 3 + pi) * A.n_inc + t] = res;
+      }
+      if (tid == 0) A.n_streams_out[b] = n_incs;
+      for (int j = tid; j < n; j += NT)
+        A.stream_angles[(size_t)b * n + j] = (j < n_incs) ? acos(outmu[inc[j]]) * (180.0 / SMRT_PI) : nan("");
+    }
+    if (tid == 0) {
+      A.optical_depth[b] = tau_report;
+      if (shallow) atomicOr(&A.status[b], ST_WARN_SHALLOW);
+    }
+    __syncthreads();
+  }
+}

@@ -1,0 +1,140 @@
+// simt.h — one source, two targets.
+//
+// Under nvcc this header is (almost) empty: the kernels use the real CUDA built-ins.
+// Under a plain host compiler (g++ -DSMRT_SIMT_EMULATION) it provides a tiny SIMT emulator: one OS thread per CUDA
+// thread of ONE block at a time, __syncthreads()/named barriers as pthread barriers, warp shuffles through a per-warp
+// mailbox.  The emulator exists so that the device code can be exercised by the CPU test-suite in the authoring
+// container, which has nvcc but no GPU (tests/test_simt_emulation.py).  It is test infrastructure: the shipped
+// library (libsmrt_dort_b200.so) is compiled by nvcc for sm_100a only and contains none of it.
+#pragma once
+
+#ifdef __CUDACC__
+
+#include <cuda_runtime.h>
+#define SMRT_DEV __device__ __forceinline__
+#define SMRT_HD __host__ __device__ __forceinline__
+#define SMRT_DEV_NOINLINE __device__ __noinline__
+#define SMRT_GLOBAL __global__
+#define SMRT_SHARED __shared__
+#define SMRT_RESTRICT __restrict__
+
+SMRT_DEV void smrt_named_barrier(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+#else  // ------------------------------------------------------------------------------------------ host emulation
+
+#include <pthread.h>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define SMRT_DEV inline
+#define SMRT_HD inline
+#define SMRT_DEV_NOINLINE inline
+#define SMRT_GLOBAL
+#define SMRT_SHARED static
+#define SMRT_RESTRICT __restrict__
+#define __launch_bounds__(...)
+#define __forceinline__ inline
+#define __device__
+#define __host__
+#define __global__
+#define __constant__ static
+
+struct simt_dim3 {
+  unsigned x = 1, y = 1, z = 1;
+};
+extern thread_local simt_dim3 threadIdx;
+extern thread_local simt_dim3 blockIdx;
+extern simt_dim3 blockDim;
+extern simt_dim3 gridDim;
+
+namespace simt {
+struct BlockState {
+  int nthreads = 0;
+  pthread_barrier_t block_barrier;
+  std::vector<pthread_barrier_t> warp_barrier;        // one per warp
+  std::vector<std::vector<uint64_t>> warp_mailbox;    // [warp][32]
+  std::map<std::pair<int, int>, pthread_barrier_t*> named;
+  std::mutex named_mutex;
+  std::atomic<int> or_flag[2];
+};
+extern BlockState* g_block;
+
+// Run `body()` for every thread of every block of the grid; blocks run one after the other.
+void launch(unsigned grid, unsigned block, const std::function<void()>& body);
+unsigned char* dynamic_smem(size_t bytes);  // per-launch scratch, shared by the threads of the current block
+}  // namespace simt
+
+void __syncthreads();
+int __syncthreads_or(int pred);
+void __syncwarp(unsigned mask = 0xffffffffu);
+void simt_group_barrier(unsigned mask);
+void __threadfence();
+void smrt_named_barrier(int id, int nthreads);
+
+uint64_t simt_shfl_raw(unsigned mask, uint64_t v, int src_lane);
+
+template <typename T>
+inline T __shfl_sync(unsigned mask, T v, int src_lane, int width = 32) {
+  static_assert(sizeof(T) <= 8, "shuffle of <= 8 byte types only");
+  uint64_t raw = 0;
+  std::memcpy(&raw, &v, sizeof(T));
+  int lane = threadIdx.x & 31;
+  int base = lane & ~(width - 1);
+  raw = simt_shfl_raw(mask, raw, base + (src_lane & (width - 1)));
+  T out;
+  std::memcpy(&out, &raw, sizeof(T));
+  return out;
+}
+template <typename T>
+inline T __shfl_xor_sync(unsigned m, T v, int lane_mask, int width = 32) {
+  int lane = threadIdx.x & 31;
+  return __shfl_sync(m, v, (lane ^ lane_mask) & (width - 1) | (lane & ~(width - 1)), 32);
+}
+template <typename T>
+inline T __shfl_down_sync(unsigned m, T v, unsigned delta, int width = 32) {
+  int lane = threadIdx.x & 31;
+  int src = lane + (int)delta;
+  if ((src & ~(width - 1)) != (lane & ~(width - 1))) src = lane;
+  return __shfl_sync(m, v, src, 32);
+}
+
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicMax(int* p, int v) {
+  int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+  }
+  return old;
+}
+
+inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+inline double fma_(double a, double b, double c) { return std::fma(a, b, c); }
+inline void sincos(double x, double* s, double* c) {
+  *s = std::sin(x);
+  *c = std::cos(x);
+}
+inline void sincospi(double x, double* s, double* c) {
+  // exact at the multiples of 1/2 like the CUDA intrinsic
+  double r = std::fmod(x, 2.0);
+  if (r == 0.0) { *s = 0.0; *c = 1.0; }
+  else if (r == 0.5) { *s = 1.0; *c = 0.0; }
+  else if (r == 1.0) { *s = 0.0; *c = -1.0; }
+  else if (r == 1.5) { *s = -1.0; *c = 0.0; }
+  else { *s = std::sin(3.141592653589793238462643383279502884 * r); *c = std::cos(3.141592653589793238462643383279502884 * r); }
+}
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __dadd_rn(double a, double b) { return a + b; }
+
+#endif

@@ -1,0 +1,94 @@
+// TEST INFRASTRUCTURE ONLY — runs the device code of smrt_b200/csrc on the CPU through the SIMT emulator so that the
+// kernels can be checked against the oracle in the authoring container (no GPU).  Built by tests/simt_emu/Makefile into
+// tests/simt_emu/libsmrt_emu.so; loaded by tests/test_simt_emulation.py with ctypes.  Same batch struct as the C ABI,
+// host pointers.
+#include <cstdio>
+#include <vector>
+
+#include "dort_host.h"
+
+extern "C" {
+
+int emu_gauss_legendre(int n, double* mu) {
+  smrt_host::gauss_legendre_positive_nodes(n, mu);
+  return 0;
+}
+
+// runs optics + eigen + boundary for the whole batch with `threads` emulated threads per block
+int emu_solve_batch(const smrtb200_options* opt, const smrtb200_batch* batch, int threads, int* sweeps_out) {
+  const char* err = smrt_host::validate_options(*opt);
+  if (err) {
+    std::fprintf(stderr, "emu: %s\n", err);
+    return -1;
+  }
+  smrt_host::Layout L = smrt_host::make_layout(*opt);
+  const int B = batch->B;
+  const size_t BL = (size_t)B * opt->max_layers;
+  std::vector<double> gl(L.n), aux(BL * SMRT_AUX_STRIDE), eig(BL * (size_t)L.eig_stride), kmin(BL * SMRT_MAX_MODES);
+  std::vector<int> scat(BL, 0), counters(2, 0);
+  smrt_host::gauss_legendre_positive_nodes(L.n, gl.data());
+  std::vector<double> scratch((size_t)std::max(L.eigen_scratch_doubles, L.boundary_scratch_doubles) + 64);
+
+  KArgs A = smrt_host::make_kargs(*opt, L, *batch, 0, B);
+  A.gl_mu = gl.data();
+  A.aux = aux.data();
+  A.eig = eig.data();
+  A.kmin = kmin.data();
+  A.scat_flag = scat.data();
+  A.counters = counters.data();
+  A.scratch = scratch.data();
+  A.scratch_stride = (long long)scratch.size();
+  A.use_global_scratch = 1;  // the emulator's "shared memory" is 1 MiB: keep matrices in the scratch
+  for (int b = 0; b < B; ++b) batch->status[b] = 0;
+
+  simt::launch((unsigned)((BL + 127) / 128), 128, [&]() { optics_kernel(A); });
+  simt::launch(1, (unsigned)threads, [&]() { eigen_kernel(A); });
+  simt::launch(1, (unsigned)threads, [&]() { boundary_kernel(A); });
+  (void)sweeps_out;
+  return 0;
+}
+
+// unit hooks -----------------------------------------------------------------------------------------------------
+int emu_layer_optics(double frequency, double f, double e0r, double e0i, double esr, double esi, int emmodel,
+                     int ms_kind, double p0, double p1, int invert, double* out /* eps_re, eps_im, ks, ka, iba */) {
+  MicroParams mp;
+  LayerOptics o = layer_optics(frequency, f, c_make(e0r, e0i), c_make(esr, esi), emmodel, ms_kind, p0, p1, invert, &mp);
+  out[0] = o.eps_eff.re;
+  out[1] = o.eps_eff.im;
+  out[2] = o.ks;
+  out[3] = o.ka;
+  out[4] = o.iba_coeff;
+  return o.status;
+}
+
+int emu_fresnel(int kind, double e1r, double e1i, double e2r, double e2i, double mu, double* out /* R[3], T[3] */) {
+  FresnelRT f = fresnel_power(kind, c_make(e1r, e1i), c_make(e2r, e2i), mu);
+  for (int p = 0; p < 3; ++p) {
+    out[p] = f.R[p];
+    out[3 + p] = f.T[p];
+  }
+  return 0;
+}
+
+// Fourier mode m of the IBA phase matrix for one stream pair: out[npol*npol]
+int emu_iba_phase_mode(int m, int m_max, double mu_s, double mu_i, double iba_coeff, double kk, int ms_kind, double f,
+                       double p0, double p1, double* out) {
+  int K = smrt_host::azimuth_half_samples(m_max);
+  std::vector<double> ct(2 * K), st(2 * K);
+  for (int j = 0; j < 2 * K; ++j) sincospi((double)j / K, &st[j], &ct[j]);
+  MicroParams mp = micro_prepare(ms_kind, f, p0, p1);
+  iba_phase_mode(m, K, ct.data(), st.data(), mu_s, mu_i, iba_coeff, kk, mp, out);
+  return 0;
+}
+
+// one-sided Jacobi on an h x h column-major matrix (ld = h); returns sweeps
+int emu_jacobi(double* W, int h, int threads) {
+  int sweeps = 0;
+  std::vector<int> ctrl(8, 0);
+  simt::launch(1, (unsigned)threads, [&]() {
+    int s = block_jacobi_svd(W, h, h, ctrl.data());
+    if (threadIdx.x == 0) sweeps = s;
+  });
+  return sweeps;
+}
+}
