@@ -1,0 +1,371 @@
+"""``make_model(emmodel, "dort").run(sensor, snowpacks)`` on the B200 — the drop-in boundary of SURVEY.md §8(b).
+
+Same call surface as the reference (``smrt/core/model.py:120-127, 310-320``): ``make_model(emmodel, rtsolver,
+emmodel_options=, rtsolver_options=)`` returns an object whose ``run(sensor, snowpack, ...)`` accepts a snowpack, a
+list / dict / pandas Series / DataFrame of snowpacks and returns a ``Result`` with the reference's dims, coords and
+``other_data``.  What differs is *how*: instead of one Python emmodel object per layer and one ``DORT`` instance per
+(snowpack, frequency) simulation fanned out over joblib processes (``model.py:395-398, 584-619``), every simulation of
+the call is packed into struct-of-arrays form and solved by ONE batched call into the CUDA library; the N-d result is
+assembled from the output block in one shot.
+
+Three seams are offered:
+
+* ``smrt_b200.make_model(...)``                       — stand-alone replacement of ``smrt.make_model`` for the DORT path
+* ``smrt_b200.B200Runner``                            — a *runner* for an unmodified SMRT: ``Model.run(..., runner=B200Runner())``
+* ``smrt_b200.DORT``                                  — an *rtsolver plugin* class: ``smrt.make_model("iba", smrt_b200.DORT)``
+"""
+
+from __future__ import annotations
+
+import itertools
+import warnings
+from collections.abc import Mapping
+from typing import Optional, Sequence
+
+import numpy as np
+import pandas as pd
+
+from . import capi
+from .error import SMRTError, SMRTWarning, smrt_warn
+from .labelled import DataArray
+from .pack import MODE_ACTIVE, MODE_PASSIVE, ProblemBatch, emmodel_code, pack_simulations
+from .result import ActiveResult, PassiveResult, Result, concat_results
+
+# DORT options of the reference (smrt/rtsolver/dort.py:148-161)
+_DORT_DEFAULTS = dict(n_max_stream=32, m_max=2, stream_mode="most_refringent", phase_normalization="auto",
+                      phase_symmetrization=False, error_handling="exception", process_coherent_layers=False,
+                      prune_deep_snowpack=None, diagonalization_method="schur_forcedtriu",
+                      diagonalization_cache=False, rayleigh_jeans_approximation=False)
+_DIAG_METHODS = ("eig", "schur", "schur_forcedtriu", "half_rank_eig", "stamnes88")
+
+_SHALLOW_MSG = ("DORT has detected that the snowpack is optically shallow (tau={tau:g}) and no substrate has been set, "
+                "meaning that the space under the snowpack is 'empty' with snowpack shallow enough to affect the "
+                "measured signal at the surface. This is usually not wanted and can produce wrong results. Either "
+                "increase the thickness of the snowpack or set a substrate. If wanted, add a transparent substrate to "
+                "supress this warning")
+
+
+def _is_sequence(x):
+    return isinstance(x, (Sequence, np.ndarray)) and not isinstance(x, str)
+
+
+def check_dort_options(options: Optional[dict]) -> dict:
+    """Validate rtsolver_options against the reference's DORT signature; reject what the device path does not do."""
+    opts = dict(_DORT_DEFAULTS)
+    for k, v in (options or {}).items():
+        if k not in opts:
+            raise TypeError(f"DORT.__init__() got an unexpected keyword argument '{k}'")
+        opts[k] = v
+    if opts["stream_mode"] not in (None, "most_refringent"):
+        raise SMRTError(f"stream_mode={opts['stream_mode']!r} is not implemented on the B200 path "
+                        "(only 'most_refringent')")
+    if opts["process_coherent_layers"]:
+        raise SMRTError("process_coherent_layers=True is not implemented on the B200 path")
+    if opts["phase_symmetrization"]:
+        raise SMRTError("phase_symmetrization=True is not implemented on the B200 path")
+    if opts["diagonalization_method"] not in _DIAG_METHODS:
+        raise SMRTError(f"Unknown method '{opts['diagonalization_method']}' to diagonalize the matrix")
+    # diagonalization_method / diagonalization_cache: accepted and ignored — the answer does not depend on the
+    # eigenbasis and the device path always uses the symmetrised half-rank solve
+    if opts["error_handling"] not in ("exception", "nan"):
+        raise SMRTError("error_handling must be 'exception' or 'nan'")
+    if not (2 <= int(opts["n_max_stream"]) <= 256):
+        raise SMRTError("n_max_stream must be between 2 and 256")
+    if not (0 <= int(opts["m_max"]) <= 3):
+        raise SMRTError("m_max larger than 3 is not implemented on the B200 path")
+    return opts
+
+
+class _PlanCache:
+    """One plan per (device, option set); plans own GBs of workspace, so they are reused across run() calls."""
+
+    def __init__(self):
+        self._plans = {}
+
+    def get(self, batch: ProblemBatch, opts: dict, device: int) -> capi.Plan:
+        o = capi.make_options(batch, n_max_stream=opts["n_max_stream"], m_max=opts["m_max"],
+                              phase_normalization=opts["phase_normalization"],
+                              prune_deep_snowpack=opts["prune_deep_snowpack"],
+                              rayleigh_jeans_approximation=opts["rayleigh_jeans_approximation"], device=device)
+        key = (device, o.mode, o.n_max_stream, o.m_max, o.max_layers, o.n_theta, o.n_inc, o.normalization,
+               o.rayleigh_jeans, o.prune_deep_snowpack)
+        plan = self._plans.get(key)
+        if plan is None or plan.options.max_batch < batch.B:
+            if plan is not None:
+                plan.close()
+            o.max_batch = max(batch.B, 1)
+            plan = capi.Plan(o)
+            self._plans[key] = plan
+        return plan
+
+    def clear(self):
+        for p in self._plans.values():
+            p.close()
+        self._plans.clear()
+
+
+_PLANS = _PlanCache()
+
+
+def solve_batch(batch: ProblemBatch, rtsolver_options: Optional[dict] = None, device: int = 0) -> capi.HostOutputs:
+    """Solve a packed batch on one GPU through the C ABI (host buffers in, host buffers out)."""
+    opts = check_dort_options(rtsolver_options)
+    plan = _PLANS.get(batch, opts, device)
+    return plan.solve_host(batch)
+
+
+def _raise_or_nan(out: capi.HostOutputs, opts: dict):
+    err = out.status & capi.ST_ERR_MASK
+    if np.any(err) and opts["error_handling"] == "exception":
+        b = int(np.flatnonzero(err)[0])
+        raise SMRTError(f"simulation #{b}: " + capi.STATUS_MESSAGES.get(int(err[b]), "DORT failed")
+                        + "\nFor mass simulations, exceptions may be annoying: return NaN instead with "
+                        "rtsolver_options=dict(error_handling='nan').")
+    for b in np.flatnonzero(out.status & capi.ST_WARN_SHALLOW):
+        smrt_warn(_SHALLOW_MSG.format(tau=float(out.optical_depth[b])))
+        break  # once per run() call is enough
+
+
+def _simulation_result(mode, sensor, batch: ProblemBatch, out: capi.HostOutputs, b: int) -> Result:
+    """Result of ONE simulation, with the reference's coords and other_data (rtsolver_utils.py:322-344, 373-398)."""
+    n = int(batch.nlayer[b])
+    layer_index = ("layer", range(n))
+    ns = int(out.n_streams[b])
+    other = {
+        "stream_angles": DataArray(out.stream_angles[b, :ns].copy(), coords=[range(ns)]),
+        "effective_permittivity": DataArray(out.eps_eff[b, :n].copy(), coords=[layer_index]),
+        "ks": DataArray(out.ks[b, :n].copy(), coords=[layer_index], name="ks"),
+        "ke": DataArray(out.ks[b, :n] + out.ka[b, :n], coords=[layer_index], name="ke"),
+        "ka": DataArray(out.ka[b, :n].copy(), coords=[layer_index], name="ka"),
+        "thickness": DataArray(batch.thickness[b, :n].copy(), coords=[layer_index], name="thickness"),
+    }
+    if mode == "P":
+        coords = [("polarization", ["V", "H"]), ("theta", sensor.theta_deg)]
+        return PassiveResult(out.values[b].copy(), coords, channel_map=sensor.channel_map, other_data=other)
+    pola = ["V", "H", "U"]
+    coords = [("polarization_inc", pola), ("polarization", pola), ("theta_inc", sensor.theta_inc_deg)]
+    return ActiveResult(out.values[b].copy(), coords, channel_map=sensor.channel_map, other_data=other)
+
+
+class Model:
+    """Batched B200 counterpart of ``smrt.core.model.Model`` for emmodel in {iba, dmrt_qca_shortrange,
+    dmrt_qcacp_shortrange, nonscattering} and rtsolver "dort"."""
+
+    _broadcast_capability = {"theta_inc", "polarization_inc", "theta", "phi", "polarization"}  # dort.py:140-146
+
+    def __init__(self, emmodel, rtsolver="dort", emmodel_options=None, rtsolver_options=None, device: int = 0):
+        if rtsolver is not None and not (rtsolver == "dort" or getattr(rtsolver, "__name__", "") == "DORT"):
+            raise SMRTError(f"rtsolver {rtsolver!r} is not implemented on the B200 path (only 'dort')")
+        self.emmodel = emmodel
+        if isinstance(emmodel, Mapping):
+            raise SMRTError("a dict of emmodels (per medium) is not implemented on the B200 path")
+        for em in (emmodel if _is_sequence(emmodel) else [emmodel]):
+            if em is not None:
+                emmodel_code(em)  # fail early on unsupported models
+        self.rtsolver = rtsolver
+        self.emmodel_options = dict(emmodel_options or {})
+        self.rtsolver_options = dict(rtsolver_options or {})
+        self.device = device
+        check_dort_options(self.rtsolver_options)
+
+    def set_rtsolver_options(self, options=None, **kwargs):
+        if options is not None:
+            if not isinstance(options, Mapping):
+                raise SMRTError("options must be a Mapping (eg. dict)")
+            self.rtsolver_options = dict(options)
+        self.rtsolver_options.update(kwargs)
+        check_dort_options(self.rtsolver_options)
+
+    def set_emmodel_options(self, options=None, **kwargs):
+        if options is not None:
+            if not isinstance(options, Mapping):
+                raise SMRTError("options must be a Mapping (eg. dict)")
+            self.emmodel_options = dict(options)
+        self.emmodel_options.update(kwargs)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def prepare_simulations(self, sensor, snowpack, snowpack_dimension, snowpack_column):
+        """Same normalisation and ordering as reference ``model.py:415-527`` (sensor axes outermost, snowpacks
+        innermost); returns (flat list of (sensor, snowpack), list of (dimension name, values))."""
+        if isinstance(snowpack, Mapping):
+            snowpack_dimension = "snowpack", list(snowpack.keys())
+            snowpack = list(snowpack.values())
+        if isinstance(snowpack, pd.DataFrame):
+            try:
+                snowpack = snowpack[snowpack_column]
+            except KeyError:
+                raise SMRTError(f"the snowpack DataFrame has no column named '{snowpack_column}'. "
+                                "Check the snowpack_column argument.")
+        if isinstance(snowpack, pd.Series):
+            name = snowpack.index.name or "snowpack"
+            snowpack_dimension = name, snowpack.index.tolist()
+            snowpack = snowpack.tolist()
+        if _is_sequence(snowpack):
+            if snowpack_dimension is None:
+                snowpack_dimension = "snowpack", None
+            if snowpack_dimension[1] is None:
+                snowpack_dimension = snowpack_dimension[0], range(len(snowpack))
+            if len(snowpack) != len(snowpack_dimension[1]):
+                raise SMRTError("The list of snowpacks must have the same length as the snowpack_dimension")
+        if isinstance(snowpack_dimension, tuple) and not isinstance(snowpack_dimension[0], str):
+            raise SMRTError("When the 'snowpack_dimension' argument is a tuple, the first argument must be a string")
+
+        def configurations(s):
+            return [(axis, values) for axis, values in s.configurations() if axis not in self._broadcast_capability]
+
+        def recurse(s, confs, sps):
+            if confs:
+                for sub in s.iterate(confs[0][0]):
+                    yield from recurse(sub, confs[1:], sps)
+            elif _is_sequence(sps):
+                for sp in sps:
+                    yield (s, sp)
+            else:
+                yield (s, sps)
+
+        if _is_sequence(sensor):
+            if len(sensor) != len(snowpack):
+                raise SMRTError("when sensor is a sequence, the length must be the same as snowpack sequence length")
+            confs = configurations(sensor[0])
+            sims = list(itertools.chain(*(recurse(se, confs, sp) for se, sp in zip(sensor, snowpack))))
+        else:
+            confs = configurations(sensor)
+            sims = list(recurse(sensor, list(confs), snowpack))
+        dimensions = list(confs)
+        if snowpack_dimension is not None:
+            dimensions.append(snowpack_dimension)
+        return sims, dimensions
+
+    def run(self, sensor, snowpack, atmosphere=None, snowpack_dimension=None, snowpack_column="snowpack",
+            progressbar=False, parallel_computation="outer", runner=None):
+        """Run the model — signature of reference ``Model.run`` (``model.py:310-320``).  `parallel_computation`,
+        `progressbar` and `runner` are accepted for compatibility: the whole batch is one GPU call."""
+        if atmosphere is not None:
+            raise DeprecationWarning("The atmosphere argument of the run method is depreciated.")
+        is_sensor = lambda s: hasattr(s, "mode") and hasattr(s, "frequency")  # noqa: E731
+        if not (is_sensor(sensor) or (_is_sequence(sensor) and all(is_sensor(s) for s in sensor))):
+            raise SMRTError("the first argument of 'run' must be a sensor or a sequence of sensor")
+        opts = check_dort_options(self.rtsolver_options)
+        sims, dimensions = self.prepare_simulations(sensor, snowpack, snowpack_dimension, snowpack_column)
+        if not sims:
+            raise SMRTError("nothing to simulate")
+        results = self._run_simulations(sims, opts)
+        for dimension in reversed(dimensions):
+            n = len(dimension[1])
+            results = [concat_results(results[i:i + n], dimension) for i in range(0, len(results), n)]
+        assert len(results) == 1, f"Results size is {len(results)=}"
+        result = results[0]
+        if isinstance(snowpack, pd.DataFrame):
+            result.mother_df = snowpack.drop(snowpack_column, axis=1)
+        return result
+
+    def _run_simulations(self, sims, opts):
+        """Pack, solve in one batched GPU call per sensor mode, unpack into per-simulation Results."""
+        # empty snowpacks give Tb = 0 without touching the solver (reference test/test_model.py:36-43 semantics are
+        # reproduced by the kernel: nlayer = 0 -> zeros)
+        groups = {}
+        for i, (s, sp) in enumerate(sims):
+            groups.setdefault(s.mode, []).append(i)
+        results = [None] * len(sims)
+        for mode, idx in groups.items():
+            group = [sims[i] for i in idx]
+            batch = pack_simulations(group, self.emmodel, self.emmodel_options)
+            if batch.mode == MODE_ACTIVE and not np.array_equal(batch.theta, batch.theta_inc):
+                raise SMRTError("only backscatter (theta == theta_inc) is implemented on the B200 path")
+            plan = _PLANS.get(batch, opts, self.device)
+            out = plan.solve_host(batch)
+            _raise_or_nan(out, opts)
+            for k, i in enumerate(idx):
+                results[i] = _simulation_result(mode, sims[i][0], batch, out, k)
+        return results
+
+
+def make_model(emmodel=None, rtsolver="dort", emmodel_options=None, rtsolver_options=None, emmodel_kwargs=None,
+               rtsolver_kwargs=None, device: int = 0) -> Model:
+    """Same signature as reference ``smrt.core.model.make_model`` (``model.py:120-177``)."""
+    if emmodel_kwargs is not None:
+        raise DeprecationWarning("Use emmodel_options instead of emmodel_kwargs")
+    if rtsolver_kwargs is not None:
+        raise DeprecationWarning("Use rtsolver_options instead of rtsolver_kwargs")
+    return Model(emmodel, rtsolver, emmodel_options=emmodel_options, rtsolver_options=rtsolver_options, device=device)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# seams inside an unmodified SMRT installation
+# ---------------------------------------------------------------------------------------------------------------------
+class B200Runner:
+    """Runner for the reference's ``Model.run(..., runner=B200Runner())`` (protocol: ``runner(function, argument_list)
+    -> list of Result``, ``smrt/core/model.py:395-398``; examples ``smrt/runner/sequential_runner.py:34-48``).
+
+    It ignores `function` (the reference's per-simulation ``run_single_simulation``), packs every
+    ``((sensor, snowpack), atmosphere, parallel_computation)`` tuple and makes ONE batched GPU call.  Results are
+    returned as the *reference's* Result classes when SMRT is importable (so its ``concat_results`` accepts them),
+    otherwise as ``smrt_b200`` Results.
+    """
+
+    def __init__(self, device: int = 0, progressbar: bool = False):
+        self.device = device
+
+    def __call__(self, function, argument_list):
+        ref_model = getattr(function, "__self__", None)
+        if ref_model is None:
+            raise SMRTError("B200Runner must be given Model.run_single_simulation (a bound method)")
+        args = list(argument_list)
+        sims = [a[0] for a in args]
+        for a in args:
+            if a[1] is not None:
+                raise SMRTError("atmosphere is not implemented on the B200 path")
+        rtsolver = ref_model.rtsolver
+        if getattr(rtsolver, "__name__", "") != "DORT" and "DORT" not in [c.__name__ for c in
+                                                                           getattr(rtsolver, "__mro__", [])]:
+            raise SMRTError("B200Runner accelerates the DORT rtsolver only")
+        rt_opts = dict(getattr(ref_model, "rtsolver_options", {}) or {})
+        m = Model(ref_model.emmodel, "dort", emmodel_options=getattr(ref_model, "emmodel_options", None),
+                  rtsolver_options=rt_opts, device=self.device)
+        ours = m._run_simulations(sims, check_dort_options(rt_opts))
+        try:  # hand back the reference's own Result types when available
+            from smrt.core import result as ref_result
+            import xarray as xr
+
+            out = []
+            for r in ours:
+                cls = ref_result.ActiveResult if r.mode == "A" else ref_result.PassiveResult
+                to_xr = lambda d: xr.DataArray(d.values, coords=[(k, d.coords[k].values) for k in d.dims])  # noqa
+                out.append(cls(to_xr(r.data), channel_map=r.channel_map,
+                               other_data={k: to_xr(v) for k, v in r.other_data.items()}))
+            return out
+        except ImportError:
+            return ours
+
+
+class DORT:
+    """rtsolver plugin with the reference's contract (``C(**rtsolver_options)`` once per simulation, then
+    ``solve(snowpack, emmodels, sensor, atmosphere, parallel_computation=)`` -> Result; ``smrt/core/model.py:598-617``,
+    minimal form ``smrt/test/test_model.py:98-103``).  One problem per call: a compatibility shim — batching needs
+    ``B200Runner`` or ``smrt_b200.make_model``."""
+
+    _broadcast_capability = {"theta_inc", "polarization_inc", "theta", "phi", "polarization"}
+
+    def __init__(self, device: int = 0, **rtsolver_options):
+        self.options = check_dort_options(rtsolver_options)
+        self.device = device
+
+    def solve(self, snowpack, emmodels, sensor, atmosphere=None, parallel_computation=None):
+        if atmosphere is not None or getattr(snowpack, "atmosphere", None) is not None:
+            raise SMRTError("atmosphere is not implemented on the B200 path")
+        ems = [type(em) for em in emmodels]
+        batch = pack_simulations([(sensor, snowpack)], ems)
+        plan = _PLANS.get(batch, self.options, self.device)
+        out = plan.solve_host(batch)
+        _raise_or_nan(out, self.options)
+        return _simulation_result(sensor.mode, sensor, batch, out, 0)
+
+
+def run_ensemble(batch: ProblemBatch, rtsolver_options: Optional[dict] = None, device: int = 0):
+    """Array-in / array-out entry point for large ensembles: a packed ``ProblemBatch`` (e.g.
+    from ``pack_snow_ensemble``) in, the raw output block out — no Python object per member."""
+    opts = check_dort_options(rtsolver_options)
+    out = _PLANS.get(batch, opts, device).solve_host(batch)
+    if opts["error_handling"] == "exception":
+        _raise_or_nan(out, opts)
+    return out

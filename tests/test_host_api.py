@@ -1,0 +1,130 @@
+"""Host-side logic (packer, Model.run batching/ordering, Result API, error mapping) on CPU.
+
+The batched solve is stood in by the SIMT-emulated kernels (tests/simt_emu) so that the host code is exercised end to
+end without a GPU; the `-m gpu` twin (tests/test_gpu_api.py) runs the same calls through the CUDA library."""
+import warnings
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import smrt_b200
+from emu_util import emu_solve, load_golden
+from smrt_b200 import capi, make_model, make_snowpack, model as model_mod, sensor_list
+from smrt_b200.error import SMRTError, SMRTWarning
+
+
+class EmuPlan:
+    def __init__(self, opts):
+        self.opts = opts
+        self.options = type("O", (), dict(max_batch=10 ** 9, n_max_stream=opts["n_max_stream"]))()
+
+    def solve_host(self, batch):
+        return emu_solve(batch, self.opts, threads=64)
+
+
+@pytest.fixture(autouse=True)
+def emulated_plans(monkeypatch):
+    monkeypatch.setattr(model_mod._PLANS, "get", lambda batch, opts, device: EmuPlan(opts))
+
+
+def two_layer():
+    return make_snowpack([0.1, 100], "exponential", density=[200, 400], temperature=[250.0, 250.0],
+                         corr_length=[5e-5, 5e-5])
+
+
+def test_reads_like_the_reference_test_passive():
+    # reference smrt/test/test_integration_iba.py:33-49
+    m = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=16))
+    res = m.run(sensor_list.amsre("37V"), two_layer())
+    d, batch, opts = load_golden("ref_iba_2layer_passive")
+    assert isinstance(res.TbV(), float)
+    # 16 streams instead of 32: close to, not equal to, the 32-stream literal
+    assert abs(res.TbV() - 248.09044325849692) < 1.0 and abs(res.TbH() - 237.3487270223389) < 1.0
+    assert res.Tb(channel="37V") == res.TbV()
+    assert set(res.other_data) == {"stream_angles", "effective_permittivity", "ks", "ke", "ka", "thickness"}
+    np.testing.assert_allclose(res.optical_depth().values, (res.ks().values + res.ka().values) * [0.1, 100])
+
+
+def test_dims_and_order_of_a_multi_frequency_multi_snowpack_run():
+    sps = [make_snowpack([0.3, 10], "exponential", density=[250, 350], temperature=[260, 265], corr_length=c)
+           for c in (1e-4, 2e-4, 3e-4)]
+    m = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8))
+    res = m.run(sensor_list.passive([18.7e9, 36.5e9], [40, 55]), sps)
+    assert res.data.dims == ("frequency", "snowpack", "polarization", "theta")
+    assert res.data.shape == (2, 3, 2, 2)
+    assert res.other_data["ks"].dims == ("frequency", "snowpack", "layer")
+    # same numbers as running each simulation alone (ordering: frequency outermost, snowpack innermost)
+    single = m.run(sensor_list.passive(36.5e9, [40, 55]), sps[1])
+    np.testing.assert_allclose(res.data.sel(frequency=36.5e9, snowpack=1).values, single.data.values, rtol=1e-12)
+    assert res.TbV(frequency=18.7e9, snowpack=2, theta=55) == res.data.values[0, 2, 0, 1]
+    df = res.to_dataframe(channel_axis=None)
+    assert len(df) == 24
+
+
+def test_snowpack_containers():
+    sps = [two_layer(), two_layer()]
+    m = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8))
+    s = sensor_list.passive(37e9, 55)
+    r = m.run(s, {"a": sps[0], "b": sps[1]})
+    assert list(r.coords["snowpack"].values) == ["a", "b"]
+    r = m.run(s, sps, snowpack_dimension=("time", [10.0, 20.0]))
+    np.testing.assert_allclose(r.time, [10.0, 20.0])
+    with pytest.raises(SMRTError):
+        m.run(s, sps, snowpack_dimension=([1, 2], "time"))
+    df = pd.DataFrame(dict(snowpack=sps, site=["x", "y"]), index=pd.Index([5, 6], name="id"))
+    r = m.run(s, df)
+    out = r.to_dataframe(channel_axis=None)
+    assert "site" in out.columns and list(r.coords["id"].values) == [5, 6]
+
+
+def test_active_result_accessors():
+    m = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8))
+    res = m.run(sensor_list.active(13e9, 45), two_layer())
+    assert res.data.dims == ("polarization_inc", "polarization", "theta_inc")
+    vv = res.sigmaVV()
+    assert vv == pytest.approx(4 * np.pi * np.cos(np.deg2rad(45)) * res.data.values[0, 0, 0])
+    assert res.sigmaHV() == pytest.approx(4 * np.pi * np.cos(np.deg2rad(45)) * res.data.values[1, 0, 0])
+    assert res.sigmaVV_dB() == pytest.approx(10 * np.log10(vv))
+
+
+def test_error_mapping_exception_and_nan():
+    big = make_snowpack([1, 10], "exponential", density=[300, 300], temperature=[260, 260], corr_length=[5e-3, 5e-3])
+    s = sensor_list.passive(89e9, 55)
+    with pytest.raises(SMRTError):
+        make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8)).run(s, big)
+    r = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8, error_handling="nan")).run(s, [big, two_layer()])
+    assert np.all(np.isnan(r.data.values[0])) and np.all(np.isfinite(r.data.values[1]))
+
+
+def test_shallow_warning():
+    sp = make_snowpack([0.2, 0.3], "sticky_hard_spheres", density=[290.0, 250.0], temperature=[260, 260],
+                       radius=[1e-4, 1e-4], stickiness=[0.2, 0.2])
+    m = make_model("dmrt_qcacp_shortrange", "dort", rtsolver_options=dict(n_max_stream=8))
+    with pytest.warns(SMRTWarning, match="optically shallow"):
+        m.run(sensor_list.active(10e9, 45), sp)
+
+
+def test_unsupported_features_are_rejected_loudly():
+    with pytest.raises(SMRTError):
+        make_model("sft_rayleigh", "dort")
+    with pytest.raises(SMRTError):
+        make_model("iba", "iterative_first_order")
+    with pytest.raises(SMRTError):
+        make_model("iba", "dort", rtsolver_options=dict(process_coherent_layers=True))
+    with pytest.raises(TypeError):
+        make_model("iba", "dort", rtsolver_options=dict(not_an_option=1))
+    with pytest.raises(SMRTError):
+        make_model("iba", "dort").run("not a sensor", two_layer())
+
+
+def test_rtsolver_plugin_seam():
+    """smrt_b200.DORT has the reference's plugin contract: C(**options).solve(snowpack, emmodels, sensor, atmosphere)"""
+    class IBA:  # stands for the reference's emmodel instance: only its class name matters to the packer
+        pass
+
+    sp = two_layer()
+    solver = smrt_b200.DORT(n_max_stream=8)
+    res = solver.solve(sp, [IBA(), IBA()], sensor_list.passive(37e9, 55), None, parallel_computation="none")
+    ref = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8)).run(sensor_list.passive(37e9, 55), sp)
+    assert res.TbV() == ref.TbV()

@@ -1,0 +1,120 @@
+"""The CUDA device code (smrt_b200/csrc/*.cuh) compiled for the HOST through the SIMT emulator (tests/simt_emu) and
+checked against the reference fixtures and the oracle.  This is what keeps the kernels honest in the authoring
+container, where nvcc cross-compiles but no GPU exists; the `-m gpu` tests repeat the comparison on the B200."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from emu_util import emu_lib, emu_solve, load_golden, rel_err
+from oracle import dort_oracle as O
+
+SMALL = ["cfg1_iba_onelayer", "ref_iba_2layer_passive", "ref_dmrt_qcacp_2layer_passive", "nonscattering_transparent",
+         "iba_options_prune_rj", "iba_exp_substrate_passive"]
+SMALL_ACTIVE = ["ref_dmrt_less_refringent_active", "nonscattering_active"]
+
+
+@pytest.mark.parametrize("name", SMALL + SMALL_ACTIVE)
+def test_emulated_kernels_match_reference_fixture(name):
+    d, batch, opts = load_golden(name)
+    batch = batch.subset(slice(0, 2))
+    out = emu_solve(batch, opts, threads=64)
+    ref = d["ref_values"][:batch.B]
+    tol = 1e-10 if batch.mode == 0 else 1e-6
+    assert np.all((out.status & 15) == 0)
+    assert rel_err(out.values, ref, batch.mode) <= tol
+    for b in range(batch.B):
+        n = batch.nlayer[b]
+        np.testing.assert_allclose(out.ks[b, :n], d["ref_ks"][b, :n], rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(out.ka[b, :n], d["ref_ka"][b, :n], rtol=1e-12)
+        np.testing.assert_allclose(out.eps_eff[b, :n], d["ref_eps_eff"][b, :n], rtol=1e-13)
+        assert out.n_streams[b] == d["ref_n_air"][b]
+
+
+def test_emulated_kernels_full_warp_block():
+    """same code with 256 threads per block (the launch configuration used on the GPU)"""
+    d, batch, opts = load_golden("ref_iba_2layer_passive")
+    out = emu_solve(batch, opts, threads=256)
+    assert rel_err(out.values, d["ref_values"], 0) <= 1e-10
+
+
+def test_gauss_legendre_nodes_match_scipy():
+    lib = emu_lib()
+    for n in (2, 16, 32, 64, 128):
+        mu = np.zeros(n)
+        lib.emu_gauss_legendre(n, mu.ctypes.data_as(C.POINTER(C.c_double)))
+        np.testing.assert_allclose(mu, O.gauss_legendre_quadrature(n), rtol=0, atol=3e-16)
+
+
+def test_layer_optics_device_functions():
+    lib = emu_lib()
+    lib.emu_layer_optics.argtypes = [C.c_double] * 6 + [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                                        C.POINTER(C.c_double)]
+    rng = np.random.default_rng(3)
+    for em, ms in ((0, 0), (0, 1), (1, 1), (3, 1), (2, 2)):
+        for _ in range(5):
+            f = rng.uniform(0.1, 0.45)
+            freq = rng.choice([6.925e9, 36.5e9, 89e9])
+            es = O.ice_permittivity_maetzler06(freq, rng.uniform(240, 272))
+            p0 = rng.uniform(5e-5, 3e-4)
+            out = np.zeros(5)
+            st = lib.emu_layer_optics(freq, f, 1.0, 0.0, es.real, es.imag, em, ms, p0, 0.2, 1,
+                                      out.ctypes.data_as(C.POINTER(C.c_double)))
+            assert st == 0
+            ref = O.layer_optics(freq, f, 1.0, es, em, ms, p0, 0.2, True)
+            np.testing.assert_allclose(out[0] + 1j * out[1], ref["eps_eff"], rtol=1e-14)
+            np.testing.assert_allclose(out[2], ref["ks"], rtol=1e-13)
+            np.testing.assert_allclose(out[3], ref["ka"], rtol=1e-13)
+
+
+def test_fresnel_device_function():
+    lib = emu_lib()
+    lib.emu_fresnel.argtypes = [C.c_int] + [C.c_double] * 5 + [C.POINTER(C.c_double)]
+    rng = np.random.default_rng(4)
+    for _ in range(20):
+        e1 = complex(rng.uniform(1, 3.2), rng.uniform(0, 0.01))
+        e2 = complex(rng.uniform(1, 80), rng.uniform(0, 40))
+        mu = rng.uniform(0.05, 1.0)
+        out = np.zeros(6)
+        lib.emu_fresnel(0, e1.real, e1.imag, e2.real, e2.imag, mu, out.ctypes.data_as(C.POINTER(C.c_double)))
+        R, T = O.interface_R_T(O.IF_FLAT, e1, e2, np.array([mu]), 3)
+        np.testing.assert_allclose(out[:3], R[:, 0], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(out[3:], T[:, 0], rtol=1e-12, atol=1e-15)
+
+
+def test_iba_phase_fourier_modes_device_function():
+    """cosine / sine sums over the azimuth samples == the reference's FFT-based decomposition, m = 0, 1, 2"""
+    lib = emu_lib()
+    lib.emu_iba_phase_mode.argtypes = [C.c_int, C.c_int] + [C.c_double] * 4 + [C.c_int] + [C.c_double] * 3 + [
+        C.POINTER(C.c_double)]
+    opt = O.layer_optics(36.5e9, 0.3, 1.0, O.ice_permittivity_maetzler06(36.5e9, 260.0), O.EM_IBA, O.MS_EXPONENTIAL,
+                         2e-4, 0.0)
+    kk = (2 * opt["k0"] * np.sqrt(opt["eps_eff"]).real) ** 2
+    mus = np.array([0.93, 0.41])
+    mui = np.array([0.77, -0.35, 0.12])
+    for m_max, npol in ((0, 2), (2, 3)):
+        P5 = O.iba_ft_even_phase(opt, mus, mui, m_max, npol)
+        for m in range(m_max + 1):
+            np_m = 2 if m == 0 else 3
+            for a, ms_ in enumerate(mus):
+                for b, mi_ in enumerate(mui):
+                    out = np.zeros(9)
+                    lib.emu_iba_phase_mode(m, m_max, ms_, mi_, opt["iba_coeff"], kk, 0, 0.3, 2e-4, 0.0,
+                                           out.ctypes.data_as(C.POINTER(C.c_double)))
+                    ref = P5[:np_m, :np_m, m, a, b]
+                    np.testing.assert_allclose(out[:np_m * np_m].reshape(np_m, np_m), ref, rtol=1e-11,
+                                               atol=1e-14 * np.abs(P5).max())
+
+
+@pytest.mark.parametrize("h,threads", [(8, 64), (33, 64), (64, 256)])
+def test_one_sided_jacobi_device_function(h, threads):
+    lib = emu_lib()
+    rng = np.random.default_rng(h)
+    M = rng.normal(size=(h, h)) + np.diag(rng.uniform(1, 5, h))
+    W = np.asfortranarray(M.copy())
+    sweeps = lib.emu_jacobi(W.ctypes.data_as(C.POINTER(C.c_double)), h, threads)
+    assert 0 < sweeps < 20
+    sig = np.sort(np.linalg.norm(W, axis=0))[::-1]
+    np.testing.assert_allclose(sig, np.linalg.svd(M, compute_uv=False), rtol=1e-13)
+    U = W / np.linalg.norm(W, axis=0)
+    assert np.abs(U.T @ U - np.eye(h)).max() < 1e-13
