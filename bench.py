@@ -297,9 +297,24 @@ def run_ours(args):
         return
 
     # roofline -------------------------------------------------------------------------------------------------------
+    # per-kernel durations are measured live with CUDA events in a separate pass with the chunks serialised on one
+    # stream: in the throughput pass above the two slots overlap and a kernel's event interval includes queueing
     peak_tflops = capi.measure_fp64_peak(local_rank, 300.0)
     fe, fb = f_alg_per_solve()
-    n_launch = chunks * args.steps
+    sopts = capi.make_options(batch, n_max_stream=N_STREAMS, device=local_rank, serialize=True)
+    splan = capi.Plan(sopts)
+    eig_ms, bnd_ms = [], []
+    for it in range(3):
+        flush.fill_(1)
+        splan.solve_device(bt, stream)
+        splan.sync_timing(stream)
+        tm = splan.last_timing()
+        if it > 0:
+            eig_ms.append(tm["eigen_ms"]); bnd_ms.append(tm["boundary_ms"])
+        chunks = tm["chunks"]
+    launches_roof = splan.launch_count
+    splan.close()
+    n_launch = chunks * len(eig_ms)
     eig_avg_ms = float(np.sum(eig_ms)) / max(n_launch, 1)
     bnd_avg_ms = float(np.sum(bnd_ms)) / max(n_launch, 1)
     solves_per_launch = batch.B / max(chunks, 1)

@@ -81,7 +81,7 @@ typedef struct {
   int rayleigh_jeans;  /* 1 = Rayleigh-Jeans approximation: B(T) = T (dort.py:160, rtsolver_utils.py:411-419) */
   double prune_deep_snowpack; /* optical depth beyond which layers are dropped (dort.py:117-120, 444-452); <= 0: off */
   int chunk;           /* problems processed per kernel wave; 0 = automatic */
-  int reserved;
+  int reserved;        /* flags; bit 0: run the chunks one after the other on a single stream (clean per-kernel timings) */
 } smrtb200_options;
 
 /* One batch of B independent (snowpack x frequency) problems.  Arrays marked [B, L] have row stride max_layers. */

@@ -10,7 +10,8 @@ banded LU of the whole multi-layer boundary system.  The device path computes th
       positive definite.  Cholesky X- = L L^T, X+ = C C^T gives k = singular values of M = C^T L; with M V = U Sigma:
       E+ = S C^-T (U Sigma),  E- = -S C U.   The device obtains U Sigma by one-sided Jacobi on M.
   (2) bottom-up elimination of the block-tridiagonal boundary system carrying only the h x h reflection operator
-      R_l and the source vector s_l of the stack below each layer (only x_0 is needed, dort.py:472-476).
+      R_l and the source vector s_l of the stack below each layer (only x_0 is needed, dort.py:472-476); each layer
+      step is two h x h Gauss-Jordan eliminations and three h x h products (see solve_mode).
 
 This file exists so the algebra is checked against the oracle on the CPU (tests/test_b200_algorithm_model.py) before
 and independently of the CUDA implementation.  It is never imported by the product.
@@ -133,22 +134,17 @@ def solve_mode(problem, mode, streams, layers, iface, intensity_down, planck, co
         k, F, G = lay(l)
         t = np.exp(-k * thickness[l])
         D = Dsign(h)
-        Eu_tp = np.hstack((F * t[None, :], G))  # Eu tau+
-        Ed_tp = D[:, None] * np.hstack((G * t[None, :], F))  # Ed tau+
-        Eu_tm = np.hstack((F, G * t[None, :]))  # Eu tau-
-        Ed_tm = D[:, None] * np.hstack((G, F * t[None, :]))  # Ed tau-
-        Rtop = cdiag(Rtop_, l)
-        Rbot = cdiag(Rbot_, l)
-        if Rbot is None:
-            Rbot = np.zeros(h)
-        Dtop = Ed_tp - Rtop[:, None] * Eu_tp
-        Dbot = Eu_tm - Rbot[:, None] * Ed_tm
+        Rt = cdiag(Rtop_, l)
+        Rb = cdiag(Rbot_, l)
+        if Rb is None:
+            Rb = np.zeros(h)
+        Rbm = np.diag(Rb)  # effective bottom reflection: interface + (T R T) of the stack below
         b_top = np.zeros((h, nrhs))
         b_bot = np.zeros((h, nrhs))
         Tl = temperature[l] if temperature is not None else None
         if mode == 0 and Tl is not None and Tl > 0:
-            b_top -= ((1.0 - Rtop) * planck(Tl))[:, None]
-            b_bot -= ((1.0 - Rbot) * planck(Tl))[:, None]
+            b_top -= ((1.0 - Rt) * planck(Tl))[:, None]
+            b_bot -= ((1.0 - Rb) * planck(Tl))[:, None]
         # contribution of the layer above (l-1) into the top rows of l
         if l > 0 and mode == 0 and temperature is not None and temperature[l - 1] > 0:
             Tb_lm1 = cdiag(Tbot_, l - 1)
@@ -165,25 +161,36 @@ def solve_mode(problem, mode, streams, layers, iface, intensity_down, planck, co
             if mode == 0 and temperature is not None and temperature[l + 1] > 0:
                 b_bot[:r] += (Tt_lp1 * planck(temperature[l + 1]))[:r, None]
             Tb_l = cdiag(Tbot_, l)
-            Dbot[:r] -= Tt_lp1[:r, None] * (Rop[:r, :r] @ (Tb_l[:, None] * Ed_tm)[:r, :])
+            Rbm[:r, :r] += Tt_lp1[:r, None] * Rop[:r, :r] * Tb_l[None, :r]
             b_bot[:r] += Tt_lp1[:r, None] * svec[:r]
         elif (l == L - 1 and mode == 0 and problem.get("substrate_kind", 0) != 0 and temperature is not None):
             Tsub = cdiag(Tbot_, l)
             b_bot += (Tsub * planck(problem["substrate_temperature"]))[:, None]
-        Mfull = np.vstack((Dtop, Dbot))
-        if l > 0:
-            rhs = np.hstack((np.vstack((np.eye(h), np.zeros((h, h)))), np.vstack((b_top, b_bot))))
-        else:
-            rhs = np.vstack((b_top, b_bot))
+        # Unknowns x+ (modes referenced at the bottom), x- (referenced at the top); with Eu = [F | G], Ed = D [G | F]:
+        #   bottom rows: A21 x+ + A22 x- = b_bot,  A21 = F - Rb' D G,      A22 = (G - Rb' D F) t
+        #   top rows   : A11 x+ + A12 x- = b_top,  A11 = (D G - Rt F) t,   A12 = D F - Rt G
+        # Gauss-Jordan on [A21 | A22 | b_bot] gives Y22 = A21^-1 A22, Yr = A21^-1 b_bot; with Y~ = t Y22, y~r = t Yr:
+        #   P = F - G Y~,  K = G - F Y~,  Schur S = D P - Rt K,  b' = b_top - D G y~r + Rt F y~r
+        #   reflection operator of the stack seen from above  R = K S^-1,  source  s = F y~r + R b'
+        DG = D[:, None] * G
+        DF = D[:, None] * F
+        Tm = np.hstack((F - Rbm @ DG, (G - Rbm @ DF) * t[None, :], b_bot))
         try:
-            Z = np.linalg.solve(Mfull, rhs)
+            sol = np.linalg.solve(Tm[:, :h], Tm[:, h:])
+            Yt = t[:, None] * sol[:, :h]
+            yr = t[:, None] * sol[:, h:]
+            P = F - G @ Yt
+            K = G - F @ Yt
+            S = D[:, None] * P - Rt[:, None] * K
+            v = F @ yr
+            bp = b_top - D[:, None] * (G @ yr) + Rt[:, None] * v
+            if l > 0:
+                Rop = np.linalg.solve(S.T, K.T).T
+                svec = v + Rop @ bp
+            else:
+                svec = v + K @ np.linalg.solve(S, bp)
         except np.linalg.LinAlgError:
             raise O.OracleError(O.ST_SINGULAR, "singular boundary block")
-        out = Eu_tp @ Z
-        if l > 0:
-            Rop, svec = out[:, :h], out[:, h:]
-        else:
-            svec = out
 
     I1up = svec
     if mode == 0 and temperature is not None and temperature[0] > 0:

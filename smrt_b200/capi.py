@@ -138,7 +138,7 @@ def normalization_code(phase_normalization) -> int:
 
 def make_options(batch: ProblemBatch, *, n_max_stream=32, m_max=2, phase_normalization="auto",
                  prune_deep_snowpack=None, rayleigh_jeans_approximation=False, device=0, max_batch=None,
-                 chunk=0) -> Options:
+                 chunk=0, serialize=False) -> Options:
     if prune_deep_snowpack is True:
         prune_deep_snowpack = 6
     return Options(
@@ -147,7 +147,7 @@ def make_options(batch: ProblemBatch, *, n_max_stream=32, m_max=2, phase_normali
         max_batch=int(max_batch or batch.B), n_theta=len(batch.theta), n_inc=max(len(batch.theta_inc), 0),
         normalization=normalization_code(phase_normalization),
         rayleigh_jeans=1 if rayleigh_jeans_approximation else 0,
-        prune_deep_snowpack=float(prune_deep_snowpack) if prune_deep_snowpack else 0.0, chunk=int(chunk), reserved=0)
+        prune_deep_snowpack=float(prune_deep_snowpack) if prune_deep_snowpack else 0.0, chunk=int(chunk), reserved=1 if serialize else 0)
 
 
 class HostOutputs:

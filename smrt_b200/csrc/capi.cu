@@ -61,6 +61,9 @@ struct smrtb200_plan {
   int chunk = 0;
   bool use_global_scratch = false;
   int eigen_grid = 0, boundary_grid = 0;
+  int boundary_threads = SMRT_NT_B;
+  void (*eigen_fn)(KArgs) = nullptr;
+  void (*boundary_fn)(KArgs) = nullptr;
   size_t eigen_smem = 0, boundary_smem = 0;
   long long scratch_stride = 0;
   double* gl_mu = nullptr;
@@ -160,11 +163,19 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
     if (_e != cudaSuccess) return bail(fail(-2, "%s failed: %s", #expr, cudaGetErrorString(_e)));     \
   } while (0)
 
-  PLAN_CUDA(cudaFuncSetAttribute(eigen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->eigen_smem));
-  PLAN_CUDA(cudaFuncSetAttribute(boundary_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->boundary_smem));
+  p->eigen_fn = p->use_global_scratch ? eigen_kernel<true> : eigen_kernel<false>;
+  p->boundary_fn = p->use_global_scratch ? boundary_kernel<true> : boundary_kernel<false>;
+  // the attribute belongs to the FUNCTION, not to the plan: always raise it to the opt-in maximum so that plans with
+  // different shared-memory footprints can coexist
+  PLAN_CUDA(cudaFuncSetAttribute(p->eigen_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemOptin));
+  PLAN_CUDA(cudaFuncSetAttribute(p->boundary_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemOptin));
   int occ_e = 0, occ_b = 0;
-  PLAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, eigen_kernel, SMRT_NT, p->eigen_smem));
-  PLAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, boundary_kernel, SMRT_NT, p->boundary_smem));
+  PLAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, p->eigen_fn, SMRT_NT, p->eigen_smem));
+  if (const char* e = std::getenv("SMRT_B200_BOUNDARY_THREADS")) {
+    int v = std::atoi(e);
+    if (v >= 64 && v <= SMRT_NT_B && (v % 64) == 0) p->boundary_threads = v;
+  }
+  PLAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, p->boundary_fn, p->boundary_threads, p->boundary_smem));
   if (occ_e < 1 || occ_b < 1) return bail(fail(-2, "kernels do not fit on an SM (occupancy %d / %d)", occ_e, occ_b));
   if (p->use_global_scratch) {  // keep the scratch L2-resident: at most 2 CTAs per SM
     occ_e = std::min(occ_e, 2);
@@ -179,6 +190,10 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
     const double bytes_per_problem = (double)options->max_layers * (double)(L.eig_stride + SMRT_AUX_STRIDE + SMRT_MAX_MODES) * 8.0;
     long long by_mem = (long long)(6.0e9 / std::max(bytes_per_problem, 1.0));
     long long want = options->chunk > 0 ? options->chunk : std::max<long long>(4LL * p->boundary_grid, 1024);
+    if (const char* e = std::getenv("SMRT_B200_CHUNK")) {
+      long long v = std::atoll(e);
+      if (v > 0) want = v;
+    }
     long long c = std::min<long long>(std::min<long long>(want, std::max<long long>(by_mem, 1)), options->max_batch);
     p->chunk = (int)std::max<long long>(c, 1);
   }
@@ -258,9 +273,10 @@ extern "C" int smrtb200_solve_batch_device(smrtb200_plan* p, const smrtb200_batc
     s.used = false;
   }
   int nchunks = 0;
+  const int nslots = (p->opt.reserved & 1) ? 1 : kSlots;  // bit 0 of `reserved`: serialise the chunks on one stream
   for (int b0 = 0; b0 < B; b0 += p->chunk, ++nchunks) {
     const int nb = std::min(p->chunk, B - b0);
-    Slot& s = p->slots[nchunks % kSlots];
+    Slot& s = p->slots[nchunks % nslots];
     KArgs A = smrt_host::make_kargs(p->opt, L, *batch, b0, nb);
     A.gl_mu = p->gl_mu;
     A.aux = s.aux;
@@ -282,9 +298,9 @@ extern "C" int smrtb200_solve_batch_device(smrtb200_plan* p, const smrtb200_batc
     cudaEvent_t* ev = &p->chunk_events[3 * (size_t)nchunks];
     optics_kernel<<<(items + nthreads_opt - 1) / nthreads_opt, nthreads_opt, 0, s.stream>>>(A);
     CUDA_TRY(cudaEventRecord(ev[0], s.stream));
-    eigen_kernel<<<std::min(p->eigen_grid, items), SMRT_NT, p->eigen_smem, s.stream>>>(A);
+    p->eigen_fn<<<std::min(p->eigen_grid, items), SMRT_NT, p->eigen_smem, s.stream>>>(A);
     CUDA_TRY(cudaEventRecord(ev[1], s.stream));
-    boundary_kernel<<<std::min(p->boundary_grid, nb), SMRT_NT, p->boundary_smem, s.stream>>>(A);
+    p->boundary_fn<<<std::min(p->boundary_grid, nb), p->boundary_threads, p->boundary_smem, s.stream>>>(A);
     CUDA_TRY(cudaEventRecord(ev[2], s.stream));
     CUDA_TRY(cudaGetLastError());
     p->launches += 3;

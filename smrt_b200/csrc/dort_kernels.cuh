@@ -17,7 +17,8 @@
 #define SMRT_MAX_MODES 4      // m = 0 .. 3
 #define SMRT_MAX_INC 16       // incident streams (<= 2 per incidence angle, n_inc <= 8)
 #define SMRT_AUX_STRIDE 4     // per (problem, layer): iba_coeff, kk, f_eff, spare
-#define SMRT_NT 256           // threads per CTA of the eigen and boundary kernels
+#define SMRT_NT 256           // threads per CTA of the eigen kernel
+#define SMRT_NT_B 512         // max threads per CTA of the boundary kernel
 
 struct KArgs {
   int B, L;  // problems in this launch (all pointers are already offset to its first problem), row stride
@@ -43,6 +44,7 @@ struct KArgs {
   double* kmin;         // [B, L, SMRT_MAX_MODES]
   int* scat_flag;       // [B, L]
   int* counters;        // [2]: eigen / boundary work counters
+  int* diag;            // optional [2] diagnostics: total Jacobi sweeps, number of eigenproblems (may be NULL)
   double* scratch;      // [gridDim.x, scratch_stride] when use_global_scratch
   long long eig_stride, scratch_stride;
   int use_global_scratch;
@@ -102,7 +104,8 @@ SMRT_DEV void set_error(int* status, int b, int code) {
 SMRT_HD size_t eigen_vec_doubles(int n, int hmax, int K) { return (size_t)4 * n + 4 * hmax + 4 * K + 8; }
 SMRT_HD size_t eigen_mat_doubles(int hmax) { return (size_t)3 * hmax * (hmax + 1); }
 
-SMRT_GLOBAL void __launch_bounds__(SMRT_NT) eigen_kernel(KArgs A) {
+template <bool kGlobalScratch>
+SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 2) eigen_kernel(KArgs A) {
   SMRT_DYN_SMEM(smem);
   SMRT_SHARED int s_item;
   SMRT_SHARED int s_ctrl[8];
@@ -122,8 +125,9 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT) eigen_kernel(KArgs A) {
   double* sigma = dk + hmax;
   double* ctab = sigma + hmax;
   double* stab = ctab + 2 * K;
-  double* mats = A.use_global_scratch ? (A.scratch + (size_t)blockIdx.x * A.scratch_stride)
-                                      : (smem + eigen_vec_doubles(n, hmax, K));
+  // compile-time choice so that the shared-memory instantiation addresses its matrices with LDS/STS, not generic LD/ST
+  double* mats = kGlobalScratch ? (A.scratch + (size_t)blockIdx.x * A.scratch_stride)
+                                : (smem + eigen_vec_doubles(n, hmax, K));
   const size_t matsz = (size_t)hmax * (hmax + 1);
   double* A1 = mats;
   double* A2 = mats + matsz;
@@ -285,7 +289,13 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT) eigen_kernel(KArgs A) {
       __syncthreads();
 
       // singular values / right rotations by one-sided Jacobi: A3 <- W = U Sigma
-      block_jacobi_svd(A3, ld, h, s_ctrl);
+      {
+        int sw = block_jacobi_svd(A3, ld, h, s_ctrl);
+        if (tid == 0 && A.diag) {
+          atomicAdd(&A.diag[0], sw);
+          atomicAdd(&A.diag[1], 1);
+        }
+      }
       __syncthreads();
       for (int j = tid; j < h; j += NT) {
         double s2 = 0.0;
@@ -354,13 +364,15 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT) eigen_kernel(KArgs A) {
 // --------------------------------------------------------------------------------------------------------------------
 // kernel 3: boundary system, mode summation, output stage
 // --------------------------------------------------------------------------------------------------------------------
-// vector region (doubles): mu[n] outmu[n] outw[n] kvec[hmax] tvec[hmax] Rt Tt Rb Tb Ttprev [hmax each] Rair Tair [hmax]
-//                          acc[9 * SMRT_MAX_INC] coh[4 * SMRT_MAX_INC] ; ints: perm1[hmax] perm2[hmax] inc[SMRT_MAX_INC]
+// vector region (doubles): mu[n] outmu[n] outw[n] kvec tvec Rt Tt Rb Tb Ttprev ipiv [hmax each]
+//                          acc[9 * SMRT_MAX_INC] coh[4 * SMRT_MAX_INC] ; ints: rowstep[hmax] rowof[hmax] inc[SMRT_MAX_INC]
 SMRT_HD size_t boundary_vec_doubles(int n, int hmax) {
-  return (size_t)3 * n + 9 * hmax + 13 * SMRT_MAX_INC + hmax /* two int arrays */ + SMRT_MAX_INC + 16;
+  return (size_t)3 * n + 8 * hmax + 13 * SMRT_MAX_INC + hmax /* two int arrays */ + SMRT_MAX_INC + 16;
 }
+// matrix region: BF, BG (compact), BR (ld odd), T = [left | right | rhs] (ld odd), btop, svec, ytr, vvec
 SMRT_HD size_t boundary_mat_doubles(int hmax, int nrhs_max) {
-  return (size_t)2 * hmax * hmax + 3 * (size_t)hmax * (hmax + 1) + 3 * (size_t)hmax * nrhs_max + 16;
+  return (size_t)2 * hmax * hmax + (size_t)hmax * (hmax + 1) + (size_t)(hmax + 1) * (2 * hmax + nrhs_max) +
+         4 * (size_t)hmax * nrhs_max + 16;
 }
 
 struct BoundaryCtx {
@@ -370,7 +382,8 @@ struct BoundaryCtx {
   cplx eps_star;
 };
 
-SMRT_GLOBAL void __launch_bounds__(SMRT_NT) boundary_kernel(KArgs A) {
+template <bool kGlobalScratch>
+SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
   SMRT_DYN_SMEM(smem);
   SMRT_SHARED int s_item;
   SMRT_SHARED int s_ctrl[8];
@@ -392,24 +405,23 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT) boundary_kernel(KArgs A) {
   double* Rb = Tt + hmax;
   double* Tb = Rb + hmax;
   double* Ttprev = Tb + hmax;
-  double* Rair = Ttprev + hmax;
-  double* Tair = Rair + hmax;
-  double* acc_act = Tair + hmax;                  // [3][3][SMRT_MAX_INC]
+  double* ipiv = Ttprev + hmax;
+  double* acc_act = ipiv + hmax;                  // [3][3][SMRT_MAX_INC]
   double* coh_act = acc_act + 9 * SMRT_MAX_INC;   // [2][2][SMRT_MAX_INC]
-  int* perm1 = reinterpret_cast<int*>(coh_act + 4 * SMRT_MAX_INC);
-  int* perm2 = perm1 + hmax;
-  int* inc = perm2 + hmax;
-  double* mats = A.use_global_scratch ? (A.scratch + (size_t)blockIdx.x * A.scratch_stride)
-                                      : (smem + boundary_vec_doubles(n, hmax));
+  int* rowstep = reinterpret_cast<int*>(coh_act + 4 * SMRT_MAX_INC);
+  int* rowof = rowstep + hmax;
+  int* inc = rowof + hmax;
+  double* mats = kGlobalScratch ? (A.scratch + (size_t)blockIdx.x * A.scratch_stride)
+                                : (smem + boundary_vec_doubles(n, hmax));
   const size_t szc = (size_t)hmax * hmax, szp = (size_t)hmax * (hmax + 1), szr = (size_t)hmax * nrhs_max;
   double* BF = mats;
   double* BG = BF + szc;
   double* BR = BG + szc;
-  double* B1 = BR + szp;
-  double* B2 = B1 + szp;
-  double* btop = B2 + szp;
-  double* bbot = btop + szr;
-  double* svec = bbot + szr;
+  double* TT = BR + szp;  // h x (2h + nrhs), ld = ldp
+  double* btop = TT + (size_t)(hmax + 1) * (2 * hmax + nrhs_max);
+  double* svec = btop + szr;
+  double* ytr = svec + szr;
+  double* vvec = ytr + szr;
 
   for (;;) {
     if (tid == 0) s_item = atomicAdd(&A.counters[1], 1);
@@ -530,7 +542,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT) boundary_kernel(KArgs A) {
 
       int h_prev = 0, ldr_prev = 1;
       bool have_prev = false;
-      bool r_transposed = false;
+      bool src_prev = false;  // the stack below carries a source vector (false for the source-free active layers)
 
       for (int l = l_end; l >= 0 && !failed; --l) {
         const cplx eps_l = c_make(eps_b[2 * l], eps_b[2 * l + 1]);
@@ -541,6 +553,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT) boundary_kernel(KArgs A) {
         const double thick = A.thickness[bL + l];
         const double ke = A.ks[bL + l] + A.ka[bL + l];
         const bool scat = (!coherent) && (A.scat_flag[bL + l] != 0);
+        const int nr = (A.mode == 1 && l > 0) ? 0 : nrhs;  // active mode: sources only at the air-snow interface
         for (int j = tid; j < n_l; j += NT) mu[j] = stream_mu(rindex, A.gl_mu, j);
         __syncthreads();
 
@@ -587,11 +600,12 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT) boundary_kernel(KArgs A) {
 
         // right-hand sides ---------------------------------------------------------------------- dort.py:375-441
         const int r = have_prev ? (h < h_prev ? h : h_prev) : 0;
-        {
+        double* Trhs = TT + (size_t)(2 * h) * ldp;  // b_bot lives in the augmented columns of T
+        if (nr > 0) {
           const bool thermal = (A.mode == 0 && m == 0);
           const double Tl = A.temperature[bL + l];
           const double Bl = (thermal && Tl > 0.0) ? planck_function(freq, Tl, A.rayleigh_jeans) : 0.0;
-          for (int e = tid; e < h * nrhs; e += NT) {
+          for (int e = tid; e < h * nr; e += NT) {
             int a = e % h, c = e / h;
             int j = a / npol, p = a % npol;
             double vt = 0.0, vb = 0.0;
@@ -618,15 +632,15 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT) boundary_kernel(KArgs A) {
                 vb += Tb[a] * planck_function(freq, A.substrate_temperature[b], A.rayleigh_jeans);
               }
             }
-            if (l < l_end && a < r) vb += Ttprev[a] * SMRT_AT(svec, h_prev, a, c);
+            if (l < l_end && a < r && src_prev) vb += Ttprev[a] * SMRT_AT(svec, h_prev, a, c);
             SMRT_AT(btop, h, a, c) = vt;
-            SMRT_AT(bbot, h, a, c) = vb;
+            SMRT_AT(Trhs, ldp, a, c) = vb;
           }
         }
         __syncthreads();
         if (l == 0 && A.mode == 1) {
           // incident beams (rtsolver_utils.py:109-135) through the air-snow interface: b_top += T_air I_down
-          for (int c = tid; c < nrhs; c += NT) {
+          for (int c = tid; c < nr; c += NT) {
             int jinc = c / npol, ipol = c % npol;
             int i = inc[jinc];
             if (i < n_l) {  // rows beyond the layer's streams are truncated (dort.py:391-395)
@@ -637,98 +651,108 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT) boundary_kernel(KArgs A) {
             }
           }
         }
-        __syncthreads();
-
-        // A21 = F - Rb' D G  -> B1 ;  A22 = (G - Rb' D F) t  -> B2, with Rb' = diag(Rb) + Tt(l+1) R(l+1) Tb(l) truncated
-        {
-          Team tm = block_team();
-          const double* Rm = BR;
-          const int ldr = ldr_prev;
-          const bool rt = r_transposed;
-          auto aop = [&](int i, int k) {
-            if (i >= r) return 0.0;
-            double rv = rt ? SMRT_AT(Rm, ldr, k, i) : SMRT_AT(Rm, ldr, i, k);
-            double dsgn = ((k % npol) == 2) ? -1.0 : 1.0;
-            return Ttprev[i] * rv * (Tb[k] * dsgn);
-          };
-          team_gemm(
-              tm, h, h, r, aop, [&](int k, int j) { return SMRT_AT(BG, h, k, j); },
-              [&](int i, int j, double acc) {
-                double dsgn = ((i % npol) == 2) ? -1.0 : 1.0;
-                SMRT_AT(B1, ldp, i, j) = SMRT_AT(BF, h, i, j) - Rb[i] * dsgn * SMRT_AT(BG, h, i, j) - acc;
-              });
-          team_gemm(
-              tm, h, h, r, aop, [&](int k, int j) { return SMRT_AT(BF, h, k, j); },
-              [&](int i, int j, double acc) {
-                double dsgn = ((i % npol) == 2) ? -1.0 : 1.0;
-                SMRT_AT(B2, ldp, i, j) =
-                    (SMRT_AT(BG, h, i, j) - Rb[i] * dsgn * SMRT_AT(BF, h, i, j) - acc) * tvec[j];
-              });
+        // T = [A21 | A22] without the coupling term:  A21 = F - Rb D G,  A22 = (G - Rb D F) t
+        for (int e = tid; e < h * h; e += NT) {
+          int i = e % h, j = e / h;
+          double dsgn = (npol == 3 && (i % 3) == 2) ? -1.0 : 1.0;
+          double f = BF[e], g = BG[e];
+          SMRT_AT(TT, ldp, i, j) = f - Rb[i] * dsgn * g;
+          SMRT_AT(TT, ldp, i, h + j) = (g - Rb[i] * dsgn * f) * tvec[j];
+        }
+        // coupling operator of the stack below: R' = T_top(l+1) R(l+1) T_bottom(l) D on the common streams
+        for (int e = tid; e < r * r; e += NT) {
+          int i = e % r, k = e / r;
+          double dsgn = (npol == 3 && (k % 3) == 2) ? -1.0 : 1.0;
+          SMRT_AT(BR, ldr_prev, i, k) *= Ttprev[i] * Tb[k] * dsgn;
         }
         __syncthreads();
-        if (block_lu(B1, ldp, h, perm1, s_ctrl)) {
-          failed = true;
-          break;
-        }
-        block_lu_solve(B1, ldp, h, perm1, B2, ldp, h, 0);     // Y22 = A21^-1 A22
-        block_lu_solve(B1, ldp, h, perm1, bbot, h, nrhs, 0);  // Yr  = A21^-1 b_bot
-
-        // Schur complement S = A12 - A11 Y22 -> BR ;  b_top' = b_top - A11 Yr
-        {
-          Team tm = block_team();
-          auto a11 = [&](int i, int k) {
-            double dsgn = ((i % npol) == 2) ? -1.0 : 1.0;
-            return (dsgn * SMRT_AT(BG, h, i, k) - Rt[i] * SMRT_AT(BF, h, i, k)) * tvec[k];
-          };
-          team_gemm(
-              tm, h, h, h, a11, [&](int k, int j) { return SMRT_AT(B2, ldp, k, j); },
-              [&](int i, int j, double acc) {
-                double dsgn = ((i % npol) == 2) ? -1.0 : 1.0;
-                SMRT_AT(BR, ldp, i, j) = dsgn * SMRT_AT(BF, h, i, j) - Rt[i] * SMRT_AT(BG, h, i, j) - acc;
-              });
-          team_gemm(
-              tm, h, nrhs, h, a11, [&](int k, int c) { return SMRT_AT(bbot, h, k, c); },
-              [&](int i, int c, double acc) { SMRT_AT(btop, h, i, c) -= acc; });
-        }
-        __syncthreads();
-        if (block_lu(BR, ldp, h, perm2, s_ctrl)) {
-          failed = true;
-          break;
-        }
-        block_lu_solve(BR, ldp, h, perm2, btop, h, nrhs, 0);  // z- = S^-1 b_top'
-        // z+ = Yr - Y22 z-  (in place in bbot), then s = F t z+ + G z-
-        {
-          Team tm = block_team();
-          team_gemm(
-              tm, h, nrhs, h, [&](int i, int k) { return SMRT_AT(B2, ldp, i, k); },
-              [&](int k, int c) { return SMRT_AT(btop, h, k, c); },
-              [&](int i, int c, double acc) { SMRT_AT(bbot, h, i, c) -= acc; });
+        if (r > 0) {
+          block_gemm_ptr(r, h, r, BR, ldr_prev, BG, h,
+                         [&](int i, int j, double acc) { SMRT_AT(TT, ldp, i, j) -= acc; });
+          block_gemm_ptr(r, h, r, BR, ldr_prev, BF, h,
+                         [&](int i, int j, double acc) { SMRT_AT(TT, ldp, i, h + j) -= acc * tvec[j]; });
           __syncthreads();
-          team_gemm(
-              tm, h, nrhs, 2 * h,
-              [&](int i, int k) { return (k < h) ? SMRT_AT(BF, h, i, k) * tvec[k] : SMRT_AT(BG, h, i, k - h); },
-              [&](int k, int c) { return (k < h) ? SMRT_AT(bbot, h, k, c) : SMRT_AT(btop, h, k - h, c); },
-              [&](int i, int c, double acc) { SMRT_AT(svec, h, i, c) = acc; });
+        }
+        // [A21 | A22 | b_bot] -> [I | Y22 | Yr] (implicit row permutation, unscaled rows)
+        if (block_gj_rows(TT, ldp, h, 2 * h + nr, rowstep, rowof)) {
+          failed = true;
+          break;
+        }
+        for (int k = tid; k < h; k += NT) ipiv[k] = tvec[k] / SMRT_AT(TT, ldp, rowof[k], k);
+        __syncthreads();
+        // Y~ = diag(t) Y22 -> left block of T ;  y~r = diag(t) Yr -> ytr
+        for (int e = tid; e < h * h; e += NT) {
+          int k = e % h, c = e / h;
+          SMRT_AT(TT, ldp, k, c) = SMRT_AT(TT, ldp, rowof[k], h + c) * ipiv[k];
+        }
+        for (int e = tid; e < h * nr; e += NT) {
+          int k = e % h, c = e / h;
+          SMRT_AT(ytr, h, k, c) = SMRT_AT(Trhs, ldp, rowof[k], c) * ipiv[k];
         }
         __syncthreads();
-
+        // P = F - G Y~, K = G - F Y~ ;  Schur S = D P - Rt K -> right block of T ;  K -> BR
+        double* TS = TT + (size_t)h * ldp;
+        block_gemm_dual(h, h, h, BG, BF, h, TT, ldp, [&](int i, int j, double c1, double c2) {
+          double dsgn = (npol == 3 && (i % 3) == 2) ? -1.0 : 1.0;
+          double pv = SMRT_AT(BF, h, i, j) - c1;
+          double kv = SMRT_AT(BG, h, i, j) - c2;
+          SMRT_AT(TS, ldp, i, j) = dsgn * pv - Rt[i] * kv;
+          SMRT_AT(BR, ldp, i, j) = kv;
+        });
+        // v = F y~r ;  b' = b_top - D (G y~r) + Rt v  (b' goes next to S, in the augmented columns)
+        if (nr > 0) {
+          block_gemm_dual(h, nr, h, BG, BF, h, ytr, h, [&](int i, int c, double c1, double c2) {
+            double dsgn = (npol == 3 && (i % 3) == 2) ? -1.0 : 1.0;
+            SMRT_AT(vvec, h, i, c) = c2;
+            SMRT_AT(Trhs, ldp, i, c) = SMRT_AT(btop, h, i, c) - dsgn * c1 + Rt[i] * c2;
+          });
+        }
+        __syncthreads();
         if (l > 0) {
-          // reflection operator of the stack seen from the layer above: R = (G - F t Y22) S^-1, kept transposed in B1
-          Team tm = block_team();
-          team_gemm(
-              tm, h, h, h, [&](int i, int k) { return SMRT_AT(BF, h, i, k) * tvec[k]; },
-              [&](int k, int j) { return SMRT_AT(B2, ldp, k, j); },
-              [&](int i, int j, double acc) { SMRT_AT(B1, ldp, j, i) = SMRT_AT(BG, h, i, j) - acc; });
+          // keep b' (the column elimination below does not touch the augmented columns)
+          // R_new = K S^-1 by column elimination of [S; K]
+          if (block_gj_cols(TS, ldp, BR, ldp, h, h, rowstep, rowof)) {
+            failed = true;
+            break;
+          }
+          for (int k = tid; k < h; k += NT) ipiv[k] = 1.0 / SMRT_AT(TS, ldp, k, rowof[k]);
           __syncthreads();
-          block_lu_solve(BR, ldp, h, perm2, B1, ldp, h, 1);  // S^T R^T = K^T
-          double* tmp = BR;
-          BR = B1;
-          B1 = tmp;
-          r_transposed = true;
-          ldr_prev = ldp;
+          // un-permute / scale through the (dead) left block of T, then back into BR
+          for (int e = tid; e < h * h; e += NT) {
+            int i = e % h, k = e / h;
+            SMRT_AT(TT, ldp, i, k) = SMRT_AT(BR, ldp, i, rowof[k]) * ipiv[k];
+          }
+          __syncthreads();
+          for (int e = tid; e < h * h; e += NT) {
+            int i = e % h, k = e / h;
+            SMRT_AT(BR, ldp, i, k) = SMRT_AT(TT, ldp, i, k);
+          }
+          __syncthreads();
+          if (nr > 0) {  // s = v + R_new b'
+            block_gemm_ptr(h, nr, h, BR, ldp, Trhs, ldp,
+                           [&](int i, int c, double acc) { SMRT_AT(svec, h, i, c) = SMRT_AT(vvec, h, i, c) + acc; });
+          }
           for (int a = tid; a < h; a += NT) Ttprev[a] = Tt[a];
           h_prev = h;
+          ldr_prev = ldp;
           have_prev = true;
+          src_prev = (nr > 0);
+          __syncthreads();
+        } else {
+          // top layer: z = S^-1 b' by row elimination of [S | b'], then s = v + K z
+          if (block_gj_rows(TS, ldp, h, h + nr, rowstep, rowof)) {
+            failed = true;
+            break;
+          }
+          for (int k = tid; k < h; k += NT) ipiv[k] = 1.0 / SMRT_AT(TS, ldp, rowof[k], k);
+          __syncthreads();
+          for (int e = tid; e < h * nr; e += NT) {
+            int k = e % h, c = e / h;
+            SMRT_AT(ytr, h, k, c) = SMRT_AT(Trhs, ldp, rowof[k], c) * ipiv[k];
+          }
+          __syncthreads();
+          block_gemm_ptr(h, nr, h, BR, ldp, ytr, h,
+                         [&](int i, int c, double acc) { SMRT_AT(svec, h, i, c) = SMRT_AT(vvec, h, i, c) + acc; });
           __syncthreads();
         }
       }  // layers

@@ -127,37 +127,87 @@ SMRT_DEV int team_cholesky(const Team& tm, double* A, int ld, int h, int* flag) 
 // Round-robin ("circle") ordering: hp = h rounded up to even, hp - 1 rounds per sweep, hp / 2 disjoint column pairs per
 // round, TPP threads per pair (power of two <= 32).  `ctrl` is a block-shared int[4] scratch.
 // Returns the number of sweeps performed (every thread gets the same value).
-#define SMRT_JACOBI_TOL 1e-15        // rotate only when |w_p . w_q| > tol |w_p| |w_q|
-#define SMRT_JACOBI_DONE 1e-13       // a sweep whose largest cosine is below this ends the iteration
-#define SMRT_JACOBI_QUAD 1e-9        // ... or below this before its own rotations (quadratic convergence finishes it)
+#define SMRT_JACOBI_TOL2 1e-30       // rotate only when (w_p . w_q)^2 > tol^2 |w_p|^2 |w_q|^2   (tol = 1e-15)
+#define SMRT_JACOBI_QUAD2 1e-18      // a sweep whose largest squared cosine (before its own rotations) stays below this
+                                     // is the last one: the quadratic convergence of the cyclic method finishes the job
 #define SMRT_JACOBI_MAX_SWEEPS 40
+
+// one column pair: R rows per lane held in registers between the dot products and the rotation
+template <int R>
+SMRT_DEV int jacobi_pair(double* SMRT_RESTRICT wp, double* SMRT_RESTRICT wq, int h, int lane, int tpp, unsigned gmask) {
+  double x[R], y[R];
+  double a0 = 0.0, b0 = 0.0, g0 = 0.0, a1 = 0.0, b1 = 0.0, g1 = 0.0;
+#pragma unroll
+  for (int u = 0; u < R; ++u) {
+    const int i = lane + u * tpp;
+    const bool ok = i < h;
+    x[u] = ok ? wp[i] : 0.0;
+    y[u] = ok ? wq[i] : 0.0;
+  }
+#pragma unroll
+  for (int u = 0; u < R; u += 2) {
+    a0 = fma(x[u], x[u], a0);
+    b0 = fma(y[u], y[u], b0);
+    g0 = fma(x[u], y[u], g0);
+    if (u + 1 < R) {
+      a1 = fma(x[u + 1], x[u + 1], a1);
+      b1 = fma(y[u + 1], y[u + 1], b1);
+      g1 = fma(x[u + 1], y[u + 1], g1);
+    }
+  }
+  double a = a0 + a1, b = b0 + b1, g = g0 + g1;
+  for (int off = tpp >> 1; off > 0; off >>= 1) {
+    a += __shfl_xor_sync(gmask, a, off, 32);
+    b += __shfl_xor_sync(gmask, b, off, 32);
+    g += __shfl_xor_sync(gmask, g, off, 32);
+  }
+  const double g2 = g * g, ab = a * b;
+  if (!(g2 > SMRT_JACOBI_TOL2 * ab)) return 0;
+  // tan of the rotation angle: t = sgn(d) 2 g / (|d| + sqrt(d^2 + 4 g^2)), d = |w_q|^2 - |w_p|^2
+  const double d = b - a;
+  const double t = copysign(2.0 * g, (d >= 0.0) ? g : -g) / (fabs(d) + sqrt(fma(d, d, 4.0 * g2)));
+  const double c = rsqrt(fma(t, t, 1.0));
+  const double s = c * t;
+#pragma unroll
+  for (int u = 0; u < R; ++u) {
+    const int i = lane + u * tpp;
+    if (i < h) {
+      wp[i] = fma(c, x[u], -s * y[u]);
+      wq[i] = fma(s, x[u], c * y[u]);
+    }
+  }
+  return (g2 > SMRT_JACOBI_QUAD2 * ab) ? 1 : 0;
+}
 
 SMRT_DEV int block_jacobi_svd(double* W, int ld, int h, int* ctrl) {
   const int NT = blockDim.x;
   const int tid = threadIdx.x;
   const int hp = (h + 1) & ~1;
+  const int hm1 = hp - 1;
   const int npairs = hp / 2;
   int tpp = 32;
   while (tpp > 1 && npairs * tpp > NT) tpp >>= 1;
-  // if there are more pairs than threads (h > 2 NT) each group loops over several pairs
+  // if there are more pairs than groups (h > 2 NT) each group loops over several pairs
   const int ngroups = NT / tpp;
   const int grp = tid / tpp, lane = tid % tpp;
   // lanes of this thread's group inside its warp (shuffles are issued per group, groups may diverge)
   const unsigned gmask = (tpp == 32) ? 0xffffffffu : (((1u << tpp) - 1u) << ((tid & 31) & ~(tpp - 1)));
+  const int rows = (h + tpp - 1) / tpp;  // rows per lane
+  (void)ctrl;
   int sweeps = 0;
-  for (; sweeps < SMRT_JACOBI_MAX_SWEEPS; ++sweeps) {
-    if (tid == 0) ctrl[0] = 0;  // max cosine of the sweep, as ordered int bits of a non-negative double's high word
-    __syncthreads();
-    double maxcos = 0.0;
-    for (int r = 0; r < hp - 1; ++r) {
+  for (;;) {
+    int notconv = 0;
+    for (int r = 0; r < hm1; ++r) {
       for (int pi = grp; pi < npairs; pi += ngroups) {
         int p, q;
         if (pi == 0) {
           p = r;
-          q = hp - 1;
+          q = hm1;
         } else {
-          p = (r + pi) % (hp - 1);
-          q = (r - pi + (hp - 1)) % (hp - 1);
+          p = r + pi;
+          if (p >= hm1) p -= hm1;
+          q = r - pi;
+          if (q < 0) q += hm1;
         }
         if (p > q) {
           int t = p;
@@ -167,53 +217,48 @@ SMRT_DEV int block_jacobi_svd(double* W, int ld, int h, int* ctrl) {
         if (q < h) {  // skip the padding column of an odd-sized problem
           double* wp = W + (size_t)p * ld;
           double* wq = W + (size_t)q * ld;
-          double a = 0.0, b = 0.0, g = 0.0;
-          for (int i = lane; i < h; i += tpp) {
-            double x = wp[i], y = wq[i];
-            a = fma(x, x, a);
-            b = fma(y, y, b);
-            g = fma(x, y, g);
-          }
-          for (int off = tpp >> 1; off > 0; off >>= 1) {
-            a += __shfl_xor_sync(gmask, a, off, 32);
-            b += __shfl_xor_sync(gmask, b, off, 32);
-            g += __shfl_xor_sync(gmask, g, off, 32);
-          }
-          double denom = sqrt(a * b);
-          double cosv = (denom > 0.0) ? fabs(g) / denom : 0.0;
-          maxcos = fmax(maxcos, cosv);
-          if (cosv > SMRT_JACOBI_TOL) {
-            double zeta = (b - a) / (2.0 * g);
-            double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            double c = 1.0 / sqrt(1.0 + t * t);
-            double s = c * t;
+          if (rows <= 2)
+            notconv |= jacobi_pair<2>(wp, wq, h, lane, tpp, gmask);
+          else if (rows <= 4)
+            notconv |= jacobi_pair<4>(wp, wq, h, lane, tpp, gmask);
+          else if (rows <= 8)
+            notconv |= jacobi_pair<8>(wp, wq, h, lane, tpp, gmask);
+          else if (rows <= 16)
+            notconv |= jacobi_pair<16>(wp, wq, h, lane, tpp, gmask);
+          else {
+            // very large problems (global scratch path): plain loops
+            double a = 0.0, b = 0.0, g = 0.0;
             for (int i = lane; i < h; i += tpp) {
               double x = wp[i], y = wq[i];
-              wp[i] = c * x - s * y;
-              wq[i] = s * x + c * y;
+              a = fma(x, x, a);
+              b = fma(y, y, b);
+              g = fma(x, y, g);
+            }
+            for (int off = tpp >> 1; off > 0; off >>= 1) {
+              a += __shfl_xor_sync(gmask, a, off, 32);
+              b += __shfl_xor_sync(gmask, b, off, 32);
+              g += __shfl_xor_sync(gmask, g, off, 32);
+            }
+            const double g2 = g * g, ab = a * b;
+            if (g2 > SMRT_JACOBI_TOL2 * ab) {
+              if (g2 > SMRT_JACOBI_QUAD2 * ab) notconv = 1;
+              const double d = b - a;
+              const double t = copysign(2.0 * g, (d >= 0.0) ? g : -g) / (fabs(d) + sqrt(fma(d, d, 4.0 * g2)));
+              const double c = rsqrt(fma(t, t, 1.0));
+              const double s = c * t;
+              for (int i = lane; i < h; i += tpp) {
+                double x = wp[i], y = wq[i];
+                wp[i] = fma(c, x, -s * y);
+                wq[i] = fma(s, x, c * y);
+              }
             }
           }
         }
       }
       __syncthreads();
     }
-    // block-wide max of maxcos (non-negative doubles order like their bit patterns: compare the high 32 bits + 1)
-    {
-      unsigned long long bits;
-      memcpy(&bits, &maxcos, 8);
-      int hi = (int)(bits >> 33);  // drop the sign bit position, keep 31 bits: monotone for non-negative values
-      atomicMax(&ctrl[0], hi);
-    }
-    __syncthreads();
-    int hi = ctrl[0];
-    __syncthreads();
-    unsigned long long bits = ((unsigned long long)(unsigned)hi) << 33;
-    double mc;
-    memcpy(&mc, &bits, 8);  // lower bound of the max cosine (truncated mantissa)
-    if (mc < SMRT_JACOBI_QUAD) {
-      ++sweeps;
-      break;
-    }
+    ++sweeps;
+    if (!__syncthreads_or(notconv) || sweeps >= SMRT_JACOBI_MAX_SWEEPS) break;
   }
   return sweeps;
 }
@@ -351,4 +396,271 @@ SMRT_DEV void block_lu_solve(const double* LU, int ld, int h, const int* perm, d
     }
   }
   __syncthreads();
+}
+
+// =====================================================================================================================
+// Second-generation primitives used by the boundary kernel: pointer-operand GEMMs without guards in the inner loop and
+// Gauss-Jordan eliminations whose every step is ONE block barrier (pivot search done redundantly by every warp,
+// implicit permutation instead of physical swaps, no separate scaling pass).
+// =====================================================================================================================
+
+// C(i,j) = epi(i, j, sum_{k<K} A(i,k) B(k,j)) for i < M, j < N; A, B column-major in shared memory.
+// Loads of out-of-range rows / columns are clamped to the last valid one (harmless), stores are guarded.
+template <typename FE>
+SMRT_DEV void block_gemm_ptr(int M, int N, int K, const double* SMRT_RESTRICT Am, int lda,
+                             const double* SMRT_RESTRICT Bm, int ldb, FE epi) {
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int TX = 16, TY = NT / TX;
+  const int tx = tid % TX, ty = tid / TX;
+  if (M <= 0 || N <= 0) return;
+  for (int j0 = 0; j0 < N; j0 += TY * 4) {
+    for (int i0 = 0; i0 < M; i0 += TX * 4) {
+      int ir[4], jc[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ir[u] = i0 + tx + u * TX;
+        jc[u] = j0 + ty + u * TY;
+      }
+      const double* ap[4];
+      const double* bp[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ap[u] = Am + (ir[u] < M ? ir[u] : M - 1);
+        bp[u] = Bm + (size_t)(jc[u] < N ? jc[u] : N - 1) * ldb;
+      }
+      double acc[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) {
+        double av[4], bv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) av[u] = ap[u][(size_t)k * lda];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) bv[v] = bp[v][k];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) acc[u][v] = fma(av[u], bv[v], acc[u][v]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (ir[u] < M && jc[v] < N) epi(ir[u], jc[v], acc[u][v]);
+    }
+  }
+}
+
+// Two products sharing the B operand: C1 = A1 B, C2 = A2 B (M x N, inner K).
+template <typename FE>
+SMRT_DEV void block_gemm_dual(int M, int N, int K, const double* SMRT_RESTRICT A1, const double* SMRT_RESTRICT A2,
+                              int lda, const double* SMRT_RESTRICT Bm, int ldb, FE epi) {
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int TX = 16, TY = NT / TX;
+  const int tx = tid % TX, ty = tid / TX;
+  if (M <= 0 || N <= 0) return;
+  for (int j0 = 0; j0 < N; j0 += TY * 4) {
+    for (int i0 = 0; i0 < M; i0 += TX * 2) {
+      int ir[2], jc[4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) ir[u] = i0 + tx + u * TX;
+#pragma unroll
+      for (int v = 0; v < 4; ++v) jc[v] = j0 + ty + v * TY;
+      size_t ao[2];
+      const double* bp[4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) ao[u] = (size_t)(ir[u] < M ? ir[u] : M - 1);
+#pragma unroll
+      for (int v = 0; v < 4; ++v) bp[v] = Bm + (size_t)(jc[v] < N ? jc[v] : N - 1) * ldb;
+      double c1[2][4], c2[2][4];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) c1[u][v] = c2[u][v] = 0.0;
+#pragma unroll 4
+      for (int k = 0; k < K; ++k) {
+        double a1[2], a2[2], bv[4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          a1[u] = A1[ao[u] + (size_t)k * lda];
+          a2[u] = A2[ao[u] + (size_t)k * lda];
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) bv[v] = bp[v][k];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            c1[u][v] = fma(a1[u], bv[v], c1[u][v]);
+            c2[u][v] = fma(a2[u], bv[v], c2[u][v]);
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (ir[u] < M && jc[v] < N) epi(ir[u], jc[v], c1[u][v], c2[u][v]);
+    }
+  }
+}
+
+// warp-wide argmax of (value, index) with ties to the smaller index; every lane returns the winner
+SMRT_DEV void warp_argmax(double& best, int& bi) {
+  for (int off = 16; off > 0; off >>= 1) {
+    double ob = __shfl_xor_sync(0xffffffffu, best, off, 32);
+    int oi = __shfl_xor_sync(0xffffffffu, bi, off, 32);
+    if (ob > best || (ob == best && oi < bi)) {
+      best = ob;
+      bi = oi;
+    }
+  }
+}
+
+// elimination pass of one Gauss-Jordan step: lanes along rows (RPL rows per lane), warps along columns, two columns per
+// iteration for instruction-level parallelism
+template <int RPL>
+SMRT_DEV void gj_rows_update(double* T, int ld, int h, int W, int j, int p, double inv, int lane, int warp, int nwarp) {
+  const double* colj = T + (size_t)j * ld;
+  double mrow[RPL];
+#pragma unroll
+  for (int u = 0; u < RPL; ++u) {
+    const int i = lane + 32 * u;
+    mrow[u] = (i < h && i != p) ? -(colj[i] * inv) : 0.0;
+  }
+  int c = j + 1 + warp;
+  for (; c + nwarp < W; c += 2 * nwarp) {
+    double* col0 = T + (size_t)c * ld;
+    double* col1 = col0 + (size_t)nwarp * ld;
+    const double p0 = col0[p], p1 = col1[p];
+#pragma unroll
+    for (int u = 0; u < RPL; ++u) {
+      const int i = lane + 32 * u;
+      if (i < h) {
+        const double v0 = col0[i], v1 = col1[i];
+        col0[i] = fma(mrow[u], p0, v0);
+        col1[i] = fma(mrow[u], p1, v1);
+      }
+    }
+  }
+  if (c < W) {
+    double* col0 = T + (size_t)c * ld;
+    const double p0 = col0[p];
+#pragma unroll
+    for (int u = 0; u < RPL; ++u) {
+      const int i = lane + 32 * u;
+      if (i < h) col0[i] = fma(mrow[u], p0, col0[i]);
+    }
+  }
+}
+
+// Gauss-Jordan elimination by ROWS with partial pivoting on T = [A | R] (h rows, W >= h columns, column-major, ld):
+// afterwards, for every unknown k, row rowof[k] of the right block holds piv_k * (A^-1 R)(k, :), piv_k = T(rowof[k], k).
+// No physical swaps, no scaling pass, one barrier per step.  rowstep/rowof: block-shared int[h].
+// Returns 1 if a pivot vanishes (singular / non finite), else 0 — the same value in every thread.
+SMRT_DEV int block_gj_rows(double* T, int ld, int h, int W, int* rowstep, int* rowof) {
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+  for (int i = tid; i < h; i += NT) rowstep[i] = -1;
+  __syncthreads();
+  for (int j = 0; j < h; ++j) {
+    const double* colj = T + (size_t)j * ld;
+    double best = -1.0;
+    int bi = 0x7fffffff;
+    for (int i = lane; i < h; i += 32) {
+      int st = rowstep[i];
+      if (st < 0 || st == j) {
+        double v = fabs(colj[i]);
+        if (v > best) {
+          best = v;
+          bi = i;
+        }
+      }
+    }
+    warp_argmax(best, bi);
+    if (!(best > 0.0) || !(best < 1e300)) return 1;  // identical decision in every warp
+    const int p = bi;
+    if (tid == 0) {
+      rowstep[p] = j;
+      rowof[j] = p;
+    }
+    const double inv = 1.0 / colj[p];
+    // columns still to update: (j, h) of the left block and the whole right block
+    if (h <= 64)
+      gj_rows_update<2>(T, ld, h, W, j, p, inv, lane, warp, nwarp);
+    else if (h <= 128)
+      gj_rows_update<4>(T, ld, h, W, j, p, inv, lane, warp, nwarp);
+    else
+      gj_rows_update<8>(T, ld, h, W, j, p, inv, lane, warp, nwarp);
+    __syncthreads();
+  }
+  return 0;
+}
+
+// Gauss-Jordan elimination by COLUMNS with partial (column) pivoting on the stacked pair [S; K] (S: h x h, K: m x h):
+// afterwards (K S^-1)(:, k) = K(:, colof[k]) / S(k, colof[k]).  One barrier per step.
+SMRT_DEV int block_gj_cols(double* S, int lds, double* Km, int ldk, int h, int m, int* colstep, int* colof) {
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+  for (int i = tid; i < h; i += NT) colstep[i] = -1;
+  __syncthreads();
+  for (int j = 0; j < h; ++j) {
+    double best = -1.0;
+    int bi = 0x7fffffff;
+    for (int c = lane; c < h; c += 32) {
+      int st = colstep[c];
+      if (st < 0 || st == j) {
+        double v = fabs(SMRT_AT(S, lds, j, c));
+        if (v > best) {
+          best = v;
+          bi = c;
+        }
+      }
+    }
+    warp_argmax(best, bi);
+    if (!(best > 0.0) || !(best < 1e300)) return 1;
+    const int p = bi;
+    if (tid == 0) {
+      colstep[p] = j;
+      colof[j] = p;
+    }
+    const double inv = 1.0 / SMRT_AT(S, lds, j, p);
+    const double* sp = S + (size_t)p * lds;
+    const double* kp = Km + (size_t)p * ldk;
+    // warps along columns (two per iteration for ILP), lanes along rows
+    for (int c0 = warp; c0 < h; c0 += 2 * nwarp) {
+      const int c1 = c0 + nwarp;
+      const bool ok0 = (c0 != p), ok1 = (c1 < h) && (c1 != p);
+      double* s0 = S + (size_t)c0 * lds;
+      double* s1 = S + (size_t)(ok1 ? c1 : c0) * lds;
+      double* k0 = Km + (size_t)c0 * ldk;
+      double* k1 = Km + (size_t)(ok1 ? c1 : c0) * ldk;
+      const double m0 = ok0 ? -(s0[j] * inv) : 0.0;
+      const double m1 = ok1 ? -(s1[j] * inv) : 0.0;
+      if (ok0 && ok1) {
+        for (int i = j + 1 + lane; i < h; i += 32) {
+          const double pv = sp[i];
+          s0[i] = fma(m0, pv, s0[i]);
+          s1[i] = fma(m1, pv, s1[i]);
+        }
+        for (int i = lane; i < m; i += 32) {
+          const double pv = kp[i];
+          k0[i] = fma(m0, pv, k0[i]);
+          k1[i] = fma(m1, pv, k1[i]);
+        }
+      } else if (ok0 || ok1) {
+        double* sc = ok0 ? s0 : s1;
+        double* kc = ok0 ? k0 : k1;
+        const double mm = ok0 ? m0 : m1;
+        for (int i = j + 1 + lane; i < h; i += 32) sc[i] = fma(mm, sp[i], sc[i]);
+        for (int i = lane; i < m; i += 32) kc[i] = fma(mm, kp[i], kc[i]);
+      }
+      // S(j, c) is mathematically zero now; it is never read again, and must NOT be written here: slower warps may
+      // still be scanning row j for the pivot of this step
+    }
+    __syncthreads();
+  }
+  return 0;
 }

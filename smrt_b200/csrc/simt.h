@@ -43,7 +43,7 @@ SMRT_DEV void smrt_named_barrier(int id, int nthreads) {
 #define SMRT_GLOBAL
 #define SMRT_SHARED static
 #define SMRT_RESTRICT __restrict__
-#define __launch_bounds__(...)
+#define __launch_bounds__(...)  /* nothing */
 #define __forceinline__ inline
 #define __device__
 #define __host__

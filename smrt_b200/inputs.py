@@ -82,15 +82,18 @@ class Sensor:
 
 def passive(frequency, theta, polarization=None, channel_map=None, name=None):
     """Generic radiometer (reference ``smrt/core/sensor.py:24-75``)."""
-    return Sensor(frequency, None, theta, None, None, polarization or ["V", "H"], channel_map=channel_map, name=name)
+    return Sensor(frequency, None, theta, None, None, ["V", "H"] if polarization is None else list(polarization),
+                  channel_map=channel_map, name=name)
 
 
 def active(frequency, theta_inc, theta=None, phi=None, polarization_inc=None, polarization=None, channel_map=None,
            name=None):
     """Generic radar, backscatter by default (reference ``smrt/core/sensor.py:119-199``)."""
     return Sensor(frequency, theta_inc_deg=theta_inc, theta_deg=theta_inc if theta is None else theta,
-                  phi_deg=180.0 if phi is None else phi, polarization_inc=polarization_inc or ["V", "H"],
-                  polarization=polarization or ["V", "H"], channel_map=channel_map, name=name)
+                  phi_deg=180.0 if phi is None else phi,
+                  polarization_inc=["V", "H"] if polarization_inc is None else list(polarization_inc),
+                  polarization=["V", "H"] if polarization is None else list(polarization),
+                  channel_map=channel_map, name=name)
 
 
 _AMSRE = {"06": 6.925e9, "10": 10.65e9, "19": 18.7e9, "23": 23.8e9, "37": 36.5e9, "89": 89e9}

@@ -40,8 +40,10 @@ def emu_solve(batch, opts, threads=64):
     out = capi.HostOutputs(batch, o.n_max_stream)
     keep = []
     bt = capi.host_batch_struct(batch, out, keep)
-    rc = lib.emu_solve_batch(C.byref(o), C.byref(bt), threads, None)
+    diag = (C.c_int * 2)()
+    rc = lib.emu_solve_batch(C.byref(o), C.byref(bt), threads, C.cast(diag, C.c_void_p))
     assert rc == 0
+    out.jacobi_sweeps, out.eigenproblems = diag[0], diag[1]
     return out
 
 

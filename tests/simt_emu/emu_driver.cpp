@@ -39,12 +39,17 @@ int emu_solve_batch(const smrtb200_options* opt, const smrtb200_batch* batch, in
   A.scratch = scratch.data();
   A.scratch_stride = (long long)scratch.size();
   A.use_global_scratch = 1;  // the emulator's "shared memory" is 1 MiB: keep matrices in the scratch
+  int diag[2] = {0, 0};
+  A.diag = diag;
   for (int b = 0; b < B; ++b) batch->status[b] = 0;
 
   simt::launch((unsigned)((BL + 127) / 128), 128, [&]() { optics_kernel(A); });
-  simt::launch(1, (unsigned)threads, [&]() { eigen_kernel(A); });
-  simt::launch(1, (unsigned)threads, [&]() { boundary_kernel(A); });
-  (void)sweeps_out;
+  simt::launch(1, (unsigned)threads, [&]() { eigen_kernel<true>(A); });
+  simt::launch(1, (unsigned)threads, [&]() { boundary_kernel<true>(A); });
+  if (sweeps_out) {
+    sweeps_out[0] = diag[0];
+    sweeps_out[1] = diag[1];
+  }
   return 0;
 }
 
