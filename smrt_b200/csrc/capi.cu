@@ -37,7 +37,7 @@ static int fail(int code, const char* fmt, ...) {
 namespace {
 
 constexpr int kSlots = 2;
-constexpr size_t kMaxSmemOptin = 227 * 1024;
+constexpr size_t kMaxSmemOptin = 227 * 1024 - 256;  // opt-in limit minus the kernels' static shared memory
 
 struct Slot {
   cudaStream_t stream = nullptr;
@@ -167,8 +167,17 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
   p->boundary_fn = p->use_global_scratch ? boundary_kernel<true> : boundary_kernel<false>;
   // the attribute belongs to the FUNCTION, not to the plan: always raise it to the opt-in maximum so that plans with
   // different shared-memory footprints can coexist
-  PLAN_CUDA(cudaFuncSetAttribute(p->eigen_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemOptin));
-  PLAN_CUDA(cudaFuncSetAttribute(p->boundary_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemOptin));
+  {
+    int optin = 0;
+    PLAN_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, options->device));
+    cudaFuncAttributes fa;
+    PLAN_CUDA(cudaFuncGetAttributes(&fa, p->eigen_fn));
+    PLAN_CUDA(cudaFuncSetAttribute(p->eigen_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   optin - (int)fa.sharedSizeBytes));
+    PLAN_CUDA(cudaFuncGetAttributes(&fa, p->boundary_fn));
+    PLAN_CUDA(cudaFuncSetAttribute(p->boundary_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   optin - (int)fa.sharedSizeBytes));
+  }
   int occ_e = 0, occ_b = 0;
   PLAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, p->eigen_fn, SMRT_NT, p->eigen_smem));
   if (const char* e = std::getenv("SMRT_B200_BOUNDARY_THREADS")) {

@@ -315,20 +315,24 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 2) eigen_kernel
       __syncthreads();
 
       // E~+ = C^-T W: back substitution with the upper-triangular C^T, in place on the columns of A3
+      // (uniform trip counts: every lane of every warp takes part in the __syncwarp()s)
       {
         int tpc = 32;
         while (tpc > 1 && h * tpc > NT) tpc >>= 1;
         const int ngroups = NT / tpc;
         const int grp = tid / tpc, lane = tid % tpc;
-        const unsigned gmask = (tpc == 32) ? 0xffffffffu : (((1u << tpc) - 1u) << ((tid & 31) & ~(tpc - 1)));
-        for (int c = grp; c < h; c += ngroups) {
-          double* x = A3 + (size_t)c * ld;
+        for (int c0 = 0; c0 < h; c0 += ngroups) {
+          const int c = c0 + grp;
+          const bool valid = c < h;
+          double* x = A3 + (size_t)(valid ? c : 0) * ld;
           for (int j = h - 1; j >= 0; --j) {
-            if (lane == 0) x[j] = x[j] / SMRT_AT(A2, ld, j, j);
-            __syncwarp(gmask);
-            double xj = x[j];
-            for (int i = lane; i < j; i += tpc) x[i] = fma(-SMRT_AT(A2, ld, j, i), xj, x[i]);
-            __syncwarp(gmask);
+            if (valid && lane == 0) x[j] = x[j] / SMRT_AT(A2, ld, j, j);
+            __syncwarp();
+            if (valid) {
+              const double xj = x[j];
+              for (int i = lane; i < j; i += tpc) x[i] = fma(-SMRT_AT(A2, ld, j, i), xj, x[i]);
+            }
+            __syncwarp();
           }
         }
       }

@@ -134,7 +134,8 @@ SMRT_DEV int team_cholesky(const Team& tm, double* A, int ld, int h, int* flag) 
 
 // one column pair: R rows per lane held in registers between the dot products and the rotation
 template <int R>
-SMRT_DEV int jacobi_pair(double* SMRT_RESTRICT wp, double* SMRT_RESTRICT wq, int h, int lane, int tpp, unsigned gmask) {
+SMRT_DEV int jacobi_pair(double* SMRT_RESTRICT wp, double* SMRT_RESTRICT wq, int h, int lane, int tpp) {
+  // called by EVERY lane of the warp (groups without a pair pass h = 0): the shuffles use the full, compile-time mask
   double x[R], y[R];
   double a0 = 0.0, b0 = 0.0, g0 = 0.0, a1 = 0.0, b1 = 0.0, g1 = 0.0;
 #pragma unroll
@@ -157,9 +158,9 @@ SMRT_DEV int jacobi_pair(double* SMRT_RESTRICT wp, double* SMRT_RESTRICT wq, int
   }
   double a = a0 + a1, b = b0 + b1, g = g0 + g1;
   for (int off = tpp >> 1; off > 0; off >>= 1) {
-    a += __shfl_xor_sync(gmask, a, off, 32);
-    b += __shfl_xor_sync(gmask, b, off, 32);
-    g += __shfl_xor_sync(gmask, g, off, 32);
+    a += __shfl_xor_sync(0xffffffffu, a, off, 32);
+    b += __shfl_xor_sync(0xffffffffu, b, off, 32);
+    g += __shfl_xor_sync(0xffffffffu, g, off, 32);
   }
   const double g2 = g * g, ab = a * b;
   if (!(g2 > SMRT_JACOBI_TOL2 * ab)) return 0;
@@ -190,15 +191,16 @@ SMRT_DEV int block_jacobi_svd(double* W, int ld, int h, int* ctrl) {
   // if there are more pairs than groups (h > 2 NT) each group loops over several pairs
   const int ngroups = NT / tpp;
   const int grp = tid / tpp, lane = tid % tpp;
-  // lanes of this thread's group inside its warp (shuffles are issued per group, groups may diverge)
-  const unsigned gmask = (tpp == 32) ? 0xffffffffu : (((1u << tpp) - 1u) << ((tid & 31) & ~(tpp - 1)));
   const int rows = (h + tpp - 1) / tpp;  // rows per lane
   (void)ctrl;
   int sweeps = 0;
   for (;;) {
     int notconv = 0;
     for (int r = 0; r < hm1; ++r) {
-      for (int pi = grp; pi < npairs; pi += ngroups) {
+      // uniform trip count: every thread of the block walks the same number of pair slots, threads without a pair
+      // (padding column of an odd-sized problem, or more groups than pairs) run the pair code on an empty column
+      for (int pi0 = 0; pi0 < npairs; pi0 += ngroups) {
+        const int pi = pi0 + grp;
         int p, q;
         if (pi == 0) {
           p = r;
@@ -214,43 +216,41 @@ SMRT_DEV int block_jacobi_svd(double* W, int ld, int h, int* ctrl) {
           p = q;
           q = t;
         }
-        if (q < h) {  // skip the padding column of an odd-sized problem
-          double* wp = W + (size_t)p * ld;
-          double* wq = W + (size_t)q * ld;
-          if (rows <= 2)
-            notconv |= jacobi_pair<2>(wp, wq, h, lane, tpp, gmask);
-          else if (rows <= 4)
-            notconv |= jacobi_pair<4>(wp, wq, h, lane, tpp, gmask);
-          else if (rows <= 8)
-            notconv |= jacobi_pair<8>(wp, wq, h, lane, tpp, gmask);
-          else if (rows <= 16)
-            notconv |= jacobi_pair<16>(wp, wq, h, lane, tpp, gmask);
-          else {
-            // very large problems (global scratch path): plain loops
-            double a = 0.0, b = 0.0, g = 0.0;
-            for (int i = lane; i < h; i += tpp) {
+        const bool valid = (pi < npairs) && (q < h);
+        const int hh = valid ? h : 0;
+        double* wp = W + (size_t)(valid ? p : 0) * ld;
+        double* wq = W + (size_t)(valid ? q : 0) * ld;
+        if (rows <= 2)
+          notconv |= jacobi_pair<2>(wp, wq, hh, lane, tpp);
+        else if (rows <= 4)
+          notconv |= jacobi_pair<4>(wp, wq, hh, lane, tpp);
+        else if (rows <= 8)
+          notconv |= jacobi_pair<8>(wp, wq, hh, lane, tpp);
+        else {
+          // large problems (global scratch path): plain loops
+          double a = 0.0, b = 0.0, g = 0.0;
+          for (int i = lane; i < hh; i += tpp) {
+            double x = wp[i], y = wq[i];
+            a = fma(x, x, a);
+            b = fma(y, y, b);
+            g = fma(x, y, g);
+          }
+          for (int off = tpp >> 1; off > 0; off >>= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, off, 32);
+            b += __shfl_xor_sync(0xffffffffu, b, off, 32);
+            g += __shfl_xor_sync(0xffffffffu, g, off, 32);
+          }
+          const double g2 = g * g, ab = a * b;
+          if (g2 > SMRT_JACOBI_TOL2 * ab) {
+            if (g2 > SMRT_JACOBI_QUAD2 * ab) notconv = 1;
+            const double d = b - a;
+            const double t = copysign(2.0 * g, (d >= 0.0) ? g : -g) / (fabs(d) + sqrt(fma(d, d, 4.0 * g2)));
+            const double c = rsqrt(fma(t, t, 1.0));
+            const double s = c * t;
+            for (int i = lane; i < hh; i += tpp) {
               double x = wp[i], y = wq[i];
-              a = fma(x, x, a);
-              b = fma(y, y, b);
-              g = fma(x, y, g);
-            }
-            for (int off = tpp >> 1; off > 0; off >>= 1) {
-              a += __shfl_xor_sync(gmask, a, off, 32);
-              b += __shfl_xor_sync(gmask, b, off, 32);
-              g += __shfl_xor_sync(gmask, g, off, 32);
-            }
-            const double g2 = g * g, ab = a * b;
-            if (g2 > SMRT_JACOBI_TOL2 * ab) {
-              if (g2 > SMRT_JACOBI_QUAD2 * ab) notconv = 1;
-              const double d = b - a;
-              const double t = copysign(2.0 * g, (d >= 0.0) ? g : -g) / (fabs(d) + sqrt(fma(d, d, 4.0 * g2)));
-              const double c = rsqrt(fma(t, t, 1.0));
-              const double s = c * t;
-              for (int i = lane; i < h; i += tpp) {
-                double x = wp[i], y = wq[i];
-                wp[i] = fma(c, x, -s * y);
-                wq[i] = fma(s, x, c * y);
-              }
+              wp[i] = fma(c, x, -s * y);
+              wq[i] = fma(s, x, c * y);
             }
           }
         }
