@@ -192,7 +192,9 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
   }
   p->eigen_grid = p->sm_count * occ_e;
   p->boundary_grid = p->sm_count * occ_b;
-  p->scratch_stride = p->use_global_scratch ? std::max(L.eigen_scratch_doubles, L.boundary_scratch_doubles) + 16 : 0;
+  // stride in doubles, a multiple of 16 (128 B): the kernels use 16-byte vector accesses on the per-CTA scratch
+  p->scratch_stride =
+      p->use_global_scratch ? ((std::max(L.eigen_scratch_doubles, L.boundary_scratch_doubles) + 31) & ~15LL) : 0;
 
   // chunk: enough problems to fill the machine several times, bounded by a workspace budget of ~6 GB per slot
   {

@@ -55,6 +55,11 @@ struct KArgs {
 SMRT_HD int smrt_npol(int m) { return m == 0 ? 2 : 3; }
 SMRT_HD long long smrt_even(long long x) { return (x + 1) & ~1LL; }
 
+// 2-D element loop without integer division: warps walk the columns, lanes the rows (coalesced / conflict-free)
+#define SMRT_FOR_2D(i, j, nrows, ncols)                                   \
+  for (int j = (int)(threadIdx.x >> 5); j < (ncols); j += (int)(blockDim.x >> 5)) \
+    for (int i = (int)(threadIdx.x & 31); i < (nrows); i += 32)
+
 #ifdef __CUDACC__
 #define SMRT_DYN_SMEM(ptr)                                        \
   extern __shared__ __align__(16) unsigned char smrt_smem_raw[]; \
@@ -101,11 +106,17 @@ SMRT_DEV void set_error(int* status, int b, int code) {
 // kernel 2: per-layer eigenproblem
 // --------------------------------------------------------------------------------------------------------------------
 // shared-memory vector region (doubles): mu[n] w[n] norm0[2n] g[hmax] sdiag[hmax] dk[hmax] sigma[hmax] ctab[2K] stab[2K]
-SMRT_HD size_t eigen_vec_doubles(int n, int hmax, int K) { return (size_t)4 * n + 4 * hmax + 4 * K + 8; }
-SMRT_HD size_t eigen_mat_doubles(int hmax) { return (size_t)3 * hmax * (hmax + 1); }
+//                                        panel[SMRT_PANEL * hmax]
+// matrix region: A1 (X- -> L -> M -> W -> E~+), A2 (X+ -> C); two (hmax x (hmax+1)) blocks = 67 KB at 32 streams, so
+// that three CTAs fit on an SM
+#define SMRT_PANEL 8  // columns of L staged per step of the in-place product M = C^T L
+SMRT_HD size_t eigen_vec_doubles(int n, int hmax, int K) {
+  return ((size_t)4 * n + 5 * hmax + 4 * K + (size_t)SMRT_PANEL * hmax + 8 + 1) & ~(size_t)1;
+}
+SMRT_HD size_t eigen_mat_doubles(int hmax) { return (size_t)2 * hmax * (hmax + 1); }
 
 template <bool kGlobalScratch>
-SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 2) eigen_kernel(KArgs A) {
+SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 3) eigen_kernel(KArgs A) {
   SMRT_DYN_SMEM(smem);
   SMRT_SHARED int s_item;
   SMRT_SHARED int s_ctrl[8];
@@ -125,13 +136,14 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 2) eigen_kernel
   double* sigma = dk + hmax;
   double* ctab = sigma + hmax;
   double* stab = ctab + 2 * K;
+  double* panel = stab + 2 * K;
+  double* gq = panel + (size_t)SMRT_PANEL * hmax;
   // compile-time choice so that the shared-memory instantiation addresses its matrices with LDS/STS, not generic LD/ST
   double* mats = kGlobalScratch ? (A.scratch + (size_t)blockIdx.x * A.scratch_stride)
                                 : (smem + eigen_vec_doubles(n, hmax, K));
   const size_t matsz = (size_t)hmax * (hmax + 1);
   double* A1 = mats;
   double* A2 = mats + matsz;
-  double* A3 = mats + 2 * matsz;
 
   for (int j = tid; j < 2 * K; j += NT) {
     double s, c;
@@ -239,6 +251,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 2) eigen_kernel
         double q = (p == 2) ? 2.0 : 1.0;
         double cw = coef * w[j];
         gvec[a] = sqrt(norm * q * cw / mu[j]);
+        gq[a] = gvec[a] / q;
         sdiag[a] = sqrt(norm * q / (mu[j] * cw));
         dk[a] = ke / mu[j];
       }
@@ -249,10 +262,9 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 2) eigen_kernel
         break;
       }
       // X- = diag(ke/mu) - g Ps++ g + g Ps+-' g   (A1),   X+ = diag(ke/mu) - g Ps++ g - g Ps+-' g   (A2)
-      for (int e = tid; e < h * h; e += NT) {
-        int a = e % h, c = e / h;
-        double q = ((a % npol) == 2) ? 2.0 : 1.0;
-        double sc = gvec[a] * gvec[c] / q;
+      // (gq = g / q: the reciprocity weight of the row is folded into the row scale)
+      SMRT_FOR_2D(a, c, h, h) {
+        double sc = gq[a] * gvec[c];
         double x1 = sc * SMRT_AT(A1, ld, a, c), x2 = sc * SMRT_AT(A2, ld, a, c);
         double d = (a == c) ? dk[a] : 0.0;
         SMRT_AT(A1, ld, a, c) = d - x1 + x2;
@@ -278,19 +290,35 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 2) eigen_kernel
         break;
       }
 
-      // M = C^T L  -> A3
-      {
-        Team tm = block_team();
-        team_gemm(
-            tm, h, h, h, [&](int i, int k) { return (k >= i) ? SMRT_AT(A2, ld, k, i) : 0.0; },
-            [&](int k, int j) { return (k >= j) ? SMRT_AT(A1, ld, k, j) : 0.0; },
-            [&](int i, int j, double acc) { SMRT_AT(A3, ld, i, j) = acc; });
+      // M = C^T L in place over L (A1): M(i, j) = sum_{k >= max(i, j)} C(k, i) L(k, j) needs only column j of L,
+      // staged SMRT_PANEL columns at a time
+      for (int jp = 0; jp < h; jp += SMRT_PANEL) {
+        const int pw = (h - jp < SMRT_PANEL) ? (h - jp) : SMRT_PANEL;
+        for (int e = tid; e < h * pw; e += NT) {
+          int k = e % h, jj = e / h;
+          panel[jj * h + k] = (k >= jp + jj) ? SMRT_AT(A1, ld, k, jp + jj) : 0.0;
+        }
+        __syncthreads();
+        for (int e = tid; e < h * pw; e += NT) {
+          int i = e % h, jj = e / h;
+          int j = jp + jj;
+          const double* cc = A2 + (size_t)i * ld;
+          const double* pl = panel + jj * h;
+          double acc0 = 0.0, acc1 = 0.0;
+          int k = (i > j) ? i : j;
+          for (; k + 1 < h; k += 2) {
+            acc0 = fma(cc[k], pl[k], acc0);
+            acc1 = fma(cc[k + 1], pl[k + 1], acc1);
+          }
+          if (k < h) acc0 = fma(cc[k], pl[k], acc0);
+          SMRT_AT(A1, ld, i, j) = acc0 + acc1;
+        }
+        __syncthreads();
       }
-      __syncthreads();
 
-      // singular values / right rotations by one-sided Jacobi: A3 <- W = U Sigma
+      // singular values / right rotations by one-sided Jacobi: A1 <- W = U Sigma
       {
-        int sw = block_jacobi_svd(A3, ld, h, s_ctrl);
+        int sw = block_jacobi_svd(A1, ld, h, s_ctrl);
         if (tid == 0 && A.diag) {
           atomicAdd(&A.diag[0], sw);
           atomicAdd(&A.diag[1], 1);
@@ -299,22 +327,25 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 2) eigen_kernel
       __syncthreads();
       for (int j = tid; j < h; j += NT) {
         double s2 = 0.0;
-        for (int i = 0; i < h; ++i) s2 = fma(SMRT_AT(A3, ld, i, j), SMRT_AT(A3, ld, i, j), s2);
+        for (int i = 0; i < h; ++i) s2 = fma(SMRT_AT(A1, ld, i, j), SMRT_AT(A1, ld, i, j), s2);
         sigma[j] = sqrt(s2);
       }
       __syncthreads();
 
-      // E~- = -C U = -C W Sigma^-1  -> A1
+      double* rk = rec + A.eig_off[m];
+      double* rF = rk + smrt_even(smrt_npol(m) * n);
+      double* rG = rF + smrt_even((long long)h * h);
+      // E~- = -C U = -C W Sigma^-1, staged in the G slot of the layer record (global memory; read back below)
       {
         Team tm = block_team();
         team_gemm(
             tm, h, h, h, [&](int i, int k) { return (k <= i) ? SMRT_AT(A2, ld, i, k) : 0.0; },
-            [&](int k, int j) { return SMRT_AT(A3, ld, k, j); },
-            [&](int i, int j, double acc) { SMRT_AT(A1, ld, i, j) = -acc / sigma[j]; });
+            [&](int k, int j) { return SMRT_AT(A1, ld, k, j); },
+            [&](int i, int j, double acc) { rG[(size_t)j * h + i] = -acc / sigma[j]; });
       }
       __syncthreads();
 
-      // E~+ = C^-T W: back substitution with the upper-triangular C^T, in place on the columns of A3
+      // E~+ = C^-T W: back substitution with the upper-triangular C^T, in place on the columns of A1
       // (uniform trip counts: every lane of every warp takes part in the __syncwarp()s)
       {
         int tpc = 32;
@@ -324,7 +355,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 2) eigen_kernel
         for (int c0 = 0; c0 < h; c0 += ngroups) {
           const int c = c0 + grp;
           const bool valid = c < h;
-          double* x = A3 + (size_t)(valid ? c : 0) * ld;
+          double* x = A1 + (size_t)(valid ? c : 0) * ld;
           for (int j = h - 1; j >= 0; --j) {
             if (valid && lane == 0) x[j] = x[j] / SMRT_AT(A2, ld, j, j);
             __syncwarp();
@@ -340,13 +371,10 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 2) eigen_kernel
 
       // store k, F = s (E~+ - E~-) / 2, G = s (E~+ + E~-) / 2
       {
-        double* rk = rec + A.eig_off[m];
-        double* rF = rk + smrt_even(smrt_npol(m) * n);
-        double* rG = rF + smrt_even((long long)h * h);
         for (int j = tid; j < h; j += NT) rk[j] = sigma[j];
-        for (int e = tid; e < h * h; e += NT) {
-          int a = e % h, j = e / h;
-          double ep = SMRT_AT(A3, ld, a, j), em = SMRT_AT(A1, ld, a, j);
+        SMRT_FOR_2D(a, j, h, h) {
+          const size_t e = (size_t)j * h + a;
+          double ep = SMRT_AT(A1, ld, a, j), em = rG[e];
           double s = 0.5 * sdiag[a];
           rF[e] = s * (ep - em);
           rG[e] = s * (ep + em);
@@ -368,15 +396,15 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 2) eigen_kernel
 // --------------------------------------------------------------------------------------------------------------------
 // kernel 3: boundary system, mode summation, output stage
 // --------------------------------------------------------------------------------------------------------------------
-// vector region (doubles): mu[n] outmu[n] outw[n] kvec tvec Rt Tt Rb Tb Ttprev ipiv [hmax each]
+// vector region (doubles): mu[n] outmu[n] outw[n] kvec tvec Rt Tt Rb Tb Ttprev ipiv RbD Dsg [hmax each]
 //                          acc[9 * SMRT_MAX_INC] coh[4 * SMRT_MAX_INC] ; ints: rowstep[hmax] rowof[hmax] inc[SMRT_MAX_INC]
 SMRT_HD size_t boundary_vec_doubles(int n, int hmax) {
-  return (size_t)3 * n + 8 * hmax + 13 * SMRT_MAX_INC + hmax /* two int arrays */ + SMRT_MAX_INC + 16;
+  return ((size_t)3 * n + 10 * hmax + 13 * SMRT_MAX_INC + hmax /* two int arrays */ + SMRT_MAX_INC + 16 + 1) & ~(size_t)1;
 }
 // matrix region: BF, BG (compact), BR (ld odd), T = [left | right | rhs] (ld odd), btop, svec, ytr, vvec
 SMRT_HD size_t boundary_mat_doubles(int hmax, int nrhs_max) {
-  return (size_t)2 * hmax * hmax + (size_t)hmax * (hmax + 1) + (size_t)(hmax + 1) * (2 * hmax + nrhs_max) +
-         4 * (size_t)hmax * nrhs_max + 16;
+  return (size_t)2 * (((size_t)hmax * hmax + 1) & ~(size_t)1) + (size_t)hmax * (hmax + 1) +
+         (size_t)(hmax + 1) * (2 * hmax + nrhs_max) + 4 * (size_t)hmax * nrhs_max + 16;
 }
 
 struct BoundaryCtx {
@@ -393,11 +421,15 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
   SMRT_SHARED int s_ctrl[8];
   SMRT_SHARED double s_tau;
   SMRT_SHARED int s_lend;
+  SMRT_SHARED smrt_mbar_t s_mbar;  // completion barrier of the TMA bulk prefetch of the next layer's (F, G) record
   const int tid = threadIdx.x;
   const int NT = blockDim.x;
   const int n = A.n;
   const int hmax = smrt_npol(A.m_max) * n;
   const int nrhs_max = (A.mode == 0) ? 1 : 3 * 2 * A.n_inc;
+  if (tid == 0) smrt_mbar_init(&s_mbar, 1);
+  unsigned pf_parity = 0;  // parity of the next phase to wait for
+  __syncthreads();
 
   double* mu = smem;
   double* outmu = mu + n;
@@ -410,15 +442,18 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
   double* Tb = Rb + hmax;
   double* Ttprev = Tb + hmax;
   double* ipiv = Ttprev + hmax;
-  double* acc_act = ipiv + hmax;                  // [3][3][SMRT_MAX_INC]
+  double* RbD = ipiv + hmax;
+  double* Dsg = RbD + hmax;
+  double* acc_act = Dsg + hmax;                   // [3][3][SMRT_MAX_INC]
   double* coh_act = acc_act + 9 * SMRT_MAX_INC;   // [2][2][SMRT_MAX_INC]
   int* rowstep = reinterpret_cast<int*>(coh_act + 4 * SMRT_MAX_INC);
   int* rowof = rowstep + hmax;
   int* inc = rowof + hmax;
   double* mats = kGlobalScratch ? (A.scratch + (size_t)blockIdx.x * A.scratch_stride)
                                 : (smem + boundary_vec_doubles(n, hmax));
-  const size_t szc = (size_t)hmax * hmax, szp = (size_t)hmax * (hmax + 1), szr = (size_t)hmax * nrhs_max;
-  double* BF = mats;
+  const size_t szc = ((size_t)hmax * hmax + 1) & ~(size_t)1, szp = (size_t)hmax * (hmax + 1);
+  const size_t szr = (size_t)hmax * nrhs_max;
+  double* BF = mats;  // 16-byte aligned (vector loads of the layer records)
   double* BG = BF + szc;
   double* BR = BG + szc;
   double* TT = BR + szp;  // h x (2h + nrhs), ld = ldp
@@ -547,6 +582,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
       int h_prev = 0, ldr_prev = 1;
       bool have_prev = false;
       bool src_prev = false;  // the stack below carries a source vector (false for the source-free active layers)
+      int pf_layer = -1;      // layer whose (F, G) record is in flight into BF / BG (TMA bulk copy), -1 = none
 
       for (int l = l_end; l >= 0 && !failed; --l) {
         const cplx eps_l = c_make(eps_b[2 * l], eps_b[2 * l + 1]);
@@ -558,6 +594,8 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
         const double ke = A.ks[bL + l] + A.ka[bL + l];
         const bool scat = (!coherent) && (A.scat_flag[bL + l] != 0);
         const int nr = (A.mode == 1 && l > 0) ? 0 : nrhs;  // active mode: sources only at the air-snow interface
+        // threads used by the dual h x h product: a 4 x 4 tile of each product per thread
+        const int gemm_thr = (16 * ((h + 3) / 4) < NT) ? 16 * ((h + 3) / 4) : NT;
         for (int j = tid; j < n_l; j += NT) mu[j] = stream_mu(rindex, A.gl_mu, j);
         __syncthreads();
 
@@ -566,15 +604,34 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
           const double* rk = A.eig + (bL + l) * A.eig_stride + A.eig_off[m];
           const double* rF = rk + smrt_even(smrt_npol(m) * n);
           const double* rG = rF + smrt_even((long long)h * h);
-          for (int e = tid; e < h * h; e += NT) {
-            BF[e] = rF[e];
-            BG[e] = rG[e];
+          if (pf_layer == l) {  // prefetched by the TMA engine while the layer below was being eliminated
+            smrt_mbar_wait(&s_mbar, pf_parity);
+            pf_parity ^= 1u;
+            pf_layer = -1;
+          } else {  // 4 independent 16-byte loads in flight per thread (records 16-byte aligned, h*h padded even)
+            const int n2 = (h * h + 1) >> 1;
+            const double2* sF = reinterpret_cast<const double2*>(rF);
+            const double2* sG = reinterpret_cast<const double2*>(rG);
+            double2* dF = reinterpret_cast<double2*>(BF);
+            double2* dG = reinterpret_cast<double2*>(BG);
+            int e = tid;
+            for (; e + NT < n2; e += 2 * NT) {
+              double2 f0 = sF[e], f1 = sF[e + NT], g0 = sG[e], g1 = sG[e + NT];
+              dF[e] = f0;
+              dF[e + NT] = f1;
+              dG[e] = g0;
+              dG[e + NT] = g1;
+            }
+            if (e < n2) {
+              dF[e] = sF[e];
+              dG[e] = sG[e];
+            }
           }
           for (int a = tid; a < h; a += NT) kvec[a] = rk[a];
         } else {
-          for (int e = tid; e < h * h; e += NT) {
-            BF[e] = ((e % h) == (e / h)) ? 1.0 : 0.0;
-            BG[e] = 0.0;
+          SMRT_FOR_2D(i, j, h, h) {
+            BF[(size_t)j * h + i] = (i == j) ? 1.0 : 0.0;
+            BG[(size_t)j * h + i] = 0.0;
           }
           for (int a = tid; a < h; a += NT) kvec[a] = ke / mu[a / npol];
         }
@@ -593,10 +650,13 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
             fb.T[0] = fb.T[1] = fb.T[2] = 0.0;
           }
           for (int p = 0; p < npol; ++p) {
+            const double dsgn = (p == 2) ? -1.0 : 1.0;
             Rt[j * npol + p] = ft.R[p];
             Tt[j * npol + p] = ft.T[p];
             Rb[j * npol + p] = fb.R[p];
             Tb[j * npol + p] = fb.T[p];
+            RbD[j * npol + p] = fb.R[p] * dsgn;
+            Dsg[j * npol + p] = dsgn;
           }
         }
         __syncthreads();
@@ -656,25 +716,23 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
           }
         }
         // T = [A21 | A22] without the coupling term:  A21 = F - Rb D G,  A22 = (G - Rb D F) t
-        for (int e = tid; e < h * h; e += NT) {
-          int i = e % h, j = e / h;
-          double dsgn = (npol == 3 && (i % 3) == 2) ? -1.0 : 1.0;
-          double f = BF[e], g = BG[e];
-          SMRT_AT(TT, ldp, i, j) = f - Rb[i] * dsgn * g;
-          SMRT_AT(TT, ldp, i, h + j) = (g - Rb[i] * dsgn * f) * tvec[j];
+        // (Dsg holds the sign D of the third Stokes component, RbD = Rb D)
+        SMRT_FOR_2D(i, j, h, h) {
+          const double f = BF[(size_t)j * h + i], g = BG[(size_t)j * h + i];
+          SMRT_AT(TT, ldp, i, j) = f - RbD[i] * g;
+          SMRT_AT(TT, ldp, i, h + j) = (g - RbD[i] * f) * tvec[j];
         }
         // coupling operator of the stack below: R' = T_top(l+1) R(l+1) T_bottom(l) D on the common streams
-        for (int e = tid; e < r * r; e += NT) {
-          int i = e % r, k = e / r;
-          double dsgn = (npol == 3 && (k % 3) == 2) ? -1.0 : 1.0;
-          SMRT_AT(BR, ldr_prev, i, k) *= Ttprev[i] * Tb[k] * dsgn;
-        }
+        SMRT_FOR_2D(i, k, r, r) { SMRT_AT(BR, ldr_prev, i, k) *= Ttprev[i] * (Tb[k] * Dsg[k]); }
         __syncthreads();
         if (r > 0) {
-          block_gemm_ptr(r, h, r, BR, ldr_prev, BG, h,
-                         [&](int i, int j, double acc) { SMRT_AT(TT, ldp, i, j) -= acc; });
-          block_gemm_ptr(r, h, r, BR, ldr_prev, BF, h,
-                         [&](int i, int j, double acc) { SMRT_AT(TT, ldp, i, h + j) -= acc * tvec[j]; });
+          // one product over the 2h columns [G | F]: all threads busy with 4 x 4 tiles
+          block_gemm_ptr(
+              NT, r, 2 * h, r, BR, ldr_prev,
+              [&](int j) { return (j < h) ? BG + (size_t)j * h : BF + (size_t)(j - h) * h; },
+              [&](int i, int j, double acc) {
+                SMRT_AT(TT, ldp, i, j) -= (j < h) ? acc : acc * tvec[j - h];
+              });
           __syncthreads();
         }
         // [A21 | A22 | b_bot] -> [I | Y22 | Yr] (implicit row permutation, unscaled rows)
@@ -685,33 +743,38 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
         for (int k = tid; k < h; k += NT) ipiv[k] = tvec[k] / SMRT_AT(TT, ldp, rowof[k], k);
         __syncthreads();
         // Y~ = diag(t) Y22 -> left block of T ;  y~r = diag(t) Yr -> ytr
-        for (int e = tid; e < h * h; e += NT) {
-          int k = e % h, c = e / h;
-          SMRT_AT(TT, ldp, k, c) = SMRT_AT(TT, ldp, rowof[k], h + c) * ipiv[k];
-        }
-        for (int e = tid; e < h * nr; e += NT) {
-          int k = e % h, c = e / h;
-          SMRT_AT(ytr, h, k, c) = SMRT_AT(Trhs, ldp, rowof[k], c) * ipiv[k];
-        }
+        SMRT_FOR_2D(k, c, h, h) { SMRT_AT(TT, ldp, k, c) = SMRT_AT(TT, ldp, rowof[k], h + c) * ipiv[k]; }
+        SMRT_FOR_2D(k, c, h, nr) { SMRT_AT(ytr, h, k, c) = SMRT_AT(Trhs, ldp, rowof[k], c) * ipiv[k]; }
         __syncthreads();
         // P = F - G Y~, K = G - F Y~ ;  Schur S = D P - Rt K -> right block of T ;  K -> BR
         double* TS = TT + (size_t)h * ldp;
-        block_gemm_dual(h, h, h, BG, BF, h, TT, ldp, [&](int i, int j, double c1, double c2) {
-          double dsgn = (npol == 3 && (i % 3) == 2) ? -1.0 : 1.0;
+        block_gemm_dual(gemm_thr, h, h, h, BG, BF, h, TT, ldp, [&](int i, int j, double c1, double c2) {
           double pv = SMRT_AT(BF, h, i, j) - c1;
           double kv = SMRT_AT(BG, h, i, j) - c2;
-          SMRT_AT(TS, ldp, i, j) = dsgn * pv - Rt[i] * kv;
+          SMRT_AT(TS, ldp, i, j) = Dsg[i] * pv - Rt[i] * kv;
           SMRT_AT(BR, ldp, i, j) = kv;
         });
         // v = F y~r ;  b' = b_top - D (G y~r) + Rt v  (b' goes next to S, in the augmented columns)
         if (nr > 0) {
-          block_gemm_dual(h, nr, h, BG, BF, h, ytr, h, [&](int i, int c, double c1, double c2) {
-            double dsgn = (npol == 3 && (i % 3) == 2) ? -1.0 : 1.0;
+          block_gemm_dual(NT, h, nr, h, BG, BF, h, ytr, h, [&](int i, int c, double c1, double c2) {
             SMRT_AT(vvec, h, i, c) = c2;
-            SMRT_AT(Trhs, ldp, i, c) = SMRT_AT(btop, h, i, c) - dsgn * c1 + Rt[i] * c2;
+            SMRT_AT(Trhs, ldp, i, c) = SMRT_AT(btop, h, i, c) - Dsg[i] * c1 + Rt[i] * c2;
           });
         }
         __syncthreads();
+        if (!kGlobalScratch && l > 0 && !coherent && A.scat_flag[bL + l - 1] != 0) {
+          // BF / BG are dead from here on: let the TMA engine fetch the record of the layer above (cp.async.bulk,
+          // completion on s_mbar) while this CTA runs the second elimination
+          if (tid == 0) {
+            const cplx eps_u = c_make(eps_b[2 * (l - 1)], eps_b[2 * (l - 1) + 1]);
+            const int h_u = npol * stream_count(real_index_of(eps_star, eps_u), A.gl_mu, n);
+            const double* uk = A.eig + (bL + l - 1) * A.eig_stride + A.eig_off[m];
+            const double* uF = uk + smrt_even(smrt_npol(m) * n);
+            const double* uG = uF + smrt_even((long long)h_u * h_u);
+            smrt_bulk_load2(&s_mbar, BF, uF, BG, uG, (unsigned)(smrt_even((long long)h_u * h_u) * sizeof(double)));
+          }
+          pf_layer = l - 1;
+        }
         if (l > 0) {
           // keep b' (the column elimination below does not touch the augmented columns)
           // R_new = K S^-1 by column elimination of [S; K]
@@ -722,18 +785,12 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
           for (int k = tid; k < h; k += NT) ipiv[k] = 1.0 / SMRT_AT(TS, ldp, k, rowof[k]);
           __syncthreads();
           // un-permute / scale through the (dead) left block of T, then back into BR
-          for (int e = tid; e < h * h; e += NT) {
-            int i = e % h, k = e / h;
-            SMRT_AT(TT, ldp, i, k) = SMRT_AT(BR, ldp, i, rowof[k]) * ipiv[k];
-          }
+          SMRT_FOR_2D(i, k, h, h) { SMRT_AT(TT, ldp, i, k) = SMRT_AT(BR, ldp, i, rowof[k]) * ipiv[k]; }
           __syncthreads();
-          for (int e = tid; e < h * h; e += NT) {
-            int i = e % h, k = e / h;
-            SMRT_AT(BR, ldp, i, k) = SMRT_AT(TT, ldp, i, k);
-          }
+          SMRT_FOR_2D(i, k, h, h) { SMRT_AT(BR, ldp, i, k) = SMRT_AT(TT, ldp, i, k); }
           __syncthreads();
           if (nr > 0) {  // s = v + R_new b'
-            block_gemm_ptr(h, nr, h, BR, ldp, Trhs, ldp,
+            block_gemm_ptr(NT, h, nr, h, BR, ldp, [&](int c) { return Trhs + (size_t)c * ldp; },
                            [&](int i, int c, double acc) { SMRT_AT(svec, h, i, c) = SMRT_AT(vvec, h, i, c) + acc; });
           }
           for (int a = tid; a < h; a += NT) Ttprev[a] = Tt[a];
@@ -750,16 +807,18 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
           }
           for (int k = tid; k < h; k += NT) ipiv[k] = 1.0 / SMRT_AT(TS, ldp, rowof[k], k);
           __syncthreads();
-          for (int e = tid; e < h * nr; e += NT) {
-            int k = e % h, c = e / h;
-            SMRT_AT(ytr, h, k, c) = SMRT_AT(Trhs, ldp, rowof[k], c) * ipiv[k];
-          }
+          SMRT_FOR_2D(k, c, h, nr) { SMRT_AT(ytr, h, k, c) = SMRT_AT(Trhs, ldp, rowof[k], c) * ipiv[k]; }
           __syncthreads();
-          block_gemm_ptr(h, nr, h, BR, ldp, ytr, h,
+          block_gemm_ptr(NT, h, nr, h, BR, ldp, [&](int c) { return ytr + (size_t)c * h; },
                          [&](int i, int c, double acc) { SMRT_AT(svec, h, i, c) = SMRT_AT(vvec, h, i, c) + acc; });
           __syncthreads();
         }
       }  // layers
+      if (pf_layer >= 0) {  // left the loop early with a bulk copy in flight: drain it before BF / BG are reused
+        smrt_mbar_wait(&s_mbar, pf_parity);
+        pf_parity ^= 1u;
+        pf_layer = -1;
+      }
       if (failed) break;
 
       // emerging intensity ---------------------------------------------------------------------------- dort.py:472-488

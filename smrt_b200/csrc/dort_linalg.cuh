@@ -404,15 +404,17 @@ SMRT_DEV void block_lu_solve(const double* LU, int ld, int h, const int* perm, d
 // implicit permutation instead of physical swaps, no separate scaling pass).
 // =====================================================================================================================
 
-// C(i,j) = epi(i, j, sum_{k<K} A(i,k) B(k,j)) for i < M, j < N; A, B column-major in shared memory.
-// Loads of out-of-range rows / columns are clamped to the last valid one (harmless), stores are guarded.
-template <typename FE>
-SMRT_DEV void block_gemm_ptr(int M, int N, int K, const double* SMRT_RESTRICT Am, int lda,
-                             const double* SMRT_RESTRICT Bm, int ldb, FE epi) {
-  const int NT = blockDim.x, tid = threadIdx.x;
-  const int TX = 16, TY = NT / TX;
+// C(i,j) = epi(i, j, sum_{k<K} A(i,k) B(k,j)) for i < M, j < N; A column-major (lda), column j of B at bcol(j).
+// 4 x 4 register tile per thread (rows strided by 16 so that consecutive lanes read consecutive rows), threads arranged
+// 16 x (nthr/16); only the first `nthr` threads of the block work.  FP64 FMA rate vs shared-memory bandwidth needs
+// >= 16 FMA per 8 loaded doubles, hence no smaller tiles.  Loads of out-of-range rows / columns are clamped to the last
+// valid one (harmless), stores are guarded.
+template <typename FB, typename FE>
+SMRT_DEV void block_gemm_ptr(int nthr, int M, int N, int K, const double* SMRT_RESTRICT Am, int lda, FB bcol, FE epi) {
+  const int tid = threadIdx.x;
+  if (tid >= nthr || M <= 0 || N <= 0) return;
+  const int TX = 16, TY = nthr / TX;
   const int tx = tid % TX, ty = tid / TX;
-  if (M <= 0 || N <= 0) return;
   for (int j0 = 0; j0 < N; j0 += TY * 4) {
     for (int i0 = 0; i0 < M; i0 += TX * 4) {
       int ir[4], jc[4];
@@ -421,12 +423,13 @@ SMRT_DEV void block_gemm_ptr(int M, int N, int K, const double* SMRT_RESTRICT Am
         ir[u] = i0 + tx + u * TX;
         jc[u] = j0 + ty + u * TY;
       }
+      if (ir[0] >= M || jc[0] >= N) continue;
       const double* ap[4];
       const double* bp[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         ap[u] = Am + (ir[u] < M ? ir[u] : M - 1);
-        bp[u] = Bm + (size_t)(jc[u] < N ? jc[u] : N - 1) * ldb;
+        bp[u] = bcol(jc[u] < N ? jc[u] : N - 1);
       }
       double acc[4][4];
 #pragma unroll
@@ -454,44 +457,47 @@ SMRT_DEV void block_gemm_ptr(int M, int N, int K, const double* SMRT_RESTRICT Am
   }
 }
 
-// Two products sharing the B operand: C1 = A1 B, C2 = A2 B (M x N, inner K).
+// Two products sharing the B operand: C1 = A1 B, C2 = A2 B (M x N, inner K); 4 x 4 tile of each product per thread.
 template <typename FE>
-SMRT_DEV void block_gemm_dual(int M, int N, int K, const double* SMRT_RESTRICT A1, const double* SMRT_RESTRICT A2,
-                              int lda, const double* SMRT_RESTRICT Bm, int ldb, FE epi) {
-  const int NT = blockDim.x, tid = threadIdx.x;
-  const int TX = 16, TY = NT / TX;
+SMRT_DEV void block_gemm_dual(int nthr, int M, int N, int K, const double* SMRT_RESTRICT A1,
+                              const double* SMRT_RESTRICT A2, int lda, const double* SMRT_RESTRICT Bm, int ldb, FE epi) {
+  const int tid = threadIdx.x;
+  if (tid >= nthr || M <= 0 || N <= 0) return;
+  const int TX = 16, TY = nthr / TX;
   const int tx = tid % TX, ty = tid / TX;
-  if (M <= 0 || N <= 0) return;
   for (int j0 = 0; j0 < N; j0 += TY * 4) {
-    for (int i0 = 0; i0 < M; i0 += TX * 2) {
-      int ir[2], jc[4];
+    for (int i0 = 0; i0 < M; i0 += TX * 4) {
+      int ir[4], jc[4];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) ir[u] = i0 + tx + u * TX;
-#pragma unroll
-      for (int v = 0; v < 4; ++v) jc[v] = j0 + ty + v * TY;
-      size_t ao[2];
+      for (int u = 0; u < 4; ++u) {
+        ir[u] = i0 + tx + u * TX;
+        jc[u] = j0 + ty + u * TY;
+      }
+      if (ir[0] >= M || jc[0] >= N) continue;
+      size_t ao[4];
       const double* bp[4];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) ao[u] = (size_t)(ir[u] < M ? ir[u] : M - 1);
+      for (int u = 0; u < 4; ++u) {
+        ao[u] = (size_t)(ir[u] < M ? ir[u] : M - 1);
+        bp[u] = Bm + (size_t)(jc[u] < N ? jc[u] : N - 1) * ldb;
+      }
+      double c1[4][4], c2[4][4];
 #pragma unroll
-      for (int v = 0; v < 4; ++v) bp[v] = Bm + (size_t)(jc[v] < N ? jc[v] : N - 1) * ldb;
-      double c1[2][4], c2[2][4];
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int v = 0; v < 4; ++v) c1[u][v] = c2[u][v] = 0.0;
-#pragma unroll 4
+#pragma unroll 2
       for (int k = 0; k < K; ++k) {
-        double a1[2], a2[2], bv[4];
+        double a1[4], a2[4], bv[4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
+        for (int u = 0; u < 4; ++u) {
           a1[u] = A1[ao[u] + (size_t)k * lda];
           a2[u] = A2[ao[u] + (size_t)k * lda];
         }
 #pragma unroll
         for (int v = 0; v < 4; ++v) bv[v] = bp[v][k];
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             c1[u][v] = fma(a1[u], bv[v], c1[u][v]);
@@ -499,7 +505,7 @@ SMRT_DEV void block_gemm_dual(int M, int N, int K, const double* SMRT_RESTRICT A
           }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int v = 0; v < 4; ++v)
           if (ir[u] < M && jc[v] < N) epi(ir[u], jc[v], c1[u][v], c2[u][v]);
@@ -663,4 +669,138 @@ SMRT_DEV int block_gj_cols(double* S, int lds, double* Km, int ldk, int h, int m
     __syncthreads();
   }
   return 0;
+}
+
+
+// =====================================================================================================================
+// Gauss-Jordan by rows with LOOK-AHEAD pivoting.  The augmented matrix is given as two column blocks:
+//   columns [0, h)      : left block  A  (column c at Lb + c * ldl)  -> reduced to a (row-permuted, unscaled) identity
+//   columns [h, h + nR) : right block R  (column c at Rb + (c - h) * ldr)
+// Afterwards, for every unknown k:  (A^-1 R)(k, :) = R(rowof[k], :) * ipiv[k]   with ipiv[k] = 1 / pivot_k.
+//
+// One block barrier per step and no pivot search on the critical path: the warp that updates column j + 1 during step j
+// finds the next pivot from the freshly updated values (still in its registers) and publishes (row, 1 / pivot) for the
+// next step before the barrier.  Lanes walk the rows (RPL rows per lane, h <= 32 RPL), warps the columns.
+// rowstep / rowof: block-shared int[h]; ipiv: block-shared double[h]; la_p: block-shared int[2]; la_inv: double[2].
+// Returns 1 (in every thread) if a pivot vanishes or is not finite.
+// =====================================================================================================================
+template <int RPL>
+SMRT_DEV int block_gj_rows_la(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowstep, int* rowof,
+                              double* ipiv, int* la_p, double* la_inv) {
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+  const int W = h + nR;
+  for (int i = tid; i < h; i += NT) rowstep[i] = -1;
+  // first pivot: searched by warp 0
+  if (warp == 0) {
+    double best = -1.0;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int u = 0; u < RPL; ++u) {
+      const int i = lane + 32 * u;
+      if (i < h) {
+        const double v = fabs(Lb[i]);
+        if (v > best) {
+          best = v;
+          bi = i;
+        }
+      }
+    }
+    warp_argmax(best, bi);
+    if (lane == 0) {
+      const bool ok = (best > 0.0) && (best < 1e300);
+      la_p[0] = ok ? bi : -1;
+      la_inv[0] = ok ? 1.0 / Lb[bi] : 0.0;
+    }
+  }
+  __syncthreads();
+  for (int j = 0; j < h; ++j) {
+    const int p = la_p[j & 1];
+    if (p < 0) return 1;
+    const double inv = la_inv[j & 1];
+    if (tid == 0) {
+      rowstep[p] = j;
+      rowof[j] = p;
+      ipiv[j] = inv;
+    }
+    const double* colj = Lb + (size_t)j * ldl;
+    double mrow[RPL];
+#pragma unroll
+    for (int u = 0; u < RPL; ++u) {
+      const int i = lane + 32 * u;
+      mrow[u] = (i < h && i != p) ? -(colj[i] * inv) : 0.0;
+    }
+    int c = j + 1 + warp;
+    if (warp == 0 && c < h) {
+      // column j + 1: update, then look ahead for the next pivot among the rows not used yet
+      double* col = Lb + (size_t)c * ldl;
+      const double pc = col[p];
+      double best = -1.0, bv = 0.0;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int u = 0; u < RPL; ++u) {
+        const int i = lane + 32 * u;
+        if (i < h) {
+          const double v = fma(mrow[u], pc, col[i]);
+          col[i] = v;
+          if (i != p && rowstep[i] < 0 && fabs(v) > best) {
+            best = fabs(v);
+            bv = v;
+            bi = i;
+          }
+        }
+      }
+      // argmax carrying the signed value along
+      for (int off = 16; off > 0; off >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, off, 32);
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, off, 32);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off, 32);
+        if (ob > best || (ob == best && oi < bi)) {
+          best = ob;
+          bv = ov;
+          bi = oi;
+        }
+      }
+      if (lane == 0) {
+        const bool ok = (best > 0.0) && (best < 1e300);
+        la_p[(j + 1) & 1] = ok ? bi : -1;
+        la_inv[(j + 1) & 1] = ok ? 1.0 / bv : 0.0;
+      }
+      c += nwarp;
+    }
+    // remaining columns, two per iteration for instruction-level parallelism
+    for (; c + nwarp < W; c += 2 * nwarp) {
+      const int c1 = c + nwarp;
+      double* col0 = (c < h) ? Lb + (size_t)c * ldl : Rb + (size_t)(c - h) * ldr;
+      double* col1 = (c1 < h) ? Lb + (size_t)c1 * ldl : Rb + (size_t)(c1 - h) * ldr;
+      const double p0 = col0[p], p1 = col1[p];
+#pragma unroll
+      for (int u = 0; u < RPL; ++u) {
+        const int i = lane + 32 * u;
+        if (i < h) {
+          const double v0 = col0[i], v1 = col1[i];
+          col0[i] = fma(mrow[u], p0, v0);
+          col1[i] = fma(mrow[u], p1, v1);
+        }
+      }
+    }
+    if (c < W) {
+      double* col0 = (c < h) ? Lb + (size_t)c * ldl : Rb + (size_t)(c - h) * ldr;
+      const double p0 = col0[p];
+#pragma unroll
+      for (int u = 0; u < RPL; ++u) {
+        const int i = lane + 32 * u;
+        if (i < h) col0[i] = fma(mrow[u], p0, col0[i]);
+      }
+    }
+    __syncthreads();
+  }
+  return 0;
+}
+
+SMRT_DEV int block_gj_rows_lookahead(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowstep, int* rowof,
+                                     double* ipiv, int* la_p, double* la_inv) {
+  if (h <= 64) return block_gj_rows_la<2>(Lb, ldl, Rb, ldr, h, nR, rowstep, rowof, ipiv, la_p, la_inv);
+  if (h <= 128) return block_gj_rows_la<4>(Lb, ldl, Rb, ldr, h, nR, rowstep, rowof, ipiv, la_p, la_inv);
+  return block_gj_rows_la<8>(Lb, ldl, Rb, ldr, h, nR, rowstep, rowof, ipiv, la_p, la_inv);
 }

@@ -22,6 +22,41 @@ SMRT_DEV void smrt_named_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- TMA bulk copy (cp.async.bulk, 1-D, global -> shared) completed on an mbarrier --------------------------------
+typedef unsigned long long smrt_mbar_t;
+SMRT_DEV unsigned smrt_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+SMRT_DEV void smrt_mbar_init(smrt_mbar_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smrt_smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// one thread: order prior generic-proxy accesses of the destination before the async-proxy writes, arm the barrier with
+// the byte count and issue the copies (each a multiple of 16 bytes, 16-byte aligned)
+SMRT_DEV void smrt_bulk_load2(smrt_mbar_t* bar, void* dst0, const void* src0, void* dst1, const void* src1,
+                              unsigned bytes_each) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smrt_smem_u32(bar)), "r"(2u * bytes_each)
+               : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smrt_smem_u32(dst0)),
+               "l"(src0), "r"(bytes_each), "r"(smrt_smem_u32(bar))
+               : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smrt_smem_u32(dst1)),
+               "l"(src1), "r"(bytes_each), "r"(smrt_smem_u32(bar))
+               : "memory");
+}
+// every consumer thread: wait for the phase with the given parity
+SMRT_DEV void smrt_mbar_wait(smrt_mbar_t* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smrt_smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
 #else  // ------------------------------------------------------------------------------------------ host emulation
 
 #include <pthread.h>
@@ -50,6 +85,9 @@ SMRT_DEV void smrt_named_barrier(int id, int nthreads) {
 #define __global__
 #define __constant__ static
 
+struct double2 {
+  double x, y;
+};
 struct simt_dim3 {
   unsigned x = 1, y = 1, z = 1;
 };
@@ -118,6 +156,17 @@ inline int atomicMax(int* p, int v) {
   }
   return old;
 }
+
+// emulation of the TMA bulk copy: the issuing thread copies synchronously; the wait is a no-op (the kernels place a
+// block barrier between the wait and the first use, which the emulator needs for visibility)
+typedef unsigned long long smrt_mbar_t;
+inline void smrt_mbar_init(smrt_mbar_t* bar, unsigned) { *bar = 0; }
+inline void smrt_bulk_load2(smrt_mbar_t*, void* dst0, const void* src0, void* dst1, const void* src1,
+                            unsigned bytes_each) {
+  std::memcpy(dst0, src0, bytes_each);
+  std::memcpy(dst1, src1, bytes_each);
+}
+inline void smrt_mbar_wait(smrt_mbar_t*, unsigned) {}
 
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 inline double fma_(double a, double b, double c) { return std::fma(a, b, c); }
