@@ -62,6 +62,7 @@ struct smrtb200_plan {
   bool use_global_scratch = false;
   int eigen_grid = 0, boundary_grid = 0;
   int boundary_threads = SMRT_NT_B;
+  int eigen_threads = SMRT_NT;
   void (*eigen_fn)(KArgs) = nullptr;
   void (*boundary_fn)(KArgs) = nullptr;
   size_t eigen_smem = 0, boundary_smem = 0;
@@ -179,7 +180,8 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
                                    optin - (int)fa.sharedSizeBytes));
   }
   int occ_e = 0, occ_b = 0;
-  PLAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, p->eigen_fn, SMRT_NT, p->eigen_smem));
+  p->eigen_threads = p->use_global_scratch ? SMRT_NT : SMRT_NT_SMEM;
+  PLAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, p->eigen_fn, p->eigen_threads, p->eigen_smem));
   if (const char* e = std::getenv("SMRT_B200_BOUNDARY_THREADS")) {
     int v = std::atoi(e);
     if (v >= 64 && v <= SMRT_NT_B && (v % 64) == 0) p->boundary_threads = v;
@@ -309,7 +311,7 @@ extern "C" int smrtb200_solve_batch_device(smrtb200_plan* p, const smrtb200_batc
     cudaEvent_t* ev = &p->chunk_events[3 * (size_t)nchunks];
     optics_kernel<<<(items + nthreads_opt - 1) / nthreads_opt, nthreads_opt, 0, s.stream>>>(A);
     CUDA_TRY(cudaEventRecord(ev[0], s.stream));
-    p->eigen_fn<<<std::min(p->eigen_grid, items), SMRT_NT, p->eigen_smem, s.stream>>>(A);
+    p->eigen_fn<<<std::min(p->eigen_grid, items), p->eigen_threads, p->eigen_smem, s.stream>>>(A);
     CUDA_TRY(cudaEventRecord(ev[1], s.stream));
     p->boundary_fn<<<std::min(p->boundary_grid, nb), p->boundary_threads, p->boundary_smem, s.stream>>>(A);
     CUDA_TRY(cudaEventRecord(ev[2], s.stream));

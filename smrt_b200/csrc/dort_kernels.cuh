@@ -17,7 +17,8 @@
 #define SMRT_MAX_MODES 4      // m = 0 .. 3
 #define SMRT_MAX_INC 16       // incident streams (<= 2 per incidence angle, n_inc <= 8)
 #define SMRT_AUX_STRIDE 4     // per (problem, layer): iba_coeff, kk, f_eff, spare
-#define SMRT_NT 256           // threads per CTA of the eigen kernel
+#define SMRT_NT 256           // threads per CTA of the eigen kernel, global-scratch instantiation (large stream counts)
+#define SMRT_NT_SMEM 128      // ... shared-memory instantiation (h <= 64): 16 Jacobi groups of 8 lanes, 3 CTAs per SM
 #define SMRT_NT_B 512         // max threads per CTA of the boundary kernel
 
 struct KArgs {
@@ -106,17 +107,17 @@ SMRT_DEV void set_error(int* status, int b, int code) {
 // kernel 2: per-layer eigenproblem
 // --------------------------------------------------------------------------------------------------------------------
 // shared-memory vector region (doubles): mu[n] w[n] norm0[2n] g[hmax] sdiag[hmax] dk[hmax] sigma[hmax] ctab[2K] stab[2K]
-//                                        panel[SMRT_PANEL * hmax]
+//                                        panel[SMRT_PANEL * hmax] gq[hmax] nrm[hmax + 4]
 // matrix region: A1 (X- -> L -> M -> W -> E~+), A2 (X+ -> C); two (hmax x (hmax+1)) blocks = 67 KB at 32 streams, so
 // that three CTAs fit on an SM
 #define SMRT_PANEL 8  // columns of L staged per step of the in-place product M = C^T L
 SMRT_HD size_t eigen_vec_doubles(int n, int hmax, int K) {
-  return ((size_t)4 * n + 5 * hmax + 4 * K + (size_t)SMRT_PANEL * hmax + 8 + 1) & ~(size_t)1;
+  return ((size_t)4 * n + 6 * hmax + 4 * K + (size_t)SMRT_PANEL * hmax + 12 + 1) & ~(size_t)1;
 }
 SMRT_HD size_t eigen_mat_doubles(int hmax) { return (size_t)2 * hmax * (hmax + 1); }
 
 template <bool kGlobalScratch>
-SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 3) eigen_kernel(KArgs A) {
+SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlobalScratch ? 1 : 3) eigen_kernel(KArgs A) {
   SMRT_DYN_SMEM(smem);
   SMRT_SHARED int s_item;
   SMRT_SHARED int s_ctrl[8];
@@ -138,6 +139,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 3) eigen_kernel
   double* stab = ctab + 2 * K;
   double* panel = stab + 2 * K;
   double* gq = panel + (size_t)SMRT_PANEL * hmax;
+  double* nrm = gq + hmax;  // tracked squared column norms of the Jacobi sweeps
   // compile-time choice so that the shared-memory instantiation addresses its matrices with LDS/STS, not generic LD/ST
   double* mats = kGlobalScratch ? (A.scratch + (size_t)blockIdx.x * A.scratch_stride)
                                 : (smem + eigen_vec_doubles(n, hmax, K));
@@ -206,7 +208,10 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 3) eigen_kernel
     for (int m = 0; m < nmodes && !failed; ++m) {
       const int npol = smrt_npol(m);
       const int h = npol * n_l;
+      // A2 (X+ -> C) is read row-wise by lanes: odd leading dimension (conflict-free); A1 (X- -> L -> M -> W) is the
+      // Jacobi operand: even leading dimension (16-byte aligned columns), the pad row of an odd h is kept at zero
       const int ld = (h & 1) ? h : h + 1;
+      const int ld1 = (h + 1) & ~1;
       const double coef = (m == 0) ? 0.5 : 0.25;
 
       // phase matrix Fourier mode m on (mu_s > 0) x (mu_i > 0 | mu_i < 0): A1 <- P++, A2 <- (P+-) D
@@ -223,7 +228,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 3) eigen_kernel
         for (int ps = 0; ps < npol; ++ps)
           for (int pi = 0; pi < npol; ++pi) {
             int a = js * npol + ps, c = ji * npol + pi;
-            SMRT_AT(A1, ld, a, c) = pp[ps * npol + pi];
+            SMRT_AT(A1, ld1, a, c) = pp[ps * npol + pi];
             SMRT_AT(A2, ld, a, c) = (pi == 2) ? -pm[ps * npol + pi] : pm[ps * npol + pi];
           }
       }
@@ -237,7 +242,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 3) eigen_kernel
         if (A.normalization != 0) {
           if (m == 0) {
             double rs = 0.0;
-            for (int c = 0; c < h; ++c) rs += (SMRT_AT(A1, ld, a, c) + SMRT_AT(A2, ld, a, c)) * w[c / npol];
+            for (int c = 0; c < h; ++c) rs += (SMRT_AT(A1, ld1, a, c) + SMRT_AT(A2, ld, a, c)) * w[c / npol];
             // A row sum = -coef * rs ; norm_0 = -ks / rowsum
             norm = ks / (coef * rs);
             norm0[a] = norm;
@@ -265,9 +270,9 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 3) eigen_kernel
       // (gq = g / q: the reciprocity weight of the row is folded into the row scale)
       SMRT_FOR_2D(a, c, h, h) {
         double sc = gq[a] * gvec[c];
-        double x1 = sc * SMRT_AT(A1, ld, a, c), x2 = sc * SMRT_AT(A2, ld, a, c);
+        double x1 = sc * SMRT_AT(A1, ld1, a, c), x2 = sc * SMRT_AT(A2, ld, a, c);
         double d = (a == c) ? dk[a] : 0.0;
-        SMRT_AT(A1, ld, a, c) = d - x1 + x2;
+        SMRT_AT(A1, ld1, a, c) = d - x1 + x2;
         SMRT_AT(A2, ld, a, c) = d - x1 - x2;
       }
       __syncthreads();
@@ -280,7 +285,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 3) eigen_kernel
         int which = tid / half;
         tm.rank = tid % half;
         tm.bar_id = 1 + which;
-        int bad = team_cholesky(tm, which == 0 ? A1 : A2, ld, h, &s_ctrl[4 + which]);
+        int bad = team_cholesky(tm, which == 0 ? A1 : A2, which == 0 ? ld1 : ld, h, &s_ctrl[4 + which]);
         (void)bad;
       }
       __syncthreads();
@@ -296,7 +301,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 3) eigen_kernel
         const int pw = (h - jp < SMRT_PANEL) ? (h - jp) : SMRT_PANEL;
         for (int e = tid; e < h * pw; e += NT) {
           int k = e % h, jj = e / h;
-          panel[jj * h + k] = (k >= jp + jj) ? SMRT_AT(A1, ld, k, jp + jj) : 0.0;
+          panel[jj * h + k] = (k >= jp + jj) ? SMRT_AT(A1, ld1, k, jp + jj) : 0.0;
         }
         __syncthreads();
         for (int e = tid; e < h * pw; e += NT) {
@@ -311,14 +316,18 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 3) eigen_kernel
             acc1 = fma(cc[k + 1], pl[k + 1], acc1);
           }
           if (k < h) acc0 = fma(cc[k], pl[k], acc0);
-          SMRT_AT(A1, ld, i, j) = acc0 + acc1;
+          SMRT_AT(A1, ld1, i, j) = acc0 + acc1;
         }
         __syncthreads();
       }
 
       // singular values / right rotations by one-sided Jacobi: A1 <- W = U Sigma
       {
-        int sw = block_jacobi_svd(A1, ld, h, s_ctrl);
+        if (h & 1) {  // zero pad row of the Jacobi operand
+          for (int j = tid; j < h; j += NT) SMRT_AT(A1, ld1, h, j) = 0.0;
+          __syncthreads();
+        }
+        int sw = (ld1 <= 8 * SMRT_JG) ? block_jacobi_svd_fast(A1, ld1, h, nrm) : block_jacobi_svd(A1, ld1, h, s_ctrl);
         if (tid == 0 && A.diag) {
           atomicAdd(&A.diag[0], sw);
           atomicAdd(&A.diag[1], 1);
@@ -327,7 +336,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 3) eigen_kernel
       __syncthreads();
       for (int j = tid; j < h; j += NT) {
         double s2 = 0.0;
-        for (int i = 0; i < h; ++i) s2 = fma(SMRT_AT(A1, ld, i, j), SMRT_AT(A1, ld, i, j), s2);
+        for (int i = 0; i < h; ++i) s2 = fma(SMRT_AT(A1, ld1, i, j), SMRT_AT(A1, ld1, i, j), s2);
         sigma[j] = sqrt(s2);
       }
       __syncthreads();
@@ -340,7 +349,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 3) eigen_kernel
         Team tm = block_team();
         team_gemm(
             tm, h, h, h, [&](int i, int k) { return (k <= i) ? SMRT_AT(A2, ld, i, k) : 0.0; },
-            [&](int k, int j) { return SMRT_AT(A1, ld, k, j); },
+            [&](int k, int j) { return SMRT_AT(A1, ld1, k, j); },
             [&](int i, int j, double acc) { rG[(size_t)j * h + i] = -acc / sigma[j]; });
       }
       __syncthreads();
@@ -355,7 +364,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 3) eigen_kernel
         for (int c0 = 0; c0 < h; c0 += ngroups) {
           const int c = c0 + grp;
           const bool valid = c < h;
-          double* x = A1 + (size_t)(valid ? c : 0) * ld;
+          double* x = A1 + (size_t)(valid ? c : 0) * ld1;
           for (int j = h - 1; j >= 0; --j) {
             if (valid && lane == 0) x[j] = x[j] / SMRT_AT(A2, ld, j, j);
             __syncwarp();
@@ -374,7 +383,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT, kGlobalScratch ? 1 : 3) eigen_kernel
         for (int j = tid; j < h; j += NT) rk[j] = sigma[j];
         SMRT_FOR_2D(a, j, h, h) {
           const size_t e = (size_t)j * h + a;
-          double ep = SMRT_AT(A1, ld, a, j), em = rG[e];
+          double ep = SMRT_AT(A1, ld1, a, j), em = rG[e];
           double s = 0.5 * sdiag[a];
           rF[e] = s * (ep - em);
           rG[e] = s * (ep + em);

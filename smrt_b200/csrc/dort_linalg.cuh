@@ -263,6 +263,203 @@ SMRT_DEV int block_jacobi_svd(double* W, int ld, int h, int* ctrl) {
   return sweeps;
 }
 
+// ------------------------------------------------------------------------- register-blocked one-sided Jacobi (h <= 64)
+// Same method as block_jacobi_svd, restructured around the two limits the profile of the first version showed
+// (shared-memory wavefronts 65 % of peak with 1/3 of them bank conflicts, FP64 pipe 26 %):
+//   * columns are handled in BLOCKS of two.  A group of 8 lanes loads two blocks (4 columns, R rows per lane, 16-byte
+//     accesses: 8 lanes x 16 B = one conflict-free 128-byte wavefront) and performs all four cross rotations in
+//     registers before storing them back: half the shared-memory traffic per rotation.  Blocks meet in round-robin
+//     order (nb - 1 block rounds per sweep); the two columns of a block are rotated against each other at the start
+//     of the sweep, together with the exact recomputation of every column norm.
+//   * within a sweep the squared column norms are TRACKED (a' = a - t g, b' = b + t g) instead of recomputed for every
+//     pair: one dot product per rotation instead of three.
+//   * tan of the rotation angle from MUFU seeds (rsqrt / rcp, one Newton step each) instead of an IEEE sqrt and a
+//     division; cos = rsqrt(1 + t^2) stays a full-precision rsqrt, so every rotation is orthogonal to rounding whatever
+//     the accuracy of t.
+// W: column-major, leading dimension ld EVEN (16-byte aligned columns), rows [h, hr) with hr = h rounded up to even are
+// zero on entry and stay zero.  nrm: block-shared double[>= 2 * nb].  Every thread of the block calls; the block size is
+// a multiple of 32.  Returns the number of sweeps (same value in every thread).
+#define SMRT_JG 8  // lanes per group
+
+template <int R>
+SMRT_DEV void jreg_load(const double* SMRT_RESTRICT col, bool valid, int lane, int hr, double (&x)[R]) {
+#pragma unroll
+  for (int v = 0; v < R / 2; ++v) {
+    const int i = 2 * lane + 16 * v;
+    if (valid && i < hr) {
+      const double2 t = *reinterpret_cast<const double2*>(col + i);
+      x[2 * v] = t.x;
+      x[2 * v + 1] = t.y;
+    } else {
+      x[2 * v] = 0.0;
+      x[2 * v + 1] = 0.0;
+    }
+  }
+}
+template <int R>
+SMRT_DEV void jreg_store(double* SMRT_RESTRICT col, bool valid, int lane, int hr, const double (&x)[R]) {
+#pragma unroll
+  for (int v = 0; v < R / 2; ++v) {
+    const int i = 2 * lane + 16 * v;
+    if (valid && i < hr) {
+      double2 t;
+      t.x = x[2 * v];
+      t.y = x[2 * v + 1];
+      *reinterpret_cast<double2*>(col + i) = t;
+    }
+  }
+}
+// sum over the 8 lanes of a group (every lane of the warp takes part; identical result in the 8 lanes)
+SMRT_DEV double jreg_group_sum(double v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1, 32);
+  v += __shfl_xor_sync(0xffffffffu, v, 2, 32);
+  v += __shfl_xor_sync(0xffffffffu, v, 4, 32);
+  return v;
+}
+template <int R>
+SMRT_DEV double jreg_dot(const double (&x)[R], const double (&y)[R]) {
+  double g0 = 0.0, g1 = 0.0;
+#pragma unroll
+  for (int u = 0; u < R; u += 2) {
+    g0 = fma(x[u], y[u], g0);
+    g1 = fma(x[u + 1], y[u + 1], g1);
+  }
+  return jreg_group_sum(g0 + g1);
+}
+// one rotation of the column pair (x, y) with squared norms (a, b), updated in place.
+// returns bit 0: the pair was not yet orthogonal to quadratic-convergence level; bit 1: the columns were modified
+template <int R>
+SMRT_DEV int jreg_rotate(double (&x)[R], double (&y)[R], double& a, double& b) {
+  const double g = jreg_dot<R>(x, y);
+  const double g2 = g * g, ab = a * b;
+  if (!(g2 > SMRT_JACOBI_TOL2 * ab)) return 0;
+  // t = sgn(d) 2 g / (|d| + sqrt(d^2 + 4 g^2)), d = |w_q|^2 - |w_p|^2
+  const double d = b - a;
+  const double q = fma(d, d, 4.0 * g2);
+  double r = smrt_rsqrt_approx(q);
+  r = r * fma(-0.5 * q * r, r, 1.5);
+  const double dd = fabs(d) + q * r;
+  double rd = smrt_rcp_approx(dd);
+  rd = fma(rd, fma(-dd, rd, 1.0), rd);
+  const double t = copysign(2.0 * g, (d >= 0.0) ? g : -g) * rd;
+  const double c = rsqrt(fma(t, t, 1.0));
+  const double s = c * t;
+#pragma unroll
+  for (int u = 0; u < R; ++u) {
+    const double xu = x[u], yu = y[u];
+    x[u] = fma(c, xu, -s * yu);
+    y[u] = fma(s, xu, c * yu);
+  }
+  const double tg = t * g;
+  a -= tg;
+  b += tg;
+  return (g2 > SMRT_JACOBI_QUAD2 * ab) ? 3 : 2;
+}
+
+template <int R>
+SMRT_DEV int block_jacobi_svd_reg(double* W, int ld, int h, double* nrm) {
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int ngroups = NT / SMRT_JG, grp = tid / SMRT_JG, lane = tid % SMRT_JG;
+  const int hr = (h + 1) & ~1;    // rows including the zero pad row of an odd-sized problem
+  const int ncb = (h + 1) >> 1;   // blocks of two columns (the last one holds a single column when h is odd)
+  const int nb = (ncb + 1) & ~1;  // padded to an even number of blocks; blocks >= ncb are empty
+  const int nb1 = nb - 1, npairs = nb >> 1;
+  int sweeps = 0;
+  for (;;) {
+    int notconv = 0;
+    // the two columns of every block against each other, with exact norms (they are tracked from here on)
+    for (int b0 = 0; b0 < nb; b0 += ngroups) {
+      const int blk = b0 + grp;
+      const int c0 = 2 * blk, c1 = c0 + 1;
+      const bool v0 = (blk < nb) && (c0 < h), v1 = (blk < nb) && (c1 < h);
+      double x[R], y[R];
+      jreg_load<R>(W + (size_t)(v0 ? c0 : 0) * ld, v0, lane, hr, x);
+      jreg_load<R>(W + (size_t)(v1 ? c1 : 0) * ld, v1, lane, hr, y);
+      double a = jreg_dot<R>(x, x), b = jreg_dot<R>(y, y);
+      const int rc = jreg_rotate<R>(x, y, a, b);
+      if (rc & 2) {
+        jreg_store<R>(W + (size_t)(v0 ? c0 : 0) * ld, v0, lane, hr, x);
+        jreg_store<R>(W + (size_t)(v1 ? c1 : 0) * ld, v1, lane, hr, y);
+      }
+      if (lane == 0) {
+        if (v0) nrm[c0] = a;
+        if (v1) nrm[c1] = b;
+      }
+      notconv |= rc & 1;
+    }
+    __syncthreads();
+    // block rounds: round-robin tournament of the nb blocks, four cross rotations per meeting
+    for (int r = 0; r < nb1; ++r) {
+      for (int p0 = 0; p0 < npairs; p0 += ngroups) {
+        const int pg = p0 + grp;
+        int P, Q;
+        if (pg == 0) {
+          P = r;
+          Q = nb1;
+        } else {
+          P = r + pg;
+          if (P >= nb1) P -= nb1;
+          Q = r - pg;
+          if (Q < 0) Q += nb1;
+        }
+        if (P > Q) {
+          const int t = P;
+          P = Q;
+          Q = t;
+        }
+        const bool act = pg < npairs;
+        const int cp0 = 2 * P, cp1 = cp0 + 1, cq0 = 2 * Q, cq1 = cq0 + 1;
+        const bool vp0 = act && cp0 < h, vp1 = act && cp1 < h, vq0 = act && cq0 < h, vq1 = act && cq1 < h;
+        double* wp0 = W + (size_t)(vp0 ? cp0 : 0) * ld;
+        double* wp1 = W + (size_t)(vp1 ? cp1 : 0) * ld;
+        double* wq0 = W + (size_t)(vq0 ? cq0 : 0) * ld;
+        double* wq1 = W + (size_t)(vq1 ? cq1 : 0) * ld;
+        double x0[R], x1[R], y0[R], y1[R];
+        jreg_load<R>(wp0, vp0, lane, hr, x0);
+        jreg_load<R>(wp1, vp1, lane, hr, x1);
+        jreg_load<R>(wq0, vq0, lane, hr, y0);
+        jreg_load<R>(wq1, vq1, lane, hr, y1);
+        double a0 = vp0 ? nrm[cp0] : 0.0, a1 = vp1 ? nrm[cp1] : 0.0;
+        double b0 = vq0 ? nrm[cq0] : 0.0, b1 = vq1 ? nrm[cq1] : 0.0;
+        const int r00 = jreg_rotate<R>(x0, y0, a0, b0);
+        const int r11 = jreg_rotate<R>(x1, y1, a1, b1);
+        const int r01 = jreg_rotate<R>(x0, y1, a0, b1);
+        const int r10 = jreg_rotate<R>(x1, y0, a1, b0);
+        if ((r00 | r01) & 2) {
+          jreg_store<R>(wp0, vp0, lane, hr, x0);
+          if (lane == 0 && vp0) nrm[cp0] = a0;
+        }
+        if ((r11 | r10) & 2) {
+          jreg_store<R>(wp1, vp1, lane, hr, x1);
+          if (lane == 0 && vp1) nrm[cp1] = a1;
+        }
+        if ((r00 | r10) & 2) {
+          jreg_store<R>(wq0, vq0, lane, hr, y0);
+          if (lane == 0 && vq0) nrm[cq0] = b0;
+        }
+        if ((r11 | r01) & 2) {
+          jreg_store<R>(wq1, vq1, lane, hr, y1);
+          if (lane == 0 && vq1) nrm[cq1] = b1;
+        }
+        notconv |= (r00 | r11 | r01 | r10) & 1;
+      }
+      __syncthreads();
+    }
+    ++sweeps;
+    if (!__syncthreads_or(notconv) || sweeps >= SMRT_JACOBI_MAX_SWEEPS) break;
+  }
+  return sweeps;
+}
+
+// dispatch on the number of rows per lane: 8 lanes x R rows cover hr <= 8 R
+SMRT_DEV int block_jacobi_svd_fast(double* W, int ld, int h, double* nrm) {
+  const int hr = (h + 1) & ~1;
+  if (hr <= 16) return block_jacobi_svd_reg<2>(W, ld, h, nrm);
+  if (hr <= 32) return block_jacobi_svd_reg<4>(W, ld, h, nrm);
+  if (hr <= 48) return block_jacobi_svd_reg<6>(W, ld, h, nrm);
+  return block_jacobi_svd_reg<8>(W, ld, h, nrm);
+}
+
 // ------------------------------------------------------------------------------------------ LU with partial pivoting
 // In-place LU of the h x h matrix A (column-major, ld) with row interchanges applied physically; perm[j] = pivot row
 // chosen at step j (LAPACK ipiv convention, 0-based).  Returns 0, or 1 if a pivot is exactly zero / not finite.

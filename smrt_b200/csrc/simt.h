@@ -22,6 +22,19 @@ SMRT_DEV void smrt_named_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---- single-instruction fp64 approximations (MUFU.RCP64H / MUFU.RSQ64H, ~2^-20 relative error): seeds that the
+// callers refine with Newton steps where they need more
+SMRT_DEV double smrt_rcp_approx(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+}
+SMRT_DEV double smrt_rsqrt_approx(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+}
+
 // ---- TMA bulk copy (cp.async.bulk, 1-D, global -> shared) completed on an mbarrier --------------------------------
 typedef unsigned long long smrt_mbar_t;
 SMRT_DEV unsigned smrt_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -169,6 +182,14 @@ inline void smrt_bulk_load2(smrt_mbar_t*, void* dst0, const void* src0, void* ds
 inline void smrt_mbar_wait(smrt_mbar_t*, unsigned) {}
 
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
+// the device versions are ~20-bit seeds: keep only a float mantissa so that the emulation tests the same tolerance
+inline double smrt_approx_round(double v) {
+  int e;
+  double m = std::frexp(v, &e);
+  return std::ldexp((double)(float)m, e);
+}
+inline double smrt_rcp_approx(double x) { return smrt_approx_round(1.0 / x); }
+inline double smrt_rsqrt_approx(double x) { return smrt_approx_round(1.0 / std::sqrt(x)); }
 inline double fma_(double a, double b, double c) { return std::fma(a, b, c); }
 inline void sincos(double x, double* s, double* c) {
   *s = std::sin(x);

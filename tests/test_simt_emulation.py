@@ -118,3 +118,37 @@ def test_one_sided_jacobi_device_function(h, threads):
     np.testing.assert_allclose(sig, np.linalg.svd(M, compute_uv=False), rtol=1e-13)
     U = W / np.linalg.norm(W, axis=0)
     assert np.abs(U.T @ U - np.eye(h)).max() < 1e-13
+
+
+@pytest.mark.parametrize("h,threads,kind", [(6, 64, "dense"), (15, 64, "dense"), (33, 64, "dense"), (47, 128, "dense"),
+                                            (64, 128, "dense"), (64, 128, "degenerate"), (44, 128, "neardiag"),
+                                            (64, 256, "neardiag")])
+def test_register_blocked_jacobi_device_function(h, threads, kind):
+    """block_jacobi_svd_fast (2-column blocks in registers, tracked norms, MUFU-seeded tangent): singular values and
+    orthogonality to rounding, including odd sizes (zero pad row), clusters of equal singular values and the nearly
+    diagonal matrices of weakly scattering layers"""
+    lib = emu_lib()
+    rng = np.random.default_rng(100 + h)
+    if kind == "dense":
+        M = rng.normal(size=(h, h)) + np.diag(rng.uniform(1, 5, h))
+    elif kind == "degenerate":
+        Q1, _ = np.linalg.qr(rng.normal(size=(h, h)))
+        Q2, _ = np.linalg.qr(rng.normal(size=(h, h)))
+        sv = np.repeat(rng.uniform(1, 10, h // 4), 4) * (1 + 1e-13 * rng.normal(size=h))
+        M = (Q1 * sv) @ Q2.T
+    else:
+        M = np.diag(rng.uniform(1, 11, h)) + 1e-3 * rng.normal(size=(h, h))
+    ld = (h + 1) & ~1
+    W = np.zeros((ld, h), order="F")
+    W[:h, :] = M
+    sweeps = lib.emu_jacobi_fast(W.ctypes.data_as(C.POINTER(C.c_double)), h, ld, threads)
+    assert 0 < sweeps < 20
+    assert np.all(W[h:, :] == 0.0)
+    Wh = W[:h, :]
+    sig = np.sort(np.linalg.norm(Wh, axis=0))[::-1]
+    np.testing.assert_allclose(sig, np.linalg.svd(M, compute_uv=False), rtol=1e-13)
+    U = Wh / np.linalg.norm(Wh, axis=0)
+    assert np.abs(U.T @ U - np.eye(h)).max() < 1e-13
+    # W = M V with V orthogonal: M^-1 W must be orthogonal
+    V = np.linalg.solve(M, Wh)
+    assert np.abs(V.T @ V - np.eye(h)).max() < 1e-11
