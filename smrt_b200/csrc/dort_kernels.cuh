@@ -108,13 +108,14 @@ SMRT_DEV void set_error(int* status, int b, int code) {
 // --------------------------------------------------------------------------------------------------------------------
 // shared-memory vector region (doubles): mu[n] w[n] norm0[2n] g[hmax] sdiag[hmax] dk[hmax] sigma[hmax] ctab[2K] stab[2K]
 //                                        panel[SMRT_PANEL * hmax] gq[hmax] nrm[hmax + 4]
-// matrix region: A1 (X- -> L -> M -> W -> E~+), A2 (X+ -> C); two (hmax x (hmax+1)) blocks = 67 KB at 32 streams, so
-// that three CTAs fit on an SM
+// matrix region: A1 (X- -> L -> M -> W -> E~+, hmax x (hmax + 3)), A2 (X+ -> C, hmax x (hmax + 1)): 68 KB at 32
+// streams, so that three CTAs fit on an SM
 #define SMRT_PANEL 8  // columns of L staged per step of the in-place product M = C^T L
 SMRT_HD size_t eigen_vec_doubles(int n, int hmax, int K) {
   return ((size_t)4 * n + 6 * hmax + 4 * K + (size_t)SMRT_PANEL * hmax + 12 + 1) & ~(size_t)1;
 }
-SMRT_HD size_t eigen_mat_doubles(int hmax) { return (size_t)2 * hmax * (hmax + 1); }
+SMRT_HD size_t eigen_mat1_doubles(int hmax) { return (size_t)hmax * (hmax + 3) + (hmax & 1); }  // even: A2 16-byte aligned
+SMRT_HD size_t eigen_mat_doubles(int hmax) { return eigen_mat1_doubles(hmax) + (size_t)hmax * (hmax + 1); }
 
 template <bool kGlobalScratch>
 SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlobalScratch ? 1 : 3) eigen_kernel(KArgs A) {
@@ -143,9 +144,8 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
   // compile-time choice so that the shared-memory instantiation addresses its matrices with LDS/STS, not generic LD/ST
   double* mats = kGlobalScratch ? (A.scratch + (size_t)blockIdx.x * A.scratch_stride)
                                 : (smem + eigen_vec_doubles(n, hmax, K));
-  const size_t matsz = (size_t)hmax * (hmax + 1);
   double* A1 = mats;
-  double* A2 = mats + matsz;
+  double* A2 = mats + eigen_mat1_doubles(hmax);
 
   for (int j = tid; j < 2 * K; j += NT) {
     double s, c;
@@ -211,7 +211,8 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
       // A2 (X+ -> C) is read row-wise by lanes: odd leading dimension (conflict-free); A1 (X- -> L -> M -> W) is the
       // Jacobi operand: even leading dimension (16-byte aligned columns), the pad row of an odd h is kept at zero
       const int ld = (h & 1) ? h : h + 1;
-      const int ld1 = (h + 1) & ~1;
+      const int hr = (h + 1) & ~1;
+      const int ld1 = ((hr & 3) == 2) ? hr : hr + 2;  // = 2 (mod 4): column-strided accesses stay 2-way conflict-free
       const double coef = (m == 0) ? 0.5 : 0.25;
 
       // phase matrix Fourier mode m on (mu_s > 0) x (mu_i > 0 | mu_i < 0): A1 <- P++, A2 <- (P+-) D
@@ -285,8 +286,8 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
         int which = tid / half;
         tm.rank = tid % half;
         tm.bar_id = 1 + which;
-        int bad = team_cholesky(tm, which == 0 ? A1 : A2, which == 0 ? ld1 : ld, h, &s_ctrl[4 + which]);
-        (void)bad;
+        int bad = team_cholesky_fast(tm, which == 0 ? A1 : A2, which == 0 ? ld1 : ld, h, which == 0 ? sigma : nrm);
+        if (tm.rank == 0) s_ctrl[4 + which] = bad;
       }
       __syncthreads();
       if (s_ctrl[4] | s_ctrl[5]) {
@@ -327,7 +328,7 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
           for (int j = tid; j < h; j += NT) SMRT_AT(A1, ld1, h, j) = 0.0;
           __syncthreads();
         }
-        int sw = (ld1 <= 8 * SMRT_JG) ? block_jacobi_svd_fast(A1, ld1, h, nrm) : block_jacobi_svd(A1, ld1, h, s_ctrl);
+        int sw = (hr <= 8 * SMRT_JG) ? block_jacobi_svd_fast(A1, ld1, h, nrm) : block_jacobi_svd(A1, ld1, h, s_ctrl);
         if (tid == 0 && A.diag) {
           atomicAdd(&A.diag[0], sw);
           atomicAdd(&A.diag[1], 1);
@@ -354,28 +355,11 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
       }
       __syncthreads();
 
-      // E~+ = C^-T W: back substitution with the upper-triangular C^T, in place on the columns of A1
-      // (uniform trip counts: every lane of every warp takes part in the __syncwarp()s)
-      {
-        int tpc = 32;
-        while (tpc > 1 && h * tpc > NT) tpc >>= 1;
-        const int ngroups = NT / tpc;
-        const int grp = tid / tpc, lane = tid % tpc;
-        for (int c0 = 0; c0 < h; c0 += ngroups) {
-          const int c = c0 + grp;
-          const bool valid = c < h;
-          double* x = A1 + (size_t)(valid ? c : 0) * ld1;
-          for (int j = h - 1; j >= 0; --j) {
-            if (valid && lane == 0) x[j] = x[j] / SMRT_AT(A2, ld, j, j);
-            __syncwarp();
-            if (valid) {
-              const double xj = x[j];
-              for (int i = lane; i < j; i += tpc) x[i] = fma(-SMRT_AT(A2, ld, j, i), xj, x[i]);
-            }
-            __syncwarp();
-          }
-        }
-      }
+      // E~+ = C^-T W: back substitution with the upper-triangular C^T, in place on the columns of A1 (two lanes per
+      // column, blocks of 8 unknowns in registers); gq is dead since the formation of X+-: reciprocal diagonal of C
+      for (int j = tid; j < h; j += NT) gq[j] = 1.0 / SMRT_AT(A2, ld, j, j);
+      __syncthreads();
+      block_backsolve_lt(A2, ld, A1, ld1, h, gq);
       __syncthreads();
 
       // store k, F = s (E~+ - E~-) / 2, G = s (E~+ + E~-) / 2

@@ -121,6 +121,76 @@ SMRT_DEV int team_cholesky(const Team& tm, double* A, int ld, int h, int* flag) 
   return *flag;
 }
 
+// Left-looking variant with ONE team barrier per column (the right-looking version above needs three and rewrites the
+// trailing matrix at every step).  Thread t owns the rows t, t + size, ... (NR of them); at step j it forms
+//   s_i = A(i, j) - sum_{k<j} L(i, k) L(j, k)      for its rows i > j
+// and, redundantly (the L(j, k) operands are loaded anyway), the pivot s_jj = A(j, j) - sum_k L(j, k)^2, so that
+// L(i, j) = s_i / sqrt(s_jj) can be written without a second synchronisation.  The diagonal of L is never read during
+// the factorisation; it is collected in dvec (team-shared double[h]) and copied into A at the end, which removes the
+// write-after-read race on A(j, j).  Only the lower triangle is read or written.  Returns 1 (to every thread of the
+// team) when a pivot is not positive.
+template <int NR>
+SMRT_DEV int team_cholesky_ll(const Team& tm, double* A, int ld, int h, double* dvec) {
+  int failed = 0;
+  for (int j = 0; j < h; ++j) {
+    const double* SMRT_RESTRICT Lj = A + j;  // L(j, k) = Lj[k * ld]
+    double p[4] = {0.0, 0.0, 0.0, 0.0};
+    double sacc[NR][4];
+    const double* rowp[NR];
+    bool own[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int i = tm.rank + r * tm.size;
+      own[r] = (i > j) && (i < h);
+      rowp[r] = A + (own[r] ? i : j);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sacc[r][u] = 0.0;
+    }
+    int k = 0;
+    for (; k + 3 < j; k += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double lj = Lj[(size_t)(k + u) * ld];
+        p[u] = fma(lj, lj, p[u]);
+#pragma unroll
+        for (int r = 0; r < NR; ++r) sacc[r][u] = fma(rowp[r][(size_t)(k + u) * ld], lj, sacc[r][u]);
+      }
+    }
+    for (; k < j; ++k) {
+      const double lj = Lj[(size_t)k * ld];
+      p[0] = fma(lj, lj, p[0]);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) sacc[r][0] = fma(rowp[r][(size_t)k * ld], lj, sacc[r][0]);
+    }
+    const double d = SMRT_AT(A, ld, j, j) - ((p[0] + p[1]) + (p[2] + p[3]));
+    if (!(d > 0.0)) {  // identical value in every thread: uniform exit
+      failed = 1;
+      break;
+    }
+    const double rinv = rsqrt(d);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int i = tm.rank + r * tm.size;
+      if (own[r]) {
+        const double si = SMRT_AT(A, ld, i, j) - ((sacc[r][0] + sacc[r][1]) + (sacc[r][2] + sacc[r][3]));
+        SMRT_AT(A, ld, i, j) = si * rinv;
+      }
+      if (i == j) dvec[j] = d * rinv;
+    }
+    tm.sync();
+  }
+  if (failed) return 1;
+  for (int j = tm.rank; j < h; j += tm.size) SMRT_AT(A, ld, j, j) = dvec[j];
+  tm.sync();
+  return 0;
+}
+SMRT_DEV int team_cholesky_fast(const Team& tm, double* A, int ld, int h, double* dvec) {
+  if (h <= tm.size) return team_cholesky_ll<1>(tm, A, ld, h, dvec);
+  if (h <= 2 * tm.size) return team_cholesky_ll<2>(tm, A, ld, h, dvec);
+  if (h <= 4 * tm.size) return team_cholesky_ll<4>(tm, A, ld, h, dvec);
+  return team_cholesky_ll<8>(tm, A, ld, h, dvec);
+}
+
 // ------------------------------------------------------------------------------------------------- one-sided Jacobi SVD
 // Orthogonalises the columns of the h x h matrix W (column-major, ld) in place by plane rotations applied from the
 // right (Hestenes): on exit W = M V with V orthogonal and mutually orthogonal columns, |w_j| = sigma_j.
@@ -326,6 +396,30 @@ SMRT_DEV double jreg_dot(const double (&x)[R], const double (&y)[R]) {
   }
   return jreg_group_sum(g0 + g1);
 }
+// tangent, cosine and sine of the rotation that orthogonalises a column pair with squared norms (a, b) and inner
+// product g; rot = false gives the identity.  Branch-free so that two independent pairs interleave in the pipeline.
+SMRT_DEV void jreg_angle(double a, double b, double g, bool rot, double& t, double& c, double& s) {
+  // t = sgn(d) 2 g / (|d| + sqrt(d^2 + 4 g^2)), d = |w_q|^2 - |w_p|^2
+  const double d = b - a;
+  const double q = rot ? fma(d, d, 4.0 * (g * g)) : 1.0;
+  double r = smrt_rsqrt_approx(q);
+  r = r * fma(-0.5 * q * r, r, 1.5);
+  const double dd = fabs(d) + q * r;
+  double rd = smrt_rcp_approx(dd);
+  rd = fma(rd, fma(-dd, rd, 1.0), rd);
+  t = rot ? copysign(2.0 * g, (d >= 0.0) ? g : -g) * rd : 0.0;
+  c = rsqrt(fma(t, t, 1.0));
+  s = c * t;
+}
+template <int R>
+SMRT_DEV void jreg_apply(double (&x)[R], double (&y)[R], double c, double s) {
+#pragma unroll
+  for (int u = 0; u < R; ++u) {
+    const double xu = x[u], yu = y[u];
+    x[u] = fma(c, xu, -s * yu);
+    y[u] = fma(s, xu, c * yu);
+  }
+}
 // one rotation of the column pair (x, y) with squared norms (a, b), updated in place.
 // returns bit 0: the pair was not yet orthogonal to quadratic-convergence level; bit 1: the columns were modified
 template <int R>
@@ -333,27 +427,51 @@ SMRT_DEV int jreg_rotate(double (&x)[R], double (&y)[R], double& a, double& b) {
   const double g = jreg_dot<R>(x, y);
   const double g2 = g * g, ab = a * b;
   if (!(g2 > SMRT_JACOBI_TOL2 * ab)) return 0;
-  // t = sgn(d) 2 g / (|d| + sqrt(d^2 + 4 g^2)), d = |w_q|^2 - |w_p|^2
-  const double d = b - a;
-  const double q = fma(d, d, 4.0 * g2);
-  double r = smrt_rsqrt_approx(q);
-  r = r * fma(-0.5 * q * r, r, 1.5);
-  const double dd = fabs(d) + q * r;
-  double rd = smrt_rcp_approx(dd);
-  rd = fma(rd, fma(-dd, rd, 1.0), rd);
-  const double t = copysign(2.0 * g, (d >= 0.0) ? g : -g) * rd;
-  const double c = rsqrt(fma(t, t, 1.0));
-  const double s = c * t;
-#pragma unroll
-  for (int u = 0; u < R; ++u) {
-    const double xu = x[u], yu = y[u];
-    x[u] = fma(c, xu, -s * yu);
-    y[u] = fma(s, xu, c * yu);
-  }
+  double t, c, s;
+  jreg_angle(a, b, g, true, t, c, s);
+  jreg_apply<R>(x, y, c, s);
   const double tg = t * g;
   a -= tg;
   b += tg;
   return (g2 > SMRT_JACOBI_QUAD2 * ab) ? 3 : 2;
+}
+// two INDEPENDENT rotations (x0, y0) and (x1, y1) issued together: the dependent chain dot -> shuffles -> MUFU seeds ->
+// Newton steps -> rsqrt of one pair fills the latency slots of the other.  Return codes as jreg_rotate, in rc0 / rc1.
+template <int R>
+SMRT_DEV void jreg_rotate2(double (&x0)[R], double (&y0)[R], double& a0, double& b0, double (&x1)[R], double (&y1)[R],
+                           double& a1, double& b1, int& rc0, int& rc1) {
+  double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+#pragma unroll
+  for (int u = 0; u < R; u += 2) {
+    p0 = fma(x0[u], y0[u], p0);
+    q0 = fma(x1[u], y1[u], q0);
+    p1 = fma(x0[u + 1], y0[u + 1], p1);
+    q1 = fma(x1[u + 1], y1[u + 1], q1);
+  }
+  double g0 = p0 + p1, g1 = q0 + q1;
+#pragma unroll
+  for (int off = 1; off < SMRT_JG; off <<= 1) {
+    const double o0 = __shfl_xor_sync(0xffffffffu, g0, off, 32);
+    const double o1 = __shfl_xor_sync(0xffffffffu, g1, off, 32);
+    g0 += o0;
+    g1 += o1;
+  }
+  const double g20 = g0 * g0, ab0 = a0 * b0, g21 = g1 * g1, ab1 = a1 * b1;
+  const bool rot0 = g20 > SMRT_JACOBI_TOL2 * ab0, rot1 = g21 > SMRT_JACOBI_TOL2 * ab1;
+  rc0 = rc1 = 0;
+  if (!(rot0 || rot1)) return;
+  double t0, c0, s0, t1, c1, s1;
+  jreg_angle(a0, b0, g0, rot0, t0, c0, s0);
+  jreg_angle(a1, b1, g1, rot1, t1, c1, s1);
+  jreg_apply<R>(x0, y0, c0, s0);
+  jreg_apply<R>(x1, y1, c1, s1);
+  const double tg0 = t0 * g0, tg1 = t1 * g1;
+  a0 -= tg0;
+  b0 += tg0;
+  a1 -= tg1;
+  b1 += tg1;
+  rc0 = rot0 ? ((g20 > SMRT_JACOBI_QUAD2 * ab0) ? 3 : 2) : 0;
+  rc1 = rot1 ? ((g21 > SMRT_JACOBI_QUAD2 * ab1) ? 3 : 2) : 0;
 }
 
 template <int R>
@@ -421,10 +539,9 @@ SMRT_DEV int block_jacobi_svd_reg(double* W, int ld, int h, double* nrm) {
         jreg_load<R>(wq1, vq1, lane, hr, y1);
         double a0 = vp0 ? nrm[cp0] : 0.0, a1 = vp1 ? nrm[cp1] : 0.0;
         double b0 = vq0 ? nrm[cq0] : 0.0, b1 = vq1 ? nrm[cq1] : 0.0;
-        const int r00 = jreg_rotate<R>(x0, y0, a0, b0);
-        const int r11 = jreg_rotate<R>(x1, y1, a1, b1);
-        const int r01 = jreg_rotate<R>(x0, y1, a0, b1);
-        const int r10 = jreg_rotate<R>(x1, y0, a1, b0);
+        int r00, r11, r01, r10;
+        jreg_rotate2<R>(x0, y0, a0, b0, x1, y1, a1, b1, r00, r11);
+        jreg_rotate2<R>(x0, y1, a0, b1, x1, y0, a1, b0, r01, r10);
         if ((r00 | r01) & 2) {
           jreg_store<R>(wp0, vp0, lane, hr, x0);
           if (lane == 0 && vp0) nrm[cp0] = a0;
@@ -458,6 +575,72 @@ SMRT_DEV int block_jacobi_svd_fast(double* W, int ld, int h, double* nrm) {
   if (hr <= 32) return block_jacobi_svd_reg<4>(W, ld, h, nrm);
   if (hr <= 48) return block_jacobi_svd_reg<6>(W, ld, h, nrm);
   return block_jacobi_svd_reg<8>(W, ld, h, nrm);
+}
+
+// ------------------------------------------------------------------------------- triangular solve C^T Z = W, in place
+// C: h x h lower triangular (column-major, ldc); W: h x h (column-major, ldw), overwritten by Z = C^-T W; rdiag[j] =
+// 1 / C(j, j) (block-shared).  Every column of W is an independent back substitution: TWO adjacent lanes own a column
+// and walk it bottom-up in blocks of 8 unknowns held in registers (both lanes solve the 8 x 8 diagonal block
+// redundantly, then split the update of the rows above between them), so the only synchronisation is one __syncwarp
+// per block and all C operands are warp-wide broadcasts.  Called by every thread of the block.
+SMRT_DEV void block_backsolve_lt(const double* SMRT_RESTRICT C, int ldc, double* W, int ldw, int h,
+                                 const double* SMRT_RESTRICT rdiag) {
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int half = tid & 1;
+  const int nblk = (h + 7) >> 3;
+  for (int c0 = 0; c0 < h; c0 += NT / 2) {
+    const int c = c0 + (tid >> 1);
+    const bool act = c < h;
+    double* x = W + (size_t)(act ? c : 0) * ldw;
+    for (int jbk = nblk - 1; jbk >= 0; --jbk) {
+      const int jb = jbk * 8;
+      const int nv = (h - jb < 8) ? (h - jb) : 8;
+      double z[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) z[jj] = (act && jj < nv) ? x[jb + jj] : 0.0;
+      __syncwarp();  // the partner lane has read the block too before lane 0 overwrites it with the solution
+#pragma unroll
+      for (int jj = 7; jj >= 0; --jj) {
+        if (jj < nv) {
+          z[jj] *= rdiag[jb + jj];
+#pragma unroll
+          for (int ii = 0; ii < jj; ++ii) z[ii] = fma(-SMRT_AT(C, ldc, jb + jj, jb + ii), z[jj], z[ii]);
+        }
+      }
+      if (act && half == 0) {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          if (jj < nv) x[jb + jj] = z[jj];
+      }
+      // rows above the block, interleaved between the two lanes, two rows in flight per lane
+      if (act) {
+        int i = half;
+        for (; i + 2 < jb; i += 4) {
+          const double* ca = C + (size_t)i * ldc + jb;
+          const double* cb = C + (size_t)(i + 2) * ldc + jb;
+          double xa = x[i], xb = x[i + 2];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            if (jj < nv) {
+              xa = fma(-ca[jj], z[jj], xa);
+              xb = fma(-cb[jj], z[jj], xb);
+            }
+          }
+          x[i] = xa;
+          x[i + 2] = xb;
+        }
+        if (i < jb) {
+          const double* ca = C + (size_t)i * ldc + jb;
+          double xa = x[i];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj)
+            if (jj < nv) xa = fma(-ca[jj], z[jj], xa);
+          x[i] = xa;
+        }
+      }
+      __syncwarp();
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------ LU with partial pivoting
