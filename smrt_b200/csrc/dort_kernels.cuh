@@ -107,14 +107,14 @@ SMRT_DEV void set_error(int* status, int b, int code) {
 // kernel 2: per-layer eigenproblem
 // --------------------------------------------------------------------------------------------------------------------
 // shared-memory vector region (doubles): mu[n] w[n] norm0[2n] g[hmax] sdiag[hmax] dk[hmax] sigma[hmax] ctab[2K] stab[2K]
-//                                        panel[SMRT_PANEL * hmax] gq[hmax] nrm[hmax + 4]
+//                                        panel[SMRT_PANEL * hmax] gq[hmax] nrm[hmax + 4]; in front: zcol[64] (zeros)
 // matrix region: A1 (X- -> L -> M -> W -> E~+, hmax x (hmax + 3)), A2 (X+ -> C, hmax x (hmax + 1)): 68 KB at 32
 // streams, so that three CTAs fit on an SM
 #define SMRT_PANEL 8  // columns of L staged per step of the in-place product M = C^T L
 SMRT_HD size_t eigen_vec_doubles(int n, int hmax, int K) {
-  return ((size_t)4 * n + 6 * hmax + 4 * K + (size_t)SMRT_PANEL * hmax + 12 + 1) & ~(size_t)1;
+  return ((size_t)64 + 4 * n + 6 * hmax + 4 * K + (size_t)SMRT_PANEL * hmax + 12 + 1) & ~(size_t)1;
 }
-SMRT_HD size_t eigen_mat1_doubles(int hmax) { return (size_t)hmax * (hmax + 3) + (hmax & 1); }  // even: A2 16-byte aligned
+SMRT_HD size_t eigen_mat1_doubles(int hmax) { return (size_t)hmax * jacobi_ld(hmax); }  // even: A2 16-byte aligned
 SMRT_HD size_t eigen_mat_doubles(int hmax) { return eigen_mat1_doubles(hmax) + (size_t)hmax * (hmax + 1); }
 
 template <bool kGlobalScratch>
@@ -129,7 +129,8 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
   const int hmax = smrt_npol(A.m_max) * n;
   const int K = A.K;
 
-  double* mu = smem;
+  double* zcol = smem;  // a column of zeros: stands for the missing columns of the register-blocked Jacobi
+  double* mu = zcol + 64;
   double* w = mu + n;
   double* norm0 = w + n;
   double* gvec = norm0 + 2 * n;
@@ -147,6 +148,7 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
   double* A1 = mats;
   double* A2 = mats + eigen_mat1_doubles(hmax);
 
+  for (int j = tid; j < 64; j += NT) zcol[j] = 0.0;
   for (int j = tid; j < 2 * K; j += NT) {
     double s, c;
     sincospi((double)j / (double)K, &s, &c);
@@ -211,8 +213,7 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
       // A2 (X+ -> C) is read row-wise by lanes: odd leading dimension (conflict-free); A1 (X- -> L -> M -> W) is the
       // Jacobi operand: even leading dimension (16-byte aligned columns), the pad row of an odd h is kept at zero
       const int ld = (h & 1) ? h : h + 1;
-      const int hr = (h + 1) & ~1;
-      const int ld1 = ((hr & 3) == 2) ? hr : hr + 2;  // = 2 (mod 4): column-strided accesses stay 2-way conflict-free
+      const int ld1 = jacobi_ld(h);
       const double coef = (m == 0) ? 0.5 : 0.25;
 
       // phase matrix Fourier mode m on (mu_s > 0) x (mu_i > 0 | mu_i < 0): A1 <- P++, A2 <- (P+-) D
@@ -324,11 +325,13 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
 
       // singular values / right rotations by one-sided Jacobi: A1 <- W = U Sigma
       {
-        if (h & 1) {  // zero pad row of the Jacobi operand
-          for (int j = tid; j < h; j += NT) SMRT_AT(A1, ld1, h, j) = 0.0;
+        const bool fastj = h <= 64;
+        if (fastj) {  // zero pad rows of the register-blocked Jacobi operand: rows [h, ld1 - 2)
+          const int npad = ld1 - 2 - h;
+          for (int e = tid; e < npad * h; e += NT) SMRT_AT(A1, ld1, h + e % npad, e / npad) = 0.0;
           __syncthreads();
         }
-        int sw = (hr <= 8 * SMRT_JG) ? block_jacobi_svd_fast(A1, ld1, h, nrm) : block_jacobi_svd(A1, ld1, h, s_ctrl);
+        int sw = fastj ? block_jacobi_svd_fast(A1, ld1, h, nrm, zcol) : block_jacobi_svd(A1, ld1, h, s_ctrl);
         if (tid == 0 && A.diag) {
           atomicAdd(&A.diag[0], sw);
           atomicAdd(&A.diag[1], 1);

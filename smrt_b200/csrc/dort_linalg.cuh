@@ -346,58 +346,74 @@ SMRT_DEV int block_jacobi_svd(double* W, int ld, int h, int* ctrl) {
 //   * tan of the rotation angle from MUFU seeds (rsqrt / rcp, one Newton step each) instead of an IEEE sqrt and a
 //     division; cos = rsqrt(1 + t^2) stays a full-precision rsqrt, so every rotation is orthogonal to rounding whatever
 //     the accuracy of t.
-// W: column-major, leading dimension ld EVEN (16-byte aligned columns), rows [h, hr) with hr = h rounded up to even are
-// zero on entry and stay zero.  nrm: block-shared double[>= 2 * nb].  Every thread of the block calls; the block size is
-// a multiple of 32.  Returns the number of sweeps (same value in every thread).
-#define SMRT_JG 8  // lanes per group
+//   * no predicates in the inner loops: the rows [h, 8 R) of every column are zero (and stay zero under rotations),
+//     missing columns (odd h, padding blocks, idle groups) are read from a column of zeros and can never rotate, and
+//     the rotation angles of the two pairs handled together are computed by the two halves of the group.
+// W: column-major, leading dimension ld = jacobi_ld(h) (16-byte aligned columns, >= 8 R rows), rows [h, 8 R) zero on
+// entry.  nrm: block-shared double[>= 2 * nb + 1]; zcol: >= 8 R zeros, 16-byte aligned.  Every thread of the block
+// calls; the block size is a multiple of 32.  Returns the number of sweeps (same value in every thread).
+// lanes per group: JG = 8 with 128-thread blocks, 16 with 256-thread blocks (more warps in flight for the same
+// shared-memory footprint: the rotation chain is latency bound); R = rows per lane, JG * R = padded row count.
+// leading dimension of the Jacobi operand: rows padded to a multiple of 16, = 2 (mod 4) so that column-strided accesses
+// (two lanes per column in the back substitution) stay conflict-free
+SMRT_HD int jacobi_ld(int h) {
+  const int hr = (h + 1) & ~1;
+  if (hr <= 16) return 18;
+  if (hr <= 32) return 34;
+  if (hr <= 48) return 50;
+  if (hr <= 64) return 66;
+  return ((hr & 3) == 2) ? hr : hr + 2;
+}
 
-template <int R>
-SMRT_DEV void jreg_load(const double* SMRT_RESTRICT col, bool valid, int lane, int hr, double (&x)[R]) {
+// row owned by lane `lane` in register slot u: 16-byte pairs when R is even, single doubles otherwise
+template <int JG, int R>
+SMRT_DEV void jreg_load(const double* SMRT_RESTRICT col, int lane, double (&x)[R]) {
+  if (R % 2 == 0) {
 #pragma unroll
-  for (int v = 0; v < R / 2; ++v) {
-    const int i = 2 * lane + 16 * v;
-    if (valid && i < hr) {
-      const double2 t = *reinterpret_cast<const double2*>(col + i);
+    for (int v = 0; v < R / 2; ++v) {
+      const double2 t = *reinterpret_cast<const double2*>(col + 2 * lane + 2 * JG * v);
       x[2 * v] = t.x;
       x[2 * v + 1] = t.y;
-    } else {
-      x[2 * v] = 0.0;
-      x[2 * v + 1] = 0.0;
     }
+  } else {
+#pragma unroll
+    for (int u = 0; u < R; ++u) x[u] = col[lane + JG * u];
   }
 }
-template <int R>
-SMRT_DEV void jreg_store(double* SMRT_RESTRICT col, bool valid, int lane, int hr, const double (&x)[R]) {
+template <int JG, int R>
+SMRT_DEV void jreg_store(double* SMRT_RESTRICT col, int lane, const double (&x)[R]) {
+  if (R % 2 == 0) {
 #pragma unroll
-  for (int v = 0; v < R / 2; ++v) {
-    const int i = 2 * lane + 16 * v;
-    if (valid && i < hr) {
+    for (int v = 0; v < R / 2; ++v) {
       double2 t;
       t.x = x[2 * v];
       t.y = x[2 * v + 1];
-      *reinterpret_cast<double2*>(col + i) = t;
+      *reinterpret_cast<double2*>(col + 2 * lane + 2 * JG * v) = t;
     }
+  } else {
+#pragma unroll
+    for (int u = 0; u < R; ++u) col[lane + JG * u] = x[u];
   }
 }
-// sum over the 8 lanes of a group (every lane of the warp takes part; identical result in the 8 lanes)
+// sum over the JG lanes of a group (every lane of the warp takes part; identical result in all lanes of the group)
+template <int JG>
 SMRT_DEV double jreg_group_sum(double v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 1, 32);
-  v += __shfl_xor_sync(0xffffffffu, v, 2, 32);
-  v += __shfl_xor_sync(0xffffffffu, v, 4, 32);
+#pragma unroll
+  for (int off = 1; off < JG; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off, 32);
   return v;
 }
-template <int R>
+template <int JG, int R>
 SMRT_DEV double jreg_dot(const double (&x)[R], const double (&y)[R]) {
   double g0 = 0.0, g1 = 0.0;
 #pragma unroll
   for (int u = 0; u < R; u += 2) {
     g0 = fma(x[u], y[u], g0);
-    g1 = fma(x[u + 1], y[u + 1], g1);
+    if (u + 1 < R) g1 = fma(x[u + 1], y[u + 1], g1);
   }
-  return jreg_group_sum(g0 + g1);
+  return jreg_group_sum<JG>(g0 + g1);
 }
 // tangent, cosine and sine of the rotation that orthogonalises a column pair with squared norms (a, b) and inner
-// product g; rot = false gives the identity.  Branch-free so that two independent pairs interleave in the pipeline.
+// product g; rot = false gives the identity.  Branch-free.
 SMRT_DEV void jreg_angle(double a, double b, double g, bool rot, double& t, double& c, double& s) {
   // t = sgn(d) 2 g / (|d| + sqrt(d^2 + 4 g^2)), d = |w_q|^2 - |w_p|^2
   const double d = b - a;
@@ -422,9 +438,9 @@ SMRT_DEV void jreg_apply(double (&x)[R], double (&y)[R], double c, double s) {
 }
 // one rotation of the column pair (x, y) with squared norms (a, b), updated in place.
 // returns bit 0: the pair was not yet orthogonal to quadratic-convergence level; bit 1: the columns were modified
-template <int R>
+template <int JG, int R>
 SMRT_DEV int jreg_rotate(double (&x)[R], double (&y)[R], double& a, double& b) {
-  const double g = jreg_dot<R>(x, y);
+  const double g = jreg_dot<JG, R>(x, y);
   const double g2 = g * g, ab = a * b;
   if (!(g2 > SMRT_JACOBI_TOL2 * ab)) return 0;
   double t, c, s;
@@ -435,22 +451,26 @@ SMRT_DEV int jreg_rotate(double (&x)[R], double (&y)[R], double& a, double& b) {
   b += tg;
   return (g2 > SMRT_JACOBI_QUAD2 * ab) ? 3 : 2;
 }
-// two INDEPENDENT rotations (x0, y0) and (x1, y1) issued together: the dependent chain dot -> shuffles -> MUFU seeds ->
-// Newton steps -> rsqrt of one pair fills the latency slots of the other.  Return codes as jreg_rotate, in rc0 / rc1.
-template <int R>
-SMRT_DEV void jreg_rotate2(double (&x0)[R], double (&y0)[R], double& a0, double& b0, double (&x1)[R], double (&y1)[R],
-                           double& a1, double& b1, int& rc0, int& rc1) {
+// two INDEPENDENT rotations (x0, y0) and (x1, y1) handled together: the two dot products and their reductions
+// interleave, the lower half of the group computes the angle of the first pair and the upper half that of the second
+// one (the results are exchanged with three shuffles), then both rotations are applied.  Every lane of the WARP must
+// call (the branch around the angle computation is warp-uniform).  Return codes as jreg_rotate, in rc0 / rc1.
+template <int JG, int R>
+SMRT_DEV void jreg_rotate2(int lane, double (&x0)[R], double (&y0)[R], double& a0, double& b0, double (&x1)[R],
+                           double (&y1)[R], double& a1, double& b1, int& rc0, int& rc1) {
   double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
   for (int u = 0; u < R; u += 2) {
     p0 = fma(x0[u], y0[u], p0);
     q0 = fma(x1[u], y1[u], q0);
-    p1 = fma(x0[u + 1], y0[u + 1], p1);
-    q1 = fma(x1[u + 1], y1[u + 1], q1);
+    if (u + 1 < R) {
+      p1 = fma(x0[u + 1], y0[u + 1], p1);
+      q1 = fma(x1[u + 1], y1[u + 1], q1);
+    }
   }
   double g0 = p0 + p1, g1 = q0 + q1;
 #pragma unroll
-  for (int off = 1; off < SMRT_JG; off <<= 1) {
+  for (int off = 1; off < JG; off <<= 1) {
     const double o0 = __shfl_xor_sync(0xffffffffu, g0, off, 32);
     const double o1 = __shfl_xor_sync(0xffffffffu, g1, off, 32);
     g0 += o0;
@@ -459,29 +479,39 @@ SMRT_DEV void jreg_rotate2(double (&x0)[R], double (&y0)[R], double& a0, double&
   const double g20 = g0 * g0, ab0 = a0 * b0, g21 = g1 * g1, ab1 = a1 * b1;
   const bool rot0 = g20 > SMRT_JACOBI_TOL2 * ab0, rot1 = g21 > SMRT_JACOBI_TOL2 * ab1;
   rc0 = rc1 = 0;
-  if (!(rot0 || rot1)) return;
-  double t0, c0, s0, t1, c1, s1;
-  jreg_angle(a0, b0, g0, rot0, t0, c0, s0);
-  jreg_angle(a1, b1, g1, rot1, t1, c1, s1);
-  jreg_apply<R>(x0, y0, c0, s0);
-  jreg_apply<R>(x1, y1, c1, s1);
-  const double tg0 = t0 * g0, tg1 = t1 * g1;
-  a0 -= tg0;
-  b0 += tg0;
-  a1 -= tg1;
-  b1 += tg1;
-  rc0 = rot0 ? ((g20 > SMRT_JACOBI_QUAD2 * ab0) ? 3 : 2) : 0;
-  rc1 = rot1 ? ((g21 > SMRT_JACOBI_QUAD2 * ab1) ? 3 : 2) : 0;
+  if (!__any_sync(0xffffffffu, rot0 || rot1)) return;
+  const bool hi = (lane & (JG / 2)) != 0;
+  double t, c, s;
+  jreg_angle(hi ? a1 : a0, hi ? b1 : b0, hi ? g1 : g0, hi ? rot1 : rot0, t, c, s);
+  const double tg = t * (hi ? g1 : g0);
+  const double co = __shfl_xor_sync(0xffffffffu, c, JG / 2, 32);
+  const double so = __shfl_xor_sync(0xffffffffu, s, JG / 2, 32);
+  const double tgo = __shfl_xor_sync(0xffffffffu, tg, JG / 2, 32);
+  if (rot0) {
+    jreg_apply<R>(x0, y0, hi ? co : c, hi ? so : s);
+    const double tg0 = hi ? tgo : tg;
+    a0 -= tg0;
+    b0 += tg0;
+    rc0 = (g20 > SMRT_JACOBI_QUAD2 * ab0) ? 3 : 2;
+  }
+  if (rot1) {
+    jreg_apply<R>(x1, y1, hi ? c : co, hi ? s : so);
+    const double tg1 = hi ? tg : tgo;
+    a1 -= tg1;
+    b1 += tg1;
+    rc1 = (g21 > SMRT_JACOBI_QUAD2 * ab1) ? 3 : 2;
+  }
 }
 
-template <int R>
-SMRT_DEV int block_jacobi_svd_reg(double* W, int ld, int h, double* nrm) {
+template <int JG, int R>
+SMRT_DEV int block_jacobi_svd_reg(double* W, int ld, int h, double* nrm, const double* zcol) {
   const int NT = blockDim.x, tid = threadIdx.x;
-  const int ngroups = NT / SMRT_JG, grp = tid / SMRT_JG, lane = tid % SMRT_JG;
-  const int hr = (h + 1) & ~1;    // rows including the zero pad row of an odd-sized problem
+  const int ngroups = NT / JG, grp = tid / JG, lane = tid % JG;
   const int ncb = (h + 1) >> 1;   // blocks of two columns (the last one holds a single column when h is odd)
   const int nb = (ncb + 1) & ~1;  // padded to an even number of blocks; blocks >= ncb are empty
   const int nb1 = nb - 1, npairs = nb >> 1;
+  const int nodummy = 2 * nb;     // norm slot of the missing columns (always zero)
+  if (tid == 0) nrm[nodummy] = 0.0;
   int sweeps = 0;
   for (;;) {
     int notconv = 0;
@@ -490,18 +520,20 @@ SMRT_DEV int block_jacobi_svd_reg(double* W, int ld, int h, double* nrm) {
       const int blk = b0 + grp;
       const int c0 = 2 * blk, c1 = c0 + 1;
       const bool v0 = (blk < nb) && (c0 < h), v1 = (blk < nb) && (c1 < h);
+      double* w0 = v0 ? W + (size_t)c0 * ld : const_cast<double*>(zcol);
+      double* w1 = v1 ? W + (size_t)c1 * ld : const_cast<double*>(zcol);
       double x[R], y[R];
-      jreg_load<R>(W + (size_t)(v0 ? c0 : 0) * ld, v0, lane, hr, x);
-      jreg_load<R>(W + (size_t)(v1 ? c1 : 0) * ld, v1, lane, hr, y);
-      double a = jreg_dot<R>(x, x), b = jreg_dot<R>(y, y);
-      const int rc = jreg_rotate<R>(x, y, a, b);
-      if (rc & 2) {
-        jreg_store<R>(W + (size_t)(v0 ? c0 : 0) * ld, v0, lane, hr, x);
-        jreg_store<R>(W + (size_t)(v1 ? c1 : 0) * ld, v1, lane, hr, y);
+      jreg_load<JG, R>(w0, lane, x);
+      jreg_load<JG, R>(w1, lane, y);
+      double a = jreg_dot<JG, R>(x, x), b = jreg_dot<JG, R>(y, y);
+      const int rc = jreg_rotate<JG, R>(x, y, a, b);
+      if (rc & 2) {  // only real columns can rotate
+        jreg_store<JG, R>(w0, lane, x);
+        jreg_store<JG, R>(w1, lane, y);
       }
       if (lane == 0) {
-        if (v0) nrm[c0] = a;
-        if (v1) nrm[c1] = b;
+        nrm[v0 ? c0 : nodummy] = a;
+        nrm[v1 ? c1 : nodummy] = b;
       }
       notconv |= rc & 1;
     }
@@ -528,35 +560,37 @@ SMRT_DEV int block_jacobi_svd_reg(double* W, int ld, int h, double* nrm) {
         const bool act = pg < npairs;
         const int cp0 = 2 * P, cp1 = cp0 + 1, cq0 = 2 * Q, cq1 = cq0 + 1;
         const bool vp0 = act && cp0 < h, vp1 = act && cp1 < h, vq0 = act && cq0 < h, vq1 = act && cq1 < h;
-        double* wp0 = W + (size_t)(vp0 ? cp0 : 0) * ld;
-        double* wp1 = W + (size_t)(vp1 ? cp1 : 0) * ld;
-        double* wq0 = W + (size_t)(vq0 ? cq0 : 0) * ld;
-        double* wq1 = W + (size_t)(vq1 ? cq1 : 0) * ld;
+        double* wp0 = vp0 ? W + (size_t)cp0 * ld : const_cast<double*>(zcol);
+        double* wp1 = vp1 ? W + (size_t)cp1 * ld : const_cast<double*>(zcol);
+        double* wq0 = vq0 ? W + (size_t)cq0 * ld : const_cast<double*>(zcol);
+        double* wq1 = vq1 ? W + (size_t)cq1 * ld : const_cast<double*>(zcol);
+        const int np0 = vp0 ? cp0 : nodummy, np1 = vp1 ? cp1 : nodummy;
+        const int nq0 = vq0 ? cq0 : nodummy, nq1 = vq1 ? cq1 : nodummy;
         double x0[R], x1[R], y0[R], y1[R];
-        jreg_load<R>(wp0, vp0, lane, hr, x0);
-        jreg_load<R>(wp1, vp1, lane, hr, x1);
-        jreg_load<R>(wq0, vq0, lane, hr, y0);
-        jreg_load<R>(wq1, vq1, lane, hr, y1);
-        double a0 = vp0 ? nrm[cp0] : 0.0, a1 = vp1 ? nrm[cp1] : 0.0;
-        double b0 = vq0 ? nrm[cq0] : 0.0, b1 = vq1 ? nrm[cq1] : 0.0;
+        jreg_load<JG, R>(wp0, lane, x0);
+        jreg_load<JG, R>(wp1, lane, x1);
+        jreg_load<JG, R>(wq0, lane, y0);
+        jreg_load<JG, R>(wq1, lane, y1);
+        double a0 = nrm[np0], a1 = nrm[np1], b0 = nrm[nq0], b1 = nrm[nq1];
         int r00, r11, r01, r10;
-        jreg_rotate2<R>(x0, y0, a0, b0, x1, y1, a1, b1, r00, r11);
-        jreg_rotate2<R>(x0, y1, a0, b1, x1, y0, a1, b0, r01, r10);
+        jreg_rotate2<JG, R>(lane, x0, y0, a0, b0, x1, y1, a1, b1, r00, r11);
+        jreg_rotate2<JG, R>(lane, x0, y1, a0, b1, x1, y0, a1, b0, r01, r10);
+        // a column that rotated is a real column (missing ones have zero norm): unpredicated stores
         if ((r00 | r01) & 2) {
-          jreg_store<R>(wp0, vp0, lane, hr, x0);
-          if (lane == 0 && vp0) nrm[cp0] = a0;
+          jreg_store<JG, R>(wp0, lane, x0);
+          if (lane == 0) nrm[np0] = a0;
         }
         if ((r11 | r10) & 2) {
-          jreg_store<R>(wp1, vp1, lane, hr, x1);
-          if (lane == 0 && vp1) nrm[cp1] = a1;
+          jreg_store<JG, R>(wp1, lane, x1);
+          if (lane == 0) nrm[np1] = a1;
         }
         if ((r00 | r10) & 2) {
-          jreg_store<R>(wq0, vq0, lane, hr, y0);
-          if (lane == 0 && vq0) nrm[cq0] = b0;
+          jreg_store<JG, R>(wq0, lane, y0);
+          if (lane == 0) nrm[nq0] = b0;
         }
         if ((r11 | r01) & 2) {
-          jreg_store<R>(wq1, vq1, lane, hr, y1);
-          if (lane == 0 && vq1) nrm[cq1] = b1;
+          jreg_store<JG, R>(wq1, lane, y1);
+          if (lane == 0) nrm[nq1] = b1;
         }
         notconv |= (r00 | r11 | r01 | r10) & 1;
       }
@@ -568,13 +602,18 @@ SMRT_DEV int block_jacobi_svd_reg(double* W, int ld, int h, double* nrm) {
   return sweeps;
 }
 
-// dispatch on the number of rows per lane: 8 lanes x R rows cover hr <= 8 R
-SMRT_DEV int block_jacobi_svd_fast(double* W, int ld, int h, double* nrm) {
-  const int hr = (h + 1) & ~1;
-  if (hr <= 16) return block_jacobi_svd_reg<2>(W, ld, h, nrm);
-  if (hr <= 32) return block_jacobi_svd_reg<4>(W, ld, h, nrm);
-  if (hr <= 48) return block_jacobi_svd_reg<6>(W, ld, h, nrm);
-  return block_jacobi_svd_reg<8>(W, ld, h, nrm);
+// dispatch on the lanes per group (8 or 16) and the rows per lane: JG x R covers the padded rows of the operand
+SMRT_DEV int block_jacobi_svd_fast(double* W, int ld, int h, double* nrm, const double* zcol, int jg = 8) {
+  if (jg == 16) {
+    if (ld <= 18) return block_jacobi_svd_reg<16, 1>(W, ld, h, nrm, zcol);
+    if (ld <= 34) return block_jacobi_svd_reg<16, 2>(W, ld, h, nrm, zcol);
+    if (ld <= 50) return block_jacobi_svd_reg<16, 3>(W, ld, h, nrm, zcol);
+    return block_jacobi_svd_reg<16, 4>(W, ld, h, nrm, zcol);
+  }
+  if (ld <= 18) return block_jacobi_svd_reg<8, 2>(W, ld, h, nrm, zcol);
+  if (ld <= 34) return block_jacobi_svd_reg<8, 4>(W, ld, h, nrm, zcol);
+  if (ld <= 50) return block_jacobi_svd_reg<8, 6>(W, ld, h, nrm, zcol);
+  return block_jacobi_svd_reg<8, 8>(W, ld, h, nrm, zcol);
 }
 
 // ------------------------------------------------------------------------------- triangular solve C^T Z = W, in place

@@ -134,6 +134,7 @@ void __threadfence();
 void smrt_named_barrier(int id, int nthreads);
 
 uint64_t simt_shfl_raw(unsigned mask, uint64_t v, int src_lane);
+int __any_sync(unsigned mask, int pred);
 
 template <typename T>
 inline T __shfl_sync(unsigned mask, T v, int src_lane, int width = 32) {

@@ -97,12 +97,13 @@ int emu_jacobi(double* W, int h, int threads) {
   return sweeps;
 }
 
-// register-blocked variant (h <= 64): W column-major with even leading dimension ld >= h, pad row zero
+// register-blocked variant (h <= 64): W column-major with leading dimension emu_jacobi_ld(h), rows >= h zero
+int emu_jacobi_ld(int h) { return jacobi_ld(h); }
 int emu_jacobi_fast(double* W, int h, int ld, int threads) {
   int sweeps = 0;
-  std::vector<double> nrm(h + 8, 0.0);
+  std::vector<double> nrm(h + 8, 0.0), zcol(64, 0.0);
   simt::launch(1, (unsigned)threads, [&]() {
-    int s = block_jacobi_svd_fast(W, ld, h, nrm.data());
+    int s = block_jacobi_svd_fast(W, ld, h, nrm.data(), zcol.data());
     if (threadIdx.x == 0) sweeps = s;
   });
   return sweeps;

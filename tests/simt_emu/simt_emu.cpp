@@ -113,6 +113,23 @@ uint64_t simt_shfl_raw(unsigned mask, uint64_t v, int src_lane) {
   return out;
 }
 
+int __any_sync(unsigned mask, int pred) {
+  int lane = threadIdx.x & 31;
+  if (!(mask & (1u << lane))) {
+    std::fprintf(stderr, "simt: lane %d votes with mask %08x that excludes it\n", lane, mask);
+    std::abort();
+  }
+  auto* g = simt::group_of(threadIdx.x >> 5, mask);
+  g->mailbox[lane] = pred ? 1 : 0;
+  pthread_barrier_wait(&g->bar);
+  int any = 0;
+  int nlanes = simt::g_block->nthreads - (int)((threadIdx.x >> 5) << 5);
+  for (int l = 0; l < 32 && l < nlanes; ++l)
+    if (mask & (1u << l)) any |= (int)g->mailbox[l];
+  pthread_barrier_wait(&g->bar);
+  return any;
+}
+
 int __syncthreads_or(int pred) {
   static std::atomic<int> flag{0};
   __syncthreads();

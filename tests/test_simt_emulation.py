@@ -138,7 +138,8 @@ def test_register_blocked_jacobi_device_function(h, threads, kind):
         M = (Q1 * sv) @ Q2.T
     else:
         M = np.diag(rng.uniform(1, 11, h)) + 1e-3 * rng.normal(size=(h, h))
-    ld = (h + 1) & ~1
+    ld = lib.emu_jacobi_ld(h)
+    assert ld % 2 == 0 and ld >= h
     W = np.zeros((ld, h), order="F")
     W[:h, :] = M
     sweeps = lib.emu_jacobi_fast(W.ctypes.data_as(C.POINTER(C.c_double)), h, ld, threads)
