@@ -397,10 +397,14 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
 SMRT_HD size_t boundary_vec_doubles(int n, int hmax) {
   return ((size_t)3 * n + 10 * hmax + 13 * SMRT_MAX_INC + hmax /* two int arrays */ + SMRT_MAX_INC + 16 + 1) & ~(size_t)1;
 }
-// matrix region: BF, BG (compact), BR (ld odd), T = [left | right | rhs] (ld odd), btop, svec, ytr, vvec
+// matrix region: BF, BG (compact), scratch of the blocked Gauss-Jordan (V, TP, reciprocal pivots), BR (ld odd),
+// T = [left | right | rhs] (ld odd), btop, svec, ytr, vvec
+SMRT_HD size_t boundary_gj_doubles(int hmax, int nrhs_max) {
+  return (size_t)SMRT_GJ_NB * hmax + (size_t)SMRT_GJ_NB * ((2 * hmax + nrhs_max + 2) & ~1) + ((hmax + 1) & ~1);
+}
 SMRT_HD size_t boundary_mat_doubles(int hmax, int nrhs_max) {
-  return (size_t)2 * (((size_t)hmax * hmax + 1) & ~(size_t)1) + (size_t)hmax * (hmax + 1) +
-         (size_t)(hmax + 1) * (2 * hmax + nrhs_max) + 4 * (size_t)hmax * nrhs_max + 16;
+  return (size_t)2 * (((size_t)hmax * hmax + 1) & ~(size_t)1) + boundary_gj_doubles(hmax, nrhs_max) +
+         (size_t)hmax * (hmax + 1) + (size_t)(hmax + 1) * (2 * hmax + nrhs_max) + 4 * (size_t)hmax * nrhs_max + 16;
 }
 
 struct BoundaryCtx {
@@ -451,7 +455,10 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
   const size_t szr = (size_t)hmax * nrhs_max;
   double* BF = mats;  // 16-byte aligned (vector loads of the layer records)
   double* BG = BF + szc;
-  double* BR = BG + szc;
+  double* GJV = BG + szc;                               // blocked Gauss-Jordan: V (h x 8), 16-byte aligned
+  double* GJTP = GJV + (size_t)SMRT_GJ_NB * hmax;       // ... old pivot rows (8 x Wp), 16-byte aligned
+  double* pivinv = GJTP + (size_t)SMRT_GJ_NB * ((2 * hmax + nrhs_max + 2) & ~1);  // ... reciprocal pivots
+  double* BR = BG + szc + boundary_gj_doubles(hmax, nrhs_max);
   double* TT = BR + szp;  // h x (2h + nrhs), ld = ldp
   double* btop = TT + (size_t)(hmax + 1) * (2 * hmax + nrhs_max);
   double* svec = btop + szr;
@@ -732,11 +739,15 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
           __syncthreads();
         }
         // [A21 | A22 | b_bot] -> [I | Y22 | Yr] (implicit row permutation, unscaled rows)
-        if (block_gj_rows(TT, ldp, h, 2 * h + nr, rowstep, rowof)) {
+        const bool blocked = h <= 64;  // panel-blocked elimination (register tiles); larger blocks: one step at a time
+        if (blocked ? block_gj_rows_blocked(TT, ldp, TT + (size_t)h * ldp, ldp, h, h + nr, rowof, pivinv, GJV, GJTP,
+                                            &s_ctrl[6])
+                    : block_gj_rows(TT, ldp, h, 2 * h + nr, rowstep, rowof)) {
           failed = true;
           break;
         }
-        for (int k = tid; k < h; k += NT) ipiv[k] = tvec[k] / SMRT_AT(TT, ldp, rowof[k], k);
+        for (int k = tid; k < h; k += NT)
+          ipiv[k] = blocked ? tvec[k] * pivinv[k] : tvec[k] / SMRT_AT(TT, ldp, rowof[k], k);
         __syncthreads();
         // Y~ = diag(t) Y22 -> left block of T ;  y~r = diag(t) Yr -> ytr
         SMRT_FOR_2D(k, c, h, h) { SMRT_AT(TT, ldp, k, c) = SMRT_AT(TT, ldp, rowof[k], h + c) * ipiv[k]; }
@@ -744,11 +755,20 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
         __syncthreads();
         // P = F - G Y~, K = G - F Y~ ;  Schur S = D P - Rt K -> right block of T ;  K -> BR
         double* TS = TT + (size_t)h * ldp;
+        // (blocked path, l > 0: S and K are stored TRANSPOSED, so that R_new = K S^-1 = (S^-T K^T)^T comes out of the
+        // same row elimination as above)
+        const bool transposed = blocked && l > 0;
         block_gemm_dual(gemm_thr, h, h, h, BG, BF, h, TT, ldp, [&](int i, int j, double c1, double c2) {
           double pv = SMRT_AT(BF, h, i, j) - c1;
           double kv = SMRT_AT(BG, h, i, j) - c2;
-          SMRT_AT(TS, ldp, i, j) = Dsg[i] * pv - Rt[i] * kv;
-          SMRT_AT(BR, ldp, i, j) = kv;
+          double sv = Dsg[i] * pv - Rt[i] * kv;
+          if (transposed) {
+            SMRT_AT(TS, ldp, j, i) = sv;
+            SMRT_AT(BR, ldp, j, i) = kv;
+          } else {
+            SMRT_AT(TS, ldp, i, j) = sv;
+            SMRT_AT(BR, ldp, i, j) = kv;
+          }
         });
         // v = F y~r ;  b' = b_top - D (G y~r) + Rt v  (b' goes next to S, in the augmented columns)
         if (nr > 0) {
@@ -774,14 +794,23 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
         if (l > 0) {
           // keep b' (the column elimination below does not touch the augmented columns)
           // R_new = K S^-1 by column elimination of [S; K]
-          if (block_gj_cols(TS, ldp, BR, ldp, h, h, rowstep, rowof)) {
-            failed = true;
-            break;
+          if (transposed) {
+            // [S^T | K^T] -> rows of S^-T K^T = columns of R_new
+            if (block_gj_rows_blocked(TS, ldp, BR, ldp, h, h, rowof, pivinv, GJV, GJTP, &s_ctrl[6])) {
+              failed = true;
+              break;
+            }
+            SMRT_FOR_2D(i, k, h, h) { SMRT_AT(TT, ldp, i, k) = SMRT_AT(BR, ldp, rowof[k], i) * pivinv[k]; }
+          } else {
+            if (block_gj_cols(TS, ldp, BR, ldp, h, h, rowstep, rowof)) {
+              failed = true;
+              break;
+            }
+            for (int k = tid; k < h; k += NT) ipiv[k] = 1.0 / SMRT_AT(TS, ldp, k, rowof[k]);
+            __syncthreads();
+            // un-permute / scale through the (dead) left block of T, then back into BR
+            SMRT_FOR_2D(i, k, h, h) { SMRT_AT(TT, ldp, i, k) = SMRT_AT(BR, ldp, i, rowof[k]) * ipiv[k]; }
           }
-          for (int k = tid; k < h; k += NT) ipiv[k] = 1.0 / SMRT_AT(TS, ldp, k, rowof[k]);
-          __syncthreads();
-          // un-permute / scale through the (dead) left block of T, then back into BR
-          SMRT_FOR_2D(i, k, h, h) { SMRT_AT(TT, ldp, i, k) = SMRT_AT(BR, ldp, i, rowof[k]) * ipiv[k]; }
           __syncthreads();
           SMRT_FOR_2D(i, k, h, h) { SMRT_AT(BR, ldp, i, k) = SMRT_AT(TT, ldp, i, k); }
           __syncthreads();
@@ -797,11 +826,12 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
           __syncthreads();
         } else {
           // top layer: z = S^-1 b' by row elimination of [S | b'], then s = v + K z
-          if (block_gj_rows(TS, ldp, h, h + nr, rowstep, rowof)) {
+          if (blocked ? block_gj_rows_blocked(TS, ldp, Trhs, ldp, h, nr, rowof, pivinv, GJV, GJTP, &s_ctrl[6])
+                      : block_gj_rows(TS, ldp, h, h + nr, rowstep, rowof)) {
             failed = true;
             break;
           }
-          for (int k = tid; k < h; k += NT) ipiv[k] = 1.0 / SMRT_AT(TS, ldp, rowof[k], k);
+          for (int k = tid; k < h; k += NT) ipiv[k] = blocked ? pivinv[k] : 1.0 / SMRT_AT(TS, ldp, rowof[k], k);
           __syncthreads();
           SMRT_FOR_2D(k, c, h, nr) { SMRT_AT(ytr, h, k, c) = SMRT_AT(Trhs, ldp, rowof[k], c) * ipiv[k]; }
           __syncthreads();

@@ -135,6 +135,14 @@ void smrt_named_barrier(int id, int nthreads);
 
 uint64_t simt_shfl_raw(unsigned mask, uint64_t v, int src_lane);
 int __any_sync(unsigned mask, int pred);
+unsigned __ballot_sync(unsigned mask, int pred);
+unsigned __reduce_max_sync(unsigned mask, unsigned v);
+inline int __ffs(int v) { return __builtin_ffs(v); }
+inline int __double2hiint(double v) {
+  uint64_t b;
+  std::memcpy(&b, &v, 8);
+  return (int)(b >> 32);
+}
 
 template <typename T>
 inline T __shfl_sync(unsigned mask, T v, int src_lane, int width = 32) {

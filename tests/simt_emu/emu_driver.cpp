@@ -108,4 +108,19 @@ int emu_jacobi_fast(double* W, int h, int ld, int threads) {
   });
   return sweeps;
 }
+
+// blocked Gauss-Jordan: X = A^-1 R for column-major A (h x h, ld = h) and R (h x nR, ld = h); returns the failure flag
+int emu_gj_blocked(double* A, int h, double* R, int nR, int threads, double* X) {
+  std::vector<int> rowof(h, -1), flag(1, 0);
+  std::vector<double> ipiv(h, 0.0), Vbuf((size_t)h * SMRT_GJ_NB + 8, 0.0), TP((size_t)SMRT_GJ_NB * (h + nR + 2), 0.0);
+  int rc = 0;
+  simt::launch(1, (unsigned)threads, [&]() {
+    int r = block_gj_rows_blocked(A, h, R, h, h, nR, rowof.data(), ipiv.data(), Vbuf.data(), TP.data(), flag.data());
+    if (threadIdx.x == 0) rc = r;
+  });
+  if (rc == 0)
+    for (int k = 0; k < h; ++k)
+      for (int c = 0; c < nR; ++c) X[(size_t)c * h + k] = R[(size_t)c * h + rowof[k]] * ipiv[k];
+  return rc;
+}
 }

@@ -2,6 +2,7 @@
 // One OS thread per CUDA thread, one block at a time; barriers are pthread barriers.
 #include "simt.h"
 
+#include <algorithm>
 #include <memory>
 
 thread_local simt_dim3 threadIdx;
@@ -128,6 +129,30 @@ int __any_sync(unsigned mask, int pred) {
     if (mask & (1u << l)) any |= (int)g->mailbox[l];
   pthread_barrier_wait(&g->bar);
   return any;
+}
+
+unsigned __ballot_sync(unsigned mask, int pred) {
+  int lane = threadIdx.x & 31;
+  auto* g = simt::group_of(threadIdx.x >> 5, mask);
+  g->mailbox[lane] = pred ? 1 : 0;
+  pthread_barrier_wait(&g->bar);
+  unsigned out = 0;
+  for (int l = 0; l < 32; ++l)
+    if ((mask & (1u << l)) && g->mailbox[l]) out |= 1u << l;
+  pthread_barrier_wait(&g->bar);
+  return out;
+}
+
+unsigned __reduce_max_sync(unsigned mask, unsigned v) {
+  int lane = threadIdx.x & 31;
+  auto* g = simt::group_of(threadIdx.x >> 5, mask);
+  g->mailbox[lane] = v;
+  pthread_barrier_wait(&g->bar);
+  unsigned out = 0;
+  for (int l = 0; l < 32; ++l)
+    if (mask & (1u << l)) out = std::max(out, (unsigned)g->mailbox[l]);
+  pthread_barrier_wait(&g->bar);
+  return out;
 }
 
 int __syncthreads_or(int pred) {

@@ -153,3 +153,32 @@ def test_register_blocked_jacobi_device_function(h, threads, kind):
     # W = M V with V orthogonal: M^-1 W must be orthogonal
     V = np.linalg.solve(M, Wh)
     assert np.abs(V.T @ V - np.eye(h)).max() < 1e-11
+
+
+@pytest.mark.parametrize("h,nR,threads", [(5, 3, 64), (16, 17, 64), (33, 34, 128), (44, 45, 256), (64, 65, 512),
+                                          (64, 64, 128), (47, 1, 64)])
+def test_blocked_gauss_jordan_device_function(h, nR, threads):
+    """block_gj_rows_blocked (panel of 8 columns factorised in registers by one warp, rank-8 updates by register
+    tiles): A^-1 R against LAPACK, on matrices that need row interchanges"""
+    lib = emu_lib()
+    rng = np.random.default_rng(7 * h + nR)
+    A = rng.normal(size=(h, h))
+    A[rng.permutation(h), np.arange(h)] += 3.0   # large entries off the diagonal: pivoting is exercised
+    R = rng.normal(size=(h, nR))
+    Ac, Rc = np.asfortranarray(A.copy()), np.asfortranarray(R.copy())
+    X = np.zeros((h, nR), order="F")
+    P = C.POINTER(C.c_double)
+    rc = lib.emu_gj_blocked(Ac.ctypes.data_as(P), h, Rc.ctypes.data_as(P), nR, threads, X.ctypes.data_as(P))
+    assert rc == 0
+    ref = np.linalg.solve(A, R)
+    assert np.abs(X - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()) * np.linalg.cond(A)
+
+
+def test_blocked_gauss_jordan_reports_singular_matrix():
+    lib = emu_lib()
+    h, nR = 24, 4
+    A = np.asfortranarray(np.ones((h, h)))
+    R = np.asfortranarray(np.ones((h, nR)))
+    X = np.zeros((h, nR), order="F")
+    P = C.POINTER(C.c_double)
+    assert lib.emu_gj_blocked(A.ctypes.data_as(P), h, R.ctypes.data_as(P), nR, 64, X.ctypes.data_as(P)) == 1
