@@ -397,10 +397,11 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
 SMRT_HD size_t boundary_vec_doubles(int n, int hmax) {
   return ((size_t)3 * n + 10 * hmax + 13 * SMRT_MAX_INC + hmax /* two int arrays */ + SMRT_MAX_INC + 16 + 1) & ~(size_t)1;
 }
-// matrix region: BF, BG (compact), scratch of the blocked Gauss-Jordan (V, TP, reciprocal pivots), BR (ld odd),
+// matrix region: BF, BG (compact), scratch of the blocked Gauss-Jordan (V, reciprocal pivots), BR (ld odd),
 // T = [left | right | rhs] (ld odd), btop, svec, ytr, vvec
 SMRT_HD size_t boundary_gj_doubles(int hmax, int nrhs_max) {
-  return (size_t)SMRT_GJ_NB * hmax + (size_t)SMRT_GJ_NB * ((2 * hmax + nrhs_max + 2) & ~1) + ((hmax + 1) & ~1);
+  (void)nrhs_max;
+  return (size_t)2 * SMRT_GJ_NB * hmax + ((hmax + 1) & ~1);  // V (double buffered), reciprocal pivots
 }
 SMRT_HD size_t boundary_mat_doubles(int hmax, int nrhs_max) {
   return (size_t)2 * (((size_t)hmax * hmax + 1) & ~(size_t)1) + boundary_gj_doubles(hmax, nrhs_max) +
@@ -414,8 +415,8 @@ struct BoundaryCtx {
   cplx eps_star;
 };
 
-template <bool kGlobalScratch>
-SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
+template <bool kGlobalScratch, int kMaxThreads>
+SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
   SMRT_DYN_SMEM(smem);
   SMRT_SHARED int s_item;
   SMRT_SHARED int s_ctrl[8];
@@ -455,9 +456,8 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
   const size_t szr = (size_t)hmax * nrhs_max;
   double* BF = mats;  // 16-byte aligned (vector loads of the layer records)
   double* BG = BF + szc;
-  double* GJV = BG + szc;                               // blocked Gauss-Jordan: V (h x 8), 16-byte aligned
-  double* GJTP = GJV + (size_t)SMRT_GJ_NB * hmax;       // ... old pivot rows (8 x Wp), 16-byte aligned
-  double* pivinv = GJTP + (size_t)SMRT_GJ_NB * ((2 * hmax + nrhs_max + 2) & ~1);  // ... reciprocal pivots
+  double* GJV = BG + szc;                                  // blocked Gauss-Jordan: V (2 x h x 8)
+  double* pivinv = GJV + (size_t)2 * SMRT_GJ_NB * hmax;    // ... reciprocal pivots
   double* BR = BG + szc + boundary_gj_doubles(hmax, nrhs_max);
   double* TT = BR + szp;  // h x (2h + nrhs), ld = ldp
   double* btop = TT + (size_t)(hmax + 1) * (2 * hmax + nrhs_max);
@@ -740,7 +740,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
         }
         // [A21 | A22 | b_bot] -> [I | Y22 | Yr] (implicit row permutation, unscaled rows)
         const bool blocked = h <= 64;  // panel-blocked elimination (register tiles); larger blocks: one step at a time
-        if (blocked ? block_gj_rows_blocked(TT, ldp, TT + (size_t)h * ldp, ldp, h, h + nr, rowof, pivinv, GJV, GJTP,
+        if (blocked ? block_gj_rows_blocked(TT, ldp, TT + (size_t)h * ldp, ldp, h, h + nr, rowof, pivinv, GJV,
                                             &s_ctrl[6])
                     : block_gj_rows(TT, ldp, h, 2 * h + nr, rowstep, rowof)) {
           failed = true;
@@ -796,7 +796,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
           // R_new = K S^-1 by column elimination of [S; K]
           if (transposed) {
             // [S^T | K^T] -> rows of S^-T K^T = columns of R_new
-            if (block_gj_rows_blocked(TS, ldp, BR, ldp, h, h, rowof, pivinv, GJV, GJTP, &s_ctrl[6])) {
+            if (block_gj_rows_blocked(TS, ldp, BR, ldp, h, h, rowof, pivinv, GJV, &s_ctrl[6])) {
               failed = true;
               break;
             }
@@ -826,7 +826,7 @@ SMRT_GLOBAL void __launch_bounds__(SMRT_NT_B) boundary_kernel(KArgs A) {
           __syncthreads();
         } else {
           // top layer: z = S^-1 b' by row elimination of [S | b'], then s = v + K z
-          if (blocked ? block_gj_rows_blocked(TS, ldp, Trhs, ldp, h, nr, rowof, pivinv, GJV, GJTP, &s_ctrl[6])
+          if (blocked ? block_gj_rows_blocked(TS, ldp, Trhs, ldp, h, nr, rowof, pivinv, GJV, &s_ctrl[6])
                       : block_gj_rows(TS, ldp, h, h + nr, rowstep, rowof)) {
             failed = true;
             break;

@@ -1228,40 +1228,47 @@ SMRT_DEV int block_gj_rows_lookahead(double* Lb, int ldl, double* Rb, int ldr, i
 // BLOCKED Gauss-Jordan by rows with partial pivoting (h <= 64).  The unblocked eliminations above rewrite the whole
 // trailing matrix at every step (one FMA per shared-memory load + store: the boundary kernel spent 60 % of its time
 // there at 13 % FP64 utilisation).  Here the steps are grouped in panels of SMRT_GJ_NB columns:
-//   1. warp 0 factorises the panel with its columns in REGISTERS (lanes along rows, pivot search by a REDUX on the
-//      exponent / leading mantissa bits, pivot row broadcast by shuffles) and builds V (h x nb) such that the nb
-//      elimination steps applied to any other column x amount to  x <- x + V x[P]  (P = the panel's pivot rows, old
-//      values).  Derivation: every step is G_k = I + m_k e_{p_k}^T, so G_nb ... G_1 differs from I only in the columns
-//      P, and V(:, k) = (G e_{p_k} - e_{p_k}) obeys the same update rule as an ordinary column, starting from m_k.
-//   2. all warps gather TP = T[P, c] for the remaining columns c, then
-//   3. apply the rank-nb update with a 4-row x 2-column register tile per thread, V held in registers for the whole
-//      panel: nb FMAs per shared-memory load + store of an element.
+//   1. warp 0 factorises the panel with its columns in REGISTERS (lanes along rows; the pivot is found by ONE REDUX on
+//      a key packing the exponent / leading mantissa bits with the lane number; the pivot row is broadcast by shuffles;
+//      the reciprocal comes from a MUFU seed + two Newton steps; straight-line code for the 8 steps, the singularity
+//      test is deferred to the end of the panel) and builds V (h x nb) such that the nb elimination steps applied to
+//      any other column x amount to  x <- x + V x[P]  (P = the panel's pivot rows, old values).  Derivation: every
+//      step is G_k = I + m_k e_{p_k}^T, so G_nb ... G_1 differs from I only in the columns P, and
+//      V(:, k) = G e_{p_k} - e_{p_k} obeys the same update rule as an ordinary column, starting from m_k.
+//   2. the rank-nb update of a column is done by one half-warp (lanes along rows, 4 rows per lane, V held in
+//      registers for the whole panel): it reads the old pivot-row entries of its column, then rewrites the column:
+//      nb FMAs per shared-memory load + store of an element.
+//   3. look-ahead: warp 0 updates the columns of the NEXT panel first and factorises it while the other warps update
+//      the remaining columns: one block barrier per panel, and the (serial) panel factorisations are the only
+//      critical path.
 // Same conventions as block_gj_rows_la: two column blocks (left: the h x h system, right: nR further columns), implicit
 // row permutation, unscaled rows:  (A^-1 R)(k, :) = R(rowof[k], :) * ipiv[k].  The left block is destroyed.
-// Scratch (block-shared): Vbuf double[h * SMRT_GJ_NB], TP double[SMRT_GJ_NB * Wp] with Wp = (h + nR + 1) & ~1 (16-byte
-// aligned), rowof int[h], ipiv double[h], flag int[1].  Returns 1 in every thread if a pivot vanishes / is not finite.
+// Scratch (block-shared): Vbuf double[2 * h * SMRT_GJ_NB], rowof int[h], ipiv double[h], flag int[1].
+// Returns 1 in every thread if a pivot vanishes / is not finite.  blockDim.x >= 64.
 // =====================================================================================================================
 #define SMRT_GJ_NB 8
 
-template <int RPL>
+template <int RPL, bool FULL>
 SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int j0, int npc, unsigned& used, int lane,
-                            int* rowof, double* ipiv, double* Vbuf, int* flag) {
+                            int* rowof, double* ipiv, double* SMRT_RESTRICT Vout, int* flag) {
   double pc[RPL][SMRT_GJ_NB], v[RPL][SMRT_GJ_NB];
 #pragma unroll
   for (int u = 0; u < RPL; ++u) {
     const int row = lane + 32 * u;
 #pragma unroll
     for (int c = 0; c < SMRT_GJ_NB; ++c) {
-      pc[u][c] = (row < h && c < npc) ? Lb[(size_t)(j0 + c) * ldl + row] : 0.0;
+      pc[u][c] = (row < h && (FULL || c < npc)) ? Lb[(size_t)(j0 + c) * ldl + row] : 0.0;
       v[u][c] = 0.0;
     }
   }
+  bool bad = false;
 #pragma unroll
   for (int k = 0; k < SMRT_GJ_NB; ++k) {
-    if (k < npc) {  // uniform
-      // pivot: largest |value| of column k among the rows not used yet; the comparison key is the high word of the
-      // double (sign-free exponent + 20 mantissa bits): any element within 2^-20 of the maximum is as good a pivot
-      double bv = -1.0;
+    if (FULL || k < npc) {  // uniform
+      // pivot: largest |value| of column k among the rows not used yet.  Key = high word of |value| (exponent + 20
+      // mantissa bits) with the 5 low bits replaced by 31 - lane: one REDUX gives the maximum and its (lowest) lane;
+      // any element within 2^-15 of the maximum is as good a pivot
+      double bv = -1.0, mine = 0.0;
       int bu = 0;
 #pragma unroll
       for (int u = 0; u < RPL; ++u) {
@@ -1269,22 +1276,18 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
         if ((lane + 32 * u) < h && !((used >> u) & 1u) && a > bv) {
           bv = a;
           bu = u;
+          mine = pc[u][k];
         }
       }
-      const unsigned key = (bv >= 0.0) ? (unsigned)__double2hiint(bv) + 1u : 0u;
+      const unsigned key = (bv >= 0.0) ? (((unsigned)__double2hiint(bv) & ~31u) | (unsigned)(31 - lane)) : 0u;
       const unsigned mx = __reduce_max_sync(0xffffffffu, key);
-      const unsigned bal = __ballot_sync(0xffffffffu, key == mx);
-      const int pl = __ffs((int)bal) - 1;
+      const int pl = 31 - (int)(mx & 31u);
       const int pu = __shfl_sync(0xffffffffu, bu, pl, 32);
-      double mine = pc[0][k];
-#pragma unroll
-      for (int u = 1; u < RPL; ++u) mine = (pu == u) ? pc[u][k] : mine;
       const double pv = __shfl_sync(0xffffffffu, mine, pl, 32);
-      if (mx == 0u || !(fabs(pv) > 0.0) || !(fabs(pv) < 1e300)) {  // identical in every lane
-        if (lane == 0) *flag = 1;
-        return;
-      }
-      const double inv = 1.0 / pv;
+      bad = bad || !(fabs(pv) > 0.0) || !(fabs(pv) < 1e300);
+      double inv = smrt_rcp_approx(pv);
+      inv = fma(inv, fma(-pv, inv, 1.0), inv);
+      inv = fma(inv, fma(-pv, inv, 1.0), inv);
       if (lane == 0) {
         rowof[j0 + k] = pl + 32 * pu;
         ipiv[j0 + k] = inv;
@@ -1295,7 +1298,7 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
       for (int u = 0; u < RPL; ++u) m[u] = (lane == pl && u == pu) ? 0.0 : -(pc[u][k] * inv);
 #pragma unroll
       for (int c = k + 1; c < SMRT_GJ_NB; ++c) {
-        if (c < npc) {
+        if (FULL || c < npc) {
           double sel = pc[0][c];
 #pragma unroll
           for (int u = 1; u < RPL; ++u) sel = (pu == u) ? pc[u][c] : sel;
@@ -1317,100 +1320,114 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
       for (int u = 0; u < RPL; ++u) v[u][k] = m[u];
     }
   }
+  if (bad && lane == 0) *flag = 1;
 #pragma unroll
   for (int u = 0; u < RPL; ++u) {
     const int row = lane + 32 * u;
     if (row < h) {
 #pragma unroll
-      for (int c = 0; c < SMRT_GJ_NB; ++c) Vbuf[(size_t)c * h + row] = v[u][c];
+      for (int c = 0; c < SMRT_GJ_NB; ++c) Vout[(size_t)c * h + row] = v[u][c];
     }
   }
 }
+SMRT_DEV void gj_panel_dispatch(const double* Lb, int ldl, int h, int j0, int npc, unsigned& used, int lane, int* rowof,
+                                double* ipiv, double* Vout, int* flag) {
+  if (h <= 32) {
+    if (npc == SMRT_GJ_NB)
+      gj_panel_warp<1, true>(Lb, ldl, h, j0, npc, used, lane, rowof, ipiv, Vout, flag);
+    else
+      gj_panel_warp<1, false>(Lb, ldl, h, j0, npc, used, lane, rowof, ipiv, Vout, flag);
+  } else {
+    if (npc == SMRT_GJ_NB)
+      gj_panel_warp<2, true>(Lb, ldl, h, j0, npc, used, lane, rowof, ipiv, Vout, flag);
+    else
+      gj_panel_warp<2, false>(Lb, ldl, h, j0, npc, used, lane, rowof, ipiv, Vout, flag);
+  }
+}
 
-// rank-npc update of the columns [cstart, W): thread (lx = tid & 15, cg = tid >> 4) owns the rows lx + 16 u (u < RT) of
-// a pair of columns
+// rank-npc update  x <- x + V x[P]  of the columns c = cbeg + hw, cbeg + hw + nhw, ... < cend by half-warp number hw
+// (of nhw): lane lx owns the rows lx + 16 u (u < RT).  prow: the npc pivot rows of the panel.
 template <int RT>
-SMRT_DEV void gj_update_tile(double* Lb, int ldl, double* Rb, int ldr, int h, int W, int cstart, int npc,
-                             const double* SMRT_RESTRICT Vbuf, const double* SMRT_RESTRICT TP, int Wp) {
-  const int tid = threadIdx.x, NT = blockDim.x;
-  const int lx = tid & 15, cg = tid >> 4, ncg = NT >> 4;
+SMRT_DEV void gj_update_cols(double* Lb, int ldl, double* Rb, int ldr, int h, int cbeg, int cend, int hw, int nhw,
+                             int lx, int npc, const double* SMRT_RESTRICT Vin, const int* SMRT_RESTRICT prow) {
+  if (cbeg + hw >= cend) return;  // half-warp uniform
+  const unsigned hmask = 0xffffu << (16 * ((threadIdx.x >> 4) & 1));
   double Vr[RT][SMRT_GJ_NB];
+  int pr[SMRT_GJ_NB];
+#pragma unroll
+  for (int k = 0; k < SMRT_GJ_NB; ++k) pr[k] = (k < npc) ? prow[k] : 0;
 #pragma unroll
   for (int u = 0; u < RT; ++u) {
     const int row = lx + 16 * u;
 #pragma unroll
-    for (int k = 0; k < SMRT_GJ_NB; ++k) Vr[u][k] = (row < h && k < npc) ? Vbuf[(size_t)k * h + row] : 0.0;
+    for (int k = 0; k < SMRT_GJ_NB; ++k) Vr[u][k] = (row < h && k < npc) ? Vin[(size_t)k * h + row] : 0.0;
   }
-  for (int c2 = (cstart >> 1) + cg; 2 * c2 < W; c2 += ncg) {
-    const int c = 2 * c2;
-    const bool ok0 = c >= cstart, ok1 = c + 1 < W;
-    double* col0 = (c < h) ? Lb + (size_t)c * ldl : Rb + (size_t)(c - h) * ldr;
-    double* col1 = (c + 1 < h) ? Lb + (size_t)(c + 1) * ldl : Rb + (size_t)(c + 1 - h) * ldr;
-    double a0[RT], a1[RT];
+  for (int c = cbeg + hw; c < cend; c += nhw) {
+    double* col = (c < h) ? Lb + (size_t)c * ldl : Rb + (size_t)(c - h) * ldr;
+    double tp[SMRT_GJ_NB], acc[RT];
 #pragma unroll
-    for (int u = 0; u < RT; ++u) {
-      const int row = lx + 16 * u;
-      a0[u] = (ok0 && row < h) ? col0[row] : 0.0;
-      a1[u] = (ok1 && row < h) ? col1[row] : 0.0;
-    }
+    for (int k = 0; k < SMRT_GJ_NB; ++k) tp[k] = (k < npc) ? col[pr[k]] : 0.0;  // old pivot-row entries
 #pragma unroll
-    for (int k = 0; k < SMRT_GJ_NB; ++k) {
-      const double2 tp = *reinterpret_cast<const double2*>(TP + (size_t)k * Wp + c);
+    for (int u = 0; u < RT; ++u) acc[u] = (lx + 16 * u < h) ? col[lx + 16 * u] : 0.0;
+    __syncwarp(hmask);  // every lane of the half-warp has read the column before it is rewritten
 #pragma unroll
-      for (int u = 0; u < RT; ++u) {
-        a0[u] = fma(Vr[u][k], tp.x, a0[u]);
-        a1[u] = fma(Vr[u][k], tp.y, a1[u]);
-      }
-    }
+    for (int k = 0; k < SMRT_GJ_NB; ++k)
 #pragma unroll
-    for (int u = 0; u < RT; ++u) {
-      const int row = lx + 16 * u;
-      if (ok0 && row < h) col0[row] = a0[u];
-      if (ok1 && row < h) col1[row] = a1[u];
-    }
+      for (int u = 0; u < RT; ++u) acc[u] = fma(Vr[u][k], tp[k], acc[u]);
+#pragma unroll
+    for (int u = 0; u < RT; ++u)
+      if (lx + 16 * u < h) col[lx + 16 * u] = acc[u];
   }
+}
+SMRT_DEV void gj_update_dispatch(double* Lb, int ldl, double* Rb, int ldr, int h, int cbeg, int cend, int hw, int nhw,
+                                 int lx, int npc, const double* Vin, const int* prow) {
+  if (h <= 16)
+    gj_update_cols<1>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, prow);
+  else if (h <= 32)
+    gj_update_cols<2>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, prow);
+  else if (h <= 48)
+    gj_update_cols<3>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, prow);
+  else
+    gj_update_cols<4>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, prow);
 }
 
 SMRT_DEV int block_gj_rows_blocked(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowof, double* ipiv,
-                                   double* Vbuf, double* TP, int* flag) {
+                                   double* Vbuf, int* flag) {
   const int NT = blockDim.x, tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const int W = h + nR, Wp = (W + 1) & ~1;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
+  const int lx = tid & 15;
+  const int W = h + nR;
   unsigned used = 0u;  // warp 0: bit u = row lane + 32 u already served as a pivot
   if (tid == 0) *flag = 0;
-  // TP rows beyond the panel width are multiplied by V = 0 but must be finite
-  for (int e = tid; e < SMRT_GJ_NB * Wp; e += NT) TP[e] = 0.0;
   __syncthreads();
-  for (int j0 = 0; j0 < h; j0 += SMRT_GJ_NB) {
-    const int npc = (h - j0 < SMRT_GJ_NB) ? (h - j0) : SMRT_GJ_NB;
-    if (warp == 0) {
-      if (h <= 32)
-        gj_panel_warp<1>(Lb, ldl, h, j0, npc, used, lane, rowof, ipiv, Vbuf, flag);
-      else
-        gj_panel_warp<2>(Lb, ldl, h, j0, npc, used, lane, rowof, ipiv, Vbuf, flag);
-    }
-    __syncthreads();
+  if (warp == 0) gj_panel_dispatch(Lb, ldl, h, 0, (h < SMRT_GJ_NB) ? h : SMRT_GJ_NB, used, lane, rowof, ipiv, Vbuf, flag);
+  __syncthreads();
+  int buf = 0;
+  for (int j0 = 0; j0 < h; j0 += SMRT_GJ_NB, buf ^= 1) {
     if (*flag) return 1;
+    const int npc = (h - j0 < SMRT_GJ_NB) ? (h - j0) : SMRT_GJ_NB;
     const int cstart = j0 + npc;
-    // old values of the pivot rows in the columns still to be updated
-    {
-      const int ncols = W - cstart;
-      for (int e = tid; e < npc * ncols; e += NT) {
-        const int k = e / ncols, c = cstart + e % ncols;
-        const double* col = (c < h) ? Lb + (size_t)c * ldl : Rb + (size_t)(c - h) * ldr;
-        TP[(size_t)k * Wp + c] = col[rowof[j0 + k]];
+    const double* Vin = Vbuf + (size_t)buf * h * SMRT_GJ_NB;
+    const int* prow = rowof + j0;
+    const bool more = cstart < h;
+    const int npn = more ? ((h - cstart < SMRT_GJ_NB) ? (h - cstart) : SMRT_GJ_NB) : 0;  // width of the next panel
+    if (warp == 0) {
+      // look-ahead: bring the next panel up to date, then factorise it while the other warps update the rest
+      if (more) {
+        gj_update_dispatch(Lb, ldl, Rb, ldr, h, cstart, cstart + npn, (tid >> 4) & 1, 2, lx, npc, Vin, prow);
+        __syncwarp();
+        gj_panel_dispatch(Lb, ldl, h, cstart, npn, used, lane, rowof, ipiv, Vbuf + (size_t)(buf ^ 1) * h * SMRT_GJ_NB,
+                          flag);
+      } else if (nwarp == 1) {
+        gj_update_dispatch(Lb, ldl, Rb, ldr, h, cstart, W, (tid >> 4) & 1, 2, lx, npc, Vin, prow);
       }
     }
-    __syncthreads();
-    if (h <= 16)
-      gj_update_tile<1>(Lb, ldl, Rb, ldr, h, W, cstart, npc, Vbuf, TP, Wp);
-    else if (h <= 32)
-      gj_update_tile<2>(Lb, ldl, Rb, ldr, h, W, cstart, npc, Vbuf, TP, Wp);
-    else if (h <= 48)
-      gj_update_tile<3>(Lb, ldl, Rb, ldr, h, W, cstart, npc, Vbuf, TP, Wp);
-    else
-      gj_update_tile<4>(Lb, ldl, Rb, ldr, h, W, cstart, npc, Vbuf, TP, Wp);
+    if (warp > 0 || (nwarp == 1 && more)) {
+      const int hw0 = (nwarp == 1) ? ((tid >> 4) & 1) : ((tid >> 4) - 2);
+      const int nhw = (nwarp == 1) ? 2 : 2 * (nwarp - 1);
+      gj_update_dispatch(Lb, ldl, Rb, ldr, h, cstart + npn, W, hw0, nhw, lx, npc, Vin, prow);
+    }
     __syncthreads();
   }
-  return 0;
+  return *flag ? 1 : 0;
 }

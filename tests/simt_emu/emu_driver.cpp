@@ -45,7 +45,7 @@ int emu_solve_batch(const smrtb200_options* opt, const smrtb200_batch* batch, in
 
   simt::launch((unsigned)((BL + 127) / 128), 128, [&]() { optics_kernel(A); });
   simt::launch(1, (unsigned)threads, [&]() { eigen_kernel<true>(A); });
-  simt::launch(1, (unsigned)threads, [&]() { boundary_kernel<true>(A); });
+  simt::launch(1, (unsigned)threads, [&]() { boundary_kernel<true, 512>(A); });
   if (sweeps_out) {
     sweeps_out[0] = diag[0];
     sweeps_out[1] = diag[1];
@@ -112,10 +112,10 @@ int emu_jacobi_fast(double* W, int h, int ld, int threads) {
 // blocked Gauss-Jordan: X = A^-1 R for column-major A (h x h, ld = h) and R (h x nR, ld = h); returns the failure flag
 int emu_gj_blocked(double* A, int h, double* R, int nR, int threads, double* X) {
   std::vector<int> rowof(h, -1), flag(1, 0);
-  std::vector<double> ipiv(h, 0.0), Vbuf((size_t)h * SMRT_GJ_NB + 8, 0.0), TP((size_t)SMRT_GJ_NB * (h + nR + 2), 0.0);
+  std::vector<double> ipiv(h, 0.0), Vbuf((size_t)2 * h * SMRT_GJ_NB + 8, 0.0);
   int rc = 0;
   simt::launch(1, (unsigned)threads, [&]() {
-    int r = block_gj_rows_blocked(A, h, R, h, h, nR, rowof.data(), ipiv.data(), Vbuf.data(), TP.data(), flag.data());
+    int r = block_gj_rows_blocked(A, h, R, h, h, nR, rowof.data(), ipiv.data(), Vbuf.data(), flag.data());
     if (threadIdx.x == 0) rc = r;
   });
   if (rc == 0)
