@@ -364,7 +364,7 @@ SMRT_DEV double stream_weight(const double* mu, int n, int j) {
 struct FresnelRT {
   double R[3], T[3];
 };
-SMRT_DEV FresnelRT fresnel_power(int kind, cplx eps_1, cplx eps_2, double mu) {
+SMRT_DEV_NOINLINE FresnelRT fresnel_power(int kind, cplx eps_1, cplx eps_2, double mu) {
   FresnelRT o;
   if (kind == IF_TRANSPARENT) {  // interface/transparent.py:12-46
     o.R[0] = o.R[1] = o.R[2] = 0.0;

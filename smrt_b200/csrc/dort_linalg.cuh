@@ -250,7 +250,7 @@ SMRT_DEV int jacobi_pair(double* SMRT_RESTRICT wp, double* SMRT_RESTRICT wq, int
   return (g2 > SMRT_JACOBI_QUAD2 * ab) ? 1 : 0;
 }
 
-SMRT_DEV int block_jacobi_svd(double* W, int ld, int h, int* ctrl) {
+SMRT_DEV_NOINLINE int block_jacobi_svd(double* W, int ld, int h, int* ctrl) {
   const int NT = blockDim.x;
   const int tid = threadIdx.x;
   const int hp = (h + 1) & ~1;
@@ -985,7 +985,7 @@ SMRT_DEV void gj_rows_update(double* T, int ld, int h, int W, int j, int p, doub
 // afterwards, for every unknown k, row rowof[k] of the right block holds piv_k * (A^-1 R)(k, :), piv_k = T(rowof[k], k).
 // No physical swaps, no scaling pass, one barrier per step.  rowstep/rowof: block-shared int[h].
 // Returns 1 if a pivot vanishes (singular / non finite), else 0 — the same value in every thread.
-SMRT_DEV int block_gj_rows(double* T, int ld, int h, int W, int* rowstep, int* rowof) {
+SMRT_DEV_NOINLINE int block_gj_rows(double* T, int ld, int h, int W, int* rowstep, int* rowof) {
   const int NT = blockDim.x, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
   for (int i = tid; i < h; i += NT) rowstep[i] = -1;
@@ -1026,7 +1026,7 @@ SMRT_DEV int block_gj_rows(double* T, int ld, int h, int W, int* rowstep, int* r
 
 // Gauss-Jordan elimination by COLUMNS with partial (column) pivoting on the stacked pair [S; K] (S: h x h, K: m x h):
 // afterwards (K S^-1)(:, k) = K(:, colof[k]) / S(k, colof[k]).  One barrier per step.
-SMRT_DEV int block_gj_cols(double* S, int lds, double* Km, int ldk, int h, int m, int* colstep, int* colof) {
+SMRT_DEV_NOINLINE int block_gj_cols(double* S, int lds, double* Km, int ldk, int h, int m, int* colstep, int* colof) {
   const int NT = blockDim.x, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
   for (int i = tid; i < h; i += NT) colstep[i] = -1;
@@ -1248,7 +1248,7 @@ SMRT_DEV int block_gj_rows_lookahead(double* Lb, int ldl, double* Rb, int ldr, i
 // =====================================================================================================================
 #define SMRT_GJ_NB 8
 
-template <int RPL, bool FULL>
+template <int RPL>
 SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int j0, int npc, unsigned& used, int lane,
                             int* rowof, double* ipiv, double* SMRT_RESTRICT Vout, int* flag) {
   double pc[RPL][SMRT_GJ_NB], v[RPL][SMRT_GJ_NB];
@@ -1257,14 +1257,14 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
     const int row = lane + 32 * u;
 #pragma unroll
     for (int c = 0; c < SMRT_GJ_NB; ++c) {
-      pc[u][c] = (row < h && (FULL || c < npc)) ? Lb[(size_t)(j0 + c) * ldl + row] : 0.0;
+      pc[u][c] = (row < h && c < npc) ? Lb[(size_t)(j0 + c) * ldl + row] : 0.0;
       v[u][c] = 0.0;
     }
   }
   bool bad = false;
 #pragma unroll
   for (int k = 0; k < SMRT_GJ_NB; ++k) {
-    if (FULL || k < npc) {  // uniform
+    if (k < npc) {  // uniform
       // pivot: largest |value| of column k among the rows not used yet.  Key = high word of |value| (exponent + 20
       // mantissa bits) with the 5 low bits replaced by 31 - lane: one REDUX gives the maximum and its (lowest) lane;
       // any element within 2^-15 of the maximum is as good a pivot
@@ -1298,7 +1298,7 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
       for (int u = 0; u < RPL; ++u) m[u] = (lane == pl && u == pu) ? 0.0 : -(pc[u][k] * inv);
 #pragma unroll
       for (int c = k + 1; c < SMRT_GJ_NB; ++c) {
-        if (FULL || c < npc) {
+        if (c < npc) {
           double sel = pc[0][c];
 #pragma unroll
           for (int u = 1; u < RPL; ++u) sel = (pu == u) ? pc[u][c] : sel;
@@ -1328,20 +1328,6 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
 #pragma unroll
       for (int c = 0; c < SMRT_GJ_NB; ++c) Vout[(size_t)c * h + row] = v[u][c];
     }
-  }
-}
-SMRT_DEV void gj_panel_dispatch(const double* Lb, int ldl, int h, int j0, int npc, unsigned& used, int lane, int* rowof,
-                                double* ipiv, double* Vout, int* flag) {
-  if (h <= 32) {
-    if (npc == SMRT_GJ_NB)
-      gj_panel_warp<1, true>(Lb, ldl, h, j0, npc, used, lane, rowof, ipiv, Vout, flag);
-    else
-      gj_panel_warp<1, false>(Lb, ldl, h, j0, npc, used, lane, rowof, ipiv, Vout, flag);
-  } else {
-    if (npc == SMRT_GJ_NB)
-      gj_panel_warp<2, true>(Lb, ldl, h, j0, npc, used, lane, rowof, ipiv, Vout, flag);
-    else
-      gj_panel_warp<2, false>(Lb, ldl, h, j0, npc, used, lane, rowof, ipiv, Vout, flag);
   }
 }
 
@@ -1379,20 +1365,12 @@ SMRT_DEV void gj_update_cols(double* Lb, int ldl, double* Rb, int ldr, int h, in
       if (lx + 16 * u < h) col[lx + 16 * u] = acc[u];
   }
 }
-SMRT_DEV void gj_update_dispatch(double* Lb, int ldl, double* Rb, int ldr, int h, int cbeg, int cend, int hw, int nhw,
-                                 int lx, int npc, const double* Vin, const int* prow) {
-  if (h <= 16)
-    gj_update_cols<1>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, prow);
-  else if (h <= 32)
-    gj_update_cols<2>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, prow);
-  else if (h <= 48)
-    gj_update_cols<3>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, prow);
-  else
-    gj_update_cols<4>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, prow);
-}
 
-SMRT_DEV int block_gj_rows_blocked(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowof, double* ipiv,
-                                   double* Vbuf, int* flag) {
+// one instance per (rows per lane of the panel warp, rows per lane of the update tiles); NOT inlined: the boundary
+// kernel calls it from three places and the straight-line panel code is large (instruction-cache footprint)
+template <int RPL, int RT>
+SMRT_DEV_NOINLINE int block_gj_rows_blocked_t(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowof,
+                                              double* ipiv, double* Vbuf, int* flag) {
   const int NT = blockDim.x, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
   const int lx = tid & 15;
@@ -1400,34 +1378,38 @@ SMRT_DEV int block_gj_rows_blocked(double* Lb, int ldl, double* Rb, int ldr, int
   unsigned used = 0u;  // warp 0: bit u = row lane + 32 u already served as a pivot
   if (tid == 0) *flag = 0;
   __syncthreads();
-  if (warp == 0) gj_panel_dispatch(Lb, ldl, h, 0, (h < SMRT_GJ_NB) ? h : SMRT_GJ_NB, used, lane, rowof, ipiv, Vbuf, flag);
-  __syncthreads();
-  int buf = 0;
-  for (int j0 = 0; j0 < h; j0 += SMRT_GJ_NB, buf ^= 1) {
-    if (*flag) return 1;
-    const int npc = (h - j0 < SMRT_GJ_NB) ? (h - j0) : SMRT_GJ_NB;
-    const int cstart = j0 + npc;
+  int buf = 1;
+  // iteration j0 = -NB only factorises the first panel; iteration j0 >= 0 applies panel j0 (V in Vbuf[buf]) while warp 0
+  // looks ahead to the next one
+  for (int j0 = -SMRT_GJ_NB; j0 < h; j0 += SMRT_GJ_NB, buf ^= 1) {
+    const bool cur = j0 >= 0;
+    const int npc = cur ? ((h - j0 < SMRT_GJ_NB) ? (h - j0) : SMRT_GJ_NB) : 0;
+    const int cstart = cur ? j0 + npc : 0;
     const double* Vin = Vbuf + (size_t)buf * h * SMRT_GJ_NB;
-    const int* prow = rowof + j0;
     const bool more = cstart < h;
     const int npn = more ? ((h - cstart < SMRT_GJ_NB) ? (h - cstart) : SMRT_GJ_NB) : 0;  // width of the next panel
-    if (warp == 0) {
-      // look-ahead: bring the next panel up to date, then factorise it while the other warps update the rest
-      if (more) {
-        gj_update_dispatch(Lb, ldl, Rb, ldr, h, cstart, cstart + npn, (tid >> 4) & 1, 2, lx, npc, Vin, prow);
-        __syncwarp();
-        gj_panel_dispatch(Lb, ldl, h, cstart, npn, used, lane, rowof, ipiv, Vbuf + (size_t)(buf ^ 1) * h * SMRT_GJ_NB,
-                          flag);
-      } else if (nwarp == 1) {
-        gj_update_dispatch(Lb, ldl, Rb, ldr, h, cstart, W, (tid >> 4) & 1, 2, lx, npc, Vin, prow);
-      }
+    if (cur) {
+      // warp 0 brings the next panel up to date, the other warps share the remaining columns
+      const int cbeg = (warp == 0) ? cstart : cstart + npn;
+      const int cend = (warp == 0) ? cstart + npn : W;
+      const int hw = (warp == 0) ? ((tid >> 4) & 1) : ((tid >> 4) - 2);
+      const int nhw = (warp == 0) ? 2 : 2 * (nwarp - 1);
+      gj_update_cols<RT>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, rowof + j0);
     }
-    if (warp > 0 || (nwarp == 1 && more)) {
-      const int hw0 = (nwarp == 1) ? ((tid >> 4) & 1) : ((tid >> 4) - 2);
-      const int nhw = (nwarp == 1) ? 2 : 2 * (nwarp - 1);
-      gj_update_dispatch(Lb, ldl, Rb, ldr, h, cstart + npn, W, hw0, nhw, lx, npc, Vin, prow);
+    if (warp == 0 && more) {
+      __syncwarp();
+      gj_panel_warp<RPL>(Lb, ldl, h, cstart, npn, used, lane, rowof, ipiv, Vbuf + (size_t)(buf ^ 1) * h * SMRT_GJ_NB, flag);
     }
     __syncthreads();
+    if (*flag) return 1;
   }
-  return *flag ? 1 : 0;
+  return 0;
+}
+// blockDim.x >= 64 (warp 0 factorises, the others update)
+SMRT_DEV int block_gj_rows_blocked(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowof, double* ipiv,
+                                   double* Vbuf, int* flag) {
+  if (h <= 16) return block_gj_rows_blocked_t<1, 1>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
+  if (h <= 32) return block_gj_rows_blocked_t<1, 2>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
+  if (h <= 48) return block_gj_rows_blocked_t<2, 3>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
+  return block_gj_rows_blocked_t<2, 4>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
 }
