@@ -392,10 +392,10 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
 // --------------------------------------------------------------------------------------------------------------------
 // kernel 3: boundary system, mode summation, output stage
 // --------------------------------------------------------------------------------------------------------------------
-// vector region (doubles): mu[n] outmu[n] outw[n] kvec tvec Rt Tt Rb Tb Ttprev ipiv RbD Dsg [hmax each]
+// vector region (doubles): mu[n] outmu[n] outw[n] kvec tvec Rt Tt Rb Tb Ttprev ipiv RbD Dsg Tup [hmax each]
 //                          acc[9 * SMRT_MAX_INC] coh[4 * SMRT_MAX_INC] ; ints: rowstep[hmax] rowof[hmax] inc[SMRT_MAX_INC]
 SMRT_HD size_t boundary_vec_doubles(int n, int hmax) {
-  return ((size_t)3 * n + 10 * hmax + 13 * SMRT_MAX_INC + hmax /* two int arrays */ + SMRT_MAX_INC + 16 + 1) & ~(size_t)1;
+  return ((size_t)3 * n + 11 * hmax + 13 * SMRT_MAX_INC + hmax /* two int arrays */ + SMRT_MAX_INC + 16 + 1) & ~(size_t)1;
 }
 // matrix region: BF, BG (compact), scratch of the blocked Gauss-Jordan (V, reciprocal pivots), BR (ld odd),
 // T = [left | right | rhs] (ld odd), btop, svec, ytr, vvec
@@ -445,7 +445,8 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
   double* ipiv = Ttprev + hmax;
   double* RbD = ipiv + hmax;
   double* Dsg = RbD + hmax;
-  double* acc_act = Dsg + hmax;                   // [3][3][SMRT_MAX_INC]
+  double* Tup = Dsg + hmax;                       // transmission of the layer above's emission into this layer
+  double* acc_act = Tup + hmax;                   // [3][3][SMRT_MAX_INC]
   double* coh_act = acc_act + 9 * SMRT_MAX_INC;   // [2][2][SMRT_MAX_INC]
   int* rowstep = reinterpret_cast<int*>(coh_act + 4 * SMRT_MAX_INC);
   int* rowof = rowstep + hmax;
@@ -639,27 +640,48 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
           for (int a = tid; a < h; a += NT) kvec[a] = ke / mu[a / npol];
         }
         // interface coefficients on this layer's streams ------------------------ rtsolver_utils.py:473-644 (flat only)
-        for (int j = tid; j < n_l; j += NT) {
-          cplx eps_up = (l > 0) ? c_make(eps_b[2 * (l - 1)], eps_b[2 * (l - 1) + 1]) : c_make(1.0, 0.0);
-          FresnelRT ft = fresnel_power(A.interface_kind[bL + l], eps_l, eps_up, mu[j]);
-          FresnelRT fb;
-          if (l < nl - 1) {
-            fb = fresnel_power(A.interface_kind[bL + l + 1], eps_l, c_make(eps_b[2 * (l + 1)], eps_b[2 * (l + 1) + 1]),
-                               mu[j]);
-          } else if (A.substrate_kind[b] == SUB_FLAT) {
-            fb = fresnel_power(IF_FLAT, eps_l, c_make(A.substrate_eps[2 * b], A.substrate_eps[2 * b + 1]), mu[j]);
+        // one Fresnel evaluation per thread: (stream j) x (top of the layer | bottom of the layer | transmission of
+        // the emission of the layer above into this layer, on the upper layer's streams: dort.py:383-395)
+        const bool thermal = (A.mode == 0 && m == 0);
+        for (int e = tid; e < 3 * n_l; e += NT) {
+          const int which = e / n_l, j = e - which * n_l;
+          if (which == 0) {
+            cplx eps_up = (l > 0) ? c_make(eps_b[2 * (l - 1)], eps_b[2 * (l - 1) + 1]) : c_make(1.0, 0.0);
+            FresnelRT ft = fresnel_power(A.interface_kind[bL + l], eps_l, eps_up, mu[j]);
+            for (int p = 0; p < npol; ++p) {
+              Rt[j * npol + p] = ft.R[p];
+              Tt[j * npol + p] = ft.T[p];
+              Dsg[j * npol + p] = (p == 2) ? -1.0 : 1.0;
+            }
+          } else if (which == 1) {
+            FresnelRT fb;
+            if (l < nl - 1) {
+              fb = fresnel_power(A.interface_kind[bL + l + 1], eps_l, c_make(eps_b[2 * (l + 1)], eps_b[2 * (l + 1) + 1]),
+                                 mu[j]);
+            } else if (A.substrate_kind[b] == SUB_FLAT) {
+              fb = fresnel_power(IF_FLAT, eps_l, c_make(A.substrate_eps[2 * b], A.substrate_eps[2 * b + 1]), mu[j]);
+            } else {
+              fb.R[0] = fb.R[1] = fb.R[2] = 0.0;
+              fb.T[0] = fb.T[1] = fb.T[2] = 0.0;
+            }
+            for (int p = 0; p < npol; ++p) {
+              Rb[j * npol + p] = fb.R[p];
+              Tb[j * npol + p] = fb.T[p];
+              RbD[j * npol + p] = (p == 2) ? -fb.R[p] : fb.R[p];
+            }
           } else {
-            fb.R[0] = fb.R[1] = fb.R[2] = 0.0;
-            fb.T[0] = fb.T[1] = fb.T[2] = 0.0;
-          }
-          for (int p = 0; p < npol; ++p) {
-            const double dsgn = (p == 2) ? -1.0 : 1.0;
-            Rt[j * npol + p] = ft.R[p];
-            Tt[j * npol + p] = ft.T[p];
-            Rb[j * npol + p] = fb.R[p];
-            Tb[j * npol + p] = fb.T[p];
-            RbD[j * npol + p] = fb.R[p] * dsgn;
-            Dsg[j * npol + p] = dsgn;
+            double tu[3] = {0.0, 0.0, 0.0};
+            if (thermal && l > 0 && A.temperature[bL + l - 1] > 0.0) {
+              cplx eps_up = c_make(eps_b[2 * (l - 1)], eps_b[2 * (l - 1) + 1]);
+              double ri_up = real_index_of(eps_star, eps_up);
+              if (j < stream_count(ri_up, A.gl_mu, n)) {
+                FresnelRT fu = fresnel_power(A.interface_kind[bL + l], eps_up, eps_l, stream_mu(ri_up, A.gl_mu, j));
+                tu[0] = fu.T[0];
+                tu[1] = fu.T[1];
+                tu[2] = fu.T[2];
+              }
+            }
+            for (int p = 0; p < npol; ++p) Tup[j * npol + p] = tu[p];
           }
         }
         __syncthreads();
@@ -669,7 +691,6 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
         const int r = have_prev ? (h < h_prev ? h : h_prev) : 0;
         double* Trhs = TT + (size_t)(2 * h) * ldp;  // b_bot lives in the augmented columns of T
         if (nr > 0) {
-          const bool thermal = (A.mode == 0 && m == 0);
           const double Tl = A.temperature[bL + l];
           const double Bl = (thermal && Tl > 0.0) ? planck_function(freq, Tl, A.rayleigh_jeans) : 0.0;
           for (int e = tid; e < h * nr; e += NT) {
@@ -682,14 +703,8 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
                 vb -= (1.0 - Rb[a]) * Bl;
               }
               if (l > 0) {  // emission of the layer above transmitted into this layer (its own streams, truncated)
-                double Tup = A.temperature[bL + l - 1];
-                cplx eps_up = c_make(eps_b[2 * (l - 1)], eps_b[2 * (l - 1) + 1]);
-                double ri_up = real_index_of(eps_star, eps_up);
-                int n_up = stream_count(ri_up, A.gl_mu, n);
-                if (Tup > 0.0 && j < n_up) {
-                  FresnelRT fu = fresnel_power(A.interface_kind[bL + l], eps_up, eps_l, stream_mu(ri_up, A.gl_mu, j));
-                  vt += fu.T[p] * planck_function(freq, Tup, A.rayleigh_jeans);
-                }
+                const double Tabove = A.temperature[bL + l - 1];
+                if (Tabove > 0.0) vt += Tup[a] * planck_function(freq, Tabove, A.rayleigh_jeans);
               }
               if (l < l_end && a < r) {
                 double Tdn = A.temperature[bL + l + 1];
@@ -771,13 +786,20 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
           }
         });
         // v = F y~r ;  b' = b_top - D (G y~r) + Rt v  (b' goes next to S, in the augmented columns)
-        if (nr > 0) {
-          block_gemm_dual(NT, h, nr, h, BG, BF, h, ytr, h, [&](int i, int c, double c1, double c2) {
-            SMRT_AT(vvec, h, i, c) = c2;
-            SMRT_AT(Trhs, ldp, i, c) = SMRT_AT(btop, h, i, c) - Dsg[i] * c1 + Rt[i] * c2;
+        if (nr == 1 && NT >= h) {  // one right-hand side: whole-block matrix-vector products (GJV is free: scratch)
+          block_matvec_dual(h, h, BG, BF, h, ytr, GJV, [&](int i, double c1, double c2) {
+            vvec[i] = c2;
+            Trhs[i] = btop[i] - Dsg[i] * c1 + Rt[i] * c2;
           });
+        } else {
+          if (nr > 0) {
+            block_gemm_dual(NT, h, nr, h, BG, BF, h, ytr, h, [&](int i, int c, double c1, double c2) {
+              SMRT_AT(vvec, h, i, c) = c2;
+              SMRT_AT(Trhs, ldp, i, c) = SMRT_AT(btop, h, i, c) - Dsg[i] * c1 + Rt[i] * c2;
+            });
+          }
+          __syncthreads();
         }
-        __syncthreads();
         if (!kGlobalScratch && l > 0 && !coherent && A.scat_flag[bL + l - 1] != 0) {
           // BF / BG are dead from here on: let the TMA engine fetch the record of the layer above (cp.async.bulk,
           // completion on s_mbar) while this CTA runs the second elimination
@@ -814,7 +836,10 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
           __syncthreads();
           SMRT_FOR_2D(i, k, h, h) { SMRT_AT(BR, ldp, i, k) = SMRT_AT(TT, ldp, i, k); }
           __syncthreads();
-          if (nr > 0) {  // s = v + R_new b'
+          if (nr == 1 && NT >= h) {  // s = v + R_new b'
+            block_matvec_dual(h, h, BR, (const double*)nullptr, ldp, Trhs, GJV,
+                              [&](int i, double acc, double) { svec[i] = vvec[i] + acc; });
+          } else if (nr > 0) {
             block_gemm_ptr(NT, h, nr, h, BR, ldp, [&](int c) { return Trhs + (size_t)c * ldp; },
                            [&](int i, int c, double acc) { SMRT_AT(svec, h, i, c) = SMRT_AT(vvec, h, i, c) + acc; });
           }

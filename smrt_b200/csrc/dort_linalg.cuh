@@ -932,6 +932,50 @@ SMRT_DEV void block_gemm_dual(int nthr, int M, int N, int K, const double* SMRT_
   }
 }
 
+// Matrix-vector products by the whole block (the 4 x 4 tiled GEMMs above keep only 16 threads busy for one right-hand
+// side): y1 = A1 x and y2 = A2 x for column-major M x K matrices (lda), x in shared memory.  Thread (i, p) sums the
+// columns k = p, p + tpr, ... of row i (lanes along rows: conflict-free), the tpr partial sums per row meet in `part`
+// (block-shared double[2 * tpr * M], tpr = min(blockDim.x / M, 8) >= 1).  epi(i, y1_i, y2_i) is called once per row.
+// A2 may be NULL (single product, y2 = 0).  Synchronises internally (two barriers); requires blockDim.x >= M.
+template <typename FE>
+SMRT_DEV void block_matvec_dual(int M, int K, const double* SMRT_RESTRICT A1, const double* SMRT_RESTRICT A2, int lda,
+                                const double* SMRT_RESTRICT x, double* part, FE epi) {
+  const int NT = blockDim.x, tid = threadIdx.x;
+  int tpr = NT / M;
+  if (tpr > 8) tpr = 8;
+  const int i = tid % M, p = tid / M;
+  if (p < tpr) {
+    double s1a = 0.0, s1b = 0.0, s2a = 0.0, s2b = 0.0;
+    int k = p;
+    for (; k + tpr < K; k += 2 * tpr) {
+      const double x0 = x[k], x1 = x[k + tpr];
+      s1a = fma(A1[(size_t)k * lda + i], x0, s1a);
+      s1b = fma(A1[(size_t)(k + tpr) * lda + i], x1, s1b);
+      if (A2) {
+        s2a = fma(A2[(size_t)k * lda + i], x0, s2a);
+        s2b = fma(A2[(size_t)(k + tpr) * lda + i], x1, s2b);
+      }
+    }
+    if (k < K) {
+      const double x0 = x[k];
+      s1a = fma(A1[(size_t)k * lda + i], x0, s1a);
+      if (A2) s2a = fma(A2[(size_t)k * lda + i], x0, s2a);
+    }
+    part[(size_t)(2 * p) * M + i] = s1a + s1b;
+    part[(size_t)(2 * p + 1) * M + i] = s2a + s2b;
+  }
+  __syncthreads();
+  if (tid < M) {
+    double y1 = 0.0, y2 = 0.0;
+    for (int q = 0; q < tpr; ++q) {
+      y1 += part[(size_t)(2 * q) * M + tid];
+      y2 += part[(size_t)(2 * q + 1) * M + tid];
+    }
+    epi(tid, y1, y2);
+  }
+  __syncthreads();
+}
+
 // warp-wide argmax of (value, index) with ties to the smaller index; every lane returns the winner
 SMRT_DEV void warp_argmax(double& best, int& bi) {
   for (int off = 16; off > 0; off >>= 1) {
@@ -1248,6 +1292,35 @@ SMRT_DEV int block_gj_rows_lookahead(double* Lb, int ldl, double* Rb, int ldr, i
 // =====================================================================================================================
 #define SMRT_GJ_NB 8
 
+// pivot of a panel column held in registers (col[u] = row lane + 32 u): largest |value| among the rows not used yet.
+// Key = high word of |value| (exponent + 20 mantissa bits) with the 5 low bits replaced by 31 - lane: ONE REDUX gives
+// the maximum and its (lowest) lane; any element within 2^-15 of the maximum is as good a pivot.  Returns the lane and
+// register slot of the pivot row and the (signed) pivot; no candidate / zero column -> pv = 0.
+template <int RPL>
+SMRT_DEV void gj_pivot_search(const double (&col)[RPL], unsigned used, int lane, int h, int& pl, int& pu, double& pv) {
+  double bv = -1.0, mine = 0.0;
+  int bu = 0;
+#pragma unroll
+  for (int u = 0; u < RPL; ++u) {
+    const double a = fabs(col[u]);
+    if ((lane + 32 * u) < h && !((used >> u) & 1u) && a > bv) {
+      bv = a;
+      bu = u;
+      mine = col[u];
+    }
+  }
+  const unsigned key = (bv >= 0.0) ? (((unsigned)__double2hiint(bv) & ~31u) | (unsigned)(31 - lane)) : 0u;
+  const unsigned mx = __reduce_max_sync(0xffffffffu, key);
+  pl = 31 - (int)(mx & 31u);
+  pu = __shfl_sync(0xffffffffu, bu, pl, 32);
+  pv = __shfl_sync(0xffffffffu, mine, pl, 32);
+}
+
+// Panel factorisation by ONE warp, columns in registers.  The step loop is rolled (small instruction footprint): the
+// panel columns shift left by one position per step so that the current column is always slot 0, the V columns shift
+// right (the column created at step k ends in slot npc - 1 - k), and the pivot search of the NEXT step is issued as
+// soon as its column is up to date, ahead of the other updates of the current step (software pipelining of the only
+// loop-carried dependency).
 template <int RPL>
 SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int j0, int npc, unsigned& used, int lane,
                             int* rowof, double* ipiv, double* SMRT_RESTRICT Vout, int* flag) {
@@ -1262,63 +1335,67 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
     }
   }
   bool bad = false;
+  int pl, pu;
+  double pv;
+  {
+    double col0[RPL];
 #pragma unroll
-  for (int k = 0; k < SMRT_GJ_NB; ++k) {
-    if (k < npc) {  // uniform
-      // pivot: largest |value| of column k among the rows not used yet.  Key = high word of |value| (exponent + 20
-      // mantissa bits) with the 5 low bits replaced by 31 - lane: one REDUX gives the maximum and its (lowest) lane;
-      // any element within 2^-15 of the maximum is as good a pivot
-      double bv = -1.0, mine = 0.0;
-      int bu = 0;
-#pragma unroll
-      for (int u = 0; u < RPL; ++u) {
-        const double a = fabs(pc[u][k]);
-        if ((lane + 32 * u) < h && !((used >> u) & 1u) && a > bv) {
-          bv = a;
-          bu = u;
-          mine = pc[u][k];
-        }
-      }
-      const unsigned key = (bv >= 0.0) ? (((unsigned)__double2hiint(bv) & ~31u) | (unsigned)(31 - lane)) : 0u;
-      const unsigned mx = __reduce_max_sync(0xffffffffu, key);
-      const int pl = 31 - (int)(mx & 31u);
-      const int pu = __shfl_sync(0xffffffffu, bu, pl, 32);
-      const double pv = __shfl_sync(0xffffffffu, mine, pl, 32);
-      bad = bad || !(fabs(pv) > 0.0) || !(fabs(pv) < 1e300);
-      double inv = smrt_rcp_approx(pv);
-      inv = fma(inv, fma(-pv, inv, 1.0), inv);
-      inv = fma(inv, fma(-pv, inv, 1.0), inv);
-      if (lane == 0) {
-        rowof[j0 + k] = pl + 32 * pu;
-        ipiv[j0 + k] = inv;
-      }
-      if (lane == pl) used |= 1u << pu;
-      double m[RPL];
-#pragma unroll
-      for (int u = 0; u < RPL; ++u) m[u] = (lane == pl && u == pu) ? 0.0 : -(pc[u][k] * inv);
-#pragma unroll
-      for (int c = k + 1; c < SMRT_GJ_NB; ++c) {
-        if (c < npc) {
-          double sel = pc[0][c];
-#pragma unroll
-          for (int u = 1; u < RPL; ++u) sel = (pu == u) ? pc[u][c] : sel;
-          const double pr = __shfl_sync(0xffffffffu, sel, pl, 32);
-#pragma unroll
-          for (int u = 0; u < RPL; ++u) pc[u][c] = fma(m[u], pr, pc[u][c]);
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < k; ++c) {
-        double sel = v[0][c];
-#pragma unroll
-        for (int u = 1; u < RPL; ++u) sel = (pu == u) ? v[u][c] : sel;
-        const double vr = __shfl_sync(0xffffffffu, sel, pl, 32);
-#pragma unroll
-        for (int u = 0; u < RPL; ++u) v[u][c] = fma(m[u], vr, v[u][c]);
-      }
-#pragma unroll
-      for (int u = 0; u < RPL; ++u) v[u][k] = m[u];
+    for (int u = 0; u < RPL; ++u) col0[u] = pc[u][0];
+    gj_pivot_search<RPL>(col0, used, lane, h, pl, pu, pv);
+  }
+#pragma unroll 1
+  for (int k = 0; k < npc; ++k) {
+    bad = bad || !(fabs(pv) > 0.0) || !(fabs(pv) < 1e300);
+    double inv = smrt_rcp_approx(pv);
+    inv = fma(inv, fma(-pv, inv, 1.0), inv);
+    inv = fma(inv, fma(-pv, inv, 1.0), inv);
+    if (lane == 0) {
+      rowof[j0 + k] = pl + 32 * pu;
+      ipiv[j0 + k] = inv;
     }
+    if (lane == pl) used |= 1u << pu;
+    double m[RPL], nxt[RPL];
+#pragma unroll
+    for (int u = 0; u < RPL; ++u) m[u] = (lane == pl && u == pu) ? 0.0 : -(pc[u][0] * inv);
+    {  // the next column first, and its pivot search right away
+      double sel = pc[0][1];
+#pragma unroll
+      for (int u = 1; u < RPL; ++u) sel = (pu == u) ? pc[u][1] : sel;
+      const double pr = __shfl_sync(0xffffffffu, sel, pl, 32);
+#pragma unroll
+      for (int u = 0; u < RPL; ++u) nxt[u] = fma(m[u], pr, pc[u][1]);
+    }
+    int pl2, pu2;
+    double pv2;
+    gj_pivot_search<RPL>(nxt, used, lane, h, pl2, pu2, pv2);
+#pragma unroll
+    for (int c = 2; c < SMRT_GJ_NB; ++c) {
+      double sel = pc[0][c];
+#pragma unroll
+      for (int u = 1; u < RPL; ++u) sel = (pu == u) ? pc[u][c] : sel;
+      const double pr = __shfl_sync(0xffffffffu, sel, pl, 32);
+#pragma unroll
+      for (int u = 0; u < RPL; ++u) pc[u][c - 1] = fma(m[u], pr, pc[u][c]);
+    }
+#pragma unroll
+    for (int u = 0; u < RPL; ++u) {
+      pc[u][SMRT_GJ_NB - 1] = 0.0;
+      pc[u][0] = nxt[u];
+    }
+#pragma unroll
+    for (int c = SMRT_GJ_NB - 1; c >= 1; --c) {
+      double sel = v[0][c - 1];
+#pragma unroll
+      for (int u = 1; u < RPL; ++u) sel = (pu == u) ? v[u][c - 1] : sel;
+      const double vr = __shfl_sync(0xffffffffu, sel, pl, 32);
+#pragma unroll
+      for (int u = 0; u < RPL; ++u) v[u][c] = fma(m[u], vr, v[u][c - 1]);
+    }
+#pragma unroll
+    for (int u = 0; u < RPL; ++u) v[u][0] = m[u];
+    pl = pl2;
+    pu = pu2;
+    pv = pv2;
   }
   if (bad && lane == 0) *flag = 1;
 #pragma unroll
@@ -1326,7 +1403,10 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
     const int row = lane + 32 * u;
     if (row < h) {
 #pragma unroll
-      for (int c = 0; c < SMRT_GJ_NB; ++c) Vout[(size_t)c * h + row] = v[u][c];
+      for (int c = 0; c < SMRT_GJ_NB; ++c) {
+        const int kcol = npc - 1 - c;  // slot c holds the column created at step npc - 1 - c
+        if (kcol >= 0) Vout[(size_t)kcol * h + row] = v[u][c];
+      }
     }
   }
 }
