@@ -216,9 +216,16 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
       const int ld1 = jacobi_ld(h);
       const double coef = (m == 0) ? 0.5 : 0.25;
 
-      // phase matrix Fourier mode m on (mu_s > 0) x (mu_i > 0 | mu_i < 0): A1 <- P++, A2 <- (P+-) D
-      for (int pidx = tid; pidx < n_l * n_l; pidx += NT) {
-        int js = pidx % n_l, ji = pidx / n_l;
+      // phase matrix Fourier mode m on (mu_s > 0) x (mu_i > 0 | mu_i < 0): A1 <- P++, A2 <- (P+-) D.
+      // Only the stream pairs js <= ji are evaluated: the phase matrix is reciprocal, P_ab(i, s) = P_ba(s, i) q_a / q_b
+      // with q = (1, 1, 2) for (V, H, U), and for the backward half the same relation carries the signs D = (1, 1, -1)
+      // of the third Stokes component on both sides (both follow from the sums of emmodel/common.py:87-129 term by
+      // term), so the block (ji, js) is the mirrored, re-weighted block (js, ji).
+      for (int pidx = tid; pidx < (n_l * (n_l + 1)) / 2; pidx += NT) {
+        int ji = (int)((sqrtf(8.0f * (float)pidx + 1.0f) - 1.0f) * 0.5f);
+        while ((ji + 1) * (ji + 2) / 2 <= pidx) ++ji;
+        while (ji * (ji + 1) / 2 > pidx) --ji;
+        const int js = pidx - ji * (ji + 1) / 2;
         double pp[9], pm[9];
         if (emmodel == EM_IBA) {
           iba_phase_mode(m, K, ctab, stab, mu[js], mu[ji], iba_coeff, kk, mp, pp);
@@ -229,9 +236,15 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
         }
         for (int ps = 0; ps < npol; ++ps)
           for (int pi = 0; pi < npol; ++pi) {
-            int a = js * npol + ps, c = ji * npol + pi;
-            SMRT_AT(A1, ld1, a, c) = pp[ps * npol + pi];
-            SMRT_AT(A2, ld, a, c) = (pi == 2) ? -pm[ps * npol + pi] : pm[ps * npol + pi];
+            const int a = js * npol + ps, c = ji * npol + pi;
+            const double vp = pp[ps * npol + pi], vm = pm[ps * npol + pi];
+            SMRT_AT(A1, ld1, a, c) = vp;
+            SMRT_AT(A2, ld, a, c) = (pi == 2) ? -vm : vm;
+            if (js != ji) {  // mirrored block: row (ji, pi), column (js, ps)
+              const double qr = ((pi == 2) ? 2.0 : 1.0) / ((ps == 2) ? 2.0 : 1.0);
+              SMRT_AT(A1, ld1, c, a) = vp * qr;
+              SMRT_AT(A2, ld, c, a) = (pi == 2) ? -(vm * qr) : vm * qr;
+            }
           }
       }
       if (tid == 0) s_ctrl[2] = 0;
@@ -306,19 +319,29 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
           panel[jj * h + k] = (k >= jp + jj) ? SMRT_AT(A1, ld1, k, jp + jj) : 0.0;
         }
         __syncthreads();
-        for (int e = tid; e < h * pw; e += NT) {
-          int i = e % h, jj = e / h;
-          int j = jp + jj;
+        // one row of C^T against FOUR staged columns per thread: 5 shared-memory loads per 4 FMAs (the staged
+        // columns are zero above their diagonal, so a common lower summation bound is exact)
+        for (int e = tid; e < h * ((pw + 3) >> 2); e += NT) {
+          const int i = e % h, jq = (e / h) << 2;
           const double* cc = A2 + (size_t)i * ld;
-          const double* pl = panel + jj * h;
-          double acc0 = 0.0, acc1 = 0.0;
-          int k = (i > j) ? i : j;
-          for (; k + 1 < h; k += 2) {
-            acc0 = fma(cc[k], pl[k], acc0);
-            acc1 = fma(cc[k + 1], pl[k + 1], acc1);
+          const double* p0 = panel + (size_t)jq * h;
+          const int nj = (pw - jq < 4) ? (pw - jq) : 4;
+          const double* p1 = p0 + ((nj > 1) ? h : 0);
+          const double* p2 = p0 + ((nj > 2) ? 2 * h : 0);
+          const double* p3 = p0 + ((nj > 3) ? 3 * h : 0);
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+          const int k0 = (i > jp + jq) ? i : jp + jq;
+          for (int k = k0; k < h; ++k) {
+            const double c = cc[k];
+            a0 = fma(c, p0[k], a0);
+            a1 = fma(c, p1[k], a1);
+            a2 = fma(c, p2[k], a2);
+            a3 = fma(c, p3[k], a3);
           }
-          if (k < h) acc0 = fma(cc[k], pl[k], acc0);
-          SMRT_AT(A1, ld1, i, j) = acc0 + acc1;
+          SMRT_AT(A1, ld1, i, jp + jq) = a0;
+          if (nj > 1) SMRT_AT(A1, ld1, i, jp + jq + 1) = a1;
+          if (nj > 2) SMRT_AT(A1, ld1, i, jp + jq + 2) = a2;
+          if (nj > 3) SMRT_AT(A1, ld1, i, jp + jq + 3) = a3;
         }
         __syncthreads();
       }

@@ -132,55 +132,100 @@ SMRT_DEV int team_cholesky(const Team& tm, double* A, int ld, int h, int* flag) 
 template <int NR>
 SMRT_DEV int team_cholesky_ll(const Team& tm, double* A, int ld, int h, double* dvec) {
   int failed = 0;
-  for (int j = 0; j < h; ++j) {
-    const double* SMRT_RESTRICT Lj = A + j;  // L(j, k) = Lj[k * ld]
-    double p[4] = {0.0, 0.0, 0.0, 0.0};
-    double sacc[NR][4];
+  // two columns (j, j + 1) per step: the three operands L(i, k), L(j, k), L(j + 1, k) feed five FMAs, and the team
+  // synchronises once per pair of columns
+  int j = 0;
+  for (; j + 1 < h; j += 2) {
+    const double* SMRT_RESTRICT Lj = A + j;  // L(j, k) = Lj[k * ld], L(j + 1, k) = Lj[k * ld + 1]
+    double p00[2] = {0.0, 0.0}, p10[2] = {0.0, 0.0}, p11[2] = {0.0, 0.0};
+    double s0[NR][2], s1[NR][2];
     const double* rowp[NR];
     bool own[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       const int i = tm.rank + r * tm.size;
-      own[r] = (i > j) && (i < h);
+      own[r] = (i > j + 1) && (i < h);
       rowp[r] = A + (own[r] ? i : j);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) sacc[r][u] = 0.0;
+      s0[r][0] = s0[r][1] = s1[r][0] = s1[r][1] = 0.0;
     }
     int k = 0;
-    for (; k + 3 < j; k += 4) {
+    for (; k + 1 < j; k += 2) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const double lj = Lj[(size_t)(k + u) * ld];
-        p[u] = fma(lj, lj, p[u]);
+      for (int u = 0; u < 2; ++u) {
+        const double l0 = Lj[(size_t)(k + u) * ld], l1 = Lj[(size_t)(k + u) * ld + 1];
+        p00[u] = fma(l0, l0, p00[u]);
+        p10[u] = fma(l1, l0, p10[u]);
+        p11[u] = fma(l1, l1, p11[u]);
 #pragma unroll
-        for (int r = 0; r < NR; ++r) sacc[r][u] = fma(rowp[r][(size_t)(k + u) * ld], lj, sacc[r][u]);
+        for (int r = 0; r < NR; ++r) {
+          const double li = rowp[r][(size_t)(k + u) * ld];
+          s0[r][u] = fma(li, l0, s0[r][u]);
+          s1[r][u] = fma(li, l1, s1[r][u]);
+        }
       }
     }
-    for (; k < j; ++k) {
-      const double lj = Lj[(size_t)k * ld];
-      p[0] = fma(lj, lj, p[0]);
+    if (k < j) {
+      const double l0 = Lj[(size_t)k * ld], l1 = Lj[(size_t)k * ld + 1];
+      p00[0] = fma(l0, l0, p00[0]);
+      p10[0] = fma(l1, l0, p10[0]);
+      p11[0] = fma(l1, l1, p11[0]);
 #pragma unroll
-      for (int r = 0; r < NR; ++r) sacc[r][0] = fma(rowp[r][(size_t)k * ld], lj, sacc[r][0]);
+      for (int r = 0; r < NR; ++r) {
+        const double li = rowp[r][(size_t)k * ld];
+        s0[r][0] = fma(li, l0, s0[r][0]);
+        s1[r][0] = fma(li, l1, s1[r][0]);
+      }
     }
-    const double d = SMRT_AT(A, ld, j, j) - ((p[0] + p[1]) + (p[2] + p[3]));
-    if (!(d > 0.0)) {  // identical value in every thread: uniform exit
+    // 2 x 2 diagonal block (identical values in every thread: uniform exits)
+    const double d0 = SMRT_AT(A, ld, j, j) - (p00[0] + p00[1]);
+    if (!(d0 > 0.0)) {
       failed = 1;
       break;
     }
-    const double rinv = rsqrt(d);
+    const double r0 = rsqrt(d0);
+    const double l10 = (SMRT_AT(A, ld, j + 1, j) - (p10[0] + p10[1])) * r0;
+    const double d1 = SMRT_AT(A, ld, j + 1, j + 1) - (p11[0] + p11[1]) - l10 * l10;
+    if (!(d1 > 0.0)) {
+      failed = 1;
+      break;
+    }
+    const double r1 = rsqrt(d1);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       const int i = tm.rank + r * tm.size;
       if (own[r]) {
-        const double si = SMRT_AT(A, ld, i, j) - ((sacc[r][0] + sacc[r][1]) + (sacc[r][2] + sacc[r][3]));
-        SMRT_AT(A, ld, i, j) = si * rinv;
+        const double x0 = (SMRT_AT(A, ld, i, j) - (s0[r][0] + s0[r][1])) * r0;
+        const double x1 = (SMRT_AT(A, ld, i, j + 1) - (s1[r][0] + s1[r][1]) - x0 * l10) * r1;
+        SMRT_AT(A, ld, i, j) = x0;
+        SMRT_AT(A, ld, i, j + 1) = x1;
       }
-      if (i == j) dvec[j] = d * rinv;
+      if (i == j) {
+        dvec[j] = d0 * r0;
+        dvec[j + 1] = d1 * r1;
+      }
     }
     tm.sync();
+    // L(j + 1, j) is read as an operand by the later steps but A(j + 1, j) was also an INPUT of this step for every
+    // thread: written only after the barrier, by its owner, and published by the next step's barrier (the next step
+    // reads column j only through rows >= j + 2)
+    if (tm.rank == (j + 1) % tm.size) SMRT_AT(A, ld, j + 1, j) = l10;
   }
+  if (!failed && j < h) {  // last column of an odd-sized matrix
+    const double* SMRT_RESTRICT Lj = A + j;
+    double p[2] = {0.0, 0.0};
+    for (int k = 0; k < j; ++k) {
+      const double lj = Lj[(size_t)k * ld];
+      p[k & 1] = fma(lj, lj, p[k & 1]);
+    }
+    const double d = SMRT_AT(A, ld, j, j) - (p[0] + p[1]);
+    if (!(d > 0.0))
+      failed = 1;
+    else if (tm.rank == 0)
+      dvec[j] = sqrt(d);
+  }
+  tm.sync();
   if (failed) return 1;
-  for (int j = tm.rank; j < h; j += tm.size) SMRT_AT(A, ld, j, j) = dvec[j];
+  for (int jj = tm.rank; jj < h; jj += tm.size) SMRT_AT(A, ld, jj, jj) = dvec[jj];
   tm.sync();
   return 0;
 }
@@ -198,8 +243,10 @@ SMRT_DEV int team_cholesky_fast(const Team& tm, double* A, int ld, int h, double
 // round, TPP threads per pair (power of two <= 32).  `ctrl` is a block-shared int[4] scratch.
 // Returns the number of sweeps performed (every thread gets the same value).
 #define SMRT_JACOBI_TOL2 1e-30       // rotate only when (w_p . w_q)^2 > tol^2 |w_p|^2 |w_q|^2   (tol = 1e-15)
+#ifndef SMRT_JACOBI_QUAD2
 #define SMRT_JACOBI_QUAD2 1e-18      // a sweep whose largest squared cosine (before its own rotations) stays below this
                                      // is the last one: the quadratic convergence of the cyclic method finishes the job
+#endif
 #define SMRT_JACOBI_MAX_SWEEPS 40
 
 // one column pair: R rows per lane held in registers between the dot products and the rotation
@@ -1294,10 +1341,13 @@ SMRT_DEV int block_gj_rows_lookahead(double* Lb, int ldl, double* Rb, int ldr, i
 
 // pivot of a panel column held in registers (col[u] = row lane + 32 u): largest |value| among the rows not used yet.
 // Key = high word of |value| (exponent + 20 mantissa bits) with the 5 low bits replaced by 31 - lane: ONE REDUX gives
-// the maximum and its (lowest) lane; any element within 2^-15 of the maximum is as good a pivot.  Returns the lane and
-// register slot of the pivot row and the (signed) pivot; no candidate / zero column -> pv = 0.
+// the maximum and its (lowest) lane; any element within 2^-15 of the maximum is as good a pivot.  Every lane computes
+// the reciprocal of its own candidate while the REDUX is in flight (MUFU seed + two Newton steps), so the winner's
+// reciprocal arrives with the same shuffle round as the pivot itself.  Returns the lane and register slot of the
+// pivot row, the (signed) pivot and its reciprocal; no candidate / zero column -> pv = 0.
 template <int RPL>
-SMRT_DEV void gj_pivot_search(const double (&col)[RPL], unsigned used, int lane, int h, int& pl, int& pu, double& pv) {
+SMRT_DEV void gj_pivot_search(const double (&col)[RPL], unsigned used, int lane, int h, int& pl, int& pu, double& pv,
+                              double& pinv) {
   double bv = -1.0, mine = 0.0;
   int bu = 0;
 #pragma unroll
@@ -1311,9 +1361,13 @@ SMRT_DEV void gj_pivot_search(const double (&col)[RPL], unsigned used, int lane,
   }
   const unsigned key = (bv >= 0.0) ? (((unsigned)__double2hiint(bv) & ~31u) | (unsigned)(31 - lane)) : 0u;
   const unsigned mx = __reduce_max_sync(0xffffffffu, key);
+  double inv = smrt_rcp_approx(mine);
+  inv = fma(inv, fma(-mine, inv, 1.0), inv);
+  inv = fma(inv, fma(-mine, inv, 1.0), inv);
   pl = 31 - (int)(mx & 31u);
   pu = __shfl_sync(0xffffffffu, bu, pl, 32);
   pv = __shfl_sync(0xffffffffu, mine, pl, 32);
+  pinv = __shfl_sync(0xffffffffu, inv, pl, 32);
 }
 
 // Panel factorisation by ONE warp, columns in registers.  The step loop is rolled (small instruction footprint): the
@@ -1334,21 +1388,18 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
       v[u][c] = 0.0;
     }
   }
-  bool bad = false;
+  int bad = 0;
   int pl, pu;
-  double pv;
+  double pv, inv;
   {
     double col0[RPL];
 #pragma unroll
     for (int u = 0; u < RPL; ++u) col0[u] = pc[u][0];
-    gj_pivot_search<RPL>(col0, used, lane, h, pl, pu, pv);
+    gj_pivot_search<RPL>(col0, used, lane, h, pl, pu, pv, inv);
   }
 #pragma unroll 1
   for (int k = 0; k < npc; ++k) {
-    bad = bad || !(fabs(pv) > 0.0) || !(fabs(pv) < 1e300);
-    double inv = smrt_rcp_approx(pv);
-    inv = fma(inv, fma(-pv, inv, 1.0), inv);
-    inv = fma(inv, fma(-pv, inv, 1.0), inv);
+    bad |= (!(fabs(pv) > 0.0)) | (!(fabs(pv) < 1e300));
     if (lane == 0) {
       rowof[j0 + k] = pl + 32 * pu;
       ipiv[j0 + k] = inv;
@@ -1366,8 +1417,8 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
       for (int u = 0; u < RPL; ++u) nxt[u] = fma(m[u], pr, pc[u][1]);
     }
     int pl2, pu2;
-    double pv2;
-    gj_pivot_search<RPL>(nxt, used, lane, h, pl2, pu2, pv2);
+    double pv2, inv2;
+    gj_pivot_search<RPL>(nxt, used, lane, h, pl2, pu2, pv2, inv2);
 #pragma unroll
     for (int c = 2; c < SMRT_GJ_NB; ++c) {
       double sel = pc[0][c];
@@ -1396,6 +1447,7 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
     pl = pl2;
     pu = pu2;
     pv = pv2;
+    inv = inv2;
   }
   if (bad && lane == 0) *flag = 1;
 #pragma unroll
