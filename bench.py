@@ -327,9 +327,12 @@ def run_ours(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    # DRAM bytes per launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+    # capture (profiles/traffic.json, written by tools/make_profile_summary.py), scaled to this run's solves per launch
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dominant)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dominant)
+        traffic = float(tj["dram_bytes_per_solve"]) * solves_per_launch
     except Exception:
         pass
     alg_bytes_per_solve = N_LAYERS * (2 * 64 * 64 + 64) * 8 * 2 + 20 * 14 * 8  # eigenvector workspace write + read
