@@ -58,6 +58,71 @@ def make_batch(S, seed):
     return pack_snow_ensemble(AMSRE, th, rho, T, corr_length=pc, theta_deg=55.0)
 
 
+# Other BASELINE configs (parity-test cases; timed with --workload for the record, never the contract line) -----------
+CFG4_FREQS = (1.4135e9, 5.4e9, 6.925e9, 7.3e9, 9.6e9, 10.65e9, 13.5e9, 18.7e9, 23.8e9, 31.4e9, 36.5e9, 89.0e9)
+EXTRA_WORKLOADS = {
+    # name: (description, layers, streams, default snowpacks, algorithmic GFLOP per solve from SURVEY.md 8(d))
+    "cfg3": ("DMRT-QCA-SR + DORT active, 10 layers, 16 streams, C/X/Ku backscatter at 40 deg, m_max = 2 (seed 3)", 10, 16, 20000, 0.23),
+    "cfg4": ("IBA(exponential) + DORT passive, 50 layers, 64 streams, 12 frequencies (seed 4)", 50, 64, 250, 8.84),
+}
+
+
+def make_extra_batch(name, S):
+    from smrt_b200.pack import pack_snow_ensemble
+
+    rng = np.random.default_rng({"cfg3": 3, "cfg4": 4}[name])
+    L = EXTRA_WORKLOADS[name][1]
+    th = np.empty((S, L)); rho = np.empty((S, L)); T = np.empty((S, L)); p0 = np.empty((S, L))
+    for s in range(S):  # SURVEY.md 8(d) generators, members drawn sequentially
+        th[s] = np.concatenate((rng.uniform(0.05, 0.5, L - 1), [1000.0]))
+        if name == "cfg3":
+            rho[s] = rng.uniform(200, 400, L); T[s] = rng.uniform(240, 270, L); p0[s] = rng.uniform(1e-4, 3e-4, L)
+        else:
+            rho[s] = rng.uniform(150, 450, L); T[s] = rng.uniform(240, 272, L); p0[s] = rng.uniform(5e-5, 3e-4, L)
+    if name == "cfg3":
+        return pack_snow_ensemble((5.4e9, 9.6e9, 13.5e9), th, rho, T, microstructure="sticky_hard_spheres", radius=p0,
+                                  stickiness=0.2, emmodel="dmrt_qca_shortrange", mode="A", theta_deg=40.0,
+                                  theta_inc_deg=40.0, phi_deg=180.0)
+    return pack_snow_ensemble(CFG4_FREQS, th, rho, T, corr_length=p0, theta_deg=55.0)
+
+
+def run_extra(args):
+    """Device-resident throughput of another BASELINE config on one GPU (for DESIGN.md; not the bench contract)."""
+    import torch
+
+    from smrt_b200 import capi
+    from smrt_b200.device import DeviceBatch
+
+    desc, L, n, S_default, gflop = EXTRA_WORKLOADS[args.workload]
+    S = args.snowpacks if args.snowpacks != SNOWPACKS_PER_GPU else S_default
+    batch = make_extra_batch(args.workload, S)
+    plan = capi.Plan(capi.make_options(batch, n_max_stream=n, m_max=2))
+    dev = DeviceBatch(batch, n)
+    bt = dev.struct()
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(max(args.warmup, 1)):
+        plan.solve_device(bt, stream)
+    torch.cuda.synchronize()
+    ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+    ms, eig, bnd = [], [], []
+    for _ in range(args.steps):
+        ev0.record(); plan.solve_device(bt, stream); ev1.record(); ev1.synchronize()
+        ms.append(ev0.elapsed_time(ev1))
+        plan.sync_timing(stream); tm = plan.last_timing(); eig.append(tm["eigen_ms"]); bnd.append(tm["boundary_ms"])
+    status = dev.status.cpu().numpy()
+    vals = dev.values.cpu().numpy()
+    rate = batch.B * args.steps / (sum(ms) * 1e-3)
+    peak = capi.measure_fp64_peak(0, 300.0)
+    print(json.dumps({"workload": args.workload, "description": desc, "snowpacks": S, "solves_per_step": batch.B,
+                      "value": rate, "unit": UNIT, "ms_per_step": float(np.mean(ms)),
+                      "eigen_ms_per_step": float(np.mean(eig)), "boundary_ms_per_step": float(np.mean(bnd)),
+                      "algorithmic_gflop_per_solve": gflop, "fp64_peak_tflops": peak,
+                      "whole_path_frac_of_fp64_peak": gflop * 1e9 * rate / 1e12 / peak if peak else None,
+                      "errors": int(np.count_nonzero(status & capi.ST_ERR_MASK)),
+                      "finite": bool(np.isfinite(vals[(status & capi.ST_ERR_MASK) == 0]).all()),
+                      "workspace_gb": plan.workspace_bytes / 1e9}))
+
+
 def f_alg_per_solve(L=N_LAYERS, n=N_STREAMS, npol=2):
     """algorithmic flops of one mode-solve, split between the two kernels."""
     N = 2 * npol * n
@@ -387,8 +452,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--snowpacks", type=int, default=SNOWPACKS_PER_GPU, help="synthetic snowpacks per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2"] + sorted(EXTRA_WORKLOADS),
+                    help="cfg2 = the contract workload; cfg3 / cfg4: other BASELINE configs, one GPU, for the record")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload != "cfg2":
+        run_extra(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

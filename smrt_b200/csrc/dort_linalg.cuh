@@ -1345,11 +1345,13 @@ SMRT_DEV int block_gj_rows_lookahead(double* Lb, int ldl, double* Rb, int ldr, i
 // the reciprocal of its own candidate while the REDUX is in flight (MUFU seed + two Newton steps), so the winner's
 // reciprocal arrives with the same shuffle round as the pivot itself.  Returns the lane and register slot of the
 // pivot row, the (signed) pivot and its reciprocal; no candidate / zero column -> pv = 0.
+// split in two halves so that the caller can place independent work between the REDUX and the shuffles that depend on it
 template <int RPL>
-SMRT_DEV void gj_pivot_search(const double (&col)[RPL], unsigned used, int lane, int h, int& pl, int& pu, double& pv,
-                              double& pinv) {
-  double bv = -1.0, mine = 0.0;
-  int bu = 0;
+SMRT_DEV unsigned gj_pivot_begin(const double (&col)[RPL], unsigned used, int lane, int h, int& bu, double& mine,
+                                 double& inv) {
+  double bv = -1.0;
+  mine = 0.0;
+  bu = 0;
 #pragma unroll
   for (int u = 0; u < RPL; ++u) {
     const double a = fabs(col[u]);
@@ -1361,13 +1363,17 @@ SMRT_DEV void gj_pivot_search(const double (&col)[RPL], unsigned used, int lane,
   }
   const unsigned key = (bv >= 0.0) ? (((unsigned)__double2hiint(bv) & ~31u) | (unsigned)(31 - lane)) : 0u;
   const unsigned mx = __reduce_max_sync(0xffffffffu, key);
-  double inv = smrt_rcp_approx(mine);
+  inv = smrt_rcp_approx(mine);
   inv = fma(inv, fma(-mine, inv, 1.0), inv);
   inv = fma(inv, fma(-mine, inv, 1.0), inv);
+  return mx;
+}
+SMRT_DEV void gj_pivot_finish(unsigned mx, int bu, double mine, double myinv, int& pl, int& pu, double& pv,
+                              double& pinv) {
   pl = 31 - (int)(mx & 31u);
   pu = __shfl_sync(0xffffffffu, bu, pl, 32);
   pv = __shfl_sync(0xffffffffu, mine, pl, 32);
-  pinv = __shfl_sync(0xffffffffu, inv, pl, 32);
+  pinv = __shfl_sync(0xffffffffu, myinv, pl, 32);
 }
 
 // Panel factorisation by ONE warp, columns in registers.  The step loop is rolled (small instruction footprint): the
@@ -1392,10 +1398,12 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
   int pl, pu;
   double pv, inv;
   {
-    double col0[RPL];
+    double col0[RPL], mine, myinv;
+    int bu;
 #pragma unroll
     for (int u = 0; u < RPL; ++u) col0[u] = pc[u][0];
-    gj_pivot_search<RPL>(col0, used, lane, h, pl, pu, pv, inv);
+    const unsigned mx = gj_pivot_begin<RPL>(col0, used, lane, h, bu, mine, myinv);
+    gj_pivot_finish(mx, bu, mine, myinv, pl, pu, pv, inv);
   }
 #pragma unroll 1
   for (int k = 0; k < npc; ++k) {
@@ -1416,9 +1424,9 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
 #pragma unroll
       for (int u = 0; u < RPL; ++u) nxt[u] = fma(m[u], pr, pc[u][1]);
     }
-    int pl2, pu2;
-    double pv2, inv2;
-    gj_pivot_search<RPL>(nxt, used, lane, h, pl2, pu2, pv2, inv2);
+    int bu2;
+    double mine2, myinv2;
+    const unsigned mx2 = gj_pivot_begin<RPL>(nxt, used, lane, h, bu2, mine2, myinv2);
 #pragma unroll
     for (int c = 2; c < SMRT_GJ_NB; ++c) {
       double sel = pc[0][c];
@@ -1444,10 +1452,7 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
     }
 #pragma unroll
     for (int u = 0; u < RPL; ++u) v[u][0] = m[u];
-    pl = pl2;
-    pu = pu2;
-    pv = pv2;
-    inv = inv2;
+    gj_pivot_finish(mx2, bu2, mine2, myinv2, pl, pu, pv, inv);
   }
   if (bad && lane == 0) *flag = 1;
 #pragma unroll
