@@ -424,7 +424,8 @@ SMRT_HD size_t boundary_vec_doubles(int n, int hmax) {
 // T = [left | right | rhs] (ld odd), btop, svec, ytr, vvec
 SMRT_HD size_t boundary_gj_doubles(int hmax, int nrhs_max) {
   (void)nrhs_max;
-  return (size_t)2 * SMRT_GJ_NB * hmax + ((hmax + 1) & ~1);  // V (double buffered), reciprocal pivots
+  // V (double buffered; the same buffer is the scratch of the block matvecs: 2 * 8 * h doubles), reciprocal pivots
+  return (size_t)16 * hmax + ((hmax + 1) & ~1);
 }
 SMRT_HD size_t boundary_mat_doubles(int hmax, int nrhs_max) {
   return (size_t)2 * (((size_t)hmax * hmax + 1) & ~(size_t)1) + boundary_gj_doubles(hmax, nrhs_max) +
@@ -481,7 +482,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
   double* BF = mats;  // 16-byte aligned (vector loads of the layer records)
   double* BG = BF + szc;
   double* GJV = BG + szc;                                  // blocked Gauss-Jordan: V (2 x h x 8)
-  double* pivinv = GJV + (size_t)2 * SMRT_GJ_NB * hmax;    // ... reciprocal pivots
+  double* pivinv = GJV + (size_t)16 * hmax;                // ... reciprocal pivots
   double* BR = BG + szc + boundary_gj_doubles(hmax, nrhs_max);
   double* TT = BR + szp;  // h x (2h + nrhs), ld = ldp
   double* btop = TT + (size_t)(hmax + 1) * (2 * hmax + nrhs_max);

@@ -1337,7 +1337,9 @@ SMRT_DEV int block_gj_rows_lookahead(double* Lb, int ldl, double* Rb, int ldr, i
 // Scratch (block-shared): Vbuf double[2 * h * SMRT_GJ_NB], rowof int[h], ipiv double[h], flag int[1].
 // Returns 1 in every thread if a pivot vanishes / is not finite.  blockDim.x >= 64.
 // =====================================================================================================================
-#define SMRT_GJ_NB 8
+#ifndef SMRT_GJ_NB
+#define SMRT_GJ_NB 4
+#endif
 
 // pivot of a panel column held in registers (col[u] = row lane + 32 u): largest |value| among the rows not used yet.
 // Key = high word of |value| (exponent + 20 mantissa bits) with the 5 low bits replaced by 31 - lane: ONE REDUX gives
