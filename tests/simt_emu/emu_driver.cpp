@@ -123,4 +123,42 @@ int emu_gj_blocked(double* A, int h, double* R, int nR, int threads, double* X) 
       for (int c = 0; c < nR; ++c) X[(size_t)c * h + k] = R[(size_t)c * h + rowof[k]] * ipiv[k];
   return rc;
 }
+
+// left-looking two-column Cholesky of the lower triangle of A (h x h, ld = h), two concurrent teams like the kernel:
+// team 0 factorises A, team 1 factorises A2.  Returns the failure flags (bit 0 / bit 1).
+int emu_cholesky_pair(double* A, double* A2, int h, int threads) {
+  std::vector<double> d0(h + 2, 0.0), d1(h + 2, 0.0);
+  int bad[2] = {0, 0};
+  simt::launch(1, (unsigned)threads, [&]() {
+    Team tm;
+    const int half = (int)blockDim.x / 2;
+    const int which = (int)threadIdx.x / half;
+    tm.size = half;
+    tm.rank = (int)threadIdx.x % half;
+    tm.bar_id = 1 + which;
+    int b = team_cholesky_fast(tm, which == 0 ? A : A2, h, h, which == 0 ? d0.data() : d1.data());
+    if (tm.rank == 0) bad[which] = b;
+  });
+  return bad[0] | (bad[1] << 1);
+}
+
+// W <- C^-T W (C lower triangular h x h, ld = h; W h x h, ld = ldw)
+int emu_backsolve_lt(const double* Cm, double* W, int h, int ldw, int threads) {
+  std::vector<double> rdiag(h);
+  for (int j = 0; j < h; ++j) rdiag[j] = 1.0 / Cm[(size_t)j * h + j];
+  simt::launch(1, (unsigned)threads, [&]() { block_backsolve_lt(Cm, h, W, ldw, h, rdiag.data()); });
+  return 0;
+}
+
+// y1 = A1 x, y2 = A2 x (M x K column-major, lda = M); A2 may be NULL
+int emu_matvec_dual(const double* A1, const double* A2, int M, int K, const double* x, double* y1, double* y2, int threads) {
+  std::vector<double> part((size_t)16 * M + 8, 0.0);
+  simt::launch(1, (unsigned)threads, [&]() {
+    block_matvec_dual(M, K, A1, A2, M, x, part.data(), [&](int i, double a, double b) {
+      y1[i] = a;
+      y2[i] = b;
+    });
+  });
+  return 0;
+}
 }

@@ -182,3 +182,65 @@ def test_blocked_gauss_jordan_reports_singular_matrix():
     X = np.zeros((h, nR), order="F")
     P = C.POINTER(C.c_double)
     assert lib.emu_gj_blocked(A.ctypes.data_as(P), h, R.ctypes.data_as(P), nR, 64, X.ctypes.data_as(P)) == 1
+
+
+@pytest.mark.parametrize("h,threads", [(1, 64), (2, 64), (7, 64), (33, 64), (64, 128), (63, 128), (100, 64)])
+def test_left_looking_cholesky_device_function(h, threads):
+    """team_cholesky_fast: two concurrent teams, two columns per step, one barrier per pair of columns; only the lower
+    triangle is read or written; odd sizes and sizes larger than the team (several rows per thread)"""
+    lib = emu_lib()
+    rng = np.random.default_rng(h)
+    P = C.POINTER(C.c_double)
+    mats = []
+    for _ in range(2):
+        Q = rng.normal(size=(h, h))
+        mats.append(Q @ Q.T + h * np.eye(h))
+    A = [np.asfortranarray(np.tril(m) + np.triu(np.full((h, h), 7e77), 1)) for m in mats]   # poison above the diagonal
+    rc = lib.emu_cholesky_pair(A[0].ctypes.data_as(P), A[1].ctypes.data_as(P), h, threads)
+    assert rc == 0
+    for a, m in zip(A, mats):
+        np.testing.assert_allclose(np.tril(a), np.linalg.cholesky(m), rtol=1e-12, atol=1e-13)
+        assert np.all(a[np.triu_indices(h, 1)] == 7e77)
+
+
+def test_left_looking_cholesky_reports_indefinite_matrix():
+    lib = emu_lib()
+    P = C.POINTER(C.c_double)
+    h = 12
+    good = np.asfortranarray(np.eye(h) * 2.0)
+    bad = np.asfortranarray(np.eye(h))
+    bad[5, 5] = -1.0
+    assert lib.emu_cholesky_pair(good.ctypes.data_as(P), bad.ctypes.data_as(P), h, 64) == 2
+
+
+@pytest.mark.parametrize("h,threads", [(3, 64), (8, 64), (13, 64), (44, 128), (64, 128), (64, 32)])
+def test_paired_lane_back_substitution_device_function(h, threads):
+    lib = emu_lib()
+    lib.emu_jacobi_ld.restype = C.c_int
+    rng = np.random.default_rng(31 * h)
+    Cm = np.asfortranarray(np.tril(rng.normal(size=(h, h))) + 3 * np.eye(h))
+    ld = lib.emu_jacobi_ld(h)
+    W = np.zeros((ld, h), order="F")
+    W0 = rng.normal(size=(h, h))
+    W[:h] = W0
+    P = C.POINTER(C.c_double)
+    lib.emu_backsolve_lt(Cm.ctypes.data_as(P), W.ctypes.data_as(P), h, ld, threads)
+    ref = np.linalg.solve(Cm.T, W0)
+    np.testing.assert_allclose(W[:h], ref, rtol=1e-10, atol=1e-12 * np.abs(ref).max())
+    assert np.all(W[h:] == 0.0)
+
+
+@pytest.mark.parametrize("M,K,threads,dual", [(64, 64, 256, True), (44, 44, 256, True), (20, 20, 64, False),
+                                              (64, 64, 64, True), (7, 5, 64, True)])
+def test_block_matvec_device_function(M, K, threads, dual):
+    lib = emu_lib()
+    rng = np.random.default_rng(M + K)
+    A1 = np.asfortranarray(rng.normal(size=(M, K)))
+    A2 = np.asfortranarray(rng.normal(size=(M, K)))
+    x = rng.normal(size=K)
+    y1, y2 = np.zeros(M), np.zeros(M)
+    P = C.POINTER(C.c_double)
+    lib.emu_matvec_dual(A1.ctypes.data_as(P), A2.ctypes.data_as(P) if dual else None, M, K, x.ctypes.data_as(P),
+                        y1.ctypes.data_as(P), y2.ctypes.data_as(P), threads)
+    np.testing.assert_allclose(y1, A1 @ x, rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(y2, A2 @ x if dual else 0.0, rtol=1e-13, atol=1e-13)
