@@ -1528,12 +1528,22 @@ SMRT_DEV_NOINLINE int block_gj_rows_blocked_t(double* Lb, int ldl, double* Rb, i
     const bool more = cstart < h;
     const int npn = more ? ((h - cstart < SMRT_GJ_NB) ? (h - cstart) : SMRT_GJ_NB) : 0;  // width of the next panel
     if (cur) {
-      // warp 0 brings the next panel up to date, the other warps share the remaining columns
-      const int cbeg = (warp == 0) ? cstart : cstart + npn;
-      const int cend = (warp == 0) ? cstart + npn : W;
-      const int hw = (warp == 0) ? ((tid >> 4) & 1) : ((tid >> 4) - 2);
-      const int nhw = (warp == 0) ? 2 : 2 * (nwarp - 1);
-      gj_update_cols<RT>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, rowof + j0);
+      // the next panel is brought up to date first: by warps 0 and 1 together (one column per half-warp, then a
+      // 64-thread named barrier) when the block has more than two warps, else by warp 0 alone; the warps >= 1 share
+      // the remaining columns
+      if (more) {
+        if (nwarp > 2) {
+          if (warp < 2) {
+            gj_update_cols<RT>(Lb, ldl, Rb, ldr, h, cstart, cstart + npn, tid >> 4, 4, lx, npc, Vin, rowof + j0);
+            smrt_named_barrier(1, 64);
+          }
+        } else if (warp == 0) {
+          gj_update_cols<RT>(Lb, ldl, Rb, ldr, h, cstart, cstart + npn, (tid >> 4) & 1, 2, lx, npc, Vin, rowof + j0);
+        }
+      }
+      if (warp > 0)
+        gj_update_cols<RT>(Lb, ldl, Rb, ldr, h, cstart + npn, W, (tid >> 4) - 2, 2 * (nwarp - 1), lx, npc, Vin,
+                           rowof + j0);
     }
     if (warp == 0 && more) {
       __syncwarp();
