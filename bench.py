@@ -64,12 +64,30 @@ EXTRA_WORKLOADS = {
     # name: (description, layers, streams, default snowpacks, algorithmic GFLOP per solve from SURVEY.md 8(d))
     "cfg3": ("DMRT-QCA-SR + DORT active, 10 layers, 16 streams, C/X/Ku backscatter at 40 deg, m_max = 2 (seed 3)", 10, 16, 20000, 0.23),
     "cfg4": ("IBA(exponential) + DORT passive, 50 layers, 64 streams, 12 frequencies (seed 4)", 50, 64, 250, 8.84),
+    "cfg5": ("IBA + DORT passive, 30-layer multi-year sea ice over ocean, 32 streams, 1.4 GHz at 40 deg (seed 5)", 30, 32,
+             60000, 0.663),
 }
+
+
+def sea_ice_members(S, seed=5, L=30):
+    """SURVEY.md 8(d) cfg-5 generator: the arrays make_ice_column("multiyear", ...) would receive, member by member."""
+    rng = np.random.default_rng(seed)
+    th = np.empty((S, L)); T = np.empty((S, L)); sal = np.empty((S, L)); por = np.empty((S, 1)); pc = np.empty((S, 1))
+    for s in range(S):
+        H = rng.uniform(1, 3); dT = rng.uniform(10, 30); ss = rng.uniform(0.5, 1.5)
+        por[s] = rng.uniform(0.02, 0.12); pc[s] = rng.uniform(0.5e-3, 1.5e-3)
+        th[s] = H / L; T[s] = np.linspace(273.15 - dT, 273.15 - 1.8, L); sal[s] = np.linspace(2, 10, L) * 1e-3 * ss
+    return th, T, sal, por, pc
 
 
 def make_extra_batch(name, S):
     from smrt_b200.pack import pack_snow_ensemble
 
+    if name == "cfg5":
+        from smrt_b200.pack import pack_sea_ice_ensemble
+
+        th, T, sal, por, pc = sea_ice_members(S)
+        return pack_sea_ice_ensemble(1.4e9, th, T, sal, por, pc, theta_deg=40.0)
     rng = np.random.default_rng({"cfg3": 3, "cfg4": 4}[name])
     L = EXTRA_WORKLOADS[name][1]
     th = np.empty((S, L)); rho = np.empty((S, L)); T = np.empty((S, L)); p0 = np.empty((S, L))
@@ -455,7 +473,7 @@ def main():
     ap.add_argument("--snowpacks", type=int, default=SNOWPACKS_PER_GPU, help="synthetic snowpacks per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="cfg2", choices=["cfg2"] + sorted(EXTRA_WORKLOADS),
-                    help="cfg2 = the contract workload; cfg3 / cfg4: other BASELINE configs, one GPU, for the record")
+                    help="cfg2 = the contract workload; cfg3 / cfg4 / cfg5: other BASELINE configs, one GPU, for the record")
     args = ap.parse_args()
     if args.workload != "cfg2":
         run_extra(args)

@@ -12,7 +12,7 @@ See DESIGN.md (path, kernels, rooflines), INTEGRATION.md (how an SMRT maintainer
 from .error import SMRTError, SMRTWarning  # noqa: F401
 from .inputs import Snowpack, make_snowpack, sensor_list  # noqa: F401
 from .model import B200Runner, DORT, Model, make_model, run_ensemble, solve_batch  # noqa: F401
-from .pack import ProblemBatch, pack_simulations, pack_snow_ensemble  # noqa: F401
+from .pack import ProblemBatch, pack_sea_ice_ensemble, pack_simulations, pack_snow_ensemble  # noqa: F401
 from .result import ActiveResult, PassiveResult, Result, concat_results, make_result  # noqa: F401
 
 __version__ = "0.1.0"

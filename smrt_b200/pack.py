@@ -358,3 +358,157 @@ def pack_snow_ensemble(frequency, thickness, density, temperature, *, microstruc
         substrate_temperature=np.zeros(B), theta=theta, theta_inc=theta_inc, phi=float(np.radians(phi_deg)),
         dense_snow_correction=np.full((B, L), 1 if code in _DMRT_CODES else 0, dtype=np.int32),
     )
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# sea-ice ensembles (BASELINE config 5): the permittivity chain of make_ice_column("multiyear", ...) vectorised over
+# the whole (S, L) block.  Every function restates the reference formula it cites; pinned against the packed inputs of
+# the reference-generated fixture tests/golden/cfg5_first6.npz (tests/test_host_api.py).
+# ---------------------------------------------------------------------------------------------------------------------
+_FREEZING_POINT = 273.15
+_PSU = 1e-3
+_EPS0 = 1.0 / (4e-7 * np.pi * 299792458.0**2)  # smrt/core/globalconstants.py:32
+
+
+def water_freezing_temperature(salinity):
+    """TEOS-10 polynomial fit at sea-level pressure — reference ``smrt/permittivity/brine.py:176-229``."""
+    c = (0.017947064327968736, -6.076099099929818, 4.883198653547851, -11.88081601230542, 13.34658511480257,
+         -8.722761043208607, 2.082038908808201, -7.389420998107497, -2.110913185058476, 0.2295491578006229,
+         -0.9891538123307282, -0.08987150128406496, 0.3831132432071728, 1.054318231187074, 1.065556599652796,
+         -0.7997496801694032, 0.3850133554097069, -2.078616693017569, 0.8756340772729538, -2.079022768390933,
+         1.596435439942262, 0.1338002171109174, 1.242891021876471)
+    s_r = np.asarray(salinity, dtype=float) * 1e1
+    x = np.sqrt(s_r)
+    p_r = 10.1325 * 1e-4
+    t = (c[0] + s_r * (c[1] + x * (c[2] + x * (c[3] + x * (c[4] + x * (c[5] + c[6] * x))))) +
+         p_r * (c[7] + p_r * (c[8] + c[9] * p_r)) +
+         s_r * p_r * (c[10] + p_r * (c[12] + p_r * (c[15] + c[21] * s_r)) + s_r * (c[13] + c[17] * p_r + c[19] * s_r) +
+                      x * (c[11] + p_r * (c[14] + c[18] * p_r) + s_r * (c[16] + c[20] * p_r + c[22] * s_r))))
+    return t + 273.15
+
+
+def brine_volume_cox83_lepparanta88(temperature, salinity):
+    """Brine volume fraction (Cox & Weeks 1983; Leppäranta & Manninen 1988 above -2 degC), porosity 0 —
+    reference ``smrt/permittivity/brine.py:232-329``."""
+    temperature = np.asarray(temperature, dtype=float)
+    salinity = np.broadcast_to(np.asarray(salinity, dtype=float), temperature.shape)
+    T = temperature - _FREEZING_POINT
+    if np.any(T < -38.0):
+        raise SMRTError("the brine-volume polynomials of Cox and Weeks (1983) are unphysical below -38 degC")
+    rho_ice = 916.7 / 1e3 - 1.403e-4 * T
+    cold = T < -22.9
+    warm = T >= -2.0
+    a = np.where(warm[..., None], (-4.1221e-2, -1.8407e1, 5.8402e-1, 2.1454e-1),
+                 np.where(cold[..., None], (9.899e3, 1.309e3, 5.527e1, 7.160e-1), (-4.732, -2.245e1, -6.397e-1, -1.074e-2)))
+    b = np.where(warm[..., None], (9.0312e-2, -1.6111e-2, 1.2291e-4, 1.3603e-4),
+                 np.where(cold[..., None], (8.547, 1.089, 4.518e-2, 5.819e-4), (8.903e-2, -1.763e-2, -5.33e-4, -8.801e-6)))
+    # np.polyval([a3, a2, a1, a0], T): Horner from the highest power
+    F1 = ((a[..., 3] * T + a[..., 2]) * T + a[..., 1]) * T + a[..., 0]
+    F2 = ((b[..., 3] * T + b[..., 2]) * T + b[..., 1]) * T + b[..., 0]
+    bulk_density = rho_ice * F1 / (F1 - rho_ice * salinity * _PSU**-1 * F2) * 1e3
+    Vb = salinity / _PSU * bulk_density * 1e-3 / F1
+    tf = water_freezing_temperature(salinity)
+    Vb = np.where((Vb > 1.0) & (np.abs(temperature - tf) < 0.1), 1.0, Vb)
+    Vb = np.where(temperature > tf, 1.0, Vb)
+    if np.any((Vb < 0) | (Vb > 1)):
+        raise SMRTError("the brine-volume polynomials give a fraction outside [0, 1] for these temperatures / salinities")
+    return Vb
+
+
+def brine_permittivity_stogryn85(frequency, temperature):
+    """Brine permittivity (Stogryn & Desargant 1985) — reference ``smrt/permittivity/saline_water.py:131-155`` with
+    ``brine.py:13-46, 146-175`` (conductivity, relaxation time, static and high-frequency limits)."""
+    frequency = np.asarray(frequency, dtype=float)
+    tempC = np.asarray(temperature, dtype=float) - _FREEZING_POINT
+    eps_static = (939.66 - 19.068 * tempC) / (10.737 - tempC)
+    tau = 0.1099 + 0.13603e-2 * tempC + 0.20894e-3 * tempC**2 + 0.28167e-5 * tempC**3
+    sigma = np.where(tempC >= -22.9, -tempC * np.exp(0.5193 + 0.08755 * tempC), -tempC * np.exp(1.0334 + 0.1100 * tempC))
+    eps_inf = (82.79 + 8.19 * tempC**2) / (15.68 + tempC**2)
+    return (eps_inf + (eps_static - eps_inf) / (1.0 - tau * frequency / 1e9 * 1j)
+            + sigma / (2.0 * np.pi * _EPS0 * frequency) * 1j)
+
+
+def polder_van_santen_spheres(frac_volume, e0, eps):
+    """Polder - van Santen mixing for spherical inclusions — ``smrt/permittivity/generic_mixing_formula.py:118-141``."""
+    b_quad = eps - 2 * e0 - 3.0 * frac_volume * (eps - e0)
+    c_quad = -eps * e0
+    return (-b_quad + np.sqrt(b_quad**2 - 8.0 * c_quad)) / 4.0
+
+
+def saline_ice_permittivity_pvs_mixing(frequency, temperature, brine_volume_fraction):
+    """Pure ice + spherical brine pockets — reference ``smrt/permittivity/saline_ice.py:76-127`` (default models)."""
+    return polder_van_santen_spheres(brine_volume_fraction, ice_permittivity_maetzler06(frequency, temperature),
+                                     brine_permittivity_stogryn85(frequency, temperature))
+
+
+def seawater_permittivity_klein76(frequency, temperature, salinity):
+    """Klein & Swift (1976) — reference ``smrt/permittivity/saline_water.py:24-84``."""
+    frequency = np.asarray(frequency, dtype=float)
+    tempC = np.asarray(temperature, dtype=float) - _FREEZING_POINT
+    Sppt = np.asarray(salinity, dtype=float) / _PSU
+    tempF = -(0.0575 * Sppt - 1.710523e-3 * Sppt**1.5 + 2.154996e-4 * Sppt**2)
+    if np.any(tempC < tempF - 0.1):
+        raise SMRTError("The water temperature must be higher than the freezing point at the given salinity")
+    omega = 2 * np.pi * frequency
+    eps_inf = 4.9
+    eps_s_T = 87.134 - 1.949e-1 * tempC - 1.276e-2 * tempC**2 + 2.491e-4 * tempC**3
+    a_ST = 1.0 + 1.613e-5 * Sppt * tempC - 3.656e-3 * Sppt + 3.210e-5 * Sppt**2 - 4.232e-7 * Sppt**3
+    eps_static = eps_s_T * a_ST
+    tau_T0 = 1.768e-11 - 6.086e-13 * tempC + 1.104e-14 * tempC**2 - 8.111e-17 * tempC**3
+    b_ST = 1.0 + 2.282e-5 * Sppt * tempC - 7.638e-4 * Sppt - 7.760e-6 * Sppt**2 + 1.105e-8 * Sppt**3
+    tau = tau_T0 * b_ST
+    delta = 25 - tempC
+    beta = (2.0333e-2 + 1.266e-4 * delta + 2.464e-6 * delta**2
+            - Sppt * (1.849e-5 - 2.551e-7 * delta + 2.551e-8 * delta**2))
+    sigma_25S = Sppt * (0.182521 - 1.46192e-3 * Sppt + 2.09324e-5 * Sppt**2 - 1.28205e-7 * Sppt**3)
+    sigma = sigma_25S * np.exp(-delta * beta)
+    return eps_inf + (eps_static - eps_inf) / (1 - 1j * omega * tau) + 1j * sigma / (omega * _EPS0)
+
+
+def pack_sea_ice_ensemble(frequency, thickness, temperature, salinity, porosity, corr_length, *, theta_deg=40.0,
+                          water_substrate=True, water_temperature=_FREEZING_POINT - 1.8,
+                          water_salinity=0.032) -> ProblemBatch:
+    """Multi-year sea-ice ensemble given directly as arrays: ``(S, L)`` profiles x ``(F,)`` frequencies -> ``F*S``
+    passive problems in the reference's simulation order (frequency outermost).
+
+    Equivalent, member by member, to ``make_ice_column("multiyear", thickness=..., temperature=..., salinity=...,
+    porosity=..., microstructure_model="exponential", corr_length=..., brine_inclusion_shape="spheres",
+    add_water_substrate="ocean")`` (``smrt/inputs/make_medium.py:437-571, 573-753, 962-990``): background = saline ice
+    (Polder - van Santen mix of pure ice and Stogryn-85 brine at the Cox-Weeks brine volume), scatterers = air bubbles
+    (fractional volume = porosity), flat interfaces, semi-infinite sea water (Klein & Swift) below.  IBA + DORT.
+    """
+    thickness = np.atleast_2d(np.asarray(thickness, dtype=float))
+    S, L = thickness.shape
+    freqs = np.atleast_1d(np.asarray(frequency, dtype=float))
+    F = len(freqs)
+    B = F * S
+
+    def full(a):
+        return np.broadcast_to(np.asarray(a, dtype=float), (S, L))
+
+    def tile(a, dt=np.float64):
+        return np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=dt), (S, L))[None].repeat(F, axis=0)
+                                    .reshape(B, L))
+
+    temperature, salinity, porosity = full(temperature), full(salinity), full(porosity)
+    if np.any(salinity >= 1):
+        raise SMRTError("salinity must be given in kg/kg (multiply PSU by 1e-3)")
+    freq_b = np.repeat(freqs, S)
+    temp_b = tile(temperature)
+    vb = tile(brine_volume_cox83_lepparanta88(temperature, salinity))
+    eps_bg = saline_ice_permittivity_pvs_mixing(freq_b[:, None], temp_b, vb)
+    if water_substrate:
+        sub_kind = np.full(B, SUB_FLAT, dtype=np.int32)
+        sub_eps = np.asarray(seawater_permittivity_klein76(freq_b, water_temperature, water_salinity), dtype=np.complex128)
+        sub_T = np.full(B, float(water_temperature))
+    else:
+        sub_kind, sub_eps, sub_T = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.complex128), np.zeros(B)
+    return ProblemBatch(
+        mode=MODE_PASSIVE, frequency=freq_b, nlayer=np.full(B, L, dtype=np.int32), thickness=tile(thickness),
+        temperature=temp_b, frac_volume=tile(porosity), eps_bg=np.asarray(eps_bg, dtype=np.complex128),
+        eps_sc=np.ones((B, L), dtype=np.complex128), emmodel=np.full((B, L), emmodel_code("iba"), dtype=np.int32),
+        ms_kind=np.full((B, L), MS_EXPONENTIAL, dtype=np.int32), ms_p0=tile(corr_length), ms_p1=np.zeros((B, L)),
+        interface=np.zeros((B, L), dtype=np.int32), substrate_kind=sub_kind, substrate_eps=sub_eps,
+        substrate_temperature=sub_T, theta=np.radians(np.atleast_1d(np.asarray(theta_deg, dtype=float))),
+        theta_inc=np.zeros(0), phi=0.0, dense_snow_correction=np.zeros((B, L), dtype=np.int32),
+    )

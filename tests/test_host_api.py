@@ -128,3 +128,40 @@ def test_rtsolver_plugin_seam():
     res = solver.solve(sp, [IBA(), IBA()], sensor_list.passive(37e9, 55), None, parallel_computation="none")
     ref = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8)).run(sensor_list.passive(37e9, 55), sp)
     assert res.TbV() == ref.TbV()
+
+
+def test_sea_ice_ensemble_packer_matches_the_reference_inputs():
+    """pack_sea_ice_ensemble (vectorised brine volume / brine + saline-ice + sea-water permittivities) against the inputs
+    the reference itself produced for the first six members of BASELINE config 5 (make_ice_column("multiyear", ...,
+    add_water_substrate="ocean") -> layer.permittivity / substrate.permittivity), tests/golden/cfg5_first6.npz"""
+    import bench
+    from smrt_b200 import pack_sea_ice_ensemble
+
+    d, ref_batch, _ = load_golden("cfg5_first6")
+    th, T, sal, por, pc = bench.sea_ice_members(6)
+    b = pack_sea_ice_ensemble(1.4e9, th, T, sal, por, pc, theta_deg=40.0)
+    assert b.B == ref_batch.B and b.L == ref_batch.L and b.mode == ref_batch.mode
+    for name in ("thickness", "temperature", "frac_volume", "eps_sc", "ms_p0", "ms_p1", "substrate_temperature", "theta"):
+        np.testing.assert_allclose(getattr(b, name), getattr(ref_batch, name), rtol=1e-15, atol=0, err_msg=name)
+    np.testing.assert_allclose(b.eps_bg, ref_batch.eps_bg, rtol=1e-13)
+    np.testing.assert_allclose(b.substrate_eps, ref_batch.substrate_eps, rtol=1e-14)
+    for name in ("nlayer", "emmodel", "ms_kind", "interface", "substrate_kind", "dense_snow_correction"):
+        assert np.array_equal(getattr(b, name), getattr(ref_batch, name)), name
+
+
+def test_sea_ice_permittivity_building_blocks():
+    """spot values of the restated formulas (reference smrt/permittivity/test_saline_water.py, test_saline_ice.py style)"""
+    from smrt_b200 import pack as P
+
+    # Cox & Weeks regime boundaries are continuous enough and inside [0, 1]
+    T = np.array([250.0, 255.0, 265.0, 271.0, 271.3])
+    vb = P.brine_volume_cox83_lepparanta88(T, 0.005)
+    assert np.all((vb > 0) & (vb < 1)) and np.all(np.diff(vb) > 0)
+    # brine is lossy and strongly dispersive at L band; sea water around (77, 44) at 1.4 GHz, 271.35 K, 32 PSU
+    eb = P.brine_permittivity_stogryn85(1.4e9, 265.0)
+    assert eb.real > 40 and eb.imag > 20
+    ew = P.seawater_permittivity_klein76(1.4e9, 271.35, 0.032)
+    assert abs(ew - (76.94890621 + 44.08814627j)) < 1e-6
+    with pytest.raises(SMRTError):
+        P.seawater_permittivity_klein76(1.4e9, 260.0, 0.032)
+    assert abs(P.water_freezing_temperature(0.0) - 273.15) < 0.05
