@@ -1,8 +1,9 @@
 // dort_linalg.cuh — CTA-cooperative dense fp64 linear algebra on small column-major matrices held in shared memory
-// (or, for stream counts whose blocks exceed 227 KB, in an L2-resident global scratch): register-tiled GEMM with
-// functor operands, Cholesky, one-sided Jacobi SVD, LU with partial pivoting and the triangular solves the DORT path
-// needs.  All routines are called by every thread of the block (or of a half-block "team" for the two concurrent
-// Cholesky factorisations) and synchronise internally.
+// (or, for stream counts whose blocks exceed 227 KB, in an L2-resident global scratch): register-tiled GEMMs, block
+// matrix-vector products, left-looking Cholesky, one-sided Jacobi SVD (register-blocked for h <= 64, plain for larger
+// blocks), Gauss-Jordan eliminations with partial pivoting (panel-blocked for h <= 64) and the triangular solve the
+// DORT path needs.  All routines are called by every thread of the block (or of a half-block "team" for the two
+// concurrent Cholesky factorisations) and synchronise internally.
 #pragma once
 #include "simt.h"
 #include <math.h>
@@ -83,45 +84,8 @@ SMRT_DEV void team_gemm(const Team& tm, int M, int N, int K, FA a, FB b, FS stor
 
 // ------------------------------------------------------------------------------------------------------------ Cholesky
 // In-place lower Cholesky A = L L^T of the h x h symmetric positive definite matrix whose LOWER triangle is stored in A
-// (column-major, leading dimension ld).  The strict upper triangle is neither read nor written.
-// Returns (to every thread of the team) 0 on success, 1 if a pivot is not positive (matrix not SPD).
-// `flag` is a team-shared int scratch.
-SMRT_DEV int team_cholesky(const Team& tm, double* A, int ld, int h, int* flag) {
-  if (tm.rank == 0) *flag = 0;
-  tm.sync();
-  for (int j = 0; j < h; ++j) {
-    // column j: every thread reads the pivot, scales its rows
-    double d = SMRT_AT(A, ld, j, j);
-    if (!(d > 0.0)) {
-      if (tm.rank == 0) *flag = 1;
-      tm.sync();
-      return 1;
-    }
-    double piv = sqrt(d);
-    double inv = 1.0 / piv;
-    tm.sync();  // everybody has read A(j,j) before it is overwritten
-    for (int i = j + tm.rank; i < h; i += tm.size) {
-      double v = SMRT_AT(A, ld, i, j);
-      SMRT_AT(A, ld, i, j) = (i == j) ? piv : v * inv;
-    }
-    tm.sync();
-    // trailing update of the lower triangle: A(i, c) -= L(i, j) L(c, j) for j < c <= i < h
-    int nt = h - j - 1;  // trailing size
-    if (nt > 0) {
-      // enumerate (c, i) with c in (j, h), i in [c, h): work split by columns-of-rows pairs
-      for (int c = j + 1 + (tm.rank / 32); c < h; c += tm.size / 32) {
-        double lc = SMRT_AT(A, ld, c, j);
-        for (int i = c + (tm.rank & 31); i < h; i += 32) {
-          SMRT_AT(A, ld, i, c) = fma(-SMRT_AT(A, ld, i, j), lc, SMRT_AT(A, ld, i, c));
-        }
-      }
-    }
-    tm.sync();
-  }
-  return *flag;
-}
-
-// Left-looking variant with ONE team barrier per column (the right-looking version above needs three and rewrites the
+// (column-major, leading dimension ld); the strict upper triangle is neither read nor written.
+// Left-looking with ONE team barrier per step (a right-looking version needs three per column and rewrites the
 // trailing matrix at every step).  Thread t owns the rows t, t + size, ... (NR of them); at step j it forms
 //   s_i = A(i, j) - sum_{k<j} L(i, k) L(j, k)      for its rows i > j
 // and, redundantly (the L(j, k) operands are loaded anyway), the pivot s_jj = A(j, j) - sum_k L(j, k)^2, so that
@@ -729,141 +693,6 @@ SMRT_DEV void block_backsolve_lt(const double* SMRT_RESTRICT C, int ldc, double*
   }
 }
 
-// ------------------------------------------------------------------------------------------ LU with partial pivoting
-// In-place LU of the h x h matrix A (column-major, ld) with row interchanges applied physically; perm[j] = pivot row
-// chosen at step j (LAPACK ipiv convention, 0-based).  Returns 0, or 1 if a pivot is exactly zero / not finite.
-// `ctrl` is block-shared int[4].
-SMRT_DEV int block_lu(double* A, int ld, int h, int* perm, int* ctrl) {
-  const int NT = blockDim.x;
-  const int tid = threadIdx.x;
-  if (tid == 0) ctrl[1] = 0;
-  __syncthreads();
-  for (int j = 0; j < h; ++j) {
-    // pivot search by warp 0
-    if (tid < 32) {
-      double best = -1.0;
-      int bi = j;
-      for (int i = j + tid; i < h; i += 32) {
-        double v = fabs(SMRT_AT(A, ld, i, j));
-        if (v > best) {
-          best = v;
-          bi = i;
-        }
-      }
-      for (int off = 16; off > 0; off >>= 1) {
-        double ob = __shfl_xor_sync(0xffffffffu, best, off, 32);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, off, 32);
-        if (ob > best || (ob == best && oi < bi)) {
-          best = ob;
-          bi = oi;
-        }
-      }
-      if (tid == 0) {
-        perm[j] = bi;
-        if (!(best > 0.0) || !isfinite(best)) ctrl[1] = 1;
-      }
-    }
-    __syncthreads();
-    if (ctrl[1]) return 1;
-    int pr = perm[j];
-    // swap rows j and pr across all columns
-    if (pr != j) {
-      for (int c = tid; c < h; c += NT) {
-        double t = SMRT_AT(A, ld, j, c);
-        SMRT_AT(A, ld, j, c) = SMRT_AT(A, ld, pr, c);
-        SMRT_AT(A, ld, pr, c) = t;
-      }
-      __syncthreads();
-    }
-    double inv = 1.0 / SMRT_AT(A, ld, j, j);
-    __syncthreads();
-    // scale the column and update the trailing matrix: A(i, c) -= l_i * A(j, c)
-    // thread layout: 32 lanes along rows, warps along columns
-    int nrows = h - j - 1;
-    if (nrows > 0) {
-      for (int c = j + 1 + (tid >> 5); c < h; c += (NT >> 5)) {
-        double ujc = SMRT_AT(A, ld, j, c);
-        for (int i = j + 1 + (tid & 31); i < h; i += 32) {
-          double lij = SMRT_AT(A, ld, i, j) * inv;
-          SMRT_AT(A, ld, i, c) = fma(-lij, ujc, SMRT_AT(A, ld, i, c));
-        }
-      }
-      __syncthreads();
-      for (int i = j + 1 + tid; i < h; i += NT) SMRT_AT(A, ld, i, j) *= inv;
-      __syncthreads();
-    }
-  }
-  return 0;
-}
-
-// Solve op(A) X = B in place for the h x nrhs block B (column-major, ldb), A = P^T L U from block_lu.
-//   transposed == 0:  A X = B    (row interchanges, forward with unit-lower L, backward with U)
-//   transposed == 1:  A^T X = B  (forward with U^T, backward with unit-upper L^T, interchanges undone in reverse)
-// Columns are independent: `tpc` threads cooperate on one column through the axpy form of the substitutions.
-SMRT_DEV void block_lu_solve(const double* LU, int ld, int h, const int* perm, double* Bm, int ldb, int nrhs,
-                             int transposed) {
-  const int NT = blockDim.x;
-  const int tid = threadIdx.x;
-  int tpc = 32;
-  while (tpc > 1 && nrhs * tpc > NT) tpc >>= 1;
-  const int ngroups = NT / tpc;
-  const int grp = tid / tpc, lane = tid % tpc;
-  const unsigned gmask = (tpc == 32) ? 0xffffffffu : (((1u << tpc) - 1u) << ((tid & 31) & ~(tpc - 1)));
-  for (int c = grp; c < nrhs; c += ngroups) {
-    double* x = Bm + (size_t)c * ldb;
-    if (!transposed) {
-      if (lane == 0) {
-        for (int j = 0; j < h; ++j) {
-          int pr = perm[j];
-          if (pr != j) {
-            double t = x[j];
-            x[j] = x[pr];
-            x[pr] = t;
-          }
-        }
-      }
-      __syncwarp(gmask);
-      for (int j = 0; j < h; ++j) {  // forward: x_i -= L(i, j) x_j, i > j
-        double xj = x[j];
-        for (int i = j + 1 + lane; i < h; i += tpc) x[i] = fma(-SMRT_AT(LU, ld, i, j), xj, x[i]);
-        __syncwarp(gmask);
-      }
-      for (int j = h - 1; j >= 0; --j) {  // backward: x_j /= U(j, j); x_i -= U(i, j) x_j, i < j
-        if (lane == 0) x[j] = x[j] / SMRT_AT(LU, ld, j, j);
-        __syncwarp(gmask);
-        double xj = x[j];
-        for (int i = lane; i < j; i += tpc) x[i] = fma(-SMRT_AT(LU, ld, i, j), xj, x[i]);
-        __syncwarp(gmask);
-      }
-    } else {
-      for (int j = 0; j < h; ++j) {  // U^T w = b: w_j = b_j / U(j, j); b_i -= U(j, i) w_j, i > j
-        if (lane == 0) x[j] = x[j] / SMRT_AT(LU, ld, j, j);
-        __syncwarp(gmask);
-        double xj = x[j];
-        for (int i = j + 1 + lane; i < h; i += tpc) x[i] = fma(-SMRT_AT(LU, ld, j, i), xj, x[i]);
-        __syncwarp(gmask);
-      }
-      for (int j = h - 1; j >= 0; --j) {  // L^T z = w: z_j = w_j; w_i -= L(j, i) z_j, i < j
-        double xj = x[j];
-        for (int i = lane; i < j; i += tpc) x[i] = fma(-SMRT_AT(LU, ld, j, i), xj, x[i]);
-        __syncwarp(gmask);
-      }
-      if (lane == 0) {
-        for (int j = h - 1; j >= 0; --j) {
-          int pr = perm[j];
-          if (pr != j) {
-            double t = x[j];
-            x[j] = x[pr];
-            x[pr] = t;
-          }
-        }
-      }
-      __syncwarp(gmask);
-    }
-  }
-  __syncthreads();
-}
-
 // =====================================================================================================================
 // Second-generation primitives used by the boundary kernel: pointer-operand GEMMs without guards in the inner loop and
 // Gauss-Jordan eliminations whose every step is ONE block barrier (pivot search done redundantly by every warp,
@@ -1183,139 +1012,6 @@ SMRT_DEV_NOINLINE int block_gj_cols(double* S, int lds, double* Km, int ldk, int
 
 
 // =====================================================================================================================
-// Gauss-Jordan by rows with LOOK-AHEAD pivoting.  The augmented matrix is given as two column blocks:
-//   columns [0, h)      : left block  A  (column c at Lb + c * ldl)  -> reduced to a (row-permuted, unscaled) identity
-//   columns [h, h + nR) : right block R  (column c at Rb + (c - h) * ldr)
-// Afterwards, for every unknown k:  (A^-1 R)(k, :) = R(rowof[k], :) * ipiv[k]   with ipiv[k] = 1 / pivot_k.
-//
-// One block barrier per step and no pivot search on the critical path: the warp that updates column j + 1 during step j
-// finds the next pivot from the freshly updated values (still in its registers) and publishes (row, 1 / pivot) for the
-// next step before the barrier.  Lanes walk the rows (RPL rows per lane, h <= 32 RPL), warps the columns.
-// rowstep / rowof: block-shared int[h]; ipiv: block-shared double[h]; la_p: block-shared int[2]; la_inv: double[2].
-// Returns 1 (in every thread) if a pivot vanishes or is not finite.
-// =====================================================================================================================
-template <int RPL>
-SMRT_DEV int block_gj_rows_la(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowstep, int* rowof,
-                              double* ipiv, int* la_p, double* la_inv) {
-  const int NT = blockDim.x, tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
-  const int W = h + nR;
-  for (int i = tid; i < h; i += NT) rowstep[i] = -1;
-  // first pivot: searched by warp 0
-  if (warp == 0) {
-    double best = -1.0;
-    int bi = 0x7fffffff;
-#pragma unroll
-    for (int u = 0; u < RPL; ++u) {
-      const int i = lane + 32 * u;
-      if (i < h) {
-        const double v = fabs(Lb[i]);
-        if (v > best) {
-          best = v;
-          bi = i;
-        }
-      }
-    }
-    warp_argmax(best, bi);
-    if (lane == 0) {
-      const bool ok = (best > 0.0) && (best < 1e300);
-      la_p[0] = ok ? bi : -1;
-      la_inv[0] = ok ? 1.0 / Lb[bi] : 0.0;
-    }
-  }
-  __syncthreads();
-  for (int j = 0; j < h; ++j) {
-    const int p = la_p[j & 1];
-    if (p < 0) return 1;
-    const double inv = la_inv[j & 1];
-    if (tid == 0) {
-      rowstep[p] = j;
-      rowof[j] = p;
-      ipiv[j] = inv;
-    }
-    const double* colj = Lb + (size_t)j * ldl;
-    double mrow[RPL];
-#pragma unroll
-    for (int u = 0; u < RPL; ++u) {
-      const int i = lane + 32 * u;
-      mrow[u] = (i < h && i != p) ? -(colj[i] * inv) : 0.0;
-    }
-    int c = j + 1 + warp;
-    if (warp == 0 && c < h) {
-      // column j + 1: update, then look ahead for the next pivot among the rows not used yet
-      double* col = Lb + (size_t)c * ldl;
-      const double pc = col[p];
-      double best = -1.0, bv = 0.0;
-      int bi = 0x7fffffff;
-#pragma unroll
-      for (int u = 0; u < RPL; ++u) {
-        const int i = lane + 32 * u;
-        if (i < h) {
-          const double v = fma(mrow[u], pc, col[i]);
-          col[i] = v;
-          if (i != p && rowstep[i] < 0 && fabs(v) > best) {
-            best = fabs(v);
-            bv = v;
-            bi = i;
-          }
-        }
-      }
-      // argmax carrying the signed value along
-      for (int off = 16; off > 0; off >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, off, 32);
-        const double ov = __shfl_xor_sync(0xffffffffu, bv, off, 32);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, off, 32);
-        if (ob > best || (ob == best && oi < bi)) {
-          best = ob;
-          bv = ov;
-          bi = oi;
-        }
-      }
-      if (lane == 0) {
-        const bool ok = (best > 0.0) && (best < 1e300);
-        la_p[(j + 1) & 1] = ok ? bi : -1;
-        la_inv[(j + 1) & 1] = ok ? 1.0 / bv : 0.0;
-      }
-      c += nwarp;
-    }
-    // remaining columns, two per iteration for instruction-level parallelism
-    for (; c + nwarp < W; c += 2 * nwarp) {
-      const int c1 = c + nwarp;
-      double* col0 = (c < h) ? Lb + (size_t)c * ldl : Rb + (size_t)(c - h) * ldr;
-      double* col1 = (c1 < h) ? Lb + (size_t)c1 * ldl : Rb + (size_t)(c1 - h) * ldr;
-      const double p0 = col0[p], p1 = col1[p];
-#pragma unroll
-      for (int u = 0; u < RPL; ++u) {
-        const int i = lane + 32 * u;
-        if (i < h) {
-          const double v0 = col0[i], v1 = col1[i];
-          col0[i] = fma(mrow[u], p0, v0);
-          col1[i] = fma(mrow[u], p1, v1);
-        }
-      }
-    }
-    if (c < W) {
-      double* col0 = (c < h) ? Lb + (size_t)c * ldl : Rb + (size_t)(c - h) * ldr;
-      const double p0 = col0[p];
-#pragma unroll
-      for (int u = 0; u < RPL; ++u) {
-        const int i = lane + 32 * u;
-        if (i < h) col0[i] = fma(mrow[u], p0, col0[i]);
-      }
-    }
-    __syncthreads();
-  }
-  return 0;
-}
-
-SMRT_DEV int block_gj_rows_lookahead(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowstep, int* rowof,
-                                     double* ipiv, int* la_p, double* la_inv) {
-  if (h <= 64) return block_gj_rows_la<2>(Lb, ldl, Rb, ldr, h, nR, rowstep, rowof, ipiv, la_p, la_inv);
-  if (h <= 128) return block_gj_rows_la<4>(Lb, ldl, Rb, ldr, h, nR, rowstep, rowof, ipiv, la_p, la_inv);
-  return block_gj_rows_la<8>(Lb, ldl, Rb, ldr, h, nR, rowstep, rowof, ipiv, la_p, la_inv);
-}
-
-// =====================================================================================================================
 // BLOCKED Gauss-Jordan by rows with partial pivoting (h <= 64).  The unblocked eliminations above rewrite the whole
 // trailing matrix at every step (one FMA per shared-memory load + store: the boundary kernel spent 60 % of its time
 // there at 13 % FP64 utilisation).  Here the steps are grouped in panels of SMRT_GJ_NB columns:
@@ -1332,7 +1028,7 @@ SMRT_DEV int block_gj_rows_lookahead(double* Lb, int ldl, double* Rb, int ldr, i
 //   3. look-ahead: warp 0 updates the columns of the NEXT panel first and factorises it while the other warps update
 //      the remaining columns: one block barrier per panel, and the (serial) panel factorisations are the only
 //      critical path.
-// Same conventions as block_gj_rows_la: two column blocks (left: the h x h system, right: nR further columns), implicit
+// Conventions: two column blocks (left: the h x h system, right: nR further columns), implicit
 // row permutation, unscaled rows:  (A^-1 R)(k, :) = R(rowof[k], :) * ipiv[k].  The left block is destroyed.
 // Scratch (block-shared): Vbuf double[2 * h * SMRT_GJ_NB], rowof int[h], ipiv double[h], flag int[1].
 // Returns 1 in every thread if a pivot vanishes / is not finite.  blockDim.x >= 64.
