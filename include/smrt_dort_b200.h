@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SMRTB200_ABI_VERSION 1
+#define SMRTB200_ABI_VERSION 2
 
 /* sensor mode (reference smrt/core/sensor.py:331-339) */
 #define SMRTB200_MODE_PASSIVE 0
@@ -50,6 +50,13 @@ extern "C" {
 /* substrate */
 #define SMRTB200_SUB_NONE 0
 #define SMRTB200_SUB_FLAT 1 /* flat half-space of permittivity substrate_eps at substrate_temperature, smrt/substrate/flat.py:15-17 */
+/* Fresnel coefficients of the half-space with a per-stream adjustment of the V and H power coefficients (the third
+ * Stokes component keeps its Fresnel value, as in the reference); substrate_params holds the model parameters */
+#define SMRTB200_SUB_SOIL_WEGMULLER 2  /* params[0] = roughness_rms (m)          smrt/substrate/soil_wegmuller.py:20-81 */
+#define SMRTB200_SUB_SOIL_QNH 3        /* params = H, Q, Nv, Nh                  smrt/substrate/soil_qnh.py:22-89 */
+#define SMRTB200_SUB_REFLECTOR 4       /* params = specular reflection V, H; passive only; substrate_eps unused
+                                          smrt/substrate/reflector.py:51-111 (scalar / dict specifications) */
+#define SMRTB200_SUB_ROUGH_CHOUDHURY 5 /* params[0] = roughness_rms (m)          smrt/substrate/rough_choudhury79.py:19-79 */
 
 /* phase_normalization option (smrt/rtsolver/dort.py:94-103, 782-819) */
 #define SMRTB200_NORM_OFF 0
@@ -62,6 +69,7 @@ extern "C" {
 #define SMRTB200_ERR_EIGEN 2         /* SMRTError of dort.py:826,844,852,1068-1085 (layer matrix not diagonalisable with real positive spectrum) */
 #define SMRTB200_ERR_SINGULAR 3      /* singular boundary block (scipy.linalg.solve_banded would raise, dort.py:469) */
 #define SMRTB200_ERR_INPUT 4         /* invalid per-problem input (fewer than 2 streams in a layer, bad enum, SHS t has no solution ...) */
+#define SMRTB200_ERR_SUBSTRATE 5     /* substrate model outside its validity range (Warning of rough_choudhury79.py:29-31: k sigma > 0.1) */
 #define SMRTB200_ERR_MASK 15
 #define SMRTB200_WARN_SHALLOW 16     /* smrt_warn of dort.py:460-467: optically shallow snowpack without substrate */
 
@@ -104,6 +112,10 @@ typedef struct {
   const int* substrate_kind;          /* [B] SMRTB200_SUB_* */
   const double* substrate_eps;        /* [B, 2] */
   const double* substrate_temperature;/* [B] K; <= 0 means "no temperature" (dort.py:429-441) */
+  const double* substrate_params;     /* [B, 4] parameters of SMRTB200_SUB_* kinds >= 2; may be NULL (all zero) */
+  const double* atmosphere;           /* [B, 3] isotropic atmosphere (passive mode): tb_down, tb_up (K), transmittance
+                                         smrt/atmosphere/simple_isotropic_atmosphere.py:49-77, rtsolver_utils.py:141-147,
+                                         302-305; may be NULL = (0, 0, 1) = no atmosphere */
   const double* theta;                /* [n_theta] rad, viewing angles (passive) */
   const double* theta_inc;            /* [n_inc] rad, incidence angles (active) */
   double phi;                         /* rad, relative azimuth (active; pi = backscatter) */

@@ -273,8 +273,15 @@ def solve_problem(problem, collect=None):
     kw = dict(problem=problem, streams=streams, layers=layers, iface=iface, planck=planck,
               prune_deep_snowpack=opts["prune_deep_snowpack"], info=info)
     if mode == "P":
-        I = solve_mode(mode=0, intensity_down=np.zeros((2 * n_air, 1)), **kw)
-        intensity_up = inv_planck(I[0:2].copy())
+        atmos = problem.get("atmosphere")  # isotropic atmosphere, as in dort_oracle.solve_problem
+        idown = np.zeros((2 * n_air, 1))
+        if atmos is not None:
+            idown[:] = planck(float(atmos[0]))
+        I = solve_mode(mode=0, intensity_down=idown, **kw)
+        intensity_up = I[0:2].copy()
+        if atmos is not None:
+            intensity_up = planck(float(atmos[1])) + float(atmos[2]) * intensity_up
+        intensity_up = inv_planck(intensity_up)
         outmu = streams["outmu"]
     else:
         inc = O.prepare_incident_streams(streams["outmu"], theta)

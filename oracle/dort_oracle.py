@@ -30,7 +30,12 @@ Problem description (a plain dict, all SI units; the same fields the C ABI takes
                                   ms_p1 = stickiness)
     ms_p0, ms_p1   (L,)
     interface      (L,) int       interface ABOVE layer l: 0 = flat (Fresnel), 1 = transparent
-    substrate_kind int            0 = none, 1 = flat half-space (substrate_eps, substrate_temperature)
+    substrate_kind int            0 = none, 1 = flat half-space (substrate_eps, substrate_temperature), 2 = rough soil
+                                  of Wegmueller & Maetzler 1999 (params[0] = roughness_rms), 3 = QNH soil (params = H, Q,
+                                  Nv, Nh), 4 = reflector (params = specular reflection V, H; passive only), 5 = rough
+                                  reflectivity of Choudhury 1979 (params[0] = roughness_rms)
+    substrate_params (4,)         see substrate_kind (optional)
+    atmosphere     (3,)           isotropic atmosphere: tb_down, tb_up (K), transmittance (optional; passive only)
     theta          (n_theta,) rad          viewing angles (passive) / incidence = viewing angles (active)
     phi            float rad      relative azimuth (active; pi for backscatter)
     dense_snow_correction (L,) int  1 = model the layer as the inverted medium when frac_volume > 0.5
@@ -56,13 +61,15 @@ BOLTZMANN_CONSTANT = 1.380649e-23
 EM_IBA, EM_DMRT_QCA_SR, EM_NONSCATTERING, EM_DMRT_QCACP_SR = 0, 1, 2, 3
 MS_EXPONENTIAL, MS_SHS, MS_HOMOGENEOUS = 0, 1, 2
 IF_FLAT, IF_TRANSPARENT = 0, 1
-SUB_NONE, SUB_FLAT = 0, 1
+SUB_NONE, SUB_FLAT, SUB_SOIL_WEGMULLER, SUB_SOIL_QNH, SUB_REFLECTOR, SUB_ROUGH_CHOUDHURY = 0, 1, 2, 3, 4, 5
 
 # status codes shared with the C ABI (include/smrt_dort_b200.h)
 ST_OK = 0
 ST_NORMALIZATION = 1  # phase re-normalisation exceeds 30 % (dort.py:792-801)
 ST_EIGEN = 2  # diagonalisation failed / not real (dort.py:1068-1085)
 ST_SINGULAR = 3  # boundary system singular
+ST_INPUT = 4  # invalid per-problem input
+ST_SUBSTRATE = 5  # substrate model outside its validity range (substrate/rough_choudhury79.py:29-31 raises Warning)
 ST_SHALLOW_WARNING = 16  # flag bit: optically shallow without substrate (dort.py:460-467)
 
 
@@ -356,6 +363,58 @@ def compress_diag(mat_pol_mu, mode):
     return np.transpose(mat_pol_mu).reshape(-1)
 
 
+def substrate_R_T(problem, eps_1, mu, npol):
+    """specular_reflection_matrix / emissivity_matrix of the substrate under the last layer (permittivity eps_1) on that
+    layer's streams: reference smrt/substrate/flat.py:15-17 (+ core/interface.py:94-154), soil_wegmuller.py:20-81,
+    soil_qnh.py:22-89, reflector.py:51-111, rough_choudhury79.py:19-79.  Only the V and H components are modified by
+    the rough models, the third component keeps its Fresnel value (as in the reference)."""
+    kind = int(problem["substrate_kind"])
+    mu = np.atleast_1d(np.asarray(mu, dtype=float))
+    par = np.asarray(problem.get("substrate_params", np.zeros(4)), dtype=float)
+    if kind == SUB_REFLECTOR:
+        if npol > 2:
+            raise NotImplementedError("active model is not yet implemented, need modification for the third component")
+        R = np.zeros((npol, len(mu)))
+        R[0] = par[0]
+        R[1] = par[1]
+        return R, 1 - R
+    R, T = interface_R_T(IF_FLAT, eps_1, problem["substrate_eps"], mu, npol)
+    if kind == SUB_FLAT:
+        return R, T
+    freq = float(problem["frequency"])
+
+    def adjust(rh, rv):  # in place, like the reference
+        if kind in (SUB_SOIL_WEGMULLER, SUB_ROUGH_CHOUDHURY):
+            ksigma = (2 * np.pi * freq * np.sqrt((1 / 2.9979e8) ** 2 * complex(eps_1)) * par[0]).real
+        if kind == SUB_SOIL_WEGMULLER:
+            rh *= np.exp(-(ksigma ** (np.sqrt(0.1 * mu))))
+            mask = mu < np.cos(60 * np.pi / 180)
+            rv[~mask] = rh[~mask] * mu[~mask] ** 0.655
+            rv[mask] = rh[mask] * (0.635 - 0.0014 * (np.arccos(mu[mask]) * 180 / np.pi - 60))
+        elif kind == SUB_ROUGH_CHOUDHURY:
+            if ksigma > 0.1:
+                raise OracleError(ST_SUBSTRATE, "Reflectivity may be outside validity range. ksigma should be << 1")
+            rh *= np.exp(-4 * ksigma**2 * mu**2)
+            rv *= np.exp(-4 * ksigma**2 * mu**2)
+        elif kind == SUB_SOIL_QNH:
+            H, Q, Nv, Nh = par
+            coef_h = np.exp(-H * (mu**Nh))
+            coef_v = np.exp(-H * (mu**Nv))
+            trv = ((1 - Q) * rv + Q * rh) * coef_v
+            rh[:] = ((1 - Q) * rh + Q * rv) * coef_h
+            rv[:] = trv
+        else:
+            raise ValueError(f"unknown substrate kind {kind}")
+
+    adjust(R[1], R[0])
+    rh = 1 - T[1]
+    rv = 1 - T[0]
+    adjust(rh, rv)
+    T[1] = 1 - rh
+    T[0] = 1 - rv
+    return R, T
+
+
 def compute_interfaces(problem, eps_eff, streams, npol):
     """reference smrt/rtsolver/rtsolver_utils.py:473-644 for Flat / Transparent interfaces and a flat substrate."""
     L = len(eps_eff)
@@ -367,12 +426,8 @@ def compute_interfaces(problem, eps_eff, streams, npol):
         Rtop[l], Ttop[l] = interface_R_T(kinds[l], eps_l, eps_lm1, streams["mu"][l], npol)
         if l < L - 1:
             Rbot[l], Tbot[l] = interface_R_T(kinds[l + 1], eps_l, eps_eff[l + 1], streams["mu"][l], npol)
-        elif problem.get("substrate_kind", SUB_NONE) == SUB_FLAT:
-            # substrate/flat.py:15-17 + core/interface.py:94-154: specular reflection; emissivity = 1 - R for V, H
-            R, T = interface_R_T(IF_FLAT, eps_l, problem["substrate_eps"], streams["mu"][l], npol)
-            Rbot[l] = R
-            # emissivity matrix of a flat substrate = coherent transmission matrix (core/interface.py)
-            Tbot[l] = T
+        elif problem.get("substrate_kind", SUB_NONE) != SUB_NONE:
+            Rbot[l], Tbot[l] = substrate_R_T(problem, eps_l, streams["mu"][l], npol)
         else:
             Rbot[l] = None
             Tbot[l] = None
@@ -873,10 +928,15 @@ def solve_problem(problem, method="schur_forcedtriu", return_details=False):
         kw = dict(problem=problem, streams=streams, eigs=eigs, iface=iface, planck=planck,
                   prune_deep_snowpack=opts["prune_deep_snowpack"], info=info)
         if mode == "P":
+            atmos = problem.get("atmosphere")
             intensity_0 = np.zeros((2 * n_air, 1))
+            if atmos is not None:  # isotropic atmosphere (atmosphere/simple_isotropic_atmosphere.py:55-77,
+                intensity_0[:] = planck(float(atmos[0]))  # core/atmosphere.py:134-162, rtsolver_utils.py:141-147)
             I = dort_modem_banded(mode=0, intensity_down=intensity_0, **kw)
             intensity_up = np.zeros((2, n_air))
             intensity_up[0:2] += I[0:2]
+            if atmos is not None:  # rtsolver_utils.py:302-304
+                intensity_up = planck(float(atmos[1])) + float(atmos[2]) * intensity_up
             intensity_up = inv_planck(intensity_up)
             outmu = streams["outmu"]
         else:

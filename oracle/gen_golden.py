@@ -258,6 +258,109 @@ def cfg5_first6():
     run_case("cfg5_first6", "iba", sensor_list.passive(1.4e9, 40), sps, dict(n_max_stream=32))
 
 
+def _thin_snowpacks(seed, n, substrate_of, atmosphere_of=None, L=4):
+    """thin snowpacks (the substrate matters) with one substrate / atmosphere object each"""
+    rng = np.random.default_rng(seed)
+    sps = []
+    for i in range(n):
+        sps.append(make_snowpack(rng.uniform(0.05, 0.3, L), "exponential", density=rng.uniform(150, 450, L),
+                                 temperature=rng.uniform(240, 272, L), corr_length=rng.uniform(5e-5, 3e-4, L),
+                                 substrate=substrate_of(i, rng),
+                                 atmosphere=atmosphere_of(i, rng) if atmosphere_of else None))
+    return sps
+
+
+@case
+def soil_wegmuller_passive():  # reference substrate/soil_wegmuller.py; both branches of the V reflectivity (theta >< 60)
+    from smrt import make_soil
+
+    sps = _thin_snowpacks(21, 3, lambda i, rng: make_soil(
+        "soil_wegmuller", permittivity_model=complex(rng.uniform(4, 20), rng.uniform(0.5, 5)),
+        roughness_rms=[0.001, 0.01, 0.03][i], temperature=rng.uniform(255, 272)))
+    run_case("soil_wegmuller_passive", "iba", sensor_list.passive([10.65e9, 36.5e9], [30, 55, 70]), sps,
+             dict(n_max_stream=16))
+
+
+@case
+def soil_qnh_passive():  # reference substrate/soil_qnh.py (N, Nv / Nh, Q)
+    from smrt import make_soil
+
+    args = [dict(H=0.5, Q=0.1, N=1.0), dict(H=1.2, Q=0.0, Nv=0.5, Nh=1.5), dict(H=0.2, Q=0.3)]
+    sps = _thin_snowpacks(22, 3, lambda i, rng: make_soil(
+        "soil_qnh", permittivity_model=complex(rng.uniform(4, 20), rng.uniform(0.5, 5)),
+        temperature=rng.uniform(255, 272), **args[i]))
+    run_case("soil_qnh_passive", "iba", sensor_list.passive([1.4e9, 18.7e9], [40, 55]), sps, dict(n_max_stream=16))
+
+
+@case
+def reflector_passive():  # reference substrate/reflector.py: scalar, polarisation dict, (frequency, polarisation) dict
+    from smrt.substrate.reflector import make_reflector
+
+    specs = [0.7, {"V": 0.6, "H": 0.8}, {(18.7e9, "H"): 0.5, (18.7e9, "V"): 0.6, (36.5e9, "H"): 0.7, (36.5e9, "V"): 0.8}]
+    sps = _thin_snowpacks(23, 3, lambda i, rng: make_reflector(temperature=rng.uniform(255, 272),
+                                                               specular_reflection=specs[i]))
+    run_case("reflector_passive", "iba", sensor_list.passive([18.7e9, 36.5e9], 55), sps, dict(n_max_stream=16))
+
+
+@case
+def choudhury_passive():  # reference substrate/rough_choudhury79.py (k sigma << 1)
+    from smrt.substrate.rough_choudhury79 import ChoudhuryReflectivity
+
+    sps = _thin_snowpacks(24, 2, lambda i, rng: ChoudhuryReflectivity(
+        temperature=rng.uniform(255, 272), permittivity_model=complex(rng.uniform(4, 20), rng.uniform(0.5, 5)),
+        roughness_rms=[1e-4, 2e-4][i]))
+    run_case("choudhury_passive", "iba", sensor_list.passive([6.925e9, 10.65e9], 55), sps, dict(n_max_stream=16))
+
+
+@case
+def atmosphere_passive():  # reference atmosphere/simple_isotropic_atmosphere.py: constants and frequency dicts
+    from smrt import make_soil
+    from smrt.atmosphere.simple_isotropic_atmosphere import SimpleIsotropicAtmosphere
+
+    atm = [SimpleIsotropicAtmosphere(tb_down=25.0, tb_up=8.0, transmittance=0.9),
+           SimpleIsotropicAtmosphere(tb_down={18.7e9: 15.2, 36.5e9: 23.5}, tb_up={18.7e9: 5.0, 36.5e9: 9.0},
+                                     transmittance={18.7e9: 0.95, 36.5e9: 0.85}),
+           SimpleIsotropicAtmosphere(tb_down=30.0)]
+    sps = _thin_snowpacks(25, 3, lambda i, rng: make_soil("soil_wegmuller", permittivity_model=complex(10, 1),
+                                                          roughness_rms=0.005, temperature=268.0) if i < 2 else None,
+                          lambda i, rng: atm[i])
+    run_case("atmosphere_passive", "iba", sensor_list.passive([18.7e9, 36.5e9], [35, 55]), sps, dict(n_max_stream=16))
+
+
+@case
+def ref_physics_law():  # reference test/test_physics_law.py:9-43, 46-95 (isothermal universe, Kirchhoff's law)
+    from smrt import make_soil
+    from smrt.atmosphere.simple_isotropic_atmosphere import SimpleIsotropicAtmosphere
+
+    T = 265.0
+    sps = []
+    for pc, thickness in [(0.8e-3, 10), (0.05e-3, 10), (0.8e-3, 0.1)]:
+        for atmosphere in (SimpleIsotropicAtmosphere(tb_down=T, tb_up=0, transmittance=1), None,
+                           SimpleIsotropicAtmosphere(tb_down=1, tb_up=0, transmittance=1)):
+            substrate = make_soil("soil_wegmuller", permittivity_model=complex(10, 1), roughness_rms=0.001,
+                                  temperature=T)
+            sps.append(make_snowpack([0.3, thickness], "exponential", density=[200, 300], temperature=T,
+                                     corr_length=pc, ice_permittivity_model=complex(1.7, 0.00001),
+                                     substrate=substrate, atmosphere=atmosphere))
+    run_case("ref_physics_law", "iba", sensor_list.passive(37e9, list(range(10, 80, 5))), sps,
+             dict(rayleigh_jeans_approximation=True))
+
+
+@case
+def soil_active():  # third Stokes component untouched by the rough soil models (soil_wegmuller.py:54-58)
+    from smrt import make_soil
+
+    rng = np.random.default_rng(26)
+    sps = []
+    for i in range(2):
+        sub = make_soil(["soil_wegmuller", "soil_qnh"][i], permittivity_model=complex(8, 1.5), temperature=268.0,
+                        **([dict(roughness_rms=0.01), dict(H=0.6, Q=0.1, N=1.0)][i]))
+        sps.append(make_snowpack(rng.uniform(0.05, 0.3, 3), "sticky_hard_spheres", density=rng.uniform(200, 400, 3),
+                                 temperature=rng.uniform(240, 270, 3), radius=rng.uniform(1e-4, 3e-4, 3),
+                                 stickiness=0.3, substrate=sub))
+    run_case("soil_active", "iba", sensor_list.active(13.5e9, 40), sps, dict(n_max_stream=16))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or list(CASES)

@@ -15,10 +15,10 @@ import numpy as np
 from .error import SMRTError
 from .pack import MODE_ACTIVE, MODE_PASSIVE, ProblemBatch
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 NORM_OFF, NORM_ON, NORM_FORCED = 0, 1, 2
-ST_OK, ST_NORMALIZATION, ST_EIGEN, ST_SINGULAR, ST_INPUT = 0, 1, 2, 3, 4
+ST_OK, ST_NORMALIZATION, ST_EIGEN, ST_SINGULAR, ST_INPUT, ST_SUBSTRATE = 0, 1, 2, 3, 4, 5
 ST_ERR_MASK = 15
 ST_WARN_SHALLOW = 16
 
@@ -30,6 +30,7 @@ STATUS_MESSAGES = {
     ST_EIGEN: "The diagonalization failed in DORT (single scattering albedo > 1 in a layer, too large grains for the "
               "emmodel, or an almost diagonal matrix).",
     ST_SINGULAR: "The boundary-condition system of DORT is singular.",
+    ST_SUBSTRATE: "Reflectivity may be outside validity range. ksigma should be << 1",
     ST_INPUT: "Invalid layer input for the DORT solver (fewer than 2 streams in a layer, or the sticky hard sphere "
               "parameter t has no solution: revise the stickiness).",
 }
@@ -54,7 +55,8 @@ class Batch(C.Structure):
         ("frac_volume", C.c_void_p), ("eps_bg", C.c_void_p), ("eps_sc", C.c_void_p), ("emmodel", C.c_void_p),
         ("ms_kind", C.c_void_p), ("ms_p0", C.c_void_p), ("ms_p1", C.c_void_p), ("interface_kind", C.c_void_p),
         ("dense_snow_correction", C.c_void_p), ("substrate_kind", C.c_void_p), ("substrate_eps", C.c_void_p),
-        ("substrate_temperature", C.c_void_p), ("theta", C.c_void_p), ("theta_inc", C.c_void_p),
+        ("substrate_temperature", C.c_void_p), ("substrate_params", C.c_void_p), ("atmosphere", C.c_void_p),
+        ("theta", C.c_void_p), ("theta_inc", C.c_void_p),
         ("phi", C.c_double),
         ("values", C.c_void_p), ("ks", C.c_void_p), ("ka", C.c_void_p), ("eps_eff", C.c_void_p),
         ("n_streams_out", C.c_void_p), ("stream_angles", C.c_void_p), ("optical_depth", C.c_void_p),
@@ -70,6 +72,7 @@ INPUT_FIELDS = [  # (Batch field, ProblemBatch attribute, numpy dtype)
     ("interface_kind", "interface", np.int32), ("dense_snow_correction", "dense_snow_correction", np.int32),
     ("substrate_kind", "substrate_kind", np.int32), ("substrate_eps", "substrate_eps", np.complex128),
     ("substrate_temperature", "substrate_temperature", np.float64),
+    ("substrate_params", "substrate_params", np.float64), ("atmosphere", "atmosphere", np.float64),
 ]
 
 EXPORTED_SYMBOLS = [

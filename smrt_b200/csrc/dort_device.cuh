@@ -15,8 +15,8 @@
 enum { EM_IBA = 0, EM_DMRT_QCA_SR = 1, EM_NONSCATTERING = 2, EM_DMRT_QCACP_SR = 3 };
 enum { MS_EXPONENTIAL = 0, MS_SHS = 1, MS_HOMOGENEOUS = 2 };
 enum { IF_FLAT = 0, IF_TRANSPARENT = 1 };
-enum { SUB_NONE = 0, SUB_FLAT = 1 };
-enum { ST_OK = 0, ST_NORMALIZATION = 1, ST_EIGEN = 2, ST_SINGULAR = 3, ST_INPUT = 4, ST_WARN_SHALLOW = 16 };
+enum { SUB_NONE = 0, SUB_FLAT = 1, SUB_SOIL_WEGMULLER = 2, SUB_SOIL_QNH = 3, SUB_REFLECTOR = 4, SUB_ROUGH_CHOUDHURY = 5 };
+enum { ST_OK = 0, ST_NORMALIZATION = 1, ST_EIGEN = 2, ST_SINGULAR = 3, ST_INPUT = 4, ST_SUBSTRATE = 5, ST_WARN_SHALLOW = 16 };
 
 // ---------------------------------------------------------------------------------------------------- complex numbers
 struct cplx {
@@ -387,6 +387,62 @@ SMRT_DEV_NOINLINE FresnelRT fresnel_power(int kind, cplx eps_1, cplx eps_2, doub
   o.T[1] = 1.0 - o.R[1];
   cplx one = c_make(1.0, 0.0);
   o.T[2] = mu2 / mu * c_mul(c_add(one, rv), c_conj(c_add(one, rh))).re;
+  return o;
+}
+
+// ------------------------------------------------------------------------------------------------------- substrates
+// k sigma of the rough-surface models: Re(2 pi f sqrt((1 / 2.9979e8)^2 eps_1)) * roughness_rms
+// (substrate/soil_wegmuller.py:29-30, rough_choudhury79.py:26-27; the reference's own rounded speed of light)
+SMRT_DEV double substrate_ksigma(double freq, cplx eps_1, double roughness_rms) {
+  const double ic = 1.0 / 2.9979e8, c2 = ic * ic;
+  const cplx sq = c_sqrt(c_make(c2 * eps_1.re, c2 * eps_1.im));
+  return (2.0 * SMRT_PI * freq) * sq.re * roughness_rms;
+}
+// in-place adjustment of the H and V power reflectivities of a rough substrate
+SMRT_DEV void substrate_adjust(int kind, const double* par, double ksigma, double mu, double& rh, double& rv) {
+  if (kind == SUB_SOIL_WEGMULLER) {  // soil_wegmuller.py:24-43
+    rh *= exp(-pow(ksigma, sqrt(0.1 * mu)));
+    if (mu < 0.5000000000000001)  // np.cos(60 * np.pi / 180)
+      rv = rh * (0.635 - 0.0014 * (acos(mu) * 180.0 / SMRT_PI - 60.0));
+    else
+      rv = rh * pow(mu, 0.655);
+  } else if (kind == SUB_ROUGH_CHOUDHURY) {  // rough_choudhury79.py:23-37 (validity checked by the caller)
+    const double f = exp(-4.0 * (ksigma * ksigma) * (mu * mu));
+    rh *= f;
+    rv *= f;
+  } else if (kind == SUB_SOIL_QNH) {  // soil_qnh.py:26-42; par = H, Q, Nv, Nh
+    const double H = par[0], Q = par[1];
+    const double coef_h = exp(-H * pow(mu, par[3])), coef_v = exp(-H * pow(mu, par[2]));
+    const double trv = ((1.0 - Q) * rv + Q * rh) * coef_v;
+    rh = ((1.0 - Q) * rh + Q * rv) * coef_h;
+    rv = trv;
+  }
+}
+// specular reflection and emissivity of the substrate under a layer of permittivity eps_1, on the stream mu:
+// substrate/flat.py:15-17, soil_wegmuller.py:45-81, soil_qnh.py:44-89, reflector.py:51-81, rough_choudhury79.py:39-79.
+// The third Stokes component keeps its Fresnel value (as in the reference).
+SMRT_DEV_NOINLINE FresnelRT substrate_power(int kind, const double* par, double freq, cplx eps_1, cplx eps_2, double mu) {
+  FresnelRT o;
+  const double zero4[4] = {0.0, 0.0, 0.0, 0.0};
+  if (!par) par = zero4;
+  if (kind == SUB_REFLECTOR) {
+    o.R[0] = par[0];
+    o.R[1] = par[1];
+    o.R[2] = 0.0;
+    o.T[0] = 1.0 - par[0];
+    o.T[1] = 1.0 - par[1];
+    o.T[2] = 0.0;
+    return o;
+  }
+  o = fresnel_power(IF_FLAT, eps_1, eps_2, mu);
+  if (kind == SUB_FLAT) return o;
+  const double ksigma =
+      (kind == SUB_SOIL_WEGMULLER || kind == SUB_ROUGH_CHOUDHURY) ? substrate_ksigma(freq, eps_1, par[0]) : 0.0;
+  substrate_adjust(kind, par, ksigma, mu, o.R[1], o.R[0]);
+  double rh = 1.0 - o.T[1], rv = 1.0 - o.T[0];
+  substrate_adjust(kind, par, ksigma, mu, rh, rv);
+  o.T[1] = 1.0 - rh;
+  o.T[0] = 1.0 - rv;
   return o;
 }
 

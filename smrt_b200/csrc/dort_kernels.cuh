@@ -33,6 +33,7 @@ struct KArgs {
   const double *ms_p0, *ms_p1;
   const int *interface_kind, *dense_corr, *substrate_kind;
   const double *substrate_eps, *substrate_temperature, *theta, *theta_inc;
+  const double *substrate_params, *atmosphere;  // optional (NULL): [B, 4] substrate model parameters, [B, 3] atmosphere
   // outputs
   double *values, *ks, *ka, *eps_eff;
   int* n_streams_out;
@@ -529,6 +530,27 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
       continue;
     }
     for (int j = tid; j < n_air; j += NT) outw[j] = stream_weight(outmu, n_air, j);
+    if (A.substrate_kind[b] == SUB_ROUGH_CHOUDHURY &&
+        substrate_ksigma(freq, c_make(eps_b[2 * (nl - 1)], eps_b[2 * (nl - 1) + 1]),
+                         A.substrate_params ? A.substrate_params[4 * (size_t)b] : 0.0) > 0.1) {
+      // outside the validity range of the model: the reference raises (rough_choudhury79.py:29-31)
+      for (int i = tid; i < n_out; i += NT) out[i] = nan("");
+      if (tid == 0) {
+        set_error(A.status, b, ST_SUBSTRATE);
+        A.n_streams_out[b] = 0;
+        A.optical_depth[b] = 0.0;
+      }
+      __syncthreads();
+      continue;
+    }
+    // isotropic atmosphere (passive mode): downwelling / upwelling intensity and transmittance, identical for every
+    // air stream and polarisation (atmosphere/simple_isotropic_atmosphere.py:55-77, core/atmosphere.py:134-162)
+    double atm_down = 0.0, atm_up = 0.0, atm_trans = 1.0;
+    if (A.mode == 0 && A.atmosphere) {
+      atm_down = planck_function(freq, A.atmosphere[3 * (size_t)b], A.rayleigh_jeans);
+      atm_up = planck_function(freq, A.atmosphere[3 * (size_t)b + 1], A.rayleigh_jeans);
+      atm_trans = A.atmosphere[3 * (size_t)b + 2];
+    }
     // incident streams (active) --------------------------------------------------------- rtsolver_utils.py:91-107
     if (tid == 0) {
       int cnt = 0;
@@ -682,8 +704,9 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
             if (l < nl - 1) {
               fb = fresnel_power(A.interface_kind[bL + l + 1], eps_l, c_make(eps_b[2 * (l + 1)], eps_b[2 * (l + 1) + 1]),
                                  mu[j]);
-            } else if (A.substrate_kind[b] == SUB_FLAT) {
-              fb = fresnel_power(IF_FLAT, eps_l, c_make(A.substrate_eps[2 * b], A.substrate_eps[2 * b + 1]), mu[j]);
+            } else if (A.substrate_kind[b] != SUB_NONE) {
+              fb = substrate_power(A.substrate_kind[b], A.substrate_params ? A.substrate_params + 4 * (size_t)b : nullptr,
+                                   freq, eps_l, c_make(A.substrate_eps[2 * b], A.substrate_eps[2 * b + 1]), mu[j]);
             } else {
               fb.R[0] = fb.R[1] = fb.R[2] = 0.0;
               fb.T[0] = fb.T[1] = fb.T[2] = 0.0;
@@ -744,6 +767,14 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
           }
         }
         __syncthreads();
+        if (l == 0 && A.mode == 0 && atm_down != 0.0) {
+          // downwelling atmospheric radiation through the air-snow interface (dort.py:383-395): b_top += T_air I_down
+          // on the air streams; rows beyond the layer's streams are truncated
+          for (int a = tid; a < 2 * n_air && a < h; a += NT) {
+            FresnelRT fa = fresnel_power(A.interface_kind[bL], c_make(1.0, 0.0), eps0, outmu[a >> 1]);
+            btop[a] += fa.T[a & 1] * atm_down;
+          }
+        }
         if (l == 0 && A.mode == 1) {
           // incident beams (rtsolver_utils.py:109-135) through the air-snow interface: b_top += T_air I_down
           for (int c = tid; c < nr; c += NT) {
@@ -907,8 +938,16 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
         const double B0 = (A.mode == 0 && m == 0 && T0 > 0.0) ? planck_function(freq, T0, A.rayleigh_jeans) : 0.0;
         if (A.mode == 0) {
           // passive: I0up = T_top0 (I1up + B0) on the first npol*n_air rows; Tb(theta) by inverse Planck + interpolation
+          // with an atmosphere: + R_air I_down (dort.py:481-484), then I_up(atm) + transmittance * I (rtsolver_utils.py:302-304)
           for (int a = tid; a < 2 * n_air; a += NT) {
             double v = (a < h0) ? Tt[a] * (svec[a] + B0) : 0.0;
+            if (A.atmosphere) {
+              if (atm_down != 0.0) {
+                FresnelRT fa = fresnel_power(A.interface_kind[bL], c_make(1.0, 0.0), eps0, outmu[a >> 1]);
+                v = fa.R[a & 1] * atm_down + v;
+              }
+              v = atm_up + atm_trans * v;
+            }
             btop[a] = inverse_planck_function(freq, v, A.rayleigh_jeans);  // reuse btop: Tb per (stream, pol)
           }
           __syncthreads();

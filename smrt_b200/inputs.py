@@ -199,6 +199,84 @@ class FlatSubstrate:
 FlatSubstrate.__name__ = "Flat"  # the packer recognises substrates and interfaces by class name, like the reference's
 
 
+class SoilWegmuller(FlatSubstrate):
+    """Data of the rough soil of Wegmüller & Mätzler 1999 — reference ``smrt/substrate/soil_wegmuller.py:20-22``
+    (the reflectivity model itself runs on the device)."""
+
+    def __init__(self, temperature=None, permittivity_model=None, roughness_rms=None):
+        super().__init__(temperature, permittivity_model)
+        if roughness_rms is None:
+            raise SMRTError("Parameter roughness_rms must be specified")
+        self.roughness_rms = roughness_rms
+
+
+class ChoudhuryReflectivity(SoilWegmuller):
+    """Rough reflectivity of Choudhury et al. 1979 — reference ``smrt/substrate/rough_choudhury79.py:19-21``."""
+
+
+class SoilQNH(FlatSubstrate):
+    """QNH soil parameters — reference ``smrt/substrate/soil_qnh.py:22-24``."""
+
+    def __init__(self, temperature=None, permittivity_model=None, H=None, Q=0.0, N=0.0, Nv=np.nan, Nh=np.nan):
+        super().__init__(temperature, permittivity_model)
+        if H is None:
+            raise SMRTError("Parameter H must be specified")
+        self.H, self.Q, self.N, self.Nv, self.Nh = H, Q, N, Nv, Nh
+
+
+class Reflector:
+    """Prescribed specular reflection (scalar, or dict keyed by polarisation and / or frequency) — reference
+    ``smrt/substrate/reflector.py:51-111``."""
+
+    def __init__(self, temperature=None, specular_reflection=None):
+        self.temperature = temperature
+        self.specular_reflection = specular_reflection
+
+
+def make_reflector(temperature=None, specular_reflection=None):
+    return Reflector(temperature=temperature, specular_reflection=specular_reflection)
+
+
+_SOILS = {"flat": FlatSubstrate, "soil_wegmuller": SoilWegmuller, "soil_qnh": SoilQNH,
+          "rough_choudhury79": ChoudhuryReflectivity}
+
+
+def make_soil(substrate_model, permittivity_model=None, temperature=FREEZING_POINT, **kwargs):
+    """``make_soil("soil_wegmuller", permittivity_model=complex(10, 1), roughness_rms=0.001, temperature=265)`` as in
+    reference ``smrt/inputs/make_soil.py:50-111`` with a complex number or a function of (frequency, temperature) as
+    permittivity model (the named soil permittivity models of the reference are not re-implemented here)."""
+    if substrate_model not in _SOILS:
+        raise SMRTError(f"substrate model '{substrate_model}' is not implemented on the B200 path "
+                        f"(available: {sorted(_SOILS)})")
+    if permittivity_model is None or isinstance(permittivity_model, str):
+        raise SMRTError("give the soil permittivity as a complex number or a function of (frequency, temperature)")
+    return _SOILS[substrate_model](temperature=temperature, permittivity_model=permittivity_model, **kwargs)
+
+
+class SimpleIsotropicAtmosphere:
+    """Isotropic atmosphere given by constants or frequency-keyed dicts — reference
+    ``smrt/atmosphere/simple_isotropic_atmosphere.py:49-53``."""
+
+    def __init__(self, tb_down=0.0, tb_up=0.0, transmittance=1.0):
+        self.constant_tbdown = tb_down
+        self.constant_tbup = tb_up
+        self.constant_trans = transmittance
+
+    def __add__(self, other):  # atmosphere + snowpack, reference smrt/core/atmosphere.py / snowpack.py:263-283
+        if isinstance(other, Snowpack):
+            if other.atmosphere is not None:
+                raise SMRTError("The snowpack has already an atmosphere")
+            return Snowpack(other.layers, other.interfaces, other.substrate, self)
+        raise SMRTError("Attempt to add an incorrect object to an atmosphere. Only adding an atmosphere and a "
+                        "snowpack (in that order) is a valid operation.")
+
+
+def make_atmosphere(atmosphere_model="simple_isotropic_atmosphere", **kwargs):
+    if atmosphere_model not in ("simple_isotropic_atmosphere", "simple_isotopic_atmosphere", SimpleIsotropicAtmosphere):
+        raise SMRTError(f"atmosphere model '{atmosphere_model}' is not implemented on the B200 path")
+    return SimpleIsotropicAtmosphere(**kwargs)
+
+
 class Snowpack:
     """Container with the attributes of reference ``smrt/core/snowpack.py:37-46``."""
 
@@ -217,9 +295,9 @@ class Snowpack:
         return [lay.thickness for lay in self.layers]
 
     def __add__(self, other):
-        if isinstance(other, FlatSubstrate):
+        if isinstance(other, (FlatSubstrate, Reflector)):
             return Snowpack(self.layers, self.interfaces, other, self.atmosphere)
-        raise SMRTError("only `snowpack + substrate` is supported")
+        raise SMRTError("only `snowpack + substrate` and `atmosphere + snowpack` are supported")
 
 
 def _get(x, i):
@@ -241,13 +319,13 @@ def make_interface(interface):
 
 
 def make_snowpack(thickness, microstructure_model, density, interface=None, substrate=None, temperature=FREEZING_POINT,
-                  **kwargs):
+                  atmosphere=None, **kwargs):
     """Multi-layer dry snowpack, same call as reference ``smrt/inputs/make_medium.py:158-232``:
     ``make_snowpack([1, 10], "exponential", density=[200, 300], temperature=[240, 250], corr_length=[2e-4, 3e-4])``."""
     if not isinstance(thickness, (Sequence, np.ndarray)):
         raise SMRTError("The thickness argument must be iterable, that is, a list of numbers, numpy array or pandas "
                         "Series or DataFrame.")
-    sp = Snowpack(substrate=substrate)
+    sp = Snowpack(substrate=substrate, atmosphere=atmosphere)
     for i, dz in enumerate(thickness):
         if dz <= 0:
             continue
@@ -262,6 +340,9 @@ def make_snowpack(thickness, microstructure_model, density, interface=None, subs
         except TypeError:
             raise SMRTError(f"microstructure '{name}' requires the parameters {params}")
         extra = {k: _get(kwargs[k], i) for k in ("emmodel", "emmodel_options", "permittivity_model") if k in kwargs}
+        if "ice_permittivity_model" in kwargs:  # make_medium.py:317-358: (air background, given ice permittivity)
+            ipm = kwargs["ice_permittivity_model"]
+            extra["permittivity_model"] = (1.0, ipm if (callable(ipm) or np.isscalar(ipm)) else _get(ipm, i))
         sp.layers.append(Layer(dz, ms, temperature=_get(temperature, i), density=rho, **extra))
         sp.interfaces.append(make_interface(_get(interface, i)))
     return sp

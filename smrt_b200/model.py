@@ -116,6 +116,10 @@ def solve_batch(batch: ProblemBatch, rtsolver_options: Optional[dict] = None, de
 
 def _raise_or_nan(out: capi.HostOutputs, opts: dict):
     err = out.status & capi.ST_ERR_MASK
+    if np.any(err == capi.ST_SUBSTRATE):
+        # the reference raises a plain Warning (not an SMRTError) whatever error_handling says:
+        # smrt/substrate/rough_choudhury79.py:29-31
+        raise Warning(capi.STATUS_MESSAGES[capi.ST_SUBSTRATE])
     if np.any(err) and opts["error_handling"] == "exception":
         b = int(np.flatnonzero(err)[0])
         raise SMRTError(f"simulation #{b}: " + capi.STATUS_MESSAGES.get(int(err[b]), "DORT failed")
@@ -259,7 +263,7 @@ class Model:
             result.mother_df = snowpack.drop(snowpack_column, axis=1)
         return result
 
-    def _run_simulations(self, sims, opts):
+    def _run_simulations(self, sims, opts, atmospheres=None):
         """Pack, solve in one batched GPU call per sensor mode, unpack into per-simulation Results."""
         # empty snowpacks give Tb = 0 without touching the solver (reference test/test_model.py:36-43 semantics are
         # reproduced by the kernel: nlayer = 0 -> zeros)
@@ -269,7 +273,8 @@ class Model:
         results = [None] * len(sims)
         for mode, idx in groups.items():
             group = [sims[i] for i in idx]
-            batch = pack_simulations(group, self.emmodel, self.emmodel_options)
+            batch = pack_simulations(group, self.emmodel, self.emmodel_options,
+                                     atmospheres=[atmospheres[i] for i in idx] if atmospheres is not None else None)
             if batch.mode == MODE_ACTIVE and not np.array_equal(batch.theta, batch.theta_inc):
                 raise SMRTError("only backscatter (theta == theta_inc) is implemented on the B200 path")
             plan = _PLANS.get(batch, opts, self.device)
@@ -312,9 +317,7 @@ class B200Runner:
             raise SMRTError("B200Runner must be given Model.run_single_simulation (a bound method)")
         args = list(argument_list)
         sims = [a[0] for a in args]
-        for a in args:
-            if a[1] is not None:
-                raise SMRTError("atmosphere is not implemented on the B200 path")
+        atmospheres = [a[1] for a in args]
         rtsolver = ref_model.rtsolver
         if getattr(rtsolver, "__name__", "") != "DORT" and "DORT" not in [c.__name__ for c in
                                                                            getattr(rtsolver, "__mro__", [])]:
@@ -322,7 +325,7 @@ class B200Runner:
         rt_opts = dict(getattr(ref_model, "rtsolver_options", {}) or {})
         m = Model(ref_model.emmodel, "dort", emmodel_options=getattr(ref_model, "emmodel_options", None),
                   rtsolver_options=rt_opts, device=self.device)
-        ours = m._run_simulations(sims, check_dort_options(rt_opts))
+        ours = m._run_simulations(sims, check_dort_options(rt_opts), atmospheres=atmospheres)
         try:  # hand back the reference's own Result types when available
             from smrt.core import result as ref_result
             import xarray as xr
@@ -351,10 +354,8 @@ class DORT:
         self.device = device
 
     def solve(self, snowpack, emmodels, sensor, atmosphere=None, parallel_computation=None):
-        if atmosphere is not None or getattr(snowpack, "atmosphere", None) is not None:
-            raise SMRTError("atmosphere is not implemented on the B200 path")
         ems = [type(em) for em in emmodels]
-        batch = pack_simulations([(sensor, snowpack)], ems)
+        batch = pack_simulations([(sensor, snowpack)], ems, atmospheres=[atmosphere])
         plan = _PLANS.get(batch, self.options, self.device)
         out = plan.solve_host(batch)
         _raise_or_nan(out, self.options)

@@ -22,7 +22,7 @@ from .error import SMRTError
 EM_IBA, EM_DMRT_QCA_SR, EM_NONSCATTERING, EM_DMRT_QCACP_SR = 0, 1, 2, 3
 MS_EXPONENTIAL, MS_SHS, MS_HOMOGENEOUS = 0, 1, 2
 IF_FLAT, IF_TRANSPARENT = 0, 1
-SUB_NONE, SUB_FLAT = 0, 1
+SUB_NONE, SUB_FLAT, SUB_SOIL_WEGMULLER, SUB_SOIL_QNH, SUB_REFLECTOR, SUB_ROUGH_CHOUDHURY = 0, 1, 2, 3, 4, 5
 MODE_PASSIVE, MODE_ACTIVE = 0, 1
 
 _EMMODEL_NAMES = {
@@ -74,10 +74,16 @@ class ProblemBatch:
     theta_inc: np.ndarray  # (n_inc,) rad — incidence angles (active); empty for passive
     phi: float = np.pi
     dense_snow_correction: np.ndarray = None  # (B, L) int32: 1 = invert the medium when frac_volume > 0.5
+    substrate_params: np.ndarray = None  # (B, 4) parameters of the rough / prescribed substrates (see SUB_*)
+    atmosphere: np.ndarray = None  # (B, 3) isotropic atmosphere: tb_down, tb_up (K), transmittance; (0, 0, 1) = none
 
     def __post_init__(self):
         if self.dense_snow_correction is None:
             self.dense_snow_correction = np.zeros(self.thickness.shape, dtype=np.int32)
+        if self.substrate_params is None:
+            self.substrate_params = np.zeros((len(self.frequency), 4))
+        if self.atmosphere is None:
+            self.atmosphere = np.tile(np.array([0.0, 0.0, 1.0]), (len(self.frequency), 1))
 
     @property
     def B(self) -> int:
@@ -117,6 +123,8 @@ class ProblemBatch:
             substrate_kind=int(self.substrate_kind[i]),
             substrate_eps=complex(self.substrate_eps[i]),
             substrate_temperature=float(self.substrate_temperature[i]),
+            substrate_params=self.substrate_params[i].copy(),
+            atmosphere=self.atmosphere[i].copy(),
             theta=self.theta.copy() if self.mode == MODE_PASSIVE else self.theta_inc.copy(),
             phi=float(self.phi),
             options=opts,
@@ -129,6 +137,8 @@ class ProblemBatch:
     def from_fields(d) -> "ProblemBatch":
         kw = {}
         for k in ProblemBatch.__dataclass_fields__:
+            if k in ("substrate_params", "atmosphere") and k not in d:  # fixtures written before these fields existed
+                continue
             v = d[k]
             if k == "mode":
                 kw[k] = int(v)
@@ -148,7 +158,7 @@ def concat_batches(batches: Sequence[ProblemBatch]) -> ProblemBatch:
             parts = []
             for b in batches:
                 v = getattr(b, k)
-                if v.ndim == 2 and v.shape[1] < L:
+                if v.ndim == 2 and v.shape[1] < L and k not in ("substrate_params", "atmosphere"):
                     pad = np.zeros((v.shape[0], L - v.shape[1]), dtype=v.dtype)
                     v = np.concatenate([v, pad], axis=1)
                 parts.append(v)
@@ -186,18 +196,80 @@ def _interface_code(iface):
                     "rough interfaces make the boundary blocks dense)")
 
 
-def _substrate(substrate, frequency):
+def _reflector_value(substrate, frequency, polarization):
+    """``Reflector._get_refl`` (reference smrt/substrate/reflector.py:83-111) for scalar / dict specifications"""
+    spec = substrate.specular_reflection
+    if spec is None:
+        spec = 1
+    if isinstance(spec, dict):
+        for key in [(frequency, polarization), (polarization, frequency), frequency, polarization]:
+            if key in spec:
+                spec = spec[key]
+                break
+    if isinstance(spec, dict):
+        raise SMRTError("The specular_reflection argument must be a scalar or a dict with the frequency and/or "
+                        "polarization as a key. If both, provide frequency and polarization as a tuple key")
+    if callable(spec):
+        raise SMRTError("a Reflector with a specular_reflection function of theta is not implemented on the B200 path "
+                        "(the stream angles are computed on the device): give scalars")
+    return float(spec)
+
+
+def _substrate(substrate, frequency, mode=MODE_PASSIVE):
+    """-> (kind, permittivity, temperature, params[4]); reference smrt/substrate/flat.py, soil_wegmuller.py,
+    soil_qnh.py, reflector.py, rough_choudhury79.py (all diagonal: Fresnel coefficients with a per-stream adjustment)"""
+    par = np.zeros(4)
     if substrate is None:
-        return SUB_NONE, 0j, 0.0
+        return SUB_NONE, 0j, 0.0, par
     name = type(substrate).__name__
-    if name != "Flat":
-        raise SMRTError(f"substrate '{name}' is not implemented on the B200 path (only a flat half-space)")
-    perm = substrate.permittivity(frequency)
     temp = getattr(substrate, "temperature", None)
-    return SUB_FLAT, complex(perm), (float(temp) if temp is not None else 0.0)
+    temp = float(temp) if temp is not None else 0.0
+    if name == "Reflector":
+        if mode != MODE_PASSIVE:  # reflector.py:56-57
+            raise NotImplementedError("active model is not yet implemented, need modification for the third component")
+        par[0] = _reflector_value(substrate, frequency, "V")
+        par[1] = _reflector_value(substrate, frequency, "H")
+        return SUB_REFLECTOR, 0j, temp, par
+    if name == "Flat":
+        kind = SUB_FLAT
+    elif name == "SoilWegmuller":
+        kind = SUB_SOIL_WEGMULLER
+        par[0] = float(substrate.roughness_rms)
+    elif name == "ChoudhuryReflectivity":
+        kind = SUB_ROUGH_CHOUDHURY
+        par[0] = float(substrate.roughness_rms)
+    elif name == "SoilQNH":
+        kind = SUB_SOIL_QNH
+        N = float(getattr(substrate, "N", 0.0))
+        Nv, Nh = float(getattr(substrate, "Nv", np.nan)), float(getattr(substrate, "Nh", np.nan))
+        par[:] = [float(substrate.H), float(getattr(substrate, "Q", 0.0)), N if np.isnan(Nv) else Nv,
+                  N if np.isnan(Nh) else Nh]
+    else:
+        raise SMRTError(f"substrate '{name}' is not implemented on the B200 path (available: Flat, SoilWegmuller, "
+                        "SoilQNH, ChoudhuryReflectivity, Reflector; rough substrates with diffuse reflection make the "
+                        "boundary blocks dense)")
+    return kind, complex(substrate.permittivity(frequency)), temp, par
 
 
-def pack_simulations(simulations, emmodel, emmodel_options=None) -> ProblemBatch:
+def _atmosphere(atmosphere, frequency, mode=MODE_PASSIVE):
+    """-> (tb_down, tb_up, transmittance) of an isotropic atmosphere (reference
+    smrt/atmosphere/simple_isotropic_atmosphere.py:49-77: constants or frequency-keyed dicts)"""
+    if atmosphere is None:
+        return 0.0, 0.0, 1.0
+    name = type(atmosphere).__name__
+    if name != "SimpleIsotropicAtmosphere":
+        raise SMRTError(f"atmosphere '{name}' is not implemented on the B200 path (available: "
+                        "SimpleIsotropicAtmosphere)")
+
+    def value(x):
+        if isinstance(x, dict):
+            x = x[frequency]
+        return float(x)
+
+    return value(atmosphere.constant_tbdown), value(atmosphere.constant_tbup), value(atmosphere.constant_trans)
+
+
+def pack_simulations(simulations, emmodel, emmodel_options=None, atmospheres=None) -> ProblemBatch:
     """Pack a flat list of (sensor, snowpack) pairs (reference ``Model.prepare_simulations`` order,
     ``smrt/core/model.py:485-502``) into one ProblemBatch.
 
@@ -240,8 +312,10 @@ def pack_simulations(simulations, emmodel, emmodel_options=None) -> ProblemBatch
         th = np.atleast_1d(np.asarray(sensor.theta, dtype=float))
         if th.shape != batch.theta.shape or not np.array_equal(th, batch.theta):
             raise SMRTError("all the sensors of a batch must have the same viewing angles")
-        if getattr(sp, "atmosphere", None) is not None:
-            raise SMRTError("atmosphere is not implemented on the B200 path")
+        # smrt/core/model.py:615: snowpack.atmosphere or the (deprecated) atmosphere argument of the run
+        atmos = getattr(sp, "atmosphere", None) or (atmospheres[b] if atmospheres is not None else None)
+        if atmos is not None and mode == MODE_PASSIVE:  # active mode ignores it (rtsolver_utils.py:109-147, 302-305)
+            batch.atmosphere[b] = _atmosphere(atmos, f, mode)
         n = len(sp.layers)
         batch.nlayer[b] = n
         if len(sp.interfaces) != n:
@@ -278,8 +352,9 @@ def pack_simulations(simulations, emmodel, emmodel_options=None) -> ProblemBatch
             batch.eps_bg[b, l] = complex(layer.permittivity(0, f))
             batch.eps_sc[b, l] = complex(layer.permittivity(1, f))
             batch.interface[b, l] = _interface_code(sp.interfaces[l])
-        kind, eps, temp = _substrate(sp.substrate, f)
+        kind, eps, temp, par = _substrate(sp.substrate, f, mode)
         batch.substrate_kind[b], batch.substrate_eps[b], batch.substrate_temperature[b] = kind, eps, temp
+        batch.substrate_params[b] = par
     return batch
 
 

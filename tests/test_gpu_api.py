@@ -118,3 +118,55 @@ def test_error_handling():
         make_model("iba", "dort").run(sensor_list.passive(89e9, 55), big)
     r = make_model("iba", "dort", rtsolver_options=dict(error_handling="nan")).run(sensor_list.passive(89e9, 55), big)
     assert np.all(np.isnan(r.data.values))
+
+
+# ------------------------------------------------------------------ reference smrt/test/test_physics_law.py on the GPU
+PHYSICS_CASES = [("High scattering", 0.8e-3, 10), ("Low scattering", 0.05e-3, 10), ("Shallow", 0.8e-3, 0.1)]
+
+
+def _physics_snowpack(pc, thickness, T, atmosphere=None):
+    from smrt_b200 import make_soil
+
+    substrate = make_soil("soil_wegmuller", permittivity_model=complex(10, 1), roughness_rms=0.001, temperature=T)
+    return make_snowpack([0.3, thickness], "exponential", density=[200, 300], temperature=T, corr_length=pc,
+                         ice_permittivity_model=complex(1.7, 0.00001), substrate=substrate, atmosphere=atmosphere)
+
+
+@pytest.mark.parametrize("test,pc,thickness", PHYSICS_CASES)
+def test_isothermal_universe(test, pc, thickness):
+    """test/test_physics_law.py:9-43: soil, snow and sky at the same temperature radiate that temperature"""
+    from smrt_b200 import SimpleIsotropicAtmosphere
+
+    T = 265
+    snowpack = _physics_snowpack(pc, thickness, T, SimpleIsotropicAtmosphere(tb_down=T, tb_up=0, transmittance=1))
+    m = make_model("iba", "dort", rtsolver_options=dict(rayleigh_jeans_approximation=True))
+    sresult = m.run(sensor_list.passive(37e9, range(10, 80, 5)), snowpack)
+    np.testing.assert_allclose(sresult.TbV(), T, atol=0.01)
+    np.testing.assert_allclose(sresult.TbH(), T, atol=0.01)
+
+
+@pytest.mark.parametrize("test,pc,thickness", PHYSICS_CASES)
+def test_kirchoff_law(test, pc, thickness):
+    """test/test_physics_law.py:46-95: emissivity = 1 - reflectivity"""
+    from smrt_b200 import SimpleIsotropicAtmosphere
+
+    T = 265.0
+    snowpack = _physics_snowpack(pc, thickness, T)
+    radiometer = sensor_list.passive(37e9, range(10, 80, 5))
+    m = make_model("iba", "dort", rtsolver_options=dict(rayleigh_jeans_approximation=True))
+    sresult_0 = m.run(radiometer, snowpack)
+    sresult_1 = m.run(radiometer, SimpleIsotropicAtmosphere(tb_down=1, tb_up=0, transmittance=1) + snowpack)
+    for tb0, tb1 in ((sresult_0.TbV(), sresult_1.TbV()), (sresult_0.TbH(), sresult_1.TbH())):
+        emissivity = (tb0 + tb1) / 2 / T
+        reflectivity = tb1 - tb0
+        np.testing.assert_allclose(emissivity, 1 - reflectivity, atol=0.002)
+
+
+def test_choudhury_outside_validity_raises_like_the_reference():
+    """substrate/rough_choudhury79.py:29-31: `raise Warning(...)` when k sigma > 0.1"""
+    from smrt_b200.inputs import ChoudhuryReflectivity
+
+    sub = ChoudhuryReflectivity(temperature=265.0, permittivity_model=complex(10, 1), roughness_rms=5e-3)
+    sp = make_snowpack([0.3], "exponential", density=[300], temperature=265, corr_length=1e-4, substrate=sub)
+    with pytest.raises(Warning, match="outside validity range"):
+        make_model("iba", "dort").run(sensor_list.passive(37e9, 55), sp)

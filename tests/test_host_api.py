@@ -165,3 +165,68 @@ def test_sea_ice_permittivity_building_blocks():
     with pytest.raises(SMRTError):
         P.seawater_permittivity_klein76(1.4e9, 260.0, 0.032)
     assert abs(P.water_freezing_temperature(0.0) - 273.15) < 0.05
+
+
+def test_substrate_and_atmosphere_packing():
+    """soil / reflector substrates and the isotropic atmosphere become plain per-problem parameters
+    (reference smrt/substrate/soil_wegmuller.py, soil_qnh.py, reflector.py, atmosphere/simple_isotropic_atmosphere.py)"""
+    import smrt_b200 as S
+    from smrt_b200 import pack
+
+    sensor = S.sensor_list.passive(37e9, 55)
+
+    def sp(**kw):
+        return S.make_snowpack([0.3], "exponential", density=[300], temperature=265, corr_length=1e-4, **kw)
+
+    soil = S.make_soil("soil_wegmuller", permittivity_model=complex(10, 1), roughness_rms=0.001, temperature=265)
+    qnh = S.make_soil("soil_qnh", permittivity_model=lambda f, t: complex(8, 2), H=0.5, Q=0.1, N=1.0, temperature=260)
+    refl = S.make_reflector(temperature=250, specular_reflection={(37e9, "H"): 0.5, (37e9, "V"): 0.6})
+    atm = S.SimpleIsotropicAtmosphere(tb_down={37e9: 20.0}, tb_up=5.0, transmittance=0.9)
+    b = pack.pack_simulations([(sensor, sp(substrate=soil)), (sensor, sp(substrate=qnh)), (sensor, sp(substrate=refl)),
+                               (sensor, atm + sp())], "iba")
+    assert list(b.substrate_kind) == [pack.SUB_SOIL_WEGMULLER, pack.SUB_SOIL_QNH, pack.SUB_REFLECTOR, pack.SUB_NONE]
+    np.testing.assert_array_equal(b.substrate_params, [[0.001, 0, 0, 0], [0.5, 0.1, 1.0, 1.0], [0.6, 0.5, 0, 0],
+                                                       [0, 0, 0, 0]])
+    np.testing.assert_array_equal(b.substrate_eps[:2], [10 + 1j, 8 + 2j])
+    np.testing.assert_array_equal(b.atmosphere, [[0, 0, 1], [0, 0, 1], [0, 0, 1], [20, 5, 0.9]])
+    # the (deprecated) atmosphere argument of the solver seam, and concatenation of batches
+    b2 = pack.pack_simulations([(sensor, sp())], "iba", atmospheres=[atm])
+    np.testing.assert_array_equal(b2.atmosphere, [[20, 5, 0.9]])
+    cat = pack.concat_batches([b, b2])
+    assert cat.atmosphere.shape == (5, 3) and cat.substrate_params.shape == (5, 4)
+    with pytest.raises(NotImplementedError):  # reflector.py:56-57
+        pack.pack_simulations([(S.sensor_list.active(13e9, 40), sp(substrate=refl))], "iba")
+    with pytest.raises(S.SMRTError):
+        pack.pack_simulations([(sensor, sp(substrate=S.make_reflector(specular_reflection=np.cos)))], "iba")
+
+
+def test_physics_laws_through_the_public_api():
+    """reference smrt/test/test_physics_law.py ("Shallow" case, 16 streams) through make_model(...).run() with a soil
+    substrate and an isotropic atmosphere: isothermal universe and Kirchhoff's law"""
+    import smrt_b200 as S
+
+    T = 265.0
+
+    def snowpack(atmosphere=None):
+        substrate = S.make_soil("soil_wegmuller", permittivity_model=complex(10, 1), roughness_rms=0.001, temperature=T)
+        return make_snowpack([0.3, 0.1], "exponential", density=[200, 300], temperature=T, corr_length=0.8e-3,
+                             ice_permittivity_model=complex(1.7, 0.00001), substrate=substrate, atmosphere=atmosphere)
+
+    radiometer = sensor_list.passive(37e9, [10, 40, 70])
+    m = make_model("iba", "dort", rtsolver_options=dict(rayleigh_jeans_approximation=True, n_max_stream=16))
+    iso = m.run(radiometer, snowpack(S.SimpleIsotropicAtmosphere(tb_down=T, tb_up=0, transmittance=1)))
+    np.testing.assert_allclose(iso.TbV(), T, atol=0.01)
+    np.testing.assert_allclose(iso.TbH(), T, atol=0.01)
+    r0 = m.run(radiometer, snowpack())
+    r1 = m.run(radiometer, S.SimpleIsotropicAtmosphere(tb_down=1, tb_up=0, transmittance=1) + snowpack())
+    for tb0, tb1 in ((r0.TbV(), r1.TbV()), (r0.TbH(), r1.TbH())):
+        np.testing.assert_allclose((tb0 + tb1) / 2 / T, 1 - (tb1 - tb0), atol=0.002)
+
+
+def test_choudhury_outside_validity_raises_like_the_reference():
+    from smrt_b200.inputs import ChoudhuryReflectivity
+
+    sub = ChoudhuryReflectivity(temperature=265.0, permittivity_model=complex(10, 1), roughness_rms=5e-3)
+    sp = make_snowpack([0.3], "exponential", density=[300], temperature=265, corr_length=1e-4, substrate=sub)
+    with pytest.raises(Warning, match="outside validity range"):
+        make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8)).run(sensor_list.passive(37e9, 55), sp)

@@ -9,7 +9,8 @@ from oracle import dort_oracle as O
 FAST = ["cfg1_iba_onelayer", "ref_iba_2layer_passive", "ref_iba_2layer_active", "ref_dmrt_qcacp_2layer_passive",
         "ref_dmrt_less_refringent_active", "nonscattering_transparent", "nonscattering_active",
         "iba_multiangle_passive", "iba_options_prune_rj", "iba_shs_active_multiangle", "iba_exp_substrate_passive",
-        "cfg3_first4", "cfg5_first6", "ref_sea_ice_128streams"]
+        "cfg3_first4", "cfg5_first6", "ref_sea_ice_128streams", "soil_wegmuller_passive", "soil_qnh_passive",
+        "reflector_passive", "choudhury_passive", "atmosphere_passive", "ref_physics_law", "soil_active"]
 
 
 def solve_all(batch, opts, limit=None):
