@@ -475,6 +475,13 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=["cfg2"] + sorted(EXTRA_WORKLOADS),
                     help="cfg2 = the contract workload; cfg3 / cfg4 / cfg5: other BASELINE configs, one GPU, for the record")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner from C, and with 4 / 8
+    # ranks it ignores NCCL_DEBUG_FILE) write to file descriptor 1 directly, so fd 1 is pointed at stderr for the
+    # whole run and Python's sys.stdout keeps the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.workload != "cfg2":
         run_extra(args)
     elif args.impl == "reference":

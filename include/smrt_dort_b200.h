@@ -42,6 +42,13 @@ extern "C" {
 #define SMRTB200_MS_EXPONENTIAL 0 /* p0 = corr_length                smrt/microstructure_model/exponential.py:53-58 */
 #define SMRTB200_MS_SHS 1         /* p0 = radius, p1 = stickiness    smrt/microstructure_model/sticky_hard_spheres.py:63-167 */
 #define SMRTB200_MS_HOMOGENEOUS 2 /* no scatterers (non-scattering layers only) */
+#define SMRTB200_MS_INDEPENDENT_SPHERE 3 /* p0 = radius                    smrt/microstructure_model/independent_sphere.py:62-80 */
+#define SMRTB200_MS_TEUBNER_STREY 4      /* p0 = corr_length, p1 = repeat_distance   smrt/microstructure_model/teubner_strey.py:53-62 */
+#define SMRTB200_MS_UNIFIED_TS_1 5       /* p0 = zeta1, p1 = zeta2, polydispersity >= 1  smrt/microstructure_model/unified_teubner_strey.py:25-36, 64-80 */
+#define SMRTB200_MS_UNIFIED_TS_2 6       /* p0 = zeta1, p1 = zeta2, polydispersity < 1 */
+#define SMRTB200_MS_SHS_T 7              /* p0 = radius, p1 = t (Percus-Yevick parameter given directly)
+                                            smrt/microstructure_model/unified_sticky_hard_spheres.py:21-106 */
+/* (unified_scaled_exponential.py is SMRTB200_MS_EXPONENTIAL with corr_length = polydispersity * porod_length) */
 
 /* interface above a layer */
 #define SMRTB200_IF_FLAT 0        /* Fresnel, smrt/interface/flat.py:11-75 + smrt/core/fresnel.py:99-146,417-474 */

@@ -27,7 +27,9 @@ Problem description (a plain dict, all SI units; the same fields the C ABI takes
     eps_sc         (L,) complex   scatterer permittivity    (layer.permittivity(1, f))
     emmodel        (L,) int       0 = IBA, 1 = DMRT-QCA short range, 2 = non-scattering, 3 = DMRT-QCACP short range
     ms_kind        (L,) int       0 = exponential (ms_p0 = corr_length), 1 = sticky hard spheres (ms_p0 = radius,
-                                  ms_p1 = stickiness)
+                                  ms_p1 = stickiness), 2 = homogeneous, 3 = independent sphere (radius), 4 = Teubner-
+                                  Strey (corr_length, repeat_distance), 5 / 6 = unified Teubner-Strey, polydispersity
+                                  >= 1 / < 1 (zeta1, zeta2), 7 = sticky hard spheres with t given (radius, t)
     ms_p0, ms_p1   (L,)
     interface      (L,) int       interface ABOVE layer l: 0 = flat (Fresnel), 1 = transparent
     substrate_kind int            0 = none, 1 = flat half-space (substrate_eps, substrate_temperature), 2 = rough soil
@@ -60,6 +62,7 @@ BOLTZMANN_CONSTANT = 1.380649e-23
 
 EM_IBA, EM_DMRT_QCA_SR, EM_NONSCATTERING, EM_DMRT_QCACP_SR = 0, 1, 2, 3
 MS_EXPONENTIAL, MS_SHS, MS_HOMOGENEOUS = 0, 1, 2
+MS_INDEPENDENT_SPHERE, MS_TEUBNER_STREY, MS_UNIFIED_TS_1, MS_UNIFIED_TS_2, MS_SHS_T = 3, 4, 5, 6, 7
 IF_FLAT, IF_TRANSPARENT = 0, 1
 SUB_NONE, SUB_FLAT, SUB_SOIL_WEGMULLER, SUB_SOIL_QNH, SUB_REFLECTOR, SUB_ROUGH_CHOUDHURY = 0, 1, 2, 3, 4, 5
 
@@ -105,15 +108,18 @@ def ft_autocorr_exponential(k, frac_volume, corr_length):
     return frac_volume * (1.0 - frac_volume) * 8 * np.pi * corr_length**3 / (1.0 + X) ** 2
 
 
-def ft_autocorr_shs(k, frac_volume, radius, stickiness):
-    """Percus-Yevick sticky hard spheres — reference smrt/microstructure_model/sticky_hard_spheres.py:63-130"""
+def ft_autocorr_shs(k, frac_volume, radius, stickiness, t=None):
+    """Percus-Yevick sticky hard spheres — reference smrt/microstructure_model/sticky_hard_spheres.py:63-130; with `t`
+    given: unified_sticky_hard_spheres.py:45-106 (the same structure factor, t prescribed by the polydispersity)"""
     d = 2 * radius
     phi_2 = frac_volume
     tau = stickiness
     k = np.asarray(k, dtype=float)
     shape = k.shape
     X = np.atleast_1d(k).ravel() * d / 2.0
-    if np.isfinite(tau) and phi_2 > 0.0:
+    if t is not None:
+        pass
+    elif np.isfinite(tau) and phi_2 > 0.0:
         t = (6 * tau * phi_2 - 6 * phi_2 - 6 * tau
              + (36 * tau**2 * phi_2**2 - 72 * tau * phi_2**2 - 72 * tau**2 * phi_2 + 30 * phi_2**2
                 + 72 * tau * phi_2 + 36 * tau**2 - 12 * phi_2) ** 0.5) / (phi_2 * (-1 + phi_2))
@@ -160,11 +166,51 @@ def shs_compute_t(frac_volume, stickiness):
     return t
 
 
+def ft_autocorr_independent_sphere(k, frac_volume, radius):
+    """reference smrt/microstructure_model/independent_sphere.py:62-80"""
+    k = np.asarray(k, dtype=float)
+    X = radius * k
+    volume_sphere = 4.0 / 3 * np.pi * radius**3
+    bessel_term = np.empty_like(X)
+    zero_X = np.isclose(X, 0)
+    nz = np.logical_not(zero_X)
+    Xn = X[nz]
+    bessel_term[nz] = 9 * ((np.sin(Xn) - Xn * np.cos(Xn)) / Xn**3) ** 2
+    bessel_term[zero_X] = 1.0
+    return frac_volume * (1.0 - frac_volume) * volume_sphere * bessel_term
+
+
+def ft_autocorr_teubner_strey(k, frac_volume, corr_length, repeat_distance):
+    """reference smrt/microstructure_model/teubner_strey.py:53-62"""
+    X = (k * corr_length) ** 2
+    Y = (2 * np.pi * corr_length / repeat_distance) ** 2
+    return frac_volume * (1.0 - frac_volume) * (8 * np.pi * corr_length**3 / ((1 + Y) ** 2 + 2 * (1 - Y) * X + X**2))
+
+
+def ft_autocorr_unified_teubner_strey(k, frac_volume, zeta1, zeta2, case1):
+    """reference smrt/microstructure_model/unified_teubner_strey.py:64-80 (zeta1, zeta2 of :25-36)"""
+    if case1:
+        ft = (4 * np.pi * zeta1 * zeta2 * (zeta1 + zeta2)) / ((1 + (zeta1 * k) ** 2) * (1 + (zeta2 * k) ** 2))
+    else:
+        x1 = k * zeta1
+        r12 = zeta1 / zeta2
+        ft = 8 * np.pi * zeta1**3 / ((1 + (x1 - r12) ** 2) * (1 + (x1 + r12) ** 2))
+    return frac_volume * (1.0 - frac_volume) * ft
+
+
 def ft_autocorr(k, ms_kind, f, p0, p1):
     if ms_kind == MS_EXPONENTIAL:
         return ft_autocorr_exponential(k, f, p0)
     elif ms_kind == MS_SHS:
         return ft_autocorr_shs(k, f, p0, p1)
+    elif ms_kind == MS_INDEPENDENT_SPHERE:
+        return ft_autocorr_independent_sphere(k, f, p0)
+    elif ms_kind == MS_TEUBNER_STREY:
+        return ft_autocorr_teubner_strey(k, f, p0, p1)
+    elif ms_kind in (MS_UNIFIED_TS_1, MS_UNIFIED_TS_2):
+        return ft_autocorr_unified_teubner_strey(k, f, p0, p1, ms_kind == MS_UNIFIED_TS_1)
+    elif ms_kind == MS_SHS_T:
+        return ft_autocorr_shs(k, f, p0, None, t=p1)
     raise ValueError("unknown microstructure kind")
 
 

@@ -361,6 +361,37 @@ def soil_active():  # third Stokes component untouched by the rough soil models 
     run_case("soil_active", "iba", sensor_list.active(13.5e9, 40), sps, dict(n_max_stream=16))
 
 
+@case
+def iba_microstructures_passive():  # every microstructure model with an analytical Fourier transform, mixed in one snowpack
+    rng = np.random.default_rng(31)
+    models = ["independent_sphere", "teubner_strey", "unified_scaled_exponential", "unified_teubner_strey",
+              "unified_teubner_strey", "unified_sticky_hard_spheres", "exponential", "sticky_hard_spheres"]
+    L = len(models)
+    sps = []
+    for _ in range(2):
+        th = np.concatenate((rng.uniform(0.05, 0.5, L - 1), [1000.0]))
+        sps.append(make_snowpack(th, models, density=rng.uniform(150, 450, L), temperature=rng.uniform(240, 272, L),
+                                 radius=rng.uniform(1e-4, 3e-4, L), stickiness=0.3,
+                                 corr_length=rng.uniform(5e-5, 3e-4, L), repeat_distance=rng.uniform(5e-4, 3e-3, L),
+                                 porod_length=rng.uniform(5e-5, 2e-4, L),
+                                 polydispersity=np.array([1.0, 1.0, 1.3, 1.5, 0.7, 1.2, 1.0, 1.0])))
+    run_case("iba_microstructures_passive", "iba", sensor_list.passive([18.7e9, 36.5e9, 89e9], 55), sps,
+             dict(n_max_stream=16))
+
+
+@case
+def iba_microstructures_active():
+    rng = np.random.default_rng(32)
+    models = ["teubner_strey", "unified_teubner_strey", "independent_sphere", "unified_sticky_hard_spheres"]
+    L = len(models)
+    th = np.concatenate((rng.uniform(0.05, 0.5, L - 1), [1000.0]))
+    sp = make_snowpack(th, models, density=rng.uniform(150, 450, L), temperature=rng.uniform(240, 272, L),
+                       radius=rng.uniform(1e-4, 3e-4, L), corr_length=rng.uniform(5e-5, 3e-4, L),
+                       repeat_distance=rng.uniform(5e-4, 3e-3, L), porod_length=rng.uniform(5e-5, 2e-4, L),
+                       polydispersity=np.array([1.0, 0.8, 1.0, 1.4]))
+    run_case("iba_microstructures_active", "iba", sensor_list.active(13.5e9, 40), [sp], dict(n_max_stream=16))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or list(CASES)

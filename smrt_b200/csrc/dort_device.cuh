@@ -13,7 +13,10 @@
 
 // enumerations: keep in sync with include/smrt_dort_b200.h
 enum { EM_IBA = 0, EM_DMRT_QCA_SR = 1, EM_NONSCATTERING = 2, EM_DMRT_QCACP_SR = 3 };
-enum { MS_EXPONENTIAL = 0, MS_SHS = 1, MS_HOMOGENEOUS = 2 };
+enum {
+  MS_EXPONENTIAL = 0, MS_SHS = 1, MS_HOMOGENEOUS = 2, MS_INDEPENDENT_SPHERE = 3, MS_TEUBNER_STREY = 4,
+  MS_UNIFIED_TS_1 = 5, MS_UNIFIED_TS_2 = 6, MS_SHS_T = 7
+};
 enum { IF_FLAT = 0, IF_TRANSPARENT = 1 };
 enum { SUB_NONE = 0, SUB_FLAT = 1, SUB_SOIL_WEGMULLER = 2, SUB_SOIL_QNH = 3, SUB_REFLECTOR = 4, SUB_ROUGH_CHOUDHURY = 5 };
 enum { ST_OK = 0, ST_NORMALIZATION = 1, ST_EIGEN = 2, ST_SINGULAR = 3, ST_INPUT = 4, ST_SUBSTRATE = 5, ST_WARN_SHALLOW = 16 };
@@ -96,10 +99,27 @@ SMRT_DEV MicroParams micro_prepare(int kind, double f, double p0, double p1) {
   mp.c0 = mp.a1 = mp.a2 = mp.ct0 = 0.0;
   if (kind == MS_EXPONENTIAL) {
     mp.c0 = f * (1.0 - f) * 8.0 * SMRT_PI * p0 * p0 * p0;
-  } else if (kind == MS_SHS) {
+  } else if (kind == MS_INDEPENDENT_SPHERE) {  // independent_sphere.py:62-80: f (1 - f) * sphere volume
+    mp.c0 = f * (1.0 - f) * (4.0 / 3.0 * SMRT_PI * (p0 * p0 * p0));
+  } else if (kind == MS_TEUBNER_STREY) {  // teubner_strey.py:53-62; a1 = Y = (2 pi l / d)^2
+    const double y = 2.0 * SMRT_PI * p0 / p1;
+    mp.a1 = y * y;
+    mp.c0 = 8.0 * SMRT_PI * (p0 * p0 * p0);
+    mp.ct0 = f * (1.0 - f);
+  } else if (kind == MS_UNIFIED_TS_1) {  // unified_teubner_strey.py:70-73 (p0 = zeta1, p1 = zeta2)
+    mp.c0 = 4.0 * SMRT_PI * p0 * p1 * (p0 + p1);
+    mp.a1 = p1;
+    mp.ct0 = f * (1.0 - f);
+  } else if (kind == MS_UNIFIED_TS_2) {  // unified_teubner_strey.py:75-78; a1 = zeta1 / zeta2
+    mp.c0 = 8.0 * SMRT_PI * (p0 * p0 * p0);
+    mp.a1 = p0 / p1;
+    mp.ct0 = f * (1.0 - f);
+  } else if (kind == MS_SHS || kind == MS_SHS_T) {
     double tau = p1, phi2 = f;
     double t = 0.0;
-    if (isfinite(tau) && phi2 > 0.0) {
+    if (kind == MS_SHS_T) {  // unified_sticky_hard_spheres.py:27-31: t prescribed
+      t = p1;
+    } else if (isfinite(tau) && phi2 > 0.0) {
       double disc = 36.0 * tau * tau * phi2 * phi2 - 72.0 * tau * phi2 * phi2 - 72.0 * tau * tau * phi2 +
                     30.0 * phi2 * phi2 + 72.0 * tau * phi2 + 36.0 * tau * tau - 12.0 * phi2;
       t = (6.0 * tau * phi2 - 6.0 * phi2 - 6.0 * tau + sqrt(disc)) / (phi2 * (-1.0 + phi2));
@@ -121,7 +141,22 @@ SMRT_DEV double micro_ft(const MicroParams& mp, double k2) {
   if (mp.kind == MS_EXPONENTIAL) {
     double d = 1.0 + k2 * mp.p0 * mp.p0;
     return mp.c0 / (d * d);
-  } else if (mp.kind == MS_SHS) {
+  } else if (mp.kind == MS_INDEPENDENT_SPHERE) {
+    const double X = sqrt(k2) * mp.p0;
+    if (fabs(X) <= 1e-8) return mp.c0;  // np.isclose(X, 0)
+    double s, c;
+    sincos(X, &s, &c);
+    const double b = (s - X * c) / (X * X * X);
+    return mp.c0 * (9.0 * (b * b));
+  } else if (mp.kind == MS_TEUBNER_STREY) {
+    const double X = k2 * mp.p0 * mp.p0, Y = mp.a1;
+    return mp.ct0 * (mp.c0 / ((1.0 + Y) * (1.0 + Y) + 2.0 * (1.0 - Y) * X + X * X));
+  } else if (mp.kind == MS_UNIFIED_TS_1) {
+    return mp.ct0 * (mp.c0 / ((1.0 + mp.p0 * mp.p0 * k2) * (1.0 + mp.a1 * mp.a1 * k2)));
+  } else if (mp.kind == MS_UNIFIED_TS_2) {
+    const double x1 = sqrt(k2) * mp.p0, r12 = mp.a1;
+    return mp.ct0 * (mp.c0 / ((1.0 + (x1 - r12) * (x1 - r12)) * (1.0 + (x1 + r12) * (x1 + r12))));
+  } else if (mp.kind == MS_SHS || mp.kind == MS_SHS_T) {
     double X = sqrt(k2) * mp.p0;  // k * d / 2
     if (fabs(X) <= 1e-3) return mp.ct0;  // np.isclose(X, 0, atol=1e-3): |X| <= atol (rtol * 0 = 0)
     double s, c;

@@ -149,8 +149,61 @@ class Homogeneous:
         self.frac_volume = float(frac_volume)
 
 
+class IndependentSphere:
+    def __init__(self, frac_volume, radius):
+        self.frac_volume, self.radius = float(frac_volume), float(radius)
+
+
+class TeubnerStrey:
+    def __init__(self, frac_volume, corr_length, repeat_distance):
+        self.frac_volume, self.corr_length = float(frac_volume), float(corr_length)
+        self.repeat_distance = float(repeat_distance)
+
+
+class UnifiedScaledExponential:
+    """reference ``smrt/microstructure_model/unified_scaled_exponential.py:19-26``"""
+
+    def __init__(self, frac_volume, porod_length, polydispersity):
+        self.frac_volume, self.porod_length = float(frac_volume), float(porod_length)
+        self.polydispersity = float(polydispersity)
+        self.corr_length = self.polydispersity * self.porod_length
+
+
+class UnifiedTeubnerStrey:
+    """reference ``smrt/microstructure_model/unified_teubner_strey.py:18-36``"""
+
+    def __init__(self, frac_volume, porod_length, polydispersity):
+        self.frac_volume, self.porod_length = float(frac_volume), float(porod_length)
+        self.polydispersity = float(polydispersity)
+        K32 = self.polydispersity ** (3 / 2)
+        if self.polydispersity >= 1:
+            b = self.porod_length * K32
+            delta = np.sqrt(1 - 1 / K32)
+            self.zeta1, self.zeta2 = b * (1 - delta), b * (1 + delta)
+        else:
+            self.zeta1 = self.porod_length
+            self.zeta2 = self.porod_length * np.sqrt(1 / (1 / K32 - 1))
+
+
+class UnifiedStickyHardSpheres:
+    """reference ``smrt/microstructure_model/unified_sticky_hard_spheres.py:18-31``"""
+
+    def __init__(self, frac_volume, porod_length, polydispersity):
+        self.frac_volume, self.porod_length = float(frac_volume), float(porod_length)
+        self.polydispersity = float(polydispersity)
+        self.radius = 3 / 4 * self.porod_length / (1 - self.frac_volume)
+        K_32 = self.polydispersity ** (-3 / 2)
+        self.t = (1 + 2 * self.frac_volume - 3 / (8 * np.sqrt(2)) * K_32) / (self.frac_volume * (1.0 - self.frac_volume))
+
+
+_UNIFIED = ("porod_length", "polydispersity")
 _MICROSTRUCTURES = {"exponential": (Exponential, ("corr_length",)),
                     "sticky_hard_spheres": (StickyHardSpheres, ("radius", "stickiness")),
+                    "independent_sphere": (IndependentSphere, ("radius",)),
+                    "teubner_strey": (TeubnerStrey, ("corr_length", "repeat_distance")),
+                    "unified_scaled_exponential": (UnifiedScaledExponential, _UNIFIED),
+                    "unified_teubner_strey": (UnifiedTeubnerStrey, _UNIFIED),
+                    "unified_sticky_hard_spheres": (UnifiedStickyHardSpheres, _UNIFIED),
                     "homogeneous": (Homogeneous, ())}
 
 

@@ -21,6 +21,7 @@ from .error import SMRTError
 # enumerations shared with include/smrt_dort_b200.h
 EM_IBA, EM_DMRT_QCA_SR, EM_NONSCATTERING, EM_DMRT_QCACP_SR = 0, 1, 2, 3
 MS_EXPONENTIAL, MS_SHS, MS_HOMOGENEOUS = 0, 1, 2
+MS_INDEPENDENT_SPHERE, MS_TEUBNER_STREY, MS_UNIFIED_TS_1, MS_UNIFIED_TS_2, MS_SHS_T = 3, 4, 5, 6, 7
 IF_FLAT, IF_TRANSPARENT = 0, 1
 SUB_NONE, SUB_FLAT, SUB_SOIL_WEGMULLER, SUB_SOIL_QNH, SUB_REFLECTOR, SUB_ROUGH_CHOUDHURY = 0, 1, 2, 3, 4, 5
 MODE_PASSIVE, MODE_ACTIVE = 0, 1
@@ -182,8 +183,20 @@ def _microstructure_params(layer):
         return MS_SHS, float(ms.radius), float(getattr(ms, "stickiness", 1000))
     if name == "Homogeneous":
         return MS_HOMOGENEOUS, 0.0, 0.0
-    raise SMRTError(f"microstructure model '{name}' is not implemented on the B200 path "
-                    "(available: Exponential, StickyHardSpheres, Homogeneous)")
+    if name == "IndependentSphere":
+        return MS_INDEPENDENT_SPHERE, float(ms.radius), 0.0
+    if name == "TeubnerStrey":
+        return MS_TEUBNER_STREY, float(ms.corr_length), float(ms.repeat_distance)
+    if name == "UnifiedScaledExponential":  # unified_scaled_exponential.py:20-36: an exponential with a scaled length
+        return MS_EXPONENTIAL, float(ms.corr_length), 0.0
+    if name == "UnifiedTeubnerStrey":  # unified_teubner_strey.py:25-36: the two cases of Ruland 2010
+        kind = MS_UNIFIED_TS_1 if ms.polydispersity >= 1 else MS_UNIFIED_TS_2
+        return kind, float(ms.zeta1), float(ms.zeta2)
+    if name == "UnifiedStickyHardSpheres":
+        return MS_SHS_T, float(ms.radius), float(ms.t)
+    raise SMRTError(f"microstructure model '{name}' is not implemented on the B200 path (available: Exponential, "
+                    "StickyHardSpheres, IndependentSphere, TeubnerStrey, UnifiedScaledExponential, UnifiedTeubnerStrey, "
+                    "UnifiedStickyHardSpheres, Homogeneous; models without an analytical Fourier transform are not)")
 
 
 def _interface_code(iface):
