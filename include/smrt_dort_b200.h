@@ -37,6 +37,9 @@ extern "C" {
 #define SMRTB200_EM_DMRT_QCA_SR 1    /* smrt/emmodel/dmrt_qca_shortrange.py:55 */
 #define SMRTB200_EM_NONSCATTERING 2  /* smrt/emmodel/nonscattering.py:17 */
 #define SMRTB200_EM_DMRT_QCACP_SR 3  /* smrt/emmodel/dmrt_qcacp_shortrange.py:55 */
+#define SMRTB200_EM_RAYLEIGH 4       /* smrt/emmodel/rayleigh.py:17-39; ms_p0 = radius of the microstructure */
+#define SMRTB200_EM_PRESCRIBED_KSKAEPS 5 /* smrt/emmodel/prescribed_kskaeps.py:20-27: eps_bg = effective permittivity,
+                                            ms_p0 = ks, ms_p1 = ka (ms_kind ignored); Rayleigh phase matrix */
 
 /* microstructure model (FT of the autocorrelation function) */
 #define SMRTB200_MS_EXPONENTIAL 0 /* p0 = corr_length                smrt/microstructure_model/exponential.py:53-58 */

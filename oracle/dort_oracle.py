@@ -25,7 +25,9 @@ Problem description (a plain dict, all SI units; the same fields the C ABI takes
     frac_volume    (L,)
     eps_bg         (L,) complex   background permittivity   (layer.permittivity(0, f))
     eps_sc         (L,) complex   scatterer permittivity    (layer.permittivity(1, f))
-    emmodel        (L,) int       0 = IBA, 1 = DMRT-QCA short range, 2 = non-scattering, 3 = DMRT-QCACP short range
+    emmodel        (L,) int       0 = IBA, 1 = DMRT-QCA short range, 2 = non-scattering, 3 = DMRT-QCACP short range,
+                                  4 = Rayleigh (ms_p0 = radius), 5 = prescribed ks / ka / eps (eps_bg = effective
+                                  permittivity, ms_p0 = ks, ms_p1 = ka)
     ms_kind        (L,) int       0 = exponential (ms_p0 = corr_length), 1 = sticky hard spheres (ms_p0 = radius,
                                   ms_p1 = stickiness), 2 = homogeneous, 3 = independent sphere (radius), 4 = Teubner-
                                   Strey (corr_length, repeat_distance), 5 / 6 = unified Teubner-Strey, polydispersity
@@ -60,7 +62,7 @@ C_SPEED = 299792458.0
 PLANCK_CONSTANT = 6.62607015e-34
 BOLTZMANN_CONSTANT = 1.380649e-23
 
-EM_IBA, EM_DMRT_QCA_SR, EM_NONSCATTERING, EM_DMRT_QCACP_SR = 0, 1, 2, 3
+EM_IBA, EM_DMRT_QCA_SR, EM_NONSCATTERING, EM_DMRT_QCACP_SR, EM_RAYLEIGH, EM_PRESCRIBED_KSKAEPS = 0, 1, 2, 3, 4, 5
 MS_EXPONENTIAL, MS_SHS, MS_HOMOGENEOUS = 0, 1, 2
 MS_INDEPENDENT_SPHERE, MS_TEUBNER_STREY, MS_UNIFIED_TS_1, MS_UNIFIED_TS_2, MS_SHS_T = 3, 4, 5, 6, 7
 IF_FLAT, IF_TRANSPARENT = 0, 1
@@ -313,6 +315,17 @@ def layer_optics(frequency, f, e0, eps, emmodel, ms_kind, p0, p1, invert_dense=F
         k0 = 2 * np.pi * frequency / C_SPEED
         eeff = polder_van_santen_spheres(f, e0, eps)
         out.update(eps_eff=eeff, ks=0.0, ka=float(2 * k0 * np.sqrt(eeff).imag), iba_coeff=0.0, f=f, k0=k0)
+    elif emmodel == EM_RAYLEIGH:
+        # reference smrt/emmodel/rayleigh.py:21-39 (sparse medium: the effective permittivity is the background's)
+        lmda = C_SPEED / frequency
+        radius = p0
+        k0 = 2 * np.pi / lmda
+        ks = f * 2 * abs((eps - e0) / (eps + 2 * e0)) ** 2 * radius**3 * abs(e0) ** 2 * k0**4
+        ka = f * k0 * eps.imag * abs(3 * e0 / (eps + 2 * e0)) ** 2 + (1 - f) * 2 * k0 * np.sqrt(e0).imag
+        out.update(eps_eff=e0, ks=float(ks), ka=float(ka), iba_coeff=0.0, f=f, k0=k0)
+    elif emmodel == EM_PRESCRIBED_KSKAEPS:
+        # reference smrt/emmodel/prescribed_kskaeps.py:20-27: layer.ks, layer.ka, layer.effective_permittivity
+        out.update(eps_eff=e0, ks=float(p0), ka=float(p1), iba_coeff=0.0, f=f, k0=2 * np.pi * frequency / C_SPEED)
     else:
         raise ValueError("unknown emmodel")
     out["emmodel"] = emmodel
@@ -632,7 +645,7 @@ class LayerEigen:
                 self._phase = 0
             elif self.opt["emmodel"] == EM_IBA:
                 self._phase = iba_ft_even_phase(self.opt, fullmu, fullmu, self.m_max, self.npol_em)
-            elif self.opt["emmodel"] in (EM_DMRT_QCA_SR, EM_DMRT_QCACP_SR):
+            elif self.opt["emmodel"] in (EM_DMRT_QCA_SR, EM_DMRT_QCACP_SR, EM_RAYLEIGH, EM_PRESCRIBED_KSKAEPS):
                 self._phase = rayleigh_ft_even_phase(self.opt["ks"], fullmu, fullmu, self.m_max)
             else:
                 self._phase = 0

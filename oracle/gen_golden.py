@@ -392,6 +392,36 @@ def iba_microstructures_active():
     run_case("iba_microstructures_active", "iba", sensor_list.active(13.5e9, 40), [sp], dict(n_max_stream=16))
 
 
+@case
+def rayleigh_passive_active():  # reference emmodel/rayleigh.py (sparse media), passive and active in two fixtures
+    rng = np.random.default_rng(41)
+    sps = []
+    for _ in range(2):
+        L = 3
+        th = np.concatenate((rng.uniform(0.1, 1.0, L - 1), [1000.0]))
+        sps.append(make_snowpack(th, "independent_sphere", density=rng.uniform(50, 150, L),
+                                 temperature=rng.uniform(240, 270, L), radius=rng.uniform(1e-4, 4e-4, L)))
+    run_case("rayleigh_passive", "rayleigh", sensor_list.passive([18.7e9, 36.5e9], 55), sps, dict(n_max_stream=16))
+    run_case("rayleigh_active", "rayleigh", sensor_list.active(13.5e9, 40), sps[:1], dict(n_max_stream=16))
+
+
+@case
+def prescribed_kskaeps_passive():  # reference emmodel/prescribed_kskaeps.py: ks, ka, eps_eff set on the layers
+    rng = np.random.default_rng(42)
+    sps = []
+    for _ in range(2):
+        L = 3
+        th = np.concatenate((rng.uniform(0.1, 1.0, L - 1), [1000.0]))
+        sp = make_snowpack(th, "homogeneous", density=rng.uniform(200, 400, L), temperature=rng.uniform(240, 270, L))
+        for lay in sp.layers:
+            lay.ks = float(rng.uniform(0.05, 2.0))
+            lay.ka = float(rng.uniform(0.05, 0.5))
+            lay.effective_permittivity = complex(rng.uniform(1.3, 1.9), rng.uniform(1e-4, 1e-3))
+        sps.append(sp)
+    run_case("prescribed_kskaeps_passive", "prescribed_kskaeps", sensor_list.passive(36.5e9, [30, 55]), sps,
+             dict(n_max_stream=16))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or list(CASES)

@@ -12,7 +12,9 @@
 #define SMRT_BOLTZMANN 1.380649e-23        // core/globalconstants.py:32
 
 // enumerations: keep in sync with include/smrt_dort_b200.h
-enum { EM_IBA = 0, EM_DMRT_QCA_SR = 1, EM_NONSCATTERING = 2, EM_DMRT_QCACP_SR = 3 };
+enum {
+  EM_IBA = 0, EM_DMRT_QCA_SR = 1, EM_NONSCATTERING = 2, EM_DMRT_QCACP_SR = 3, EM_RAYLEIGH = 4, EM_PRESCRIBED_KSKAEPS = 5
+};
 enum {
   MS_EXPONENTIAL = 0, MS_SHS = 1, MS_HOMOGENEOUS = 2, MS_INDEPENDENT_SPHERE = 3, MS_TEUBNER_STREY = 4,
   MS_UNIFIED_TS_1 = 5, MS_UNIFIED_TS_2 = 6, MS_SHS_T = 7
@@ -244,6 +246,26 @@ SMRT_DEV LayerOptics layer_optics(double frequency, double f, cplx e0, cplx eps,
   o.status = ST_OK;
   o.iba_coeff = 0.0;
   o.kk = 0.0;
+  if (emmodel == EM_RAYLEIGH) {  // emmodel/rayleigh.py:21-39: sparse medium, eps_eff = background; p0 = radius
+    const double k0 = 2.0 * SMRT_PI / (SMRT_C_SPEED / frequency);
+    const cplx e2 = c_add(eps, c_scale(e0, 2.0));
+    const double a1 = c_abs(c_div(c_sub(eps, e0), e2)), a0 = c_abs(e0), a3 = c_abs(c_div(c_scale(e0, 3.0), e2));
+    const double k02 = k0 * k0;
+    o.f = f;
+    o.eps_eff = e0;
+    o.ks = f * 2.0 * (a1 * a1) * (p0 * p0 * p0) * (a0 * a0) * (k02 * k02);
+    o.ka = f * k0 * eps.im * (a3 * a3) + (1.0 - f) * 2.0 * k0 * c_sqrt(e0).im;
+    if (mp_out) *mp_out = micro_prepare(MS_HOMOGENEOUS, f, 0.0, 0.0);
+    return o;
+  }
+  if (emmodel == EM_PRESCRIBED_KSKAEPS) {  // emmodel/prescribed_kskaeps.py:20-27: eps_bg = eps_eff, p0 = ks, p1 = ka
+    o.f = f;
+    o.eps_eff = e0;
+    o.ks = p0;
+    o.ka = p1;
+    if (mp_out) *mp_out = micro_prepare(MS_HOMOGENEOUS, f, 0.0, 0.0);
+    return o;
+  }
   if (f > 0.5 && invert_dense && emmodel != EM_NONSCATTERING) {  // core/layer.py:186-201
     f = 1.0 - f;
     cplx tmp = e0;

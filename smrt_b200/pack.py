@@ -19,7 +19,7 @@ import numpy as np
 from .error import SMRTError
 
 # enumerations shared with include/smrt_dort_b200.h
-EM_IBA, EM_DMRT_QCA_SR, EM_NONSCATTERING, EM_DMRT_QCACP_SR = 0, 1, 2, 3
+EM_IBA, EM_DMRT_QCA_SR, EM_NONSCATTERING, EM_DMRT_QCACP_SR, EM_RAYLEIGH, EM_PRESCRIBED_KSKAEPS = 0, 1, 2, 3, 4, 5
 MS_EXPONENTIAL, MS_SHS, MS_HOMOGENEOUS = 0, 1, 2
 MS_INDEPENDENT_SPHERE, MS_TEUBNER_STREY, MS_UNIFIED_TS_1, MS_UNIFIED_TS_2, MS_SHS_T = 3, 4, 5, 6, 7
 IF_FLAT, IF_TRANSPARENT = 0, 1
@@ -31,9 +31,12 @@ _EMMODEL_NAMES = {
     "dmrt_qca_shortrange": EM_DMRT_QCA_SR,
     "nonscattering": EM_NONSCATTERING,
     "dmrt_qcacp_shortrange": EM_DMRT_QCACP_SR,
+    "rayleigh": EM_RAYLEIGH,
+    "prescribed_kskaeps": EM_PRESCRIBED_KSKAEPS,
 }
 _EMMODEL_CLASSNAMES = {"IBA": EM_IBA, "DMRT_QCA_ShortRange": EM_DMRT_QCA_SR, "NonScattering": EM_NONSCATTERING,
-                       "DMRT_QCACP_ShortRange": EM_DMRT_QCACP_SR}
+                       "DMRT_QCACP_ShortRange": EM_DMRT_QCACP_SR, "Rayleigh": EM_RAYLEIGH,
+                       "Prescribed_KsKaEps": EM_PRESCRIBED_KSKAEPS}
 _DMRT_CODES = (EM_DMRT_QCA_SR, EM_DMRT_QCACP_SR)
 
 
@@ -351,17 +354,27 @@ def pack_simulations(simulations, emmodel, emmodel_options=None, atmospheres=Non
             batch.dense_snow_correction[b, l] = 1 if dsc == "auto" else 0
             batch.emmodel[b, l] = code
             batch.frac_volume[b, l] = layer.frac_volume
-            kind, p0, p1 = _microstructure_params(layer)
+            kind, p0, p1 = (MS_HOMOGENEOUS, 0.0, 0.0) if code == EM_PRESCRIBED_KSKAEPS else _microstructure_params(layer)
             if code in _DMRT_CODES and kind != MS_SHS:
                 raise SMRTError("DMRT short range models are only compatible with SHS microstructure model")
             if code == EM_IBA and kind == MS_HOMOGENEOUS:
                 raise SMRTError("IBA needs a microstructure with a Fourier transform (exponential, sticky hard spheres)")
+            if code == EM_RAYLEIGH:  # emmodel/rayleigh.py:41-47
+                if not hasattr(layer.microstructure, "radius"):
+                    raise SMRTError("Only microstructure_model which defined a `radius` can be used with Rayleigh "
+                                    "scattering")
+                kind, p0, p1 = MS_HOMOGENEOUS, float(layer.microstructure.radius), 0.0
             batch.ms_kind[b, l], batch.ms_p0[b, l], batch.ms_p1[b, l] = kind, p0, p1
             if getattr(layer, "inclusion_shape", None) not in (None, "spheres"):
                 raise SMRTError("only spherical inclusions are implemented on the B200 path")
             if getattr(layer, "depolarization_factors", None) is not None or \
                     getattr(layer, "length_ratio", None) not in (None, 1, 1.0):
                 raise SMRTError("anisotropic depolarization factors are not implemented on the B200 path")
+            if code == EM_PRESCRIBED_KSKAEPS:  # emmodel/prescribed_kskaeps.py:20-27: everything is given on the layer
+                batch.ms_kind[b, l], batch.ms_p0[b, l], batch.ms_p1[b, l] = MS_HOMOGENEOUS, float(layer.ks), float(layer.ka)
+                batch.eps_bg[b, l] = batch.eps_sc[b, l] = complex(layer.effective_permittivity)
+                batch.interface[b, l] = _interface_code(sp.interfaces[l])
+                continue
             batch.eps_bg[b, l] = complex(layer.permittivity(0, f))
             batch.eps_sc[b, l] = complex(layer.permittivity(1, f))
             batch.interface[b, l] = _interface_code(sp.interfaces[l])

@@ -11,7 +11,8 @@ FAST = ["cfg1_iba_onelayer", "ref_iba_2layer_passive", "ref_iba_2layer_active", 
         "iba_multiangle_passive", "iba_options_prune_rj", "iba_shs_active_multiangle", "iba_exp_substrate_passive",
         "cfg3_first4", "cfg5_first6", "ref_sea_ice_128streams", "soil_wegmuller_passive", "soil_qnh_passive",
         "reflector_passive", "choudhury_passive", "atmosphere_passive", "ref_physics_law", "soil_active",
-        "iba_microstructures_passive", "iba_microstructures_active"]
+        "iba_microstructures_passive", "iba_microstructures_active", "rayleigh_passive", "rayleigh_active",
+        "prescribed_kskaeps_passive"]
 
 
 def solve_all(batch, opts, limit=None):

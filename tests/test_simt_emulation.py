@@ -12,8 +12,8 @@ from oracle import dort_oracle as O
 SMALL = ["cfg1_iba_onelayer", "ref_iba_2layer_passive", "ref_dmrt_qcacp_2layer_passive", "nonscattering_transparent",
          "iba_options_prune_rj", "iba_exp_substrate_passive", "soil_wegmuller_passive", "soil_qnh_passive",
          "reflector_passive", "choudhury_passive", "atmosphere_passive", "ref_physics_law",
-         "iba_microstructures_passive"]
-SMALL_ACTIVE = ["ref_dmrt_less_refringent_active", "nonscattering_active", "soil_active", "iba_microstructures_active"]
+         "iba_microstructures_passive", "rayleigh_passive", "prescribed_kskaeps_passive"]
+SMALL_ACTIVE = ["ref_dmrt_less_refringent_active", "nonscattering_active", "soil_active", "iba_microstructures_active", "rayleigh_active"]
 
 
 @pytest.mark.parametrize("name", SMALL + SMALL_ACTIVE)
