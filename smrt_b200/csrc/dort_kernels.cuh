@@ -222,29 +222,33 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
       // with q = (1, 1, 2) for (V, H, U), and for the backward half the same relation carries the signs D = (1, 1, -1)
       // of the third Stokes component on both sides (both follow from the sums of emmodel/common.py:87-129 term by
       // term), so the block (ji, js) is the mirrored, re-weighted block (js, ji).
-      for (int pidx = tid; pidx < (n_l * (n_l + 1)) / 2; pidx += NT) {
+      // (one work item = one stream pair and one half, forward or backward: twice as many, half as long items fill
+      // the last pass over the threads better)
+      for (int item2 = tid; item2 < n_l * (n_l + 1); item2 += NT) {
+        const int pidx = item2 >> 1;
+        const bool backward = (item2 & 1) != 0;
         int ji = (int)((sqrtf(8.0f * (float)pidx + 1.0f) - 1.0f) * 0.5f);
         while ((ji + 1) * (ji + 2) / 2 <= pidx) ++ji;
         while (ji * (ji + 1) / 2 > pidx) --ji;
         const int js = pidx - ji * (ji + 1) / 2;
-        double pp[9], pm[9];
+        double pv[9];
+        const double mui = backward ? -mu[ji] : mu[ji];
         if (emmodel == EM_IBA) {
-          iba_phase_mode(m, K, ctab, stab, mu[js], mu[ji], iba_coeff, kk, mp, pp);
-          iba_phase_mode(m, K, ctab, stab, mu[js], -mu[ji], iba_coeff, kk, mp, pm);
+          iba_phase_mode(m, K, ctab, stab, mu[js], mui, iba_coeff, kk, mp, pv);
         } else {
-          rayleigh_phase_mode(m, mu[js], mu[ji], ks, pp);
-          rayleigh_phase_mode(m, mu[js], -mu[ji], ks, pm);
+          rayleigh_phase_mode(m, mu[js], mui, ks, pv);
         }
+        double* dst = backward ? A2 : A1;
+        const int ldd = backward ? ld : ld1;
         for (int ps = 0; ps < npol; ++ps)
           for (int pi = 0; pi < npol; ++pi) {
             const int a = js * npol + ps, c = ji * npol + pi;
-            const double vp = pp[ps * npol + pi], vm = pm[ps * npol + pi];
-            SMRT_AT(A1, ld1, a, c) = vp;
-            SMRT_AT(A2, ld, a, c) = (pi == 2) ? -vm : vm;
+            double v = pv[ps * npol + pi];
+            if (backward && pi == 2) v = -v;
+            SMRT_AT(dst, ldd, a, c) = v;
             if (js != ji) {  // mirrored block: row (ji, pi), column (js, ps)
               const double qr = ((pi == 2) ? 2.0 : 1.0) / ((ps == 2) ? 2.0 : 1.0);
-              SMRT_AT(A1, ld1, c, a) = vp * qr;
-              SMRT_AT(A2, ld, c, a) = (pi == 2) ? -(vm * qr) : vm * qr;
+              SMRT_AT(dst, ldd, c, a) = v * qr;
             }
           }
       }
