@@ -654,8 +654,12 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
         __syncthreads();
 
         // eigen data: (k, F, G) from the workspace, or the trivial solution F = I, G = 0, k = ke / mu
+        // (the eigenvalues are not part of the prefetch: their load is issued here and consumed after the Fresnel
+        // evaluations, so that its DRAM latency overlaps them)
+        const double* rk_l = A.eig + (bL + l) * A.eig_stride + A.eig_off[m];
+        const double kpre = (scat && tid < h) ? rk_l[tid] : 0.0;
         if (scat) {
-          const double* rk = A.eig + (bL + l) * A.eig_stride + A.eig_off[m];
+          const double* rk = rk_l;
           const double* rF = rk + smrt_even(smrt_npol(m) * n);
           const double* rG = rF + smrt_even((long long)h * h);
           if (pf_layer == l) {  // prefetched by the TMA engine while the layer below was being eliminated
@@ -681,7 +685,6 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
               dG[e] = sG[e];
             }
           }
-          for (int a = tid; a < h; a += NT) kvec[a] = rk[a];
         } else {
           SMRT_FOR_2D(i, j, h, h) {
             BF[(size_t)j * h + i] = (i == j) ? 1.0 : 0.0;
@@ -693,8 +696,11 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
         // one Fresnel evaluation per thread: (stream j) x (top of the layer | bottom of the layer | transmission of
         // the emission of the layer above into this layer, on the upper layer's streams: dort.py:383-395)
         const bool thermal = (A.mode == 0 && m == 0);
-        for (int e = tid; e < 3 * n_l; e += NT) {
-          const int which = e / n_l, j = e - which * n_l;
+        // (`which` is uniform within a warp: the three branches never serialise)
+        for (int e = tid; e < 3 * 32 * ((n_l + 31) >> 5); e += NT) {
+          const int span = 32 * ((n_l + 31) >> 5);
+          const int which = e / span, j = e - which * span;
+          if (j >= n_l) continue;
           if (which == 0) {
             cplx eps_up = (l > 0) ? c_make(eps_b[2 * (l - 1)], eps_b[2 * (l - 1) + 1]) : c_make(1.0, 0.0);
             FresnelRT ft = fresnel_power(A.interface_kind[bL + l], eps_l, eps_up, mu[j]);
@@ -734,6 +740,10 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
             }
             for (int p = 0; p < npol; ++p) Tup[j * npol + p] = tu[p];
           }
+        }
+        if (scat) {
+          if (tid < h) kvec[tid] = kpre;
+          for (int a = tid + NT; a < h; a += NT) kvec[a] = rk_l[a];
         }
         __syncthreads();
         for (int a = tid; a < h; a += NT) tvec[a] = exp(-kvec[a] * thick);
