@@ -172,10 +172,37 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
     int v = std::atoi(e);
     if (v >= 64 && v <= SMRT_NT_B && (v % 64) == 0) p->boundary_threads = v;
   }
+  // two problems per SM: either the resident layout already allows it (small stream counts: 128 threads so that the
+  // registers allow it too), or the instantiation that stages F and G into [T | R] does (h <= 64, <= 113 KB per CTA)
+  const size_t two_per_sm = (size_t)(228 * 1024) / 2 - 1024 - 256;
+  bool stream_fg = false;
+  if (!p->use_global_scratch && !std::getenv("SMRT_B200_BOUNDARY_THREADS")) {
+    if (L.boundary_smem_bytes <= two_per_sm) {
+      p->boundary_threads = 128;
+    } else if (L.boundary_stream_smem_bytes > 0 && L.boundary_stream_smem_bytes <= two_per_sm) {
+      p->boundary_threads = 128;
+      stream_fg = true;
+    }
+  }
+  if (const char* e = std::getenv("SMRT_B200_STREAM_FG")) {  // experiments: force the choice
+    const bool want = std::atoi(e) != 0;
+    if (!want) {
+      if (stream_fg) p->boundary_threads = 256;
+      stream_fg = false;
+    } else if (!p->use_global_scratch && L.boundary_stream_smem_bytes > 0) {
+      stream_fg = true;
+      p->boundary_threads = 128;
+    }
+  }
+  if (stream_fg) p->boundary_smem = L.boundary_stream_smem_bytes;
   if (p->use_global_scratch)
     p->boundary_fn = boundary_kernel<true, SMRT_NT_B>;
+  else if (stream_fg)
+    p->boundary_fn = boundary_kernel<false, 128, true>;
   else
-    p->boundary_fn = (p->boundary_threads <= 256) ? boundary_kernel<false, 256> : boundary_kernel<false, SMRT_NT_B>;
+    p->boundary_fn = (p->boundary_threads <= 128)   ? boundary_kernel<false, 128>
+                     : (p->boundary_threads <= 256) ? boundary_kernel<false, 256>
+                                                    : boundary_kernel<false, SMRT_NT_B>;
   // the attribute belongs to the FUNCTION, not to the plan: always raise it to the opt-in maximum so that plans with
   // different shared-memory footprints can coexist
   {

@@ -422,18 +422,22 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
 // --------------------------------------------------------------------------------------------------------------------
 // vector region (doubles): mu[n] outmu[n] outw[n] kvec tvec Rt Tt Rb Tb Ttprev ipiv RbD Dsg Tup [hmax each]
 //                          acc[9 * SMRT_MAX_INC] coh[4 * SMRT_MAX_INC] ; ints: rowstep[hmax] rowof[hmax] inc[SMRT_MAX_INC]
-SMRT_HD size_t boundary_vec_doubles(int n, int hmax) {
-  return ((size_t)3 * n + 11 * hmax + 13 * SMRT_MAX_INC + hmax /* two int arrays */ + SMRT_MAX_INC + 16 + 1) & ~(size_t)1;
+// (the accumulators of the active mode exist only in active plans)
+SMRT_HD size_t boundary_vec_doubles(int n, int hmax, int mode = 1) {
+  const size_t nacc = (mode == 1) ? 13 * SMRT_MAX_INC : 0;
+  return ((size_t)3 * n + 11 * hmax + nacc + hmax /* two int arrays */ + SMRT_MAX_INC + 16 + 1) & ~(size_t)1;
 }
 // matrix region: BF, BG (compact), scratch of the blocked Gauss-Jordan (V, reciprocal pivots), BR (ld odd),
 // T = [left | right | rhs] (ld odd), btop, svec, ytr, vvec
-SMRT_HD size_t boundary_gj_doubles(int hmax, int nrhs_max) {
+SMRT_HD size_t boundary_gj_doubles(int hmax, int nrhs_max, bool compact = false) {
   (void)nrhs_max;
-  // V (double buffered; the same buffer is the scratch of the block matvecs: 2 * 8 * h doubles), reciprocal pivots
-  return (size_t)16 * hmax + ((hmax + 1) & ~1);
+  // V (double buffered; the same buffer is the scratch of the block matvecs: 2 * 8 * h doubles), reciprocal pivots;
+  // compact: 2 * SMRT_GJ_NB * h = 8 h doubles, enough for the matvec scratch of blocks of <= 256 threads as well
+  return (size_t)(compact ? 8 : 16) * hmax + ((hmax + 1) & ~1);
 }
-SMRT_HD size_t boundary_mat_doubles(int hmax, int nrhs_max) {
-  return (size_t)2 * (((size_t)hmax * hmax + 1) & ~(size_t)1) + boundary_gj_doubles(hmax, nrhs_max) +
+// stream = the instantiation that keeps only [T | R] resident and stages F and G into them (two CTAs per SM)
+SMRT_HD size_t boundary_mat_doubles(int hmax, int nrhs_max, bool stream = false) {
+  return (stream ? 0 : (size_t)2 * (((size_t)hmax * hmax + 1) & ~(size_t)1)) + boundary_gj_doubles(hmax, nrhs_max, stream) +
          (size_t)hmax * (hmax + 1) + (size_t)(hmax + 1) * (2 * hmax + nrhs_max) + 4 * (size_t)hmax * nrhs_max + 16;
 }
 
@@ -444,21 +448,31 @@ struct BoundaryCtx {
   cplx eps_star;
 };
 
-template <bool kGlobalScratch, int kMaxThreads>
-SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
+// kStreamFG: the operands F and G of a layer are not kept in their own buffers but staged (TMA bulk copies from the
+// layer record, L2-resident after the first touch) into the buffers the results of the step will occupy, and the
+// products keep all their tiles in registers until the block has finished reading (block_gemm_*_deferred): 114 KB
+// per problem at 32 streams instead of 186 KB, TWO problems per SM: the serial panel chain of one elimination is
+// covered by the other problem's work.  Requires h <= 64 and 128 <= blockDim.x <= 256.
+template <bool kGlobalScratch, int kMaxThreads, bool kStreamFG = false>
+SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kernel(KArgs A) {
   SMRT_DYN_SMEM(smem);
   SMRT_SHARED int s_item;
   SMRT_SHARED int s_ctrl[8];
   SMRT_SHARED double s_tau;
   SMRT_SHARED int s_lend;
   SMRT_SHARED smrt_mbar_t s_mbar;  // completion barrier of the TMA bulk prefetch of the next layer's (F, G) record
+  SMRT_SHARED smrt_mbar_t s_mbarG;  // kStreamFG: s_mbar completes the copies of F, s_mbarG those of G
   const int tid = threadIdx.x;
   const int NT = blockDim.x;
   const int n = A.n;
   const int hmax = smrt_npol(A.m_max) * n;
   const int nrhs_max = (A.mode == 0) ? 1 : 3 * 2 * A.n_inc;
-  if (tid == 0) smrt_mbar_init(&s_mbar, 1);
+  if (tid == 0) {
+    smrt_mbar_init(&s_mbar, 1);
+    smrt_mbar_init(&s_mbarG, 1);
+  }
   unsigned pf_parity = 0;  // parity of the next phase to wait for
+  unsigned pg_parity = 0;  // ... of s_mbarG
   __syncthreads();
 
   double* mu = smem;
@@ -475,20 +489,22 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
   double* RbD = ipiv + hmax;
   double* Dsg = RbD + hmax;
   double* Tup = Dsg + hmax;                       // transmission of the layer above's emission into this layer
+  const int nacc = (A.mode == 1) ? SMRT_MAX_INC : 0;  // the active-mode accumulators exist only in active plans
   double* acc_act = Tup + hmax;                   // [3][3][SMRT_MAX_INC]
-  double* coh_act = acc_act + 9 * SMRT_MAX_INC;   // [2][2][SMRT_MAX_INC]
-  int* rowstep = reinterpret_cast<int*>(coh_act + 4 * SMRT_MAX_INC);
+  double* coh_act = acc_act + 9 * nacc;           // [2][2][SMRT_MAX_INC]
+  int* rowstep = reinterpret_cast<int*>(coh_act + 4 * nacc);
   int* rowof = rowstep + hmax;
   int* inc = rowof + hmax;
   double* mats = kGlobalScratch ? (A.scratch + (size_t)blockIdx.x * A.scratch_stride)
-                                : (smem + boundary_vec_doubles(n, hmax));
+                                : (smem + boundary_vec_doubles(n, hmax, A.mode));
   const size_t szc = ((size_t)hmax * hmax + 1) & ~(size_t)1, szp = (size_t)hmax * (hmax + 1);
   const size_t szr = (size_t)hmax * nrhs_max;
+  // BF / BG: own buffers, or (kStreamFG) aliases of the staging areas inside T and R, set per layer and per phase
   double* BF = mats;  // 16-byte aligned (vector loads of the layer records)
   double* BG = BF + szc;
-  double* GJV = BG + szc;                                  // blocked Gauss-Jordan: V (2 x h x 8)
-  double* pivinv = GJV + (size_t)16 * hmax;                // ... reciprocal pivots
-  double* BR = BG + szc + boundary_gj_doubles(hmax, nrhs_max);
+  double* GJV = kStreamFG ? mats : BG + szc;               // blocked Gauss-Jordan: V (2 x h x NB)
+  double* pivinv = GJV + (size_t)(kStreamFG ? 8 : 16) * hmax;  // ... reciprocal pivots
+  double* BR = GJV + boundary_gj_doubles(hmax, nrhs_max, kStreamFG);
   double* TT = BR + szp;  // h x (2h + nrhs), ld = ldp
   double* btop = TT + (size_t)(hmax + 1) * (2 * hmax + nrhs_max);
   double* svec = btop + szr;
@@ -592,8 +608,8 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
     }
     __syncthreads();
     const int n_incs = s_ctrl[3];
-    for (int i = tid; i < 9 * SMRT_MAX_INC; i += NT) acc_act[i] = 0.0;
-    for (int i = tid; i < 4 * SMRT_MAX_INC; i += NT) coh_act[i] = 0.0;
+    for (int i = tid; i < 9 * nacc; i += NT) acc_act[i] = 0.0;
+    for (int i = tid; i < 4 * nacc; i += NT) coh_act[i] = 0.0;
     __syncthreads();
 
     const int nruns = (A.mode == 0) ? 1 : (A.m_max + 2);  // active: coherent pass + modes 0..m_max
@@ -658,7 +674,42 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
         // evaluations, so that its DRAM latency overlaps them)
         const double* rk_l = A.eig + (bL + l) * A.eig_stride + A.eig_off[m];
         const double kpre = (scat && tid < h) ? rk_l[tid] : 0.0;
-        if (scat) {
+        // kStreamFG: where the operands of the layer come from, and the staging helper.  An operand is either copied by
+        // the TMA engine (even h: 16-byte aligned destinations; completion on `bar`, returns true = wait needed),
+        // copied by the threads (odd h), or generated (non-scattering layer: F = I, G = 0).  The destination must be
+        // dead for every thread of the block (a block barrier precedes every call) and the caller places a block
+        // barrier before the first use of a thread-written copy.
+        const double* rF_l = rk_l + smrt_even(smrt_npol(m) * n);
+        const double* rG_l = rF_l + smrt_even((long long)h * h);
+        auto stage_operand = [&](double* dst, const double* src, bool identity, smrt_mbar_t* bar) -> bool {
+#ifndef SMRT_STREAM_NO_TMA
+          if (scat && (h & 1) == 0) {
+            if (tid == 0) smrt_bulk_load1(bar, dst, src, (unsigned)((size_t)h * h * sizeof(double)));
+            return true;
+          }
+#endif
+          if (scat) {
+            for (int e = tid; e < h * h; e += NT) dst[e] = src[e];
+          } else {
+            SMRT_FOR_2D(i, j, h, h) { dst[(size_t)j * h + i] = (identity && i == j) ? 1.0 : 0.0; }
+          }
+          return false;
+        };
+        bool waitF = false, waitG = false;
+        if (kStreamFG) {
+          // formation phase: F in the left block of T, G in the right block (compact, ld = h)
+          BF = TT;
+          BG = TT + (size_t)h * ldp;
+          if (pf_layer == l) {  // F was prefetched while the layer below was being eliminated
+            waitF = true;
+            pf_layer = -1;
+          } else {
+            waitF = stage_operand(BF, rF_l, true, &s_mbar);
+          }
+          waitG = stage_operand(BG, rG_l, false, &s_mbarG);
+          if (!scat)
+            for (int a = tid; a < h; a += NT) kvec[a] = ke / mu[a / npol];
+        } else if (scat) {
           const double* rk = rk_l;
           const double* rF = rk + smrt_even(smrt_npol(m) * n);
           const double* rG = rF + smrt_even((long long)h * h);
@@ -745,6 +796,16 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
           if (tid < h) kvec[tid] = kpre;
           for (int a = tid + NT; a < h; a += NT) kvec[a] = rk_l[a];
         }
+        if (kStreamFG) {
+          if (waitF) {
+            smrt_mbar_wait(&s_mbar, pf_parity);
+            pf_parity ^= 1u;
+          }
+          if (waitG) {
+            smrt_mbar_wait(&s_mbarG, pg_parity);
+            pg_parity ^= 1u;
+          }
+        }
         __syncthreads();
         for (int a = tid; a < h; a += NT) tvec[a] = exp(-kvec[a] * thick);
 
@@ -804,15 +865,35 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
         }
         // T = [A21 | A22] without the coupling term:  A21 = F - Rb D G,  A22 = (G - Rb D F) t
         // (Dsg holds the sign D of the third Stokes component, RbD = Rb D)
-        SMRT_FOR_2D(i, j, h, h) {
-          const double f = BF[(size_t)j * h + i], g = BG[(size_t)j * h + i];
-          SMRT_AT(TT, ldp, i, j) = f - RbD[i] * g;
-          SMRT_AT(TT, ldp, i, h + j) = (g - RbD[i] * f) * tvec[j];
+        if (!kStreamFG) {
+          SMRT_FOR_2D(i, j, h, h) {
+            const double f = BF[(size_t)j * h + i], g = BG[(size_t)j * h + i];
+            SMRT_AT(TT, ldp, i, j) = f - RbD[i] * g;
+            SMRT_AT(TT, ldp, i, h + j) = (g - RbD[i] * f) * tvec[j];
+          }
         }
         // coupling operator of the stack below: R' = T_top(l+1) R(l+1) T_bottom(l) D on the common streams
         SMRT_FOR_2D(i, k, r, r) { SMRT_AT(BR, ldr_prev, i, k) *= Ttprev[i] * (Tb[k] * Dsg[k]); }
         __syncthreads();
-        if (r > 0) {
+        if (kStreamFG) {
+          // F and G sit (compact) in the two blocks of T: every thread evaluates its tiles of
+          // [F - Rb D G - R' G | (G - Rb D F - R' F) t] in registers, the block synchronises, the tiles overwrite them
+          const double* Fs = BF;
+          const double* Gs = BG;
+          block_gemm_ptr_deferred(
+              h, r, 2 * h, r, BR, ldr_prev,
+              [&](int j) { return (j < h) ? Gs + (size_t)j * h : Fs + (size_t)(j - h) * h; },
+              [&](int i, int j, double acc) {
+                if (j < h) return Fs[(size_t)j * h + i] - RbD[i] * Gs[(size_t)j * h + i] - acc;
+                const int jj = j - h;
+                return (Gs[(size_t)jj * h + i] - RbD[i] * Fs[(size_t)jj * h + i] - acc) * tvec[jj];
+              },
+              [&](int i, int j, double v) { SMRT_AT(TT, ldp, i, j) = v; });
+          __syncthreads();
+          // R of the stack below is dead: G for the products after the elimination goes there while it runs
+          BG = BR;
+          waitG = stage_operand(BG, rG_l, false, &s_mbarG);
+        } else if (r > 0) {
           // one product over the 2h columns [G | F]: all threads busy with 4 x 4 tiles
           block_gemm_ptr(
               NT, r, 2 * h, r, BR, ldr_prev,
@@ -827,6 +908,10 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
         if (blocked ? block_gj_rows_blocked(TT, ldp, TT + (size_t)h * ldp, ldp, h, h + nr, rowof, pivinv, GJV,
                                             &s_ctrl[6])
                     : block_gj_rows(TT, ldp, h, 2 * h + nr, rowstep, rowof)) {
+          if (kStreamFG && waitG) {  // drain the copy of G in flight before leaving
+            smrt_mbar_wait(&s_mbarG, pg_parity);
+            pg_parity ^= 1u;
+          }
           failed = true;
           break;
         }
@@ -842,18 +927,33 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
         // (blocked path, l > 0: S and K are stored TRANSPOSED, so that R_new = K S^-1 = (S^-T K^T)^T comes out of the
         // same row elimination as above)
         const bool transposed = blocked && l > 0;
-        block_gemm_dual(gemm_thr, h, h, h, BG, BF, h, TT, ldp, [&](int i, int j, double c1, double c2) {
-          double pv = SMRT_AT(BF, h, i, j) - c1;
-          double kv = SMRT_AT(BG, h, i, j) - c2;
-          double sv = Dsg[i] * pv - Rt[i] * kv;
-          if (transposed) {
-            SMRT_AT(TS, ldp, j, i) = sv;
-            SMRT_AT(BR, ldp, j, i) = kv;
-          } else {
-            SMRT_AT(TS, ldp, i, j) = sv;
-            SMRT_AT(BR, ldp, i, j) = kv;
+        if (kStreamFG) {
+          // the right block of T is dead (Y~ was extracted): F is staged there, G already sits in R
+          BF = TS;
+          waitF = stage_operand(BF, rF_l, true, &s_mbar);
+          if (waitF) {
+            smrt_mbar_wait(&s_mbar, pf_parity);
+            pf_parity ^= 1u;
           }
-        });
+          if (waitG) {
+            smrt_mbar_wait(&s_mbarG, pg_parity);
+            pg_parity ^= 1u;
+          }
+          __syncthreads();
+        } else {
+          block_gemm_dual(gemm_thr, h, h, h, BG, BF, h, TT, ldp, [&](int i, int j, double c1, double c2) {
+            double pv = SMRT_AT(BF, h, i, j) - c1;
+            double kv = SMRT_AT(BG, h, i, j) - c2;
+            double sv = Dsg[i] * pv - Rt[i] * kv;
+            if (transposed) {
+              SMRT_AT(TS, ldp, j, i) = sv;
+              SMRT_AT(BR, ldp, j, i) = kv;
+            } else {
+              SMRT_AT(TS, ldp, i, j) = sv;
+              SMRT_AT(BR, ldp, i, j) = kv;
+            }
+          });
+        }
         // v = F y~r ;  b' = b_top - D (G y~r) + Rt v  (b' goes next to S, in the augmented columns)
         if (nr == 1 && NT >= h) {  // one right-hand side: whole-block matrix-vector products (GJV is free: scratch)
           block_matvec_dual(h, h, BG, BF, h, ytr, GJV, [&](int i, double c1, double c2) {
@@ -869,7 +969,54 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
           }
           __syncthreads();
         }
-        if (!kGlobalScratch && l > 0 && !coherent && A.scat_flag[bL + l - 1] != 0) {
+        if (kStreamFG) {
+          // (the products come after the matrix-vector part here: their results overwrite the staged operands)
+          const double* Fs = BF;
+          const double* Gs = BG;
+          block_gemm_dual_deferred(
+              h, h, h, Gs, Fs, h, TT, ldp,
+              [&](int i, int j, double& c1, double& c2) {  // (G Y~, F Y~) -> (S, K)
+                const double pv = SMRT_AT(Fs, h, i, j) - c1;
+                const double kv = SMRT_AT(Gs, h, i, j) - c2;
+                c1 = Dsg[i] * pv - Rt[i] * kv;
+                c2 = kv;
+              },
+              [&](int i, int j, double sv, double kv) {
+                if (transposed) {
+                  SMRT_AT(TS, ldp, j, i) = sv;
+                  SMRT_AT(BR, ldp, j, i) = kv;
+                } else {
+                  SMRT_AT(TS, ldp, i, j) = sv;
+                  SMRT_AT(BR, ldp, i, j) = kv;
+                }
+              });
+          // the left block of T (Y~) is dead: F of the layer above is fetched into it during the second elimination
+          // when it fits there (the layers have their own stream counts); G only as an L2 prefetch hint
+          if (l > 0 && !coherent && A.scat_flag[bL + l - 1] != 0) {
+            const cplx eps_u = c_make(eps_b[2 * (l - 1)], eps_b[2 * (l - 1) + 1]);
+            const int h_u = npol * stream_count(real_index_of(eps_star, eps_u), A.gl_mu, n);
+            const double* uk = A.eig + (bL + l - 1) * A.eig_stride + A.eig_off[m];
+            const double* uF = uk + smrt_even(smrt_npol(m) * n);
+            const double* uG = uF + smrt_even((long long)h_u * h_u);
+            const unsigned bytes = (unsigned)((size_t)h_u * h_u * sizeof(double));
+#ifdef SMRT_STREAM_NO_TMA
+            if (false) {
+#else
+            if ((h_u & 1) == 0) {
+#endif
+              const bool fits = (size_t)h_u * h_u <= (size_t)h * ldp;
+              if (tid == 0) {
+                smrt_prefetch_l2(uG, bytes);
+                if (fits)
+                  smrt_bulk_load1(&s_mbar, TT, uF, bytes);
+                else
+                  smrt_prefetch_l2(uF, bytes);
+              }
+              if (fits) pf_layer = l - 1;
+            }
+          }
+        }
+        if (!kStreamFG && !kGlobalScratch && l > 0 && !coherent && A.scat_flag[bL + l - 1] != 0) {
           // BF / BG are dead from here on: let the TMA engine fetch the record of the layer above (cp.async.bulk,
           // completion on s_mbar) while this CTA runs the second elimination
           if (tid == 0) {
@@ -882,6 +1029,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
           }
           pf_layer = l - 1;
         }
+        double* bounce = kStreamFG ? TS : TT;
         if (l > 0) {
           // keep b' (the column elimination below does not touch the augmented columns)
           // R_new = K S^-1 by column elimination of [S; K]
@@ -891,7 +1039,9 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
               failed = true;
               break;
             }
-            SMRT_FOR_2D(i, k, h, h) { SMRT_AT(TT, ldp, i, k) = SMRT_AT(BR, ldp, rowof[k], i) * pivinv[k]; }
+            // (un-permuted through a dead block of T: the left one, or the right one when the left one receives the
+            // prefetched F of the layer above)
+            SMRT_FOR_2D(i, k, h, h) { SMRT_AT(bounce, ldp, i, k) = SMRT_AT(BR, ldp, rowof[k], i) * pivinv[k]; }
           } else {
             if (block_gj_cols(TS, ldp, BR, ldp, h, h, rowstep, rowof)) {
               failed = true;
@@ -900,10 +1050,10 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads) boundary_kernel(KArgs A) {
             for (int k = tid; k < h; k += NT) ipiv[k] = 1.0 / SMRT_AT(TS, ldp, k, rowof[k]);
             __syncthreads();
             // un-permute / scale through the (dead) left block of T, then back into BR
-            SMRT_FOR_2D(i, k, h, h) { SMRT_AT(TT, ldp, i, k) = SMRT_AT(BR, ldp, i, rowof[k]) * ipiv[k]; }
+            SMRT_FOR_2D(i, k, h, h) { SMRT_AT(bounce, ldp, i, k) = SMRT_AT(BR, ldp, i, rowof[k]) * ipiv[k]; }
           }
           __syncthreads();
-          SMRT_FOR_2D(i, k, h, h) { SMRT_AT(BR, ldp, i, k) = SMRT_AT(TT, ldp, i, k); }
+          SMRT_FOR_2D(i, k, h, h) { SMRT_AT(BR, ldp, i, k) = SMRT_AT(bounce, ldp, i, k); }
           __syncthreads();
           if (nr == 1 && NT >= h) {  // s = v + R_new b'
             block_matvec_dual(h, h, BR, (const double*)nullptr, ldp, Trhs, GJV,

@@ -812,6 +812,160 @@ SMRT_DEV void block_gemm_dual(int nthr, int M, int N, int K, const double* SMRT_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// "Deferred store" variants for the boundary kernel that keeps only [T | R] resident (two CTAs per SM): the operands F
+// and G of a layer are staged by the TMA engine INTO THE BUFFERS THE RESULTS WILL OCCUPY, every thread computes ALL its
+// output tiles in registers, the block synchronises, and only then the results overwrite the operands.
+// Tiles: 4 x 4 per thread, rows tx + 16 u (M <= 64: one row pass), columns j0 + ty + TY v; at most SMRT_DEF_TILES column
+// passes per thread (N <= 4 TY SMRT_DEF_TILES).
+#ifdef SMRT_SIMT_EMULATION
+#define SMRT_DEF_TILES 8  // the CPU tests run 64-thread blocks (TY = 4): 128 columns
+#else
+#define SMRT_DEF_TILES 4  // >= 128 threads on the device (TY >= 8)
+#endif
+
+// out(i, j) = pre(i, j, sum_{k < K} A(i, k) B(k, j)) for i < M (<= 64), j < N, evaluated in registers; then a block
+// barrier; then post(i, j, value).  A column-major in shared memory (lda), column j of B at bcol(j) (K entries).
+// rows i >= Mk contribute no product (the sum is zero there).  Every thread of the block must call.
+// The k loop is the outer one: the four A operands of a step serve all the column tiles of the thread.
+template <typename FB, typename FPRE, typename FPOST>
+SMRT_DEV void block_gemm_ptr_deferred(int M, int Mk, int N, int K, const double* SMRT_RESTRICT Am, int lda, FB bcol,
+                                      FPRE pre, FPOST post) {
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int TX = 16, TY = NT / TX;
+  const int tx = tid % TX, ty = tid / TX;
+  double val[SMRT_DEF_TILES][4][4];
+  const double* bp[SMRT_DEF_TILES][4];
+  size_t ao[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = tx + u * TX;
+    ao[u] = (size_t)(i < Mk ? i : (Mk > 0 ? Mk - 1 : 0));
+  }
+#pragma unroll
+  for (int t = 0; t < SMRT_DEF_TILES; ++t)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int j = t * TY * 4 + ty + v * TY;
+      bp[t][v] = bcol(j < N ? j : N - 1);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) val[t][u][v] = 0.0;
+    }
+  if (Mk > 0 && tx < M) {
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      double av[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) av[u] = Am[ao[u] + (size_t)k * lda];
+#pragma unroll
+      for (int t = 0; t < SMRT_DEF_TILES; ++t) {
+        if (t * TY * 4 + ty < N) {  // uniform over the threads of a tile column
+          double bv[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) bv[v] = bp[t][v][k];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) val[t][u][v] = fma(av[u], bv[v], val[t][u][v]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < SMRT_DEF_TILES; ++t)
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int i = tx + u * TX, j = t * TY * 4 + ty + v * TY;
+        if (i < M && j < N) val[t][u][v] = pre(i, j, (i < Mk) ? val[t][u][v] : 0.0);
+      }
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < SMRT_DEF_TILES; ++t)
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int i = tx + u * TX, j = t * TY * 4 + ty + v * TY;
+        if (i < M && j < N) post(i, j, val[t][u][v]);
+      }
+}
+
+// Two products sharing the B operand, C1 = A1 B and C2 = A2 B (M x N, inner K, M <= 64, N <= 4 TY SMRT_DEF_TILES / 2):
+// pre(i, j, c1, c2) turns the two sums IN PLACE into the two values to keep (it may read A1 / A2), then a block
+// barrier, then post(i, j, v1, v2) stores them (it may overwrite A1 / A2).  Every thread of the block must call.
+template <typename FPRE, typename FPOST>
+SMRT_DEV void block_gemm_dual_deferred(int M, int N, int K, const double* SMRT_RESTRICT A1, const double* SMRT_RESTRICT A2,
+                                       int lda, const double* SMRT_RESTRICT Bm, int ldb, FPRE pre, FPOST post) {
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int TX = 16, TY = NT / TX;
+  const int tx = tid % TX, ty = tid / TX;
+  constexpr int NTL = SMRT_DEF_TILES / 2;
+  double v1[NTL][4][4], v2[NTL][4][4];
+  const double* bp[NTL][4];
+  size_t ao[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = tx + u * TX;
+    ao[u] = (size_t)(i < M ? i : M - 1);
+  }
+#pragma unroll
+  for (int t = 0; t < NTL; ++t)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int j = t * TY * 4 + ty + v * TY;
+      bp[t][v] = Bm + (size_t)(j < N ? j : N - 1) * ldb;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v1[t][u][v] = v2[t][u][v] = 0.0;
+    }
+  if (tx < M) {
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      double a1[4], a2[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a1[u] = A1[ao[u] + (size_t)k * lda];
+        a2[u] = A2[ao[u] + (size_t)k * lda];
+      }
+#pragma unroll
+      for (int t = 0; t < NTL; ++t) {
+        if (t * TY * 4 + ty < N) {
+          double bv[4];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) bv[v] = bp[t][v][k];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              v1[t][u][v] = fma(a1[u], bv[v], v1[t][u][v]);
+              v2[t][u][v] = fma(a2[u], bv[v], v2[t][u][v]);
+            }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < NTL; ++t)
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int i = tx + u * TX, j = t * TY * 4 + ty + v * TY;
+        if (i < M && j < N) pre(i, j, v1[t][u][v], v2[t][u][v]);
+      }
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < NTL; ++t)
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        const int i = tx + u * TX, j = t * TY * 4 + ty + v * TY;
+        if (i < M && j < N) post(i, j, v1[t][u][v], v2[t][u][v]);
+      }
+}
+
 // Matrix-vector products by the whole block (the 4 x 4 tiled GEMMs above keep only 16 threads busy for one right-hand
 // side): y1 = A1 x and y2 = A2 x for column-major M x K matrices (lda), x in shared memory.  Thread (i, p) sums the
 // columns k = p, p + tpr, ... of row i (lanes along rows: conflict-free), the tpr partial sums per row meet in `part`

@@ -58,6 +58,19 @@ SMRT_DEV void smrt_bulk_load2(smrt_mbar_t* bar, void* dst0, const void* src0, vo
                "l"(src1), "r"(bytes_each), "r"(smrt_smem_u32(bar))
                : "memory");
 }
+// single copy under one barrier phase
+SMRT_DEV void smrt_bulk_load1(smrt_mbar_t* bar, void* dst, const void* src, unsigned bytes) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smrt_smem_u32(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smrt_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smrt_smem_u32(bar))
+               : "memory");
+}
+// hint: bring [src, src + bytes) into L2 (bytes a multiple of 16)
+SMRT_DEV void smrt_prefetch_l2(const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 // every consumer thread: wait for the phase with the given parity
 SMRT_DEV void smrt_mbar_wait(smrt_mbar_t* bar, unsigned parity) {
   unsigned ok;
@@ -188,6 +201,8 @@ inline void smrt_bulk_load2(smrt_mbar_t*, void* dst0, const void* src0, void* ds
   std::memcpy(dst0, src0, bytes_each);
   std::memcpy(dst1, src1, bytes_each);
 }
+inline void smrt_bulk_load1(smrt_mbar_t*, void* dst, const void* src, unsigned bytes) { std::memcpy(dst, src, bytes); }
+inline void smrt_prefetch_l2(const void*, unsigned) {}
 inline void smrt_mbar_wait(smrt_mbar_t*, unsigned) {}
 
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }

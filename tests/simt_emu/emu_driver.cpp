@@ -3,6 +3,7 @@
 // tests/simt_emu/libsmrt_emu.so; loaded by tests/test_simt_emulation.py with ctypes.  Same batch struct as the C ABI,
 // host pointers.
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "dort_host.h"
@@ -45,7 +46,12 @@ int emu_solve_batch(const smrtb200_options* opt, const smrtb200_batch* batch, in
 
   simt::launch((unsigned)((BL + 127) / 128), 128, [&]() { optics_kernel(A); });
   simt::launch(1, (unsigned)threads, [&]() { eigen_kernel<true>(A); });
-  simt::launch(1, (unsigned)threads, [&]() { boundary_kernel<true, 512>(A); });
+  // SMRT_EMU_STREAM_FG=1: the boundary instantiation that stages F and G into [T | R] (h <= 64)
+  const char* sf = std::getenv("SMRT_EMU_STREAM_FG");
+  if (sf && sf[0] == '1' && L.hmax <= 64)
+    simt::launch(1, (unsigned)threads, [&]() { boundary_kernel<true, 512, true>(A); });
+  else
+    simt::launch(1, (unsigned)threads, [&]() { boundary_kernel<true, 512>(A); });
   if (sweeps_out) {
     sweeps_out[0] = diag[0];
     sweeps_out[1] = diag[1];

@@ -33,6 +33,20 @@ def test_emulated_kernels_match_reference_fixture(name):
         assert out.n_streams[b] == d["ref_n_air"][b]
 
 
+@pytest.mark.parametrize("name", ["ref_iba_2layer_passive", "iba_exp_substrate_passive", "nonscattering_transparent",
+                                  "atmosphere_passive", "ref_dmrt_less_refringent_active", "soil_active"])
+def test_emulated_boundary_kernel_with_staged_operands(name, monkeypatch):
+    """the boundary instantiation that keeps only [T | R] resident and stages F / G into them (two CTAs per SM on the
+    device): TMA copies for even block sizes, thread copies for odd ones, generated operands for non-scattering layers"""
+    monkeypatch.setenv("SMRT_EMU_STREAM_FG", "1")
+    d, batch, opts = load_golden(name)
+    batch = batch.subset(slice(0, 2))
+    for threads in (64, 128):
+        out = emu_solve(batch, opts, threads=threads)
+        assert np.all((out.status & 15) == 0)
+        assert rel_err(out.values, d["ref_values"][:batch.B], batch.mode) <= (1e-10 if batch.mode == 0 else 1e-6)
+
+
 def test_emulated_kernels_full_warp_block():
     """same code with 256 threads per block (the launch configuration used on the GPU)"""
     d, batch, opts = load_golden("ref_iba_2layer_passive")
