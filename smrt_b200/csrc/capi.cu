@@ -68,6 +68,7 @@ struct smrtb200_plan {
   size_t eigen_smem = 0, boundary_smem = 0;
   long long scratch_stride = 0;
   double* gl_mu = nullptr;
+  unsigned long long* prof = nullptr;  // SMRT_B200_PROFILE: cycle counters of the boundary kernel phases
   Slot slots[kSlots];
   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
   unsigned long long workspace_bytes = 0;
@@ -116,6 +117,18 @@ extern "C" int smrtb200_plan_destroy(smrtb200_plan* p) {
   for (cudaEvent_t e : p->chunk_events) cudaEventDestroy(e);
   for (void* d : p->dev_bufs) cudaFree(d);
   for (void* h : p->pinned_bufs) cudaFreeHost(h);
+  if (p->prof) {
+    unsigned long long c[16];
+    if (cudaMemcpy(c, p->prof, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess) {
+      static const char* names[8] = {"between problems", "problem setup", "layer head", "rhs + formation", "elimination 1",
+                                     "extraction + products", "elimination 2", "R + source"};
+      double tot = 0;
+      for (int i = 0; i < 8; ++i) tot += (double)c[i];
+      for (int i = 0; i < 8; ++i)
+        std::fprintf(stderr, "[smrtb200 profile] %-24s %6.2f %%  %.3e cycles\n", names[i], 100.0 * c[i] / (tot > 0 ? tot : 1), (double)c[i]);
+    }
+    cudaFree(p->prof);
+  }
   cudaFree(p->gl_mu);
   if (p->ev_begin) cudaEventDestroy(p->ev_begin);
   if (p->ev_end) cudaEventDestroy(p->ev_end);
@@ -249,6 +262,10 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
   PLAN_TRY(dev_alloc(p, &p->gl_mu, (size_t)L.n));
   PLAN_CUDA(cudaMemcpy(p->gl_mu, gl.data(), sizeof(double) * L.n, cudaMemcpyHostToDevice));
 
+  if (std::getenv("SMRT_B200_PROFILE")) {
+    PLAN_TRY(dev_alloc(p, &p->prof, (size_t)16));
+    PLAN_CUDA(cudaMemset(p->prof, 0, 16 * sizeof(unsigned long long)));
+  }
   const size_t CL = (size_t)p->chunk * options->max_layers;
   for (auto& s : p->slots) {
     PLAN_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -325,6 +342,7 @@ extern "C" int smrtb200_solve_batch_device(smrtb200_plan* p, const smrtb200_batc
     Slot& s = p->slots[nchunks % nslots];
     KArgs A = smrt_host::make_kargs(p->opt, L, *batch, b0, nb);
     A.gl_mu = p->gl_mu;
+    A.prof = p->prof;
     A.aux = s.aux;
     A.eig = s.eig;
     A.kmin = s.kmin;

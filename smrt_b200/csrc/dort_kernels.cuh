@@ -47,6 +47,7 @@ struct KArgs {
   int* scat_flag;       // [B, L]
   int* counters;        // [2]: eigen / boundary work counters
   int* diag;            // optional [2] diagnostics: total Jacobi sweeps, number of eigenproblems (may be NULL)
+  unsigned long long* prof;  // optional [16] cycle counters of the boundary kernel phases (SMRT_B200_PROFILE; may be NULL)
   double* scratch;      // [gridDim.x, scratch_stride] when use_global_scratch
   long long eig_stride, scratch_stride;
   int use_global_scratch;
@@ -453,6 +454,18 @@ struct BoundaryCtx {
 // products keep all their tiles in registers until the block has finished reading (block_gemm_*_deferred): 114 KB
 // per problem at 32 streams instead of 186 KB, TWO problems per SM: the serial panel chain of one elimination is
 // covered by the other problem's work.  Requires h <= 64 and 128 <= blockDim.x <= 256.
+#ifdef SMRT_SIMT_EMULATION
+#define SMRT_PHASE(id)
+#else
+// thread 0 charges the cycles since the previous mark to phase `id` (only when the plan was created with
+// SMRT_B200_PROFILE set: A.prof != NULL)
+#define SMRT_PHASE(id)                                             \
+  if (A.prof && threadIdx.x == 0) {                                \
+    const long long now_ = clock64();                              \
+    atomicAdd(&A.prof[id], (unsigned long long)(now_ - prof_t0));  \
+    prof_t0 = now_;                                                \
+  }
+#endif
 template <bool kGlobalScratch, int kMaxThreads, bool kStreamFG = false>
 SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kernel(KArgs A) {
   SMRT_DYN_SMEM(smem);
@@ -511,7 +524,13 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
   double* ytr = svec + szr;
   double* vvec = ytr + szr;
 
+  long long prof_t0 = 0;
+#ifndef SMRT_SIMT_EMULATION
+  prof_t0 = clock64();
+#endif
+  (void)prof_t0;
   for (;;) {
+    SMRT_PHASE(0)  // between problems: output stage of the previous one
     if (tid == 0) s_item = atomicAdd(&A.counters[1], 1);
     __syncthreads();
     const int b = s_item;
@@ -654,6 +673,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
       bool src_prev = false;  // the stack below carries a source vector (false for the source-free active layers)
       int pf_layer = -1;      // layer whose (F, G) record is in flight into BF / BG (TMA bulk copy), -1 = none
 
+      SMRT_PHASE(1)  // problem setup
       for (int l = l_end; l >= 0 && !failed; --l) {
         const cplx eps_l = c_make(eps_b[2 * l], eps_b[2 * l + 1]);
         const double rindex = real_index_of(eps_star, eps_l);
@@ -807,6 +827,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
           }
         }
         __syncthreads();
+        SMRT_PHASE(2)  // layer head: streams, record, Fresnel
         for (int a = tid; a < h; a += NT) tvec[a] = exp(-kvec[a] * thick);
 
         // right-hand sides ---------------------------------------------------------------------- dort.py:375-441
@@ -903,6 +924,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
               });
           __syncthreads();
         }
+        SMRT_PHASE(3)  // right-hand sides, formation of [A21 | A22]
         // [A21 | A22 | b_bot] -> [I | Y22 | Yr] (implicit row permutation, unscaled rows)
         const bool blocked = h <= 64;  // panel-blocked elimination (register tiles); larger blocks: one step at a time
         if (blocked ? block_gj_rows_blocked(TT, ldp, TT + (size_t)h * ldp, ldp, h, h + nr, rowof, pivinv, GJV,
@@ -915,6 +937,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
           failed = true;
           break;
         }
+        SMRT_PHASE(4)  // first elimination
         for (int k = tid; k < h; k += NT)
           ipiv[k] = blocked ? tvec[k] * pivinv[k] : tvec[k] / SMRT_AT(TT, ldp, rowof[k], k);
         __syncthreads();
@@ -1029,6 +1052,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
           }
           pf_layer = l - 1;
         }
+        SMRT_PHASE(5)  // extraction, products P / K / S, b'
         double* bounce = kStreamFG ? TS : TT;
         if (l > 0) {
           // keep b' (the column elimination below does not touch the augmented columns)
@@ -1041,6 +1065,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
             }
             // (un-permuted through a dead block of T: the left one, or the right one when the left one receives the
             // prefetched F of the layer above)
+            SMRT_PHASE(6)  // second elimination
             SMRT_FOR_2D(i, k, h, h) { SMRT_AT(bounce, ldp, i, k) = SMRT_AT(BR, ldp, rowof[k], i) * pivinv[k]; }
           } else {
             if (block_gj_cols(TS, ldp, BR, ldp, h, h, rowstep, rowof)) {
@@ -1068,6 +1093,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
           have_prev = true;
           src_prev = (nr > 0);
           __syncthreads();
+          SMRT_PHASE(7)  // R of the stack, source vector
         } else {
           // top layer: z = S^-1 b' by row elimination of [S | b'], then s = v + K z
           if (blocked ? block_gj_rows_blocked(TS, ldp, Trhs, ldp, h, nr, rowof, pivinv, GJV, &s_ctrl[6])

@@ -39,7 +39,9 @@ for r in rows[2:]:
         v = float(d[key]); u = units[hdr.index(key)].lower()
         return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
     short = "eigen_kernel" if "eigen" in name else "boundary_kernel" if "boundary" in name else name
-    nsolves = 1536 / 2.0  # two chunks of 768 problems each in the capture
+    # the capture holds the FIRST launch of each kernel: one chunk = max(4 x boundary grid, 1024) problems of the 1536
+    bgrid = [float(dict(zip(hdr, q))["launch__grid_size"]) for q in rows[2:] if "boundary" in dict(zip(hdr, q))["Kernel Name"]]
+    nsolves = min(1536.0, max(4.0 * (bgrid[0] if bgrid else 148.0), 1024.0))
     traffic[short] = {"dram_bytes_per_launch_in_capture": tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum"),
                       "solves_in_captured_launch": nsolves,
                       "dram_bytes_per_solve": (tobytes("dram__bytes_read.sum") + tobytes("dram__bytes_write.sum")) / nsolves}
