@@ -40,6 +40,9 @@ extern "C" {
 #define SMRTB200_EM_RAYLEIGH 4       /* smrt/emmodel/rayleigh.py:17-39; ms_p0 = radius of the microstructure */
 #define SMRTB200_EM_PRESCRIBED_KSKAEPS 5 /* smrt/emmodel/prescribed_kskaeps.py:20-27: eps_bg = effective permittivity,
                                             ms_p0 = ks, ms_p1 = ka (ms_kind ignored); Rayleigh phase matrix */
+#define SMRTB200_EM_IBA_ORIGINAL 6   /* smrt/emmodel/iba_original.py:15-44: IBA with the absorption of Maetzler 1998 */
+#define SMRTB200_EM_IBA_MAXWELL_GARNETT 7 /* smrt/emmodel/iba_maxwell_garnett.py:24-52: Maxwell-Garnett effective
+                                            permittivity, apparent permittivity = background */
 
 /* microstructure model (FT of the autocorrelation function) */
 #define SMRTB200_MS_EXPONENTIAL 0 /* p0 = corr_length                smrt/microstructure_model/exponential.py:53-58 */

@@ -241,7 +241,7 @@ def solve_problem(problem, collect=None):
             entry[m] = None
         if o["ks"] != 0:
             fullmu = np.concatenate((mu, -mu))
-            if o["emmodel"] == O.EM_IBA:
+            if o["emmodel"] in O.EM_IBA_FAMILY:
                 P5 = O.iba_ft_even_phase(o, mu, fullmu, m_max, npol)
             else:
                 P5 = O.rayleigh_ft_even_phase(o["ks"], mu, fullmu, m_max)

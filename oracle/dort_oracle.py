@@ -27,7 +27,8 @@ Problem description (a plain dict, all SI units; the same fields the C ABI takes
     eps_sc         (L,) complex   scatterer permittivity    (layer.permittivity(1, f))
     emmodel        (L,) int       0 = IBA, 1 = DMRT-QCA short range, 2 = non-scattering, 3 = DMRT-QCACP short range,
                                   4 = Rayleigh (ms_p0 = radius), 5 = prescribed ks / ka / eps (eps_bg = effective
-                                  permittivity, ms_p0 = ks, ms_p1 = ka)
+                                  permittivity, ms_p0 = ks, ms_p1 = ka), 6 = IBA original (Maetzler 1998 absorption),
+                                  7 = IBA with the Maxwell-Garnett effective permittivity
     ms_kind        (L,) int       0 = exponential (ms_p0 = corr_length), 1 = sticky hard spheres (ms_p0 = radius,
                                   ms_p1 = stickiness), 2 = homogeneous, 3 = independent sphere (radius), 4 = Teubner-
                                   Strey (corr_length, repeat_distance), 5 / 6 = unified Teubner-Strey, polydispersity
@@ -63,6 +64,8 @@ PLANCK_CONSTANT = 6.62607015e-34
 BOLTZMANN_CONSTANT = 1.380649e-23
 
 EM_IBA, EM_DMRT_QCA_SR, EM_NONSCATTERING, EM_DMRT_QCACP_SR, EM_RAYLEIGH, EM_PRESCRIBED_KSKAEPS = 0, 1, 2, 3, 4, 5
+EM_IBA_ORIGINAL, EM_IBA_MAXWELL_GARNETT = 6, 7
+EM_IBA_FAMILY = (EM_IBA, EM_IBA_ORIGINAL, EM_IBA_MAXWELL_GARNETT)
 MS_EXPONENTIAL, MS_SHS, MS_HOMOGENEOUS = 0, 1, 2
 MS_INDEPENDENT_SPHERE, MS_TEUBNER_STREY, MS_UNIFIED_TS_1, MS_UNIFIED_TS_2, MS_SHS_T = 3, 4, 5, 6, 7
 IF_FLAT, IF_TRANSPARENT = 0, 1
@@ -255,16 +258,25 @@ def layer_optics(frequency, f, e0, eps, emmodel, ms_kind, p0, p1, invert_dense=F
     e0 = complex(e0)
     eps = complex(eps)
     out = dict(ms_kind=ms_kind, p0=p0, p1=p1)
-    if emmodel == EM_IBA:
+    if emmodel in EM_IBA_FAMILY:
         if f > 0.5 and invert_dense:  # dense_snow_correction="auto": iba.py:95-96, core/layer.py:186-201
             f, e0, eps = 1.0 - f, eps, e0
         k0 = 2 * np.pi * frequency / C_SPEED
-        eeff = polder_van_santen_spheres(f, e0, eps)
         depol = np.array([1.0 / 3, 1.0 / 3, 1.0 / 3])  # depolarization_factors.py:9-46 for length_ratio 1
-        eapp = eeff * (1 - depol) + e0 * depol
+        if emmodel == EM_IBA_MAXWELL_GARNETT:
+            # reference smrt/permittivity/generic_mixing_formula.py:346-358, smrt/emmodel/iba_maxwell_garnett.py:47-51
+            eeff = complex(np.mean(e0 * (1 + f * (eps - e0) / (e0 + (1.0 - f) * depol * (eps - e0))),
+                                   dtype=np.complex128))
+            eapp = e0
+        else:
+            eeff = polder_van_santen_spheres(f, e0, eps)
+            eapp = eeff * (1 - depol) + e0 * depol
         y2 = (1.0 / 3.0) * np.sum(np.absolute(eapp / (eapp + (eps - e0) * depol)) ** 2.0)
         iba_coeff = (1.0 / (4.0 * np.pi)) * np.absolute(eps - e0) ** 2.0 * y2 * k0**4
-        ka = 2 * k0 * np.sqrt(eeff).imag
+        if emmodel == EM_IBA_ORIGINAL:  # reference smrt/emmodel/iba_original.py:43-44 (Maetzler 1998)
+            ka = k0 * f * eps.imag * abs(y2)
+        else:
+            ka = 2 * k0 * np.sqrt(eeff).imag
         mu = np.linspace(1, -1, 65)
         sintheta_2 = np.sqrt((1.0 - mu) / 2.0)
         k_diff = 2.0 * k0 * sintheta_2 * abs(np.sqrt(eeff))
@@ -643,7 +655,7 @@ class LayerEigen:
             fullmu = np.concatenate((self.mu, -self.mu))
             if self.opt["ks"] == 0:
                 self._phase = 0
-            elif self.opt["emmodel"] == EM_IBA:
+            elif self.opt["emmodel"] in EM_IBA_FAMILY:
                 self._phase = iba_ft_even_phase(self.opt, fullmu, fullmu, self.m_max, self.npol_em)
             elif self.opt["emmodel"] in (EM_DMRT_QCA_SR, EM_DMRT_QCACP_SR, EM_RAYLEIGH, EM_PRESCRIBED_KSKAEPS):
                 self._phase = rayleigh_ft_even_phase(self.opt["ks"], fullmu, fullmu, self.m_max)

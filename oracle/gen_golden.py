@@ -422,6 +422,30 @@ def prescribed_kskaeps_passive():  # reference emmodel/prescribed_kskaeps.py: ks
              dict(n_max_stream=16))
 
 
+@case
+def iba_variants():  # reference emmodel/iba_original.py, iba_maxwell_garnett.py, test/test_mixed_emmodel.py
+    # test/test_integration_iba_original.py:12-45 (literals TbV 247.92662874568973, TbH 237.1283359660738)
+    run_case("ref_iba_original_2layer_passive", "iba_original", sensor_list.amsre("37V"), [two_layer_iba()])
+    # test/test_mixed_emmodel.py:9-40 (one emmodel per layer)
+    run_case("ref_mixed_emmodel_passive", ["dmrt_qcacp_shortrange", "iba"], sensor_list.amsre("37V"), [two_layer_shs()])
+    rng = np.random.default_rng(43)
+    sps = []
+    for k in range(3):
+        L = 4
+        th = np.concatenate((rng.uniform(0.05, 0.6, L - 1), [1000.0]))
+        dens = rng.uniform(150, 450, L)
+        if k == 2:
+            dens[1] = 650.0  # denser than half the ice density: the medium is inverted with dense_snow_correction="auto"
+        sps.append(make_snowpack(th, "exponential", density=dens, temperature=rng.uniform(235, 270, L),
+                                 corr_length=rng.uniform(5e-5, 3e-4, L)))
+    for em in ("iba_original", "iba_maxwell_garnett"):
+        run_case(em + "_passive", em, sensor_list.passive([18.7e9, 36.5e9], [40, 55]), sps[:2], dict(n_max_stream=16))
+        # iba_original on an inverted medium has ka = k0 f Im(eps_air) |y2| = 0 exactly (a conservative layer whose
+        # eigenproblem is singular; the B200 path reports ERR_EIGEN for it): the dense layer is kept as it is there
+        run_case(em + "_dense_active", em, sensor_list.active(13.5e9, 40), sps[2:], dict(n_max_stream=16),
+                 dict(dense_snow_correction="auto") if em == "iba_maxwell_garnett" else None)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or list(CASES)

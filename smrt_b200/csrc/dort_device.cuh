@@ -13,8 +13,13 @@
 
 // enumerations: keep in sync with include/smrt_dort_b200.h
 enum {
-  EM_IBA = 0, EM_DMRT_QCA_SR = 1, EM_NONSCATTERING = 2, EM_DMRT_QCACP_SR = 3, EM_RAYLEIGH = 4, EM_PRESCRIBED_KSKAEPS = 5
+  EM_IBA = 0, EM_DMRT_QCA_SR = 1, EM_NONSCATTERING = 2, EM_DMRT_QCACP_SR = 3, EM_RAYLEIGH = 4, EM_PRESCRIBED_KSKAEPS = 5,
+  EM_IBA_ORIGINAL = 6, EM_IBA_MAXWELL_GARNETT = 7
 };
+// the IBA family shares the scattering coefficient, the phase matrix and the dense-snow inversion (iba.py:85-265)
+SMRT_DEV bool em_is_iba(int emmodel) {
+  return emmodel == EM_IBA || emmodel == EM_IBA_ORIGINAL || emmodel == EM_IBA_MAXWELL_GARNETT;
+}
 enum {
   MS_EXPONENTIAL = 0, MS_SHS = 1, MS_HOMOGENEOUS = 2, MS_INDEPENDENT_SPHERE = 3, MS_TEUBNER_STREY = 4,
   MS_UNIFIED_TS_1 = 5, MS_UNIFIED_TS_2 = 6, MS_SHS_T = 7
@@ -274,13 +279,21 @@ SMRT_DEV LayerOptics layer_optics(double frequency, double f, cplx e0, cplx eps,
   }
   o.f = f;
   MicroParams mp = micro_prepare(ms_kind, f, p0, p1);
-  if (emmodel == EM_IBA) {
+  if (em_is_iba(emmodel)) {
     double k0 = 2.0 * SMRT_PI * frequency / SMRT_C_SPEED;
-    cplx eeff = polder_van_santen_spheres(f, e0, eps);
     // mean_sq_field_ratio with depolarisation factors (1/3, 1/3, 1/3): three identical terms
     const double A = 1.0 / 3.0;
-    cplx eapp = c_add(c_scale(eeff, 1.0 - A), c_scale(e0, A));
     cplx de = c_sub(eps, e0);
+    cplx eeff, eapp;
+    if (emmodel == EM_IBA_MAXWELL_GARNETT) {
+      // generic_mixing_formula.py:346-358 (three identical components, their mean), iba_maxwell_garnett.py:47-51
+      cplx den = c_add(e0, c_scale(de, (1.0 - f) * A));
+      eeff = c_mul(e0, c_add(c_make(1.0, 0.0), c_div(c_scale(de, f), den)));
+      eapp = e0;
+    } else {
+      eeff = polder_van_santen_spheres(f, e0, eps);
+      eapp = c_add(c_scale(eeff, 1.0 - A), c_scale(e0, A));
+    }
     cplx ratio = c_div(eapp, c_add(eapp, c_scale(de, A)));
     double ar = c_abs(ratio);
     double term = ar * ar;
@@ -289,7 +302,8 @@ SMRT_DEV LayerOptics layer_optics(double frequency, double f, cplx e0, cplx eps,
     double k02 = k0 * k0;
     o.iba_coeff = (1.0 / (4.0 * SMRT_PI)) * (ade * ade) * y2 * (k02 * k02);
     cplx n = c_sqrt(eeff);
-    o.ka = 2.0 * k0 * n.im;
+    o.ka = (emmodel == EM_IBA_ORIGINAL) ? k0 * f * eps.im * fabs(y2)  // iba_original.py:43-44
+                                        : 2.0 * k0 * n.im;
     // ks: Romberg on mu = linspace(1, -1, 65) of (iba_coeff*ft).real * mu^2 + (iba_coeff*ft).real
     double absn = c_abs(n);
     double y[65];

@@ -234,7 +234,7 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
         const int js = pidx - ji * (ji + 1) / 2;
         double pv[9];
         const double mui = backward ? -mu[ji] : mu[ji];
-        if (emmodel == EM_IBA) {
+        if (em_is_iba(emmodel)) {
           iba_phase_mode(m, K, ctab, stab, mu[js], mui, iba_coeff, kk, mp, pv);
         } else {
           rayleigh_phase_mode(m, mu[js], mui, ks, pv);

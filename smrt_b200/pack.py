@@ -20,6 +20,7 @@ from .error import SMRTError
 
 # enumerations shared with include/smrt_dort_b200.h
 EM_IBA, EM_DMRT_QCA_SR, EM_NONSCATTERING, EM_DMRT_QCACP_SR, EM_RAYLEIGH, EM_PRESCRIBED_KSKAEPS = 0, 1, 2, 3, 4, 5
+EM_IBA_ORIGINAL, EM_IBA_MAXWELL_GARNETT = 6, 7  # smrt/emmodel/iba_original.py, iba_maxwell_garnett.py
 MS_EXPONENTIAL, MS_SHS, MS_HOMOGENEOUS = 0, 1, 2
 MS_INDEPENDENT_SPHERE, MS_TEUBNER_STREY, MS_UNIFIED_TS_1, MS_UNIFIED_TS_2, MS_SHS_T = 3, 4, 5, 6, 7
 IF_FLAT, IF_TRANSPARENT = 0, 1
@@ -33,11 +34,15 @@ _EMMODEL_NAMES = {
     "dmrt_qcacp_shortrange": EM_DMRT_QCACP_SR,
     "rayleigh": EM_RAYLEIGH,
     "prescribed_kskaeps": EM_PRESCRIBED_KSKAEPS,
+    "iba_original": EM_IBA_ORIGINAL,
+    "iba_maxwell_garnett": EM_IBA_MAXWELL_GARNETT,
 }
 _EMMODEL_CLASSNAMES = {"IBA": EM_IBA, "DMRT_QCA_ShortRange": EM_DMRT_QCA_SR, "NonScattering": EM_NONSCATTERING,
                        "DMRT_QCACP_ShortRange": EM_DMRT_QCACP_SR, "Rayleigh": EM_RAYLEIGH,
-                       "Prescribed_KsKaEps": EM_PRESCRIBED_KSKAEPS}
+                       "Prescribed_KsKaEps": EM_PRESCRIBED_KSKAEPS, "IBA_original": EM_IBA_ORIGINAL,
+                       "IBA_MaxwellGarnett": EM_IBA_MAXWELL_GARNETT}
 _DMRT_CODES = (EM_DMRT_QCA_SR, EM_DMRT_QCACP_SR)
+_IBA_CODES = (EM_IBA, EM_IBA_ORIGINAL, EM_IBA_MAXWELL_GARNETT)
 
 
 def emmodel_code(em) -> int:
@@ -357,7 +362,7 @@ def pack_simulations(simulations, emmodel, emmodel_options=None, atmospheres=Non
             kind, p0, p1 = (MS_HOMOGENEOUS, 0.0, 0.0) if code == EM_PRESCRIBED_KSKAEPS else _microstructure_params(layer)
             if code in _DMRT_CODES and kind != MS_SHS:
                 raise SMRTError("DMRT short range models are only compatible with SHS microstructure model")
-            if code == EM_IBA and kind == MS_HOMOGENEOUS:
+            if code in _IBA_CODES and kind == MS_HOMOGENEOUS:
                 raise SMRTError("IBA needs a microstructure with a Fourier transform (exponential, sticky hard spheres)")
             if code == EM_RAYLEIGH:  # emmodel/rayleigh.py:41-47
                 if not hasattr(layer.microstructure, "radius"):

@@ -230,3 +230,28 @@ def test_choudhury_outside_validity_raises_like_the_reference():
     sp = make_snowpack([0.3], "exponential", density=[300], temperature=265, corr_length=1e-4, substrate=sub)
     with pytest.raises(Warning, match="outside validity range"):
         make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8)).run(sensor_list.passive(37e9, 55), sp)
+
+
+def test_iba_variants_through_the_public_api():
+    """reference test/test_integration_iba_original.py:12-45 and test/test_mixed_emmodel.py:9-40 read the same here; a
+    subclass of the reference's IBA is mapped by its own name, not by its base class"""
+    from smrt_b200.pack import EM_IBA_MAXWELL_GARNETT, EM_IBA_ORIGINAL, emmodel_code
+
+    res = make_model("iba_original", "dort").run(sensor_list.amsre("37V"), two_layer())
+    assert abs(res.TbV() - 247.92662874568973) < 1e-4 and abs(res.TbH() - 237.1283359660738) < 1e-4
+    sp = make_snowpack([0.1, 100], "sticky_hard_spheres", density=[200, 400], temperature=[250.0, 250.0],
+                       radius=[2e-4, 2e-4], stickiness=[0.1, 0.1])
+    res = make_model(["dmrt_qcacp_shortrange", "iba"], "dort").run(sensor_list.amsre("37V"), sp)
+    assert abs(res.TbV() - 204.510189893163) < 1e-4 and abs(res.TbH() - 190.53692754287889) < 1e-4
+
+    class IBA:
+        pass
+
+    class IBA_original(IBA):
+        pass
+
+    class IBA_MaxwellGarnett(IBA):
+        pass
+
+    assert emmodel_code(IBA_original) == EM_IBA_ORIGINAL and emmodel_code(IBA_original()) == EM_IBA_ORIGINAL
+    assert emmodel_code(IBA_MaxwellGarnett) == EM_IBA_MAXWELL_GARNETT and emmodel_code("iba_maxwell_garnett") == 7

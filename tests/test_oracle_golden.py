@@ -12,7 +12,8 @@ FAST = ["cfg1_iba_onelayer", "ref_iba_2layer_passive", "ref_iba_2layer_active", 
         "cfg3_first4", "cfg5_first6", "ref_sea_ice_128streams", "soil_wegmuller_passive", "soil_qnh_passive",
         "reflector_passive", "choudhury_passive", "atmosphere_passive", "ref_physics_law", "soil_active",
         "iba_microstructures_passive", "iba_microstructures_active", "rayleigh_passive", "rayleigh_active",
-        "prescribed_kskaeps_passive"]
+        "prescribed_kskaeps_passive", "ref_iba_original_2layer_passive", "ref_mixed_emmodel_passive", "iba_original_passive",
+        "iba_original_dense_active", "iba_maxwell_garnett_passive", "iba_maxwell_garnett_dense_active"]
 
 
 def solve_all(batch, opts, limit=None):
@@ -59,6 +60,12 @@ def test_reference_test_literals():
     sig = 4 * np.pi * np.cos(np.deg2rad(55.0)) * v[:, :, 0]
     np.testing.assert_allclose(10 * np.log10([sig[0, 0], sig[1, 1], sig[1, 0]]),
                                [-24.044882546524693, -24.416295329469907, -51.544272924876886], atol=1e-3)
+    d, batch, opts = load_golden("ref_iba_original_2layer_passive")  # test/test_integration_iba_original.py:44-45
+    v = O.solve_problem(batch.to_problem(0, opts))["values"]
+    np.testing.assert_allclose(v[:, 0], [247.92662874568973, 237.1283359660738], atol=1e-4)
+    d, batch, opts = load_golden("ref_mixed_emmodel_passive")  # test/test_mixed_emmodel.py:39-40
+    v = O.solve_problem(batch.to_problem(0, opts))["values"]
+    np.testing.assert_allclose(v[:, 0], [204.510189893163, 190.53692754287889], atol=1e-4)
     d, batch, opts = load_golden("ref_sea_ice_128streams")  # test/test_iba_sea_ice.py:31-32
     v = np.stack([O.solve_problem(batch.to_problem(i, opts))["values"] for i in range(2)])
     np.testing.assert_allclose(v[0, :, 0], [256.0184487450634, 228.46148449852473], atol=1e-4)

@@ -12,8 +12,11 @@ from oracle import dort_oracle as O
 SMALL = ["cfg1_iba_onelayer", "ref_iba_2layer_passive", "ref_dmrt_qcacp_2layer_passive", "nonscattering_transparent",
          "iba_options_prune_rj", "iba_exp_substrate_passive", "soil_wegmuller_passive", "soil_qnh_passive",
          "reflector_passive", "choudhury_passive", "atmosphere_passive", "ref_physics_law",
-         "iba_microstructures_passive", "rayleigh_passive", "prescribed_kskaeps_passive"]
-SMALL_ACTIVE = ["ref_dmrt_less_refringent_active", "nonscattering_active", "soil_active", "iba_microstructures_active", "rayleigh_active"]
+         "iba_microstructures_passive", "rayleigh_passive", "prescribed_kskaeps_passive",
+         "ref_iba_original_2layer_passive", "ref_mixed_emmodel_passive", "iba_original_passive",
+         "iba_maxwell_garnett_passive"]
+SMALL_ACTIVE = ["ref_dmrt_less_refringent_active", "nonscattering_active", "soil_active", "iba_microstructures_active", "rayleigh_active",
+                "iba_original_dense_active", "iba_maxwell_garnett_dense_active"]
 
 
 @pytest.mark.parametrize("name", SMALL + SMALL_ACTIVE)
@@ -260,3 +263,14 @@ def test_block_matvec_device_function(M, K, threads, dual):
                         y1.ctypes.data_as(P), y2.ctypes.data_as(P), threads)
     np.testing.assert_allclose(y1, A1 @ x, rtol=1e-13, atol=1e-13)
     np.testing.assert_allclose(y2, A2 @ x if dual else 0.0, rtol=1e-13, atol=1e-13)
+
+
+def test_conservative_layer_is_reported_not_solved():
+    """iba_original on an inverted medium (dense_snow_correction="auto") has ka = k0 f Im(eps_air) |y2| = 0: scattering
+    albedo 1, the symmetric factors of the layer matrix are singular.  The reference returns whatever LAPACK's rounding
+    gives for the double eigenvalue 0; the device path reports ERR_EIGEN and NaN instead of a number."""
+    d, batch, opts = load_golden("iba_original_dense_active")
+    batch.dense_snow_correction[:] = 1
+    out = emu_solve(batch, opts, threads=64)
+    assert (out.status[0] & 15) == 2 and np.all(np.isnan(out.values[0]))
+    assert out.ka[0, 1] == 0.0 and out.ks[0, 1] > 0.0
