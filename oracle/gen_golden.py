@@ -446,6 +446,18 @@ def iba_variants():  # reference emmodel/iba_original.py, iba_maxwell_garnett.py
                  dict(dense_snow_correction="auto") if em == "iba_maxwell_garnett" else None)
 
 
+@case
+def emmodel_per_medium():  # reference core/model.py:547-548, 561-566: a dict of emmodels (and options) keyed by medium
+    ice = make_ice_column(ice_type="firstyear", thickness=[0.3, 0.7], temperature=[262.0, 268.0],
+                          microstructure_model="exponential", brine_inclusion_shape="spheres",
+                          salinity=np.array([6.0, 8.0]) * PSU, corr_length=[3e-4, 3e-4], add_water_substrate="ocean")
+    snow = make_snowpack([0.1, 0.15], "exponential", density=[250, 620], temperature=[255.0, 258.0],
+                         corr_length=[1e-4, 2e-4])
+    run_case("emmodel_per_medium_passive", {"snow": "iba", "ice": "iba_original"},
+             sensor_list.passive([6.925e9, 18.7e9], 55), [snow + ice], dict(n_max_stream=16),
+             {"snow": dict(dense_snow_correction="auto"), "ice": {}})
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or list(CASES)

@@ -221,6 +221,7 @@ class Layer:
         self.microstructure = microstructure
         self.permittivity_model = permittivity_model  # (background, scatterers): numbers or f(frequency, temperature)
         self.inclusion_shape = None
+        self.medium = "snow"  # make_medium.py:361-363 (SnowLayer): the key of a dict of emmodels
         self.emmodel = emmodel
         self.emmodel_options = emmodel_options
 

@@ -161,13 +161,12 @@ class Model:
         if rtsolver is not None and not (rtsolver == "dort" or getattr(rtsolver, "__name__", "") == "DORT"):
             raise SMRTError(f"rtsolver {rtsolver!r} is not implemented on the B200 path (only 'dort')")
         self.emmodel = emmodel
-        if isinstance(emmodel, Mapping):
-            raise SMRTError("a dict of emmodels (per medium) is not implemented on the B200 path")
-        for em in (emmodel if _is_sequence(emmodel) else [emmodel]):
+        for em in (list(emmodel.values()) if isinstance(emmodel, Mapping)  # one emmodel per medium (model.py:547-548)
+                   else emmodel if _is_sequence(emmodel) else [emmodel]):
             if em is not None:
                 emmodel_code(em)  # fail early on unsupported models
         self.rtsolver = rtsolver
-        self.emmodel_options = dict(emmodel_options or {})
+        self.emmodel_options = list(emmodel_options) if _is_sequence(emmodel_options) else dict(emmodel_options or {})
         self.rtsolver_options = dict(rtsolver_options or {})
         self.device = device
         check_dort_options(self.rtsolver_options)

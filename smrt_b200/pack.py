@@ -11,6 +11,7 @@ Anything the device path does not implement raises ``SMRTError`` naming the feat
 
 from __future__ import annotations
 
+from collections.abc import Mapping
 from dataclasses import dataclass, field
 from typing import Optional, Sequence
 
@@ -344,12 +345,30 @@ def pack_simulations(simulations, emmodel, emmodel_options=None, atmospheres=Non
         for l, layer in enumerate(sp.layers):
             batch.thickness[b, l] = layer.thickness
             batch.temperature[b, l] = layer.temperature
-            em = getattr(layer, "emmodel", None) or emmodel
+            # smrt/core/model.py:536-571: a list gives one emmodel per layer, a dict one per medium (layer.medium),
+            # else the layer's own emmodel attribute wins over the model's; the options follow the same three shapes
             if isinstance(emmodel, (list, tuple)):
+                if len(emmodel) != len(sp.layers):
+                    raise SMRTError("the list of emmodels must have one entry per layer of the snowpack")
                 em = emmodel[l]
+            elif isinstance(emmodel, Mapping):
+                medium = getattr(layer, "medium", None)
+                if medium not in emmodel:
+                    raise SMRTError(f"no emmodel is given for the medium {medium!r} of layer {l}")
+                em = emmodel[medium]
+            else:
+                em = getattr(layer, "emmodel", None) or emmodel
             code = emmodel_code(em)
             opts = dict(getattr(em, "_smrt_options", {}) or {})  # class_specializer stand-in
-            opts.update(getattr(layer, "emmodel_options", None) or emmodel_options)
+            if isinstance(emmodel_options, (list, tuple)):
+                if len(emmodel_options) != len(sp.layers):
+                    raise SMRTError("the list of emmodel options must have one entry per layer of the snowpack")
+                opts.update(emmodel_options[l] or {})
+            elif isinstance(emmodel, Mapping) and emmodel_options and \
+                    all(isinstance(o, Mapping) for o in emmodel_options.values()):
+                opts.update(emmodel_options[getattr(layer, "medium", None)])
+            else:
+                opts.update(getattr(layer, "emmodel_options", None) or emmodel_options)
             unknown = set(opts) - {"dense_snow_correction"}
             if unknown:
                 raise SMRTError(f"emmodel options {sorted(unknown)} are not implemented on the B200 path")

@@ -255,3 +255,24 @@ def test_iba_variants_through_the_public_api():
 
     assert emmodel_code(IBA_original) == EM_IBA_ORIGINAL and emmodel_code(IBA_original()) == EM_IBA_ORIGINAL
     assert emmodel_code(IBA_MaxwellGarnett) == EM_IBA_MAXWELL_GARNETT and emmodel_code("iba_maxwell_garnett") == 7
+
+
+def test_emmodels_and_options_per_medium_or_per_layer():
+    """reference core/model.py:536-571: dict keyed by layer.medium, list per layer, for emmodels and their options"""
+    sp = make_snowpack([0.1, 100], "exponential", density=[200, 600], temperature=[250.0, 250.0],
+                       corr_length=[5e-5, 5e-5])
+    sensor, opts = sensor_list.passive(37e9, 55), dict(n_max_stream=8)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", SMRTWarning)
+        ref = make_model("iba", "dort", rtsolver_options=opts,
+                         emmodel_options=dict(dense_snow_correction="auto")).run(sensor, sp)
+        by_medium = make_model({"snow": "iba"}, "dort", rtsolver_options=opts,
+                               emmodel_options={"snow": dict(dense_snow_correction="auto")}).run(sensor, sp)
+        by_layer = make_model(["iba", "iba"], "dort", rtsolver_options=opts,
+                              emmodel_options=[{}, dict(dense_snow_correction="auto")]).run(sensor, sp)
+        plain = make_model("iba", "dort", rtsolver_options=opts).run(sensor, sp)
+    assert by_medium.TbV() == ref.TbV() and by_layer.TbV() == ref.TbV() and plain.TbV() != ref.TbV()
+    with pytest.raises(SMRTError):
+        make_model({"ice": "iba"}, "dort", rtsolver_options=opts).run(sensor, sp)
+    with pytest.raises(SMRTError):
+        make_model(["iba"], "dort", rtsolver_options=opts).run(sensor, sp)

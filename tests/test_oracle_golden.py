@@ -13,7 +13,8 @@ FAST = ["cfg1_iba_onelayer", "ref_iba_2layer_passive", "ref_iba_2layer_active", 
         "reflector_passive", "choudhury_passive", "atmosphere_passive", "ref_physics_law", "soil_active",
         "iba_microstructures_passive", "iba_microstructures_active", "rayleigh_passive", "rayleigh_active",
         "prescribed_kskaeps_passive", "ref_iba_original_2layer_passive", "ref_mixed_emmodel_passive", "iba_original_passive",
-        "iba_original_dense_active", "iba_maxwell_garnett_passive", "iba_maxwell_garnett_dense_active"]
+        "iba_original_dense_active", "iba_maxwell_garnett_passive", "iba_maxwell_garnett_dense_active",
+        "emmodel_per_medium_passive"]
 
 
 def solve_all(batch, opts, limit=None):
