@@ -927,7 +927,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
         SMRT_PHASE(3)  // right-hand sides, formation of [A21 | A22]
         // [A21 | A22 | b_bot] -> [I | Y22 | Yr] (implicit row permutation, unscaled rows)
         const bool blocked = h <= 64;  // panel-blocked elimination (register tiles); larger blocks: one step at a time
-        if (blocked ? block_gj_rows_blocked(TT, ldp, TT + (size_t)h * ldp, ldp, h, h + nr, rowof, pivinv, GJV,
+        if (blocked ? block_gj_rows_blocked<!kGlobalScratch>(TT, ldp, TT + (size_t)h * ldp, ldp, h, h + nr, rowof, pivinv, GJV,
                                             &s_ctrl[6])
                     : block_gj_rows(TT, ldp, h, 2 * h + nr, rowstep, rowof)) {
           if (kStreamFG && waitG) {  // drain the copy of G in flight before leaving
@@ -1059,7 +1059,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
           // R_new = K S^-1 by column elimination of [S; K]
           if (transposed) {
             // [S^T | K^T] -> rows of S^-T K^T = columns of R_new
-            if (block_gj_rows_blocked(TS, ldp, BR, ldp, h, h, rowof, pivinv, GJV, &s_ctrl[6])) {
+            if (block_gj_rows_blocked<!kGlobalScratch>(TS, ldp, BR, ldp, h, h, rowof, pivinv, GJV, &s_ctrl[6])) {
               failed = true;
               break;
             }
@@ -1096,7 +1096,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
           SMRT_PHASE(7)  // R of the stack, source vector
         } else {
           // top layer: z = S^-1 b' by row elimination of [S | b'], then s = v + K z
-          if (blocked ? block_gj_rows_blocked(TS, ldp, Trhs, ldp, h, nr, rowof, pivinv, GJV, &s_ctrl[6])
+          if (blocked ? block_gj_rows_blocked<!kGlobalScratch>(TS, ldp, Trhs, ldp, h, nr, rowof, pivinv, GJV, &s_ctrl[6])
                       : block_gj_rows(TS, ldp, h, h + nr, rowstep, rowof)) {
             failed = true;
             break;

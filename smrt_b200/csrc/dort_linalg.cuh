@@ -1325,45 +1325,69 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
 }
 
 // rank-npc update  x <- x + V x[P]  of the columns c = cbeg + hw, cbeg + hw + nhw, ... < cend by half-warp number hw
-// (of nhw): lane lx owns the rows lx + 16 u (u < RT).  prow: the npc pivot rows of the panel.
-template <int RT>
-SMRT_DEV void gj_update_cols(double* Lb, int ldl, double* Rb, int ldr, int h, int cbeg, int cend, int hw, int nhw,
-                             int lx, int npc, const double* SMRT_RESTRICT Vin, const int* SMRT_RESTRICT prow) {
-  if (cbeg + hw >= cend) return;  // half-warp uniform
-  const unsigned hmask = 0xffffu << (16 * ((threadIdx.x >> 4) & 1));
+// (of nhw, even; the two half-warps of a warp have hw = 2 i and 2 i + 1): lane lx owns the rows lx + 16 u (u < RT).
+// prow: the npc pivot rows of the panel.  The trip count is WARP-uniform (a half-warp without a column of its own
+// repeats its sibling's: same reads before the warp barrier, same values stored after it), so that the barrier between
+// the reads of the pivot-row entries and the stores is a plain full-mask one; kFull: npc == SMRT_GJ_NB, no predicates
+// on the panel index.
+template <int RT, bool kFull>
+SMRT_DEV void gj_update_cols_t(double* Lb, int ldl, double* Rb, int ldr, int h, int cbeg, int cend, int hw, int nhw,
+                               int lx, int npc, const double* SMRT_RESTRICT Vin, const int* SMRT_RESTRICT prow) {
+  const int cw0 = cbeg + (hw & ~1);
+  if (cw0 >= cend) return;  // warp uniform
   double Vr[RT][SMRT_GJ_NB];
   int pr[SMRT_GJ_NB];
+  bool rowok[RT];
 #pragma unroll
-  for (int k = 0; k < SMRT_GJ_NB; ++k) pr[k] = (k < npc) ? prow[k] : 0;
+  for (int k = 0; k < SMRT_GJ_NB; ++k) pr[k] = (kFull || k < npc) ? prow[k] : 0;
 #pragma unroll
   for (int u = 0; u < RT; ++u) {
     const int row = lx + 16 * u;
+    rowok[u] = row < h;
 #pragma unroll
-    for (int k = 0; k < SMRT_GJ_NB; ++k) Vr[u][k] = (row < h && k < npc) ? Vin[(size_t)k * h + row] : 0.0;
+    for (int k = 0; k < SMRT_GJ_NB; ++k) Vr[u][k] = (rowok[u] && (kFull || k < npc)) ? Vin[k * h + row] : 0.0;
   }
-  for (int c = cbeg + hw; c < cend; c += nhw) {
-    double* col = (c < h) ? Lb + (size_t)c * ldl : Rb + (size_t)(c - h) * ldr;
+  for (int cw = cw0; cw < cend; cw += nhw) {
+    const int cc = cw + (hw & 1);
+    const int c = (cc < cend) ? cc : cw;
+    double* col = (c < h) ? Lb + c * ldl : Rb + (c - h) * ldr;
     double tp[SMRT_GJ_NB], acc[RT];
 #pragma unroll
-    for (int k = 0; k < SMRT_GJ_NB; ++k) tp[k] = (k < npc) ? col[pr[k]] : 0.0;  // old pivot-row entries
+    for (int k = 0; k < SMRT_GJ_NB; ++k) tp[k] = (kFull || k < npc) ? col[pr[k]] : 0.0;  // old pivot-row entries
 #pragma unroll
-    for (int u = 0; u < RT; ++u) acc[u] = (lx + 16 * u < h) ? col[lx + 16 * u] : 0.0;
-    __syncwarp(hmask);  // every lane of the half-warp has read the column before it is rewritten
+    for (int u = 0; u < RT; ++u) acc[u] = rowok[u] ? col[lx + 16 * u] : 0.0;
+    __syncwarp();  // every lane has read the column before it is rewritten
 #pragma unroll
     for (int k = 0; k < SMRT_GJ_NB; ++k)
 #pragma unroll
       for (int u = 0; u < RT; ++u) acc[u] = fma(Vr[u][k], tp[k], acc[u]);
 #pragma unroll
     for (int u = 0; u < RT; ++u)
-      if (lx + 16 * u < h) col[lx + 16 * u] = acc[u];
+      if (rowok[u]) col[lx + 16 * u] = acc[u];
   }
+}
+template <int RT>
+SMRT_DEV void gj_update_cols(double* Lb, int ldl, double* Rb, int ldr, int h, int cbeg, int cend, int hw, int nhw,
+                             int lx, int npc, const double* SMRT_RESTRICT Vin, const int* SMRT_RESTRICT prow) {
+  if (npc == SMRT_GJ_NB)
+    gj_update_cols_t<RT, true>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, prow);
+  else
+    gj_update_cols_t<RT, false>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, prow);
 }
 
 // one instance per (rows per lane of the panel warp, rows per lane of the update tiles); NOT inlined: the boundary
 // kernel calls it from three places and the straight-line panel code is large (instruction-cache footprint)
-template <int RPL, int RT>
+template <int RPL, int RT, bool kShared>
 SMRT_DEV_NOINLINE int block_gj_rows_blocked_t(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowof,
                                               double* ipiv, double* Vbuf, int* flag) {
+  if (kShared) {  // every operand lives in the block's shared memory
+    SMRT_ASSUME_SHARED(Lb);
+    SMRT_ASSUME_SHARED(Rb);
+    SMRT_ASSUME_SHARED(ipiv);
+    SMRT_ASSUME_SHARED(Vbuf);
+  }
+  SMRT_ASSUME_SHARED(rowof);
+  SMRT_ASSUME_SHARED(flag);
   const int NT = blockDim.x, tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = NT >> 5;
   const int lx = tid & 15;
@@ -1408,11 +1432,13 @@ SMRT_DEV_NOINLINE int block_gj_rows_blocked_t(double* Lb, int ldl, double* Rb, i
   }
   return 0;
 }
-// blockDim.x >= 64 (warp 0 factorises, the others update)
+// blockDim.x >= 64 (warp 0 factorises, the others update).  kShared: Lb, Rb, ipiv, Vbuf are in shared memory (rowof and
+// flag always are)
+template <bool kShared>
 SMRT_DEV int block_gj_rows_blocked(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowof, double* ipiv,
                                    double* Vbuf, int* flag) {
-  if (h <= 16) return block_gj_rows_blocked_t<1, 1>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
-  if (h <= 32) return block_gj_rows_blocked_t<1, 2>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
-  if (h <= 48) return block_gj_rows_blocked_t<2, 3>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
-  return block_gj_rows_blocked_t<2, 4>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
+  if (h <= 16) return block_gj_rows_blocked_t<1, 1, kShared>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
+  if (h <= 32) return block_gj_rows_blocked_t<1, 2, kShared>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
+  if (h <= 48) return block_gj_rows_blocked_t<2, 3, kShared>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
+  return block_gj_rows_blocked_t<2, 4, kShared>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
 }

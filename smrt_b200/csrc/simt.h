@@ -21,6 +21,9 @@
 SMRT_DEV void smrt_named_barrier(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// a routine that is not inlined (one copy serves several kernel instantiations) receives generic pointers: where the
+// caller knows they point to shared memory, saying so turns LD.E / ST.E + 64-bit address arithmetic into LDS / STS
+#define SMRT_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
 
 // ---- single-instruction fp64 approximations (MUFU.RCP64H / MUFU.RSQ64H, ~2^-20 relative error): seeds that the
 // callers refine with Newton steps where they need more
@@ -145,6 +148,7 @@ void __syncwarp(unsigned mask = 0xffffffffu);
 void simt_group_barrier(unsigned mask);
 void __threadfence();
 void smrt_named_barrier(int id, int nthreads);
+#define SMRT_ASSUME_SHARED(p) ((void)0)
 
 uint64_t simt_shfl_raw(unsigned mask, uint64_t v, int src_lane);
 int __any_sync(unsigned mask, int pred);

@@ -121,7 +121,7 @@ int emu_gj_blocked(double* A, int h, double* R, int nR, int threads, double* X) 
   std::vector<double> ipiv(h, 0.0), Vbuf((size_t)2 * h * SMRT_GJ_NB + 8, 0.0);
   int rc = 0;
   simt::launch(1, (unsigned)threads, [&]() {
-    int r = block_gj_rows_blocked(A, h, R, h, h, nR, rowof.data(), ipiv.data(), Vbuf.data(), flag.data());
+    int r = block_gj_rows_blocked<false>(A, h, R, h, h, nR, rowof.data(), ipiv.data(), Vbuf.data(), flag.data());
     if (threadIdx.x == 0) rc = r;
   });
   if (rc == 0)
