@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SMRTB200_ABI_VERSION 2
+#define SMRTB200_ABI_VERSION 3
 
 /* sensor mode (reference smrt/core/sensor.py:331-339) */
 #define SMRTB200_MODE_PASSIVE 0
@@ -129,6 +129,13 @@ typedef struct {
   const double* atmosphere;           /* [B, 3] isotropic atmosphere (passive mode): tb_down, tb_up (K), transmittance
                                          smrt/atmosphere/simple_isotropic_atmosphere.py:49-77, rtsolver_utils.py:141-147,
                                          302-305; may be NULL = (0, 0, 1) = no atmosphere */
+  const double* inclusion;            /* [B, L, 5] shape of the inclusions of a layer: weights of the "spheres" and
+                                         "random_needles" solutions in the Polder - van Santen effective permittivity
+                                         (layer.inclusion_shape / mixing_ratio: smrt/permittivity/
+                                         generic_mixing_formula.py:88-141), then the three depolarisation factors of
+                                         the IBA field ratio and of Maxwell-Garnett (layer.depolarization_factors or
+                                         length_ratio: smrt/emmodel/iba.py:112-119, smrt/permittivity/
+                                         depolarization_factors.py:9-46); may be NULL = (1, 0, 1/3, 1/3, 1/3) */
   const double* theta;                /* [n_theta] rad, viewing angles (passive) */
   const double* theta_inc;            /* [n_inc] rad, incidence angles (active) */
   double phi;                         /* rad, relative azimuth (active; pi = backscatter) */

@@ -219,7 +219,8 @@ def solve_problem(problem, collect=None):
         dsc = np.isin(np.asarray(problem["emmodel"]), (O.EM_DMRT_QCA_SR, O.EM_DMRT_QCACP_SR)).astype(int)
     optics = [O.layer_optics(freq, problem["frac_volume"][l], problem["eps_bg"][l], problem["eps_sc"][l],
                              int(problem["emmodel"][l]), int(problem["ms_kind"][l]), problem["ms_p0"][l],
-                             problem["ms_p1"][l], bool(dsc[l])) for l in range(L)]
+                             problem["ms_p1"][l], bool(dsc[l]),
+                           None if problem.get("inclusion") is None else problem["inclusion"][l]) for l in range(L)]
     eps_eff = np.array([o["eps_eff"] for o in optics])
     out = dict(status=O.ST_OK, eps_eff=eps_eff, ks=np.array([o["ks"] for o in optics]),
                ka=np.array([o["ka"] for o in optics]))

@@ -43,6 +43,8 @@ Problem description (a plain dict, all SI units; the same fields the C ABI takes
     atmosphere     (3,)           isotropic atmosphere: tb_down, tb_up (K), transmittance (optional; passive only)
     theta          (n_theta,) rad          viewing angles (passive) / incidence = viewing angles (active)
     phi            float rad      relative azimuth (active; pi for backscatter)
+    inclusion      (L, 5)         optional: weights of the spheres / needles Polder - van Santen solutions, then the
+                                  three depolarisation factors (default 1, 0, 1/3, 1/3, 1/3)
     dense_snow_correction (L,) int  1 = model the layer as the inverted medium when frac_volume > 0.5
     options        dict: n_max_stream, m_max, phase_normalization, prune_deep_snowpack, rayleigh_jeans_approximation,
                          error_handling
@@ -230,6 +232,25 @@ def polder_van_santen_spheres(frac_volume, e0, eps):
     return (-b_quad + np.sqrt(b_quad**2 - 4.0 * a_quad * c_quad + 0j)) / (2.0 * a_quad)
 
 
+def polder_van_santen_needles(frac_volume, e0, eps):
+    """reference smrt/permittivity/generic_mixing_formula.py:131-141 (randomly oriented needles)"""
+    a_quad = 1.0
+    b_quad = eps - e0 - 5.0 / 3.0 * frac_volume * (eps - e0)
+    c_quad = -eps * (e0 + 1.0 / 3.0 * frac_volume * (eps - e0))
+    return (-b_quad + np.sqrt(b_quad**2 - 4.0 * a_quad * c_quad + 0j)) / (2.0 * a_quad)
+
+
+def polder_van_santen_shapes(frac_volume, e0, eps, inclusion=None):
+    """reference smrt/permittivity/generic_mixing_formula.py:88-141: spheres, random needles or a weighted mixture;
+    inclusion = (weight of spheres, weight of needles, depolarisation factors x, y, z) or None = spheres"""
+    if inclusion is None or (inclusion[0] == 1.0 and inclusion[1] == 0.0):
+        return polder_van_santen_spheres(frac_volume, e0, eps)
+    if inclusion[0] == 0.0 and inclusion[1] == 1.0:
+        return polder_van_santen_needles(frac_volume, e0, eps)
+    return sum((float(inclusion[0]) * polder_van_santen_spheres(frac_volume, e0, eps),
+                float(inclusion[1]) * polder_van_santen_needles(frac_volume, e0, eps)))
+
+
 def romb65(y, dx):
     """scipy.integrate.romb for 2**6+1 samples, restated (the reference calls it at smrt/emmodel/iba.py:179)."""
     n_interv = 64
@@ -248,7 +269,7 @@ def romb65(y, dx):
     return R[(6, 6)]
 
 
-def layer_optics(frequency, f, e0, eps, emmodel, ms_kind, p0, p1, invert_dense=False):
+def layer_optics(frequency, f, e0, eps, emmodel, ms_kind, p0, p1, invert_dense=False, inclusion=None):
     """Return dict(eps_eff, ks, ka, iba_coeff, f, k0, ms_kind, p0, p1) for one layer.
 
     IBA: reference smrt/emmodel/iba.py:85-137, 139-162, 168-226, 246-265.
@@ -262,14 +283,15 @@ def layer_optics(frequency, f, e0, eps, emmodel, ms_kind, p0, p1, invert_dense=F
         if f > 0.5 and invert_dense:  # dense_snow_correction="auto": iba.py:95-96, core/layer.py:186-201
             f, e0, eps = 1.0 - f, eps, e0
         k0 = 2 * np.pi * frequency / C_SPEED
-        depol = np.array([1.0 / 3, 1.0 / 3, 1.0 / 3])  # depolarization_factors.py:9-46 for length_ratio 1
+        # depolarization_factors.py:9-46 (1/3 each for length_ratio 1), or the layer's own (iba.py:112-119)
+        depol = np.array([1.0 / 3, 1.0 / 3, 1.0 / 3]) if inclusion is None else np.asarray(inclusion[2:5], dtype=float)
         if emmodel == EM_IBA_MAXWELL_GARNETT:
             # reference smrt/permittivity/generic_mixing_formula.py:346-358, smrt/emmodel/iba_maxwell_garnett.py:47-51
             eeff = complex(np.mean(e0 * (1 + f * (eps - e0) / (e0 + (1.0 - f) * depol * (eps - e0))),
                                    dtype=np.complex128))
             eapp = e0
         else:
-            eeff = polder_van_santen_spheres(f, e0, eps)
+            eeff = polder_van_santen_shapes(f, e0, eps, inclusion)
             eapp = eeff * (1 - depol) + e0 * depol
         y2 = (1.0 / 3.0) * np.sum(np.absolute(eapp / (eapp + (eps - e0) * depol)) ** 2.0)
         iba_coeff = (1.0 / (4.0 * np.pi)) * np.absolute(eps - e0) ** 2.0 * y2 * k0**4
@@ -325,7 +347,7 @@ def layer_optics(frequency, f, e0, eps, emmodel, ms_kind, p0, p1, invert_dense=F
     elif emmodel == EM_NONSCATTERING:
         # reference smrt/emmodel/nonscattering.py:19-34
         k0 = 2 * np.pi * frequency / C_SPEED
-        eeff = polder_van_santen_spheres(f, e0, eps)
+        eeff = polder_van_santen_shapes(f, e0, eps, inclusion)
         out.update(eps_eff=eeff, ks=0.0, ka=float(2 * k0 * np.sqrt(eeff).imag), iba_coeff=0.0, f=f, k0=k0)
     elif emmodel == EM_RAYLEIGH:
         # reference smrt/emmodel/rayleigh.py:21-39 (sparse medium: the effective permittivity is the background's)
@@ -970,7 +992,8 @@ def solve_problem(problem, method="schur_forcedtriu", return_details=False):
         dsc = np.isin(np.asarray(problem["emmodel"]), (EM_DMRT_QCA_SR, EM_DMRT_QCACP_SR)).astype(int)
     optics = [layer_optics(freq, problem["frac_volume"][l], problem["eps_bg"][l], problem["eps_sc"][l],
                            int(problem["emmodel"][l]), int(problem["ms_kind"][l]), problem["ms_p0"][l],
-                           problem["ms_p1"][l], bool(dsc[l])) for l in range(L)]
+                           problem["ms_p1"][l], bool(dsc[l]),
+                           None if problem.get("inclusion") is None else problem["inclusion"][l]) for l in range(L)]
     eps_eff = np.array([o["eps_eff"] for o in optics])
     out.update(eps_eff=eps_eff, ks=np.array([o["ks"] for o in optics]), ka=np.array([o["ka"] for o in optics]))
     out["ke"] = out["ks"] + out["ka"]

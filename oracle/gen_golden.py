@@ -458,6 +458,34 @@ def emmodel_per_medium():  # reference core/model.py:547-548, 561-566: a dict of
              {"snow": dict(dense_snow_correction="auto"), "ice": {}})
 
 
+@case
+def inclusion_shapes():  # reference permittivity/generic_mixing_formula.py:88-141, depolarization_factors.py:9-46
+    # first-year sea ice with brine needles / a mixture of spheres and needles (examples/iba_sea_ice.py), snow on top
+    # with oblate / prolate grains (length_ratio) and explicit depolarisation factors
+    thickness = np.array([0.25, 0.35, 0.4])
+    temperature = np.array([258.0, 264.0, 269.0])
+    salinity = np.array([5.0, 7.0, 9.0]) * PSU
+    sps = []
+    for shape in ("random_needles", {"spheres": 0.3, "random_needles": 0.7}):
+        sps.append(make_ice_column(ice_type="firstyear", thickness=thickness, temperature=temperature,
+                                   microstructure_model="exponential", brine_inclusion_shape=shape, salinity=salinity,
+                                   corr_length=np.array([2e-4, 3e-4, 4e-4]), add_water_substrate="ocean"))
+    snow = make_snowpack([0.1, 0.2], "exponential", density=[220, 340], temperature=[252.0, 255.0],
+                         corr_length=[1.2e-4, 2.5e-4])
+    snow.layers[0].length_ratio = 1.4
+    snow.layers[1].length_ratio = 0.7
+    sps.append(snow + sps[0])
+    run_case("inclusion_shapes_passive", "iba", sensor_list.passive([1.4e9, 6.925e9, 18.7e9], [40, 55]), sps,
+             dict(n_max_stream=16))
+    snow2 = make_snowpack([0.3, 1000.0], "exponential", density=[250, 380], temperature=[255.0, 262.0],
+                          corr_length=[1.5e-4, 3e-4])
+    snow2.layers[0].depolarization_factors = np.array([0.25, 0.3, 0.45])
+    snow2.layers[1].length_ratio = 1.2
+    run_case("depolarization_active", "iba", sensor_list.active(13.5e9, 40), [snow2], dict(n_max_stream=16))
+    for em in ("iba_original", "iba_maxwell_garnett"):
+        run_case(em + "_depolarization_passive", em, sensor_list.passive(36.5e9, 55), [snow2], dict(n_max_stream=16))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or list(CASES)

@@ -427,6 +427,7 @@ static std::vector<FieldDesc> field_table(const smrtb200_plan* p) {
       {FOFF(substrate_kind), i, true, false},   {FOFF(substrate_eps), 2 * d, true, false},
       {FOFF(substrate_temperature), d, true, false},
       {FOFF(substrate_params), 4 * d, true, false}, {FOFF(atmosphere), 3 * d, true, false},
+      {FOFF(inclusion), 5 * Ls * d, true, false},
       {FOFF(theta), std::max<size_t>(p->opt.n_theta, 1) * d, false, false},
       {FOFF(theta_inc), std::max<size_t>(p->opt.n_inc, 1) * d, false, false},
       {FOFF(values), nout * d, true, true},     {FOFF(ks), Ls * d, true, true},
@@ -485,6 +486,7 @@ extern "C" int smrtb200_solve_batch_host(smrtb200_plan* p, const smrtb200_batch*
   smrtb200_batch db = p->dev_batch;  // optional inputs the caller did not give stay NULL on the device side
   if (!batch->substrate_params) db.substrate_params = nullptr;
   if (!batch->atmosphere) db.atmosphere = nullptr;
+  if (!batch->inclusion) db.inclusion = nullptr;
   rc = smrtb200_solve_batch_device(p, &db, st);
   if (rc) return rc;
   for (size_t k = 0; k < tab.size(); ++k) {

@@ -222,6 +222,22 @@ SMRT_DEV cplx polder_van_santen_spheres(double f, cplx e0, cplx eps) {
   return c_scale(c_sub(root, b), 0.25);  // (-b + sqrt) / (2 a)
 }
 
+// generic_mixing_formula.py:131-141 (randomly oriented needles, Shokr 1998 eq. 18)
+SMRT_DEV cplx polder_van_santen_needles(double f, cplx e0, cplx eps) {
+  cplx d = c_sub(eps, e0);
+  cplx b = c_sub(d, c_scale(d, 5.0 / 3.0 * f));
+  cplx cq = c_scale(c_mul(eps, c_add(e0, c_scale(d, 1.0 / 3.0 * f))), -1.0);
+  cplx disc = c_sub(c_mul(b, b), c_scale(cq, 4.0));  // b^2 - 4 a c, a = 1
+  return c_scale(c_sub(c_sqrt(disc), b), 0.5);
+}
+// polder_van_santen for layer.inclusion_shape = spheres, random_needles or a mixture (generic_mixing_formula.py:88-141):
+// incl = (weight of the spheres solution, weight of the needles solution, ...) or NULL = spheres
+SMRT_DEV cplx polder_van_santen_shapes(double f, cplx e0, cplx eps, const double* incl) {
+  if (!incl || (incl[0] == 1.0 && incl[1] == 0.0)) return polder_van_santen_spheres(f, e0, eps);
+  if (incl[0] == 0.0 && incl[1] == 1.0) return polder_van_santen_needles(f, e0, eps);
+  return c_add(c_scale(polder_van_santen_spheres(f, e0, eps), incl[0]), c_scale(polder_van_santen_needles(f, e0, eps), incl[1]));
+}
+
 // scipy.integrate.romb for 2^6 + 1 samples (emmodel/iba.py:176-180); y[65], dx = sample spacing
 SMRT_DEV double romb65(const double* y, double dx) {
   double R[7][7];
@@ -246,7 +262,7 @@ SMRT_DEV double romb65(const double* y, double dx) {
 // emmodel/iba.py:85-137,139-162,168-226,246-265 ; emmodel/dmrt_qca_shortrange.py:65-112 ;
 // emmodel/dmrt_qcacp_shortrange.py:63-125 ; emmodel/nonscattering.py:19-34
 SMRT_DEV LayerOptics layer_optics(double frequency, double f, cplx e0, cplx eps, int emmodel, int ms_kind, double p0,
-                                  double p1, int invert_dense, MicroParams* mp_out) {
+                                  double p1, int invert_dense, MicroParams* mp_out, const double* incl = nullptr) {
   LayerOptics o;
   o.status = ST_OK;
   o.iba_coeff = 0.0;
@@ -281,23 +297,29 @@ SMRT_DEV LayerOptics layer_optics(double frequency, double f, cplx e0, cplx eps,
   MicroParams mp = micro_prepare(ms_kind, f, p0, p1);
   if (em_is_iba(emmodel)) {
     double k0 = 2.0 * SMRT_PI * frequency / SMRT_C_SPEED;
-    // mean_sq_field_ratio with depolarisation factors (1/3, 1/3, 1/3): three identical terms
-    const double A = 1.0 / 3.0;
+    // depolarisation factors of the three axes (iba.py:112-119): (1/3, 1/3, 1/3) for spheres
+    const double Ax[3] = {incl ? incl[2] : 1.0 / 3.0, incl ? incl[3] : 1.0 / 3.0, incl ? incl[4] : 1.0 / 3.0};
     cplx de = c_sub(eps, e0);
-    cplx eeff, eapp;
+    cplx eeff;
     if (emmodel == EM_IBA_MAXWELL_GARNETT) {
-      // generic_mixing_formula.py:346-358 (three identical components, their mean), iba_maxwell_garnett.py:47-51
-      cplx den = c_add(e0, c_scale(de, (1.0 - f) * A));
-      eeff = c_mul(e0, c_add(c_make(1.0, 0.0), c_div(c_scale(de, f), den)));
-      eapp = e0;
+      // generic_mixing_formula.py:346-358: mean of the three components; iba_maxwell_garnett.py:47-51
+      cplx acc = c_make(0.0, 0.0);
+      for (int i = 0; i < 3; ++i) {
+        cplx den = c_add(e0, c_scale(de, (1.0 - f) * Ax[i]));
+        acc = c_add(acc, c_mul(e0, c_add(c_make(1.0, 0.0), c_div(c_scale(de, f), den))));
+      }
+      eeff = c_make(acc.re / 3.0, acc.im / 3.0);  // (x0 + x1 + x2) / 3, as numpy's mean evaluates it
     } else {
-      eeff = polder_van_santen_spheres(f, e0, eps);
-      eapp = c_add(c_scale(eeff, 1.0 - A), c_scale(e0, A));
+      eeff = polder_van_santen_shapes(f, e0, eps, incl);
     }
-    cplx ratio = c_div(eapp, c_add(eapp, c_scale(de, A)));
-    double ar = c_abs(ratio);
-    double term = ar * ar;
-    double y2 = (1.0 / 3.0) * (term + term + term);
+    // mean_sq_field_ratio (iba.py:150-162; apparent permittivity = background for Maxwell-Garnett)
+    double ysum = 0.0;
+    for (int i = 0; i < 3; ++i) {
+      const cplx eapp = (emmodel == EM_IBA_MAXWELL_GARNETT) ? e0 : c_add(c_scale(eeff, 1.0 - Ax[i]), c_scale(e0, Ax[i]));
+      const double ar = c_abs(c_div(eapp, c_add(eapp, c_scale(de, Ax[i]))));
+      ysum += ar * ar;
+    }
+    double y2 = (1.0 / 3.0) * ysum;
     double ade = c_abs(de);
     double k02 = k0 * k0;
     o.iba_coeff = (1.0 / (4.0 * SMRT_PI)) * (ade * ade) * y2 * (k02 * k02);
@@ -379,7 +401,7 @@ SMRT_DEV LayerOptics layer_optics(double frequency, double f, cplx e0, cplx eps,
     }
   } else {  // EM_NONSCATTERING
     double k0 = 2.0 * SMRT_PI * frequency / SMRT_C_SPEED;
-    cplx eeff = polder_van_santen_spheres(f, e0, eps);
+    cplx eeff = polder_van_santen_shapes(f, e0, eps, incl);
     o.eps_eff = eeff;
     o.ks = 0.0;
     o.ka = 2.0 * k0 * c_sqrt(eeff).im;

@@ -34,6 +34,7 @@ struct KArgs {
   const int *interface_kind, *dense_corr, *substrate_kind;
   const double *substrate_eps, *substrate_temperature, *theta, *theta_inc;
   const double *substrate_params, *atmosphere;  // optional (NULL): [B, 4] substrate model parameters, [B, 3] atmosphere
+  const double* inclusion;                      // optional (NULL): [B, L, 5] inclusion shape weights, depolarisation factors
   // outputs
   double *values, *ks, *ka, *eps_eff;
   int* n_streams_out;
@@ -83,7 +84,8 @@ SMRT_GLOBAL void __launch_bounds__(128) optics_kernel(KArgs A) {
   cplx es = c_make(A.eps_sc[2 * idx], A.eps_sc[2 * idx + 1]);
   MicroParams mp;
   LayerOptics o = layer_optics(A.frequency[b], A.frac_volume[idx], e0, es, A.emmodel[idx], A.ms_kind[idx],
-                               A.ms_p0[idx], A.ms_p1[idx], A.dense_corr[idx], &mp);
+                               A.ms_p0[idx], A.ms_p1[idx], A.dense_corr[idx], &mp,
+                               A.inclusion ? A.inclusion + 5 * (size_t)idx : nullptr);
   A.eps_eff[2 * idx] = o.eps_eff.re;
   A.eps_eff[2 * idx + 1] = o.eps_eff.im;
   A.ks[idx] = o.ks;

@@ -207,6 +207,23 @@ _MICROSTRUCTURES = {"exponential": (Exponential, ("corr_length",)),
                     "homogeneous": (Homogeneous, ())}
 
 
+def depolarization_factors_spheroids(length_ratio=None):
+    """Depolarisation factors (x, y, z) of spheroids of a given horizontal / vertical length ratio (Löwe et al. 2013
+    eq. 4, Mätzler 1996 eq. 7) — reference ``smrt/permittivity/depolarization_factors.py:9-46``; 1/3 each for spheres."""
+    if length_ratio is None:
+        length_ratio = 1.0
+    if length_ratio == 1:
+        q = 1.0 / 3.0
+    elif length_ratio > 1:
+        chi_b = np.sqrt(1.0 - 1.0 / (length_ratio**2.0))
+        ln_term = np.log((1.0 + chi_b) / (1.0 - chi_b))
+        q = 0.5 * (1.0 + (1.0 / (length_ratio**2.0 - 1.0)) * (1.0 - (1.0 / (2.0 * chi_b)) * ln_term))
+    else:
+        chi_a = np.sqrt(1.0 / length_ratio**2.0 - 1.0)
+        q = 0.5 * (1.0 + (1.0 / (length_ratio**2.0 - 1.0)) * (1.0 - (1.0 / chi_a) * np.arctan(chi_a)))
+    return np.array([q, q, (1.0 - 2.0 * q)])
+
+
 class Layer:
     """Dry-snow layer: ice scatterers (Mätzler 2006 permittivity) in air — the subset of reference
     ``smrt/core/layer.py:35-156`` + ``smrt/inputs/make_medium.py:235-315`` read by the packer."""

@@ -42,6 +42,7 @@ _EMMODEL_CLASSNAMES = {"IBA": EM_IBA, "DMRT_QCA_ShortRange": EM_DMRT_QCA_SR, "No
                        "DMRT_QCACP_ShortRange": EM_DMRT_QCACP_SR, "Rayleigh": EM_RAYLEIGH,
                        "Prescribed_KsKaEps": EM_PRESCRIBED_KSKAEPS, "IBA_original": EM_IBA_ORIGINAL,
                        "IBA_MaxwellGarnett": EM_IBA_MAXWELL_GARNETT}
+SPHERICAL_INCLUSIONS = (1.0, 0.0, 1.0 / 3.0, 1.0 / 3.0, 1.0 / 3.0)
 _DMRT_CODES = (EM_DMRT_QCA_SR, EM_DMRT_QCACP_SR)
 _IBA_CODES = (EM_IBA, EM_IBA_ORIGINAL, EM_IBA_MAXWELL_GARNETT)
 
@@ -86,6 +87,7 @@ class ProblemBatch:
     dense_snow_correction: np.ndarray = None  # (B, L) int32: 1 = invert the medium when frac_volume > 0.5
     substrate_params: np.ndarray = None  # (B, 4) parameters of the rough / prescribed substrates (see SUB_*)
     atmosphere: np.ndarray = None  # (B, 3) isotropic atmosphere: tb_down, tb_up (K), transmittance; (0, 0, 1) = none
+    inclusion: np.ndarray = None  # (B, L, 5) weights of the spheres / needles solutions, depolarisation factors x, y, z
 
     def __post_init__(self):
         if self.dense_snow_correction is None:
@@ -94,6 +96,8 @@ class ProblemBatch:
             self.substrate_params = np.zeros((len(self.frequency), 4))
         if self.atmosphere is None:
             self.atmosphere = np.tile(np.array([0.0, 0.0, 1.0]), (len(self.frequency), 1))
+        if self.inclusion is None:
+            self.inclusion = np.tile(np.array(SPHERICAL_INCLUSIONS), self.thickness.shape + (1,))
 
     @property
     def B(self) -> int:
@@ -135,6 +139,7 @@ class ProblemBatch:
             substrate_temperature=float(self.substrate_temperature[i]),
             substrate_params=self.substrate_params[i].copy(),
             atmosphere=self.atmosphere[i].copy(),
+            inclusion=self.inclusion[i, :n].copy(),
             theta=self.theta.copy() if self.mode == MODE_PASSIVE else self.theta_inc.copy(),
             phi=float(self.phi),
             options=opts,
@@ -147,7 +152,7 @@ class ProblemBatch:
     def from_fields(d) -> "ProblemBatch":
         kw = {}
         for k in ProblemBatch.__dataclass_fields__:
-            if k in ("substrate_params", "atmosphere") and k not in d:  # fixtures written before these fields existed
+            if k in ("substrate_params", "atmosphere", "inclusion") and k not in d:  # fixtures written before these fields existed
                 continue
             v = d[k]
             if k == "mode":
@@ -170,6 +175,9 @@ def concat_batches(batches: Sequence[ProblemBatch]) -> ProblemBatch:
                 v = getattr(b, k)
                 if v.ndim == 2 and v.shape[1] < L and k not in ("substrate_params", "atmosphere"):
                     pad = np.zeros((v.shape[0], L - v.shape[1]), dtype=v.dtype)
+                    v = np.concatenate([v, pad], axis=1)
+                elif k == "inclusion" and v.shape[1] < L:
+                    pad = np.tile(np.array(SPHERICAL_INCLUSIONS), (v.shape[0], L - v.shape[1], 1))
                     v = np.concatenate([v, pad], axis=1)
                 parts.append(v)
             kw[k] = np.concatenate(parts, axis=0)
@@ -291,6 +299,61 @@ def _atmosphere(atmosphere, frequency, mode=MODE_PASSIVE):
     return value(atmosphere.constant_tbdown), value(atmosphere.constant_tbup), value(atmosphere.constant_trans)
 
 
+def _shape_weights(inclusion_shape, mixing_ratio=None):
+    """-> (weight of the "spheres" solution, weight of the "random_needles" one) of the reference's polder_van_santen
+    (smrt/permittivity/generic_mixing_formula.py:88-141: a string, or a dict / sequence of shapes with mixing ratios)"""
+    if inclusion_shape is None or inclusion_shape == "spheres":
+        return 1.0, 0.0
+    if inclusion_shape == "random_needles":
+        return 0.0, 1.0
+    if isinstance(inclusion_shape, str):
+        raise SMRTError("inclusion_shape must be one of (or a list of) the following: 'spheres' (default) or "
+                        "'random_needles'.")
+    if isinstance(inclusion_shape, dict):
+        if mixing_ratio is not None:
+            raise SMRTError("Setting mixing_ratio and using a dict for inclusion_shape is ambiguous.")
+        mixing_ratio = list(inclusion_shape.values())
+        inclusion_shape = list(inclusion_shape.keys())
+    try:
+        mixing_ratio = list(mixing_ratio)
+    except TypeError:
+        mixing_ratio = [float(mixing_ratio)]
+    if len(mixing_ratio) == len(inclusion_shape) - 1:
+        mixing_ratio = mixing_ratio + [1 - np.sum(mixing_ratio)]
+    elif len(mixing_ratio) != len(inclusion_shape):
+        raise SMRTError("The length of inclusion_shape and mixing_ratio are incompatible. See the documentation.")
+    w = [0.0, 0.0]
+    for shape, mixing in zip(inclusion_shape, mixing_ratio):
+        ws, wn = _shape_weights(shape)
+        if w[0 if ws else 1] != 0.0:
+            raise SMRTError("a shape given twice in inclusion_shape is not implemented on the B200 path")
+        w[0 if ws else 1] = float(mixing)
+    return w[0], w[1]
+
+
+def _inclusion_params(layer, code):
+    """Row of ProblemBatch.inclusion for a layer: effective-permittivity shape weights (used by the Polder - van Santen
+    models: iba, iba_original, nonscattering) and the depolarisation factors of the IBA family (iba.py:112-119)."""
+    ws, wn = 1.0, 0.0
+    shape = getattr(layer, "inclusion_shape", None)
+    if code == EM_IBA_MAXWELL_GARNETT:
+        if shape not in (None, "spheres"):  # generic_mixing_formula.py:343-344
+            raise SMRTError("inclusion_shape must be set to 'spheres'")
+    elif code in _IBA_CODES or code == EM_NONSCATTERING:
+        ws, wn = _shape_weights(shape, getattr(layer, "mixing_ratio", None))
+    depol = getattr(layer, "depolarization_factors", None)
+    if depol is not None:
+        if callable(depol):
+            raise SMRTError("callable depolarization_factors are not implemented on the B200 path")
+        depol = np.asarray(depol, dtype=float)
+        if depol.shape != (3,):
+            raise SMRTError("depolarization_factors must hold three numbers")
+    else:
+        from .inputs import depolarization_factors_spheroids
+        depol = depolarization_factors_spheroids(getattr(layer, "length_ratio", None))
+    return ws, wn, float(depol[0]), float(depol[1]), float(depol[2])
+
+
 def pack_simulations(simulations, emmodel, emmodel_options=None, atmospheres=None) -> ProblemBatch:
     """Pack a flat list of (sensor, snowpack) pairs (reference ``Model.prepare_simulations`` order,
     ``smrt/core/model.py:485-502``) into one ProblemBatch.
@@ -389,11 +452,7 @@ def pack_simulations(simulations, emmodel, emmodel_options=None, atmospheres=Non
                                     "scattering")
                 kind, p0, p1 = MS_HOMOGENEOUS, float(layer.microstructure.radius), 0.0
             batch.ms_kind[b, l], batch.ms_p0[b, l], batch.ms_p1[b, l] = kind, p0, p1
-            if getattr(layer, "inclusion_shape", None) not in (None, "spheres"):
-                raise SMRTError("only spherical inclusions are implemented on the B200 path")
-            if getattr(layer, "depolarization_factors", None) is not None or \
-                    getattr(layer, "length_ratio", None) not in (None, 1, 1.0):
-                raise SMRTError("anisotropic depolarization factors are not implemented on the B200 path")
+            batch.inclusion[b, l] = _inclusion_params(layer, code)
             if code == EM_PRESCRIBED_KSKAEPS:  # emmodel/prescribed_kskaeps.py:20-27: everything is given on the layer
                 batch.ms_kind[b, l], batch.ms_p0[b, l], batch.ms_p1[b, l] = MS_HOMOGENEOUS, float(layer.ks), float(layer.ka)
                 batch.eps_bg[b, l] = batch.eps_sc[b, l] = complex(layer.effective_permittivity)

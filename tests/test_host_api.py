@@ -276,3 +276,30 @@ def test_emmodels_and_options_per_medium_or_per_layer():
         make_model({"ice": "iba"}, "dort", rtsolver_options=opts).run(sensor, sp)
     with pytest.raises(SMRTError):
         make_model(["iba"], "dort", rtsolver_options=opts).run(sensor, sp)
+
+
+def test_inclusion_shapes_and_depolarization_packing():
+    """reference permittivity/generic_mixing_formula.py:88-116 (shape mixtures), depolarization_factors.py:9-46"""
+    from smrt_b200.inputs import depolarization_factors_spheroids
+    from smrt_b200.pack import _shape_weights, pack_simulations
+
+    assert _shape_weights(None) == (1.0, 0.0) and _shape_weights("random_needles") == (0.0, 1.0)
+    assert _shape_weights({"spheres": 0.3, "random_needles": 0.7}) == (0.3, 0.7)
+    assert _shape_weights(("random_needles", "spheres"), 0.25) == (0.75, 0.25)
+    with pytest.raises(SMRTError):
+        _shape_weights("cubes")
+    with pytest.raises(SMRTError):
+        _shape_weights({"spheres": 0.5, "random_needles": 0.5}, 0.5)
+    np.testing.assert_allclose(depolarization_factors_spheroids(None), [1 / 3] * 3)
+    for lr in (0.6, 1.5):  # oblate / prolate: the three factors sum to one
+        d = depolarization_factors_spheroids(lr)
+        assert abs(d.sum() - 1.0) < 1e-15 and (d[2] > d[0]) == (lr < 1)
+    sp = two_layer()
+    sp.layers[0].length_ratio = 1.5
+    sp.layers[1].inclusion_shape = "random_needles"
+    batch = pack_simulations([(sensor_list.passive(37e9, 55), sp)], "iba")
+    np.testing.assert_allclose(batch.inclusion[0, 0], (1.0, 0.0) + tuple(depolarization_factors_spheroids(1.5)))
+    np.testing.assert_allclose(batch.inclusion[0, 1], (0.0, 1.0, 1 / 3, 1 / 3, 1 / 3))
+    res = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8)).run(sensor_list.passive(37e9, 55), sp)
+    ref = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8)).run(sensor_list.passive(37e9, 55), two_layer())
+    assert res.TbV() != ref.TbV() and abs(res.TbV() - ref.TbV()) < 5.0

@@ -14,9 +14,11 @@ SMALL = ["cfg1_iba_onelayer", "ref_iba_2layer_passive", "ref_dmrt_qcacp_2layer_p
          "reflector_passive", "choudhury_passive", "atmosphere_passive", "ref_physics_law",
          "iba_microstructures_passive", "rayleigh_passive", "prescribed_kskaeps_passive",
          "ref_iba_original_2layer_passive", "ref_mixed_emmodel_passive", "iba_original_passive",
-         "iba_maxwell_garnett_passive", "emmodel_per_medium_passive"]
+         "iba_maxwell_garnett_passive", "emmodel_per_medium_passive",
+         "inclusion_shapes_passive", "iba_original_depolarization_passive",
+         "iba_maxwell_garnett_depolarization_passive"]
 SMALL_ACTIVE = ["ref_dmrt_less_refringent_active", "nonscattering_active", "soil_active", "iba_microstructures_active", "rayleigh_active",
-                "iba_original_dense_active", "iba_maxwell_garnett_dense_active"]
+                "iba_original_dense_active", "iba_maxwell_garnett_dense_active", "depolarization_active"]
 
 
 @pytest.mark.parametrize("name", SMALL + SMALL_ACTIVE)
