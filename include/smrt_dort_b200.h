@@ -93,7 +93,7 @@ typedef struct {
   int device;          /* CUDA device ordinal */
   int mode;            /* SMRTB200_MODE_* */
   int n_max_stream;    /* DORT option n_max_stream (dort.py:150), 2..256 */
-  int m_max;           /* DORT option m_max (dort.py:151); ignored (0) in passive mode; 0..3 */
+  int m_max;           /* DORT option m_max (dort.py:151); ignored (0) in passive mode; 0..16 */
   int max_layers;      /* L: row stride of every [B, L] array */
   int max_batch;       /* largest B of one solve call (host staging is sized for it) */
   int n_theta;         /* number of viewing angles (passive) */

@@ -486,6 +486,18 @@ def inclusion_shapes():  # reference permittivity/generic_mixing_formula.py:88-1
         run_case(em + "_depolarization_passive", em, sensor_list.passive(36.5e9, 55), [snow2], dict(n_max_stream=16))
 
 
+@case
+def high_azimuthal_modes():  # reference rtsolver/test_dort.py:13-42: m_max = 6 / 16, where scipy.linalg.eig fails
+    sp1 = make_snowpack(thickness=[1000], microstructure_model="independent_sphere", density=280, temperature=265,
+                        radius=0.05e-3)
+    run_case("ref_rayleigh_mmax6_active", "rayleigh", sensor_list.active(10e9, 50), [sp1],
+             dict(m_max=6, n_max_stream=32, diagonalization_method="schur"))
+    sp2 = make_snowpack(thickness=[0.5, 1000], microstructure_model="exponential", density=[250, 330],
+                        temperature=265, corr_length=[0.2e-3, 0.3e-3])
+    run_case("iba_mmax5_active", "iba", sensor_list.active(13e9, [30, 50]), [sp2],
+             dict(m_max=5, n_max_stream=16, diagonalization_method="schur_forcedtriu"))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     names = sys.argv[1:] or list(CASES)

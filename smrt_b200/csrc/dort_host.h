@@ -143,7 +143,7 @@ inline const char* validate_options(const smrtb200_options& o) {
   if (o.abi_version != SMRTB200_ABI_VERSION) return "abi_version mismatch";
   if (o.mode != SMRTB200_MODE_PASSIVE && o.mode != SMRTB200_MODE_ACTIVE) return "mode must be passive or active";
   if (o.n_max_stream < 2 || o.n_max_stream > 256) return "n_max_stream must be in [2, 256]";
-  if (o.mode == SMRTB200_MODE_ACTIVE && (o.m_max < 0 || o.m_max > 3)) return "m_max must be in [0, 3]";
+  if (o.mode == SMRTB200_MODE_ACTIVE && (o.m_max < 0 || o.m_max >= SMRT_MAX_MODES)) return "m_max must be in [0, 16]";
   if (o.max_layers < 1) return "max_layers must be >= 1";
   if (o.max_batch < 1) return "max_batch must be >= 1";
   if (o.mode == SMRTB200_MODE_PASSIVE && o.n_theta < 1) return "n_theta must be >= 1";

@@ -14,7 +14,7 @@
 #include "dort_device.cuh"
 #include "dort_linalg.cuh"
 
-#define SMRT_MAX_MODES 4      // m = 0 .. 3
+#define SMRT_MAX_MODES 17     // m = 0 .. 16 (the reference's tests go up to m_max = 16, rtsolver/test_dort.py:13-42)
 #define SMRT_MAX_INC 16       // incident streams (<= 2 per incidence angle, n_inc <= 8)
 #define SMRT_AUX_STRIDE 4     // per (problem, layer): iba_coeff, kk, f_eff, spare
 #define SMRT_NT 256           // threads per CTA of the eigen kernel, global-scratch instantiation (large stream counts)

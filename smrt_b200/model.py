@@ -71,8 +71,8 @@ def check_dort_options(options: Optional[dict]) -> dict:
         raise SMRTError("error_handling must be 'exception' or 'nan'")
     if not (2 <= int(opts["n_max_stream"]) <= 256):
         raise SMRTError("n_max_stream must be between 2 and 256")
-    if not (0 <= int(opts["m_max"]) <= 3):
-        raise SMRTError("m_max larger than 3 is not implemented on the B200 path")
+    if not (0 <= int(opts["m_max"]) <= 16):
+        raise SMRTError("m_max larger than 16 is not implemented on the B200 path")
     return opts
 
 

@@ -170,3 +170,29 @@ def test_choudhury_outside_validity_raises_like_the_reference():
     sp = make_snowpack([0.3], "exponential", density=[300], temperature=265, corr_length=1e-4, substrate=sub)
     with pytest.raises(Warning, match="outside validity range"):
         make_model("iba", "dort").run(sensor_list.passive(37e9, 55), sp)
+
+
+@pytest.mark.parametrize("microstructure_model,m_max,emmodel", [("independent_sphere", 6, "rayleigh"),
+                                                                ("exponential", 16, "iba")])
+def test_schur_based_diagonalisation_settings_run(microstructure_model, m_max, emmodel):
+    """reference rtsolver/test_dort.py:13-42 (settings where scipy.linalg.eig fails in the reference)"""
+    sp = make_snowpack(thickness=[1000], microstructure_model=microstructure_model, density=280, temperature=265,
+                       radius=0.05e-3, corr_length=0.05e-3)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", SMRTWarning)
+        m = make_model(emmodel, "dort", rtsolver_options=dict(m_max=m_max, n_max_stream=32,
+                                                              diagonalization_method="schur"))
+        s = m.run(sensor_list.active(10e9, 50), sp).sigmaVV()
+    assert np.isfinite(s) and s > 0
+
+
+def test_iba_variants_and_per_medium_emmodels(setup_snowpack_2):
+    """reference test/test_integration_iba_original.py:44-45, test/test_mixed_emmodel.py:39-40, core/model.py:547-548"""
+    res = make_model("iba_original", "dort").run(sensor_list.amsre("37V"), setup_snowpack_2)
+    np.testing.assert_allclose([res.TbV(), res.TbH()], [247.92662874568973, 237.1283359660738], atol=1e-4)
+    sp = make_snowpack([0.1, 100], "sticky_hard_spheres", density=[200, 400], temperature=[250.0, 250.0],
+                       radius=[2e-4, 2e-4], stickiness=[0.1, 0.1])
+    res = make_model(["dmrt_qcacp_shortrange", "iba"], "dort").run(sensor_list.amsre("37V"), sp)
+    np.testing.assert_allclose([res.TbV(), res.TbH()], [204.510189893163, 190.53692754287889], atol=1e-4)
+    by_medium = make_model({"snow": "iba_original"}, "dort").run(sensor_list.amsre("37V"), setup_snowpack_2)
+    np.testing.assert_allclose(by_medium.TbV(), 247.92662874568973, atol=1e-4)

@@ -303,3 +303,20 @@ def test_inclusion_shapes_and_depolarization_packing():
     res = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8)).run(sensor_list.passive(37e9, 55), sp)
     ref = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8)).run(sensor_list.passive(37e9, 55), two_layer())
     assert res.TbV() != ref.TbV() and abs(res.TbV() - ref.TbV()) < 5.0
+
+
+def test_high_azimuthal_mode_counts_run_like_the_reference_schur_test():
+    """reference rtsolver/test_dort.py:13-42: m_max = 16 with IBA / 32 streams runs (there: only with the Schur-based
+    diagonalisation; here the symmetrised eigenproblem has no complex-eigenvalue failure mode at all)"""
+    sp = make_snowpack(thickness=[1000], microstructure_model="exponential", density=280, temperature=265,
+                       corr_length=0.05e-3)
+    scatt = sensor_list.active(10e9, 50)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", SMRTWarning)
+        s16 = make_model("iba", "dort", rtsolver_options=dict(m_max=16, n_max_stream=32,
+                                                              diagonalization_method="schur_forcedtriu")).run(scatt, sp)
+        s2 = make_model("iba", "dort", rtsolver_options=dict(m_max=2, n_max_stream=32)).run(scatt, sp)
+    assert np.isfinite(s16.sigmaVV()) and s16.sigmaVV() > 0
+    assert abs(s16.sigmaVV_dB() - s2.sigmaVV_dB()) < 0.5  # small grains: the modes beyond 2 carry almost nothing
+    with pytest.raises(SMRTError):
+        make_model("iba", "dort", rtsolver_options=dict(m_max=17))

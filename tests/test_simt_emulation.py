@@ -18,7 +18,8 @@ SMALL = ["cfg1_iba_onelayer", "ref_iba_2layer_passive", "ref_dmrt_qcacp_2layer_p
          "inclusion_shapes_passive", "iba_original_depolarization_passive",
          "iba_maxwell_garnett_depolarization_passive"]
 SMALL_ACTIVE = ["ref_dmrt_less_refringent_active", "nonscattering_active", "soil_active", "iba_microstructures_active", "rayleigh_active",
-                "iba_original_dense_active", "iba_maxwell_garnett_dense_active", "depolarization_active"]
+                "iba_original_dense_active", "iba_maxwell_garnett_dense_active", "depolarization_active",
+                "ref_rayleigh_mmax6_active", "iba_mmax5_active"]
 
 
 @pytest.mark.parametrize("name", SMALL + SMALL_ACTIVE)
