@@ -903,9 +903,8 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
           // [F - Rb D G - R' G | (G - Rb D F - R' F) t] in registers, the block synchronises, the tiles overwrite them
           const double* Fs = BF;
           const double* Gs = BG;
-          block_gemm_ptr_deferred(
-              h, r, 2 * h, r, BR, ldr_prev,
-              [&](int j) { return (j < h) ? Gs + (size_t)j * h : Fs + (size_t)(j - h) * h; },
+          block_gemm_split_deferred(
+              h, r, h, r, BR, ldr_prev, Gs, Fs,
               [&](int i, int j, double acc) {
                 if (j < h) return Fs[(size_t)j * h + i] - RbD[i] * Gs[(size_t)j * h + i] - acc;
                 const int jj = j - h;

@@ -824,49 +824,64 @@ SMRT_DEV void block_gemm_dual(int nthr, int M, int N, int K, const double* SMRT_
 #define SMRT_DEF_TILES 4  // >= 128 threads on the device (TY >= 8)
 #endif
 
-// out(i, j) = pre(i, j, sum_{k < K} A(i, k) B(k, j)) for i < M (<= 64), j < N, evaluated in registers; then a block
-// barrier; then post(i, j, value).  A column-major in shared memory (lda), column j of B at bcol(j) (K entries).
-// rows i >= Mk contribute no product (the sum is zero there).  Every thread of the block must call.
-// The k loop is the outer one: the four A operands of a step serve all the column tiles of the thread.
-template <typename FB, typename FPRE, typename FPOST>
-SMRT_DEV void block_gemm_ptr_deferred(int M, int Mk, int N, int K, const double* SMRT_RESTRICT Am, int lda, FB bcol,
-                                      FPRE pre, FPOST post) {
+// out(i, j) = pre(i, j, sum_{k < K} A(i, k) B(k, j)) for i < M (<= 64), j < 2 h, evaluated in registers; then a block
+// barrier; then post(i, j, value).  A column-major in shared memory (lda); B = [Bg | Bf], two compact h x h blocks
+// (column-major, leading dimension h; K <= h rows used).  rows i >= Mk contribute no product (the sum is zero there).
+// Every thread of the block must call.  The k loop is the outer one: the four A operands of a step serve all the
+// column tiles of the thread.  The first half of a thread's tiles covers columns of Bg, the second half the SAME
+// columns of Bf: one set of 2 SMRT_DEF_TILES element offsets and two running pointers address all the B operands
+// (the version with one pointer per column re-derived its 16 addresses in every k step: the kernel sits at the
+// register limit).  Requires h <= 2 TY SMRT_DEF_TILES.
+template <typename FPRE, typename FPOST>
+SMRT_DEV void block_gemm_split_deferred(int M, int Mk, int h, int K, const double* SMRT_RESTRICT Am, int lda,
+                                        const double* SMRT_RESTRICT Bg, const double* SMRT_RESTRICT Bf, FPRE pre,
+                                        FPOST post) {
   const int tid = threadIdx.x, NT = blockDim.x;
   const int TX = 16, TY = NT / TX;
   const int tx = tid % TX, ty = tid / TX;
+  constexpr int HT = SMRT_DEF_TILES / 2;  // tiles per half
   double val[SMRT_DEF_TILES][4][4];
-  const double* bp[SMRT_DEF_TILES][4];
-  size_t ao[4];
+  int ao[4], bo[HT][4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int i = tx + u * TX;
-    ao[u] = (size_t)(i < Mk ? i : (Mk > 0 ? Mk - 1 : 0));
+    ao[u] = i < Mk ? i : (Mk > 0 ? Mk - 1 : 0);
   }
 #pragma unroll
-  for (int t = 0; t < SMRT_DEF_TILES; ++t)
+  for (int t = 0; t < HT; ++t)
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
-      const int j = t * TY * 4 + ty + v * TY;
-      bp[t][v] = bcol(j < N ? j : N - 1);
+      const int jl = ty + TY * (4 * t + v);
+      bo[t][v] = (jl < h ? jl : h - 1) * h;  // clamped: the reads stay inside the operand
+      SMRT_KEEP_INT(bo[t][v]);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) val[t][u][v] = 0.0;
+      for (int u = 0; u < 4; ++u) val[t][u][v] = val[HT + t][u][v] = 0.0;
     }
   if (Mk > 0 && tx < M) {
+    const double* ap = Am;
+    const double* gp = Bg;
+    const double* fp = Bf;
 #pragma unroll 1
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < K; ++k, ap += lda, ++gp, ++fp) {
       double av[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) av[u] = Am[ao[u] + (size_t)k * lda];
+      for (int u = 0; u < 4; ++u) av[u] = ap[ao[u]];
 #pragma unroll
-      for (int t = 0; t < SMRT_DEF_TILES; ++t) {
-        if (t * TY * 4 + ty < N) {  // uniform over the threads of a tile column
+      for (int t = 0; t < HT; ++t) {
+        if (ty + TY * 4 * t < h) {  // uniform over the threads of a tile column
           double bv[4];
 #pragma unroll
-          for (int v = 0; v < 4; ++v) bv[v] = bp[t][v][k];
+          for (int v = 0; v < 4; ++v) bv[v] = gp[bo[t][v]];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int v = 0; v < 4; ++v) val[t][u][v] = fma(av[u], bv[v], val[t][u][v]);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) bv[v] = fp[bo[t][v]];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) val[HT + t][u][v] = fma(av[u], bv[v], val[HT + t][u][v]);
         }
       }
     }
@@ -877,8 +892,8 @@ SMRT_DEV void block_gemm_ptr_deferred(int M, int Mk, int N, int K, const double*
     for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        const int i = tx + u * TX, j = t * TY * 4 + ty + v * TY;
-        if (i < M && j < N) val[t][u][v] = pre(i, j, (i < Mk) ? val[t][u][v] : 0.0);
+        const int i = tx + u * TX, jl = ty + TY * (4 * (t % HT) + v), j = (t < HT) ? jl : h + jl;
+        if (i < M && jl < h) val[t][u][v] = pre(i, j, (i < Mk) ? val[t][u][v] : 0.0);
       }
   __syncthreads();
 #pragma unroll
@@ -887,8 +902,8 @@ SMRT_DEV void block_gemm_ptr_deferred(int M, int Mk, int N, int K, const double*
     for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
-        const int i = tx + u * TX, j = t * TY * 4 + ty + v * TY;
-        if (i < M && j < N) post(i, j, val[t][u][v]);
+        const int i = tx + u * TX, jl = ty + TY * (4 * (t % HT) + v), j = (t < HT) ? jl : h + jl;
+        if (i < M && jl < h) post(i, j, val[t][u][v]);
       }
 }
 
@@ -903,37 +918,40 @@ SMRT_DEV void block_gemm_dual_deferred(int M, int N, int K, const double* SMRT_R
   const int tx = tid % TX, ty = tid / TX;
   constexpr int NTL = SMRT_DEF_TILES / 2;
   double v1[NTL][4][4], v2[NTL][4][4];
-  const double* bp[NTL][4];
-  size_t ao[4];
+  int ao[4], bo[NTL][4];  // element offsets; the operands are addressed through three running pointers
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int i = tx + u * TX;
-    ao[u] = (size_t)(i < M ? i : M - 1);
+    ao[u] = i < M ? i : M - 1;
   }
 #pragma unroll
   for (int t = 0; t < NTL; ++t)
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
       const int j = t * TY * 4 + ty + v * TY;
-      bp[t][v] = Bm + (size_t)(j < N ? j : N - 1) * ldb;
+      bo[t][v] = (j < N ? j : N - 1) * ldb;
+      SMRT_KEEP_INT(bo[t][v]);
 #pragma unroll
       for (int u = 0; u < 4; ++u) v1[t][u][v] = v2[t][u][v] = 0.0;
     }
   if (tx < M) {
+    const double* a1p = A1;
+    const double* a2p = A2;
+    const double* bq = Bm;
 #pragma unroll 1
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < K; ++k, a1p += lda, a2p += lda, ++bq) {
       double a1[4], a2[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        a1[u] = A1[ao[u] + (size_t)k * lda];
-        a2[u] = A2[ao[u] + (size_t)k * lda];
+        a1[u] = a1p[ao[u]];
+        a2[u] = a2p[ao[u]];
       }
 #pragma unroll
       for (int t = 0; t < NTL; ++t) {
         if (t * TY * 4 + ty < N) {
           double bv[4];
 #pragma unroll
-          for (int v = 0; v < 4; ++v) bv[v] = bp[t][v][k];
+          for (int v = 0; v < 4; ++v) bv[v] = bq[bo[t][v]];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll

@@ -24,6 +24,8 @@ SMRT_DEV void smrt_named_barrier(int id, int nthreads) {
 // a routine that is not inlined (one copy serves several kernel instantiations) receives generic pointers: where the
 // caller knows they point to shared memory, saying so turns LD.E / ST.E + 64-bit address arithmetic into LDS / STS
 #define SMRT_ASSUME_SHARED(p) __builtin_assume(__isShared(p))
+// an opaque identity: the value must be kept (register or spill), it cannot be re-derived inside a loop
+#define SMRT_KEEP_INT(x) asm volatile("" : "+r"(x))
 
 // ---- single-instruction fp64 approximations (MUFU.RCP64H / MUFU.RSQ64H, ~2^-20 relative error): seeds that the
 // callers refine with Newton steps where they need more
@@ -149,6 +151,7 @@ void simt_group_barrier(unsigned mask);
 void __threadfence();
 void smrt_named_barrier(int id, int nthreads);
 #define SMRT_ASSUME_SHARED(p) ((void)0)
+#define SMRT_KEEP_INT(x) ((void)0)
 
 uint64_t simt_shfl_raw(unsigned mask, uint64_t v, int src_lane);
 int __any_sync(unsigned mask, int pred);
