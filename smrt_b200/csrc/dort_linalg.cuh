@@ -498,19 +498,22 @@ SMRT_DEV void jreg_rotate2(int lane, double (&x0)[R], double (&y0)[R], double& a
   const double co = __shfl_xor_sync(0xffffffffu, c, JG / 2, 32);
   const double so = __shfl_xor_sync(0xffffffffu, s, JG / 2, 32);
   const double tgo = __shfl_xor_sync(0xffffffffu, tg, JG / 2, 32);
-  if (rot0) {
+  // both rotations are applied unconditionally: a pair that does not rotate got the exact identity (c = 1, s = 0,
+  // t g = 0), and straight-line code keeps the 4 R operands in place (the conditional version paid one register move
+  // per operand to merge the two paths: 13 % of the instructions of the sweep)
+  {
     jreg_apply<R>(x0, y0, hi ? co : c, hi ? so : s);
     const double tg0 = hi ? tgo : tg;
     a0 -= tg0;
     b0 += tg0;
-    rc0 = (g20 > SMRT_JACOBI_QUAD2 * ab0) ? 3 : 2;
+    rc0 = rot0 ? ((g20 > SMRT_JACOBI_QUAD2 * ab0) ? 3 : 2) : 0;
   }
-  if (rot1) {
+  {
     jreg_apply<R>(x1, y1, hi ? c : co, hi ? s : so);
     const double tg1 = hi ? tg : tgo;
     a1 -= tg1;
     b1 += tg1;
-    rc1 = (g21 > SMRT_JACOBI_QUAD2 * ab1) ? 3 : 2;
+    rc1 = rot1 ? ((g21 > SMRT_JACOBI_QUAD2 * ab1) ? 3 : 2) : 0;
   }
 }
 
