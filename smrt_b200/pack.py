@@ -651,9 +651,13 @@ def seawater_permittivity_klein76(frequency, temperature, salinity):
 
 def pack_sea_ice_ensemble(frequency, thickness, temperature, salinity, porosity, corr_length, *, theta_deg=40.0,
                           water_substrate=True, water_temperature=_FREEZING_POINT - 1.8,
-                          water_salinity=0.032) -> ProblemBatch:
-    """Multi-year sea-ice ensemble given directly as arrays: ``(S, L)`` profiles x ``(F,)`` frequencies -> ``F*S``
-    passive problems in the reference's simulation order (frequency outermost).
+                          water_salinity=0.032, ice_type="multiyear", brine_inclusion_shape="spheres") -> ProblemBatch:
+    """Sea-ice ensemble given directly as arrays: ``(S, L)`` profiles x ``(F,)`` frequencies -> ``F*S`` passive
+    problems in the reference's simulation order (frequency outermost).
+
+    ``ice_type="firstyear"`` (``smrt/inputs/make_medium.py:660-681``): background = pure ice (Mätzler 2006),
+    scatterers = Stogryn-85 brine pockets at the Cox-Weeks brine volume, shaped as ``brine_inclusion_shape``
+    ("spheres", "random_needles", or a dict of mixing ratios); ``porosity`` must be 0 there.  ``"multiyear"``:
 
     Equivalent, member by member, to ``make_ice_column("multiyear", thickness=..., temperature=..., salinity=...,
     porosity=..., microstructure_model="exponential", corr_length=..., brine_inclusion_shape="spheres",
@@ -680,7 +684,23 @@ def pack_sea_ice_ensemble(frequency, thickness, temperature, salinity, porosity,
     freq_b = np.repeat(freqs, S)
     temp_b = tile(temperature)
     vb = tile(brine_volume_cox83_lepparanta88(temperature, salinity))
-    eps_bg = saline_ice_permittivity_pvs_mixing(freq_b[:, None], temp_b, vb)
+    inclusion = None
+    if ice_type == "firstyear":
+        if np.any(porosity != 0):
+            raise SMRTError("first-year ice has no air bubbles in the reference's make_ice_column: porosity must be 0")
+        eps_bg = np.asarray(ice_permittivity_maetzler06(freq_b[:, None], temp_b), dtype=np.complex128) + 0 * vb
+        eps_sc = np.asarray(brine_permittivity_stogryn85(freq_b[:, None], temp_b), dtype=np.complex128) + 0 * vb
+        frac = vb
+        ws, wn = _shape_weights(brine_inclusion_shape)
+        inclusion = np.tile(np.array((ws, wn) + SPHERICAL_INCLUSIONS[2:]), (B, L, 1))
+    elif ice_type == "multiyear":
+        if brine_inclusion_shape not in (None, "spheres"):
+            raise SMRTError("only spherical brine pockets are implemented for the multi-year ensemble")
+        eps_bg = saline_ice_permittivity_pvs_mixing(freq_b[:, None], temp_b, vb)
+        eps_sc = np.ones((B, L), dtype=np.complex128)
+        frac = tile(porosity)
+    else:
+        raise SMRTError("ice_type must be 'firstyear' or 'multiyear'")
     if water_substrate:
         sub_kind = np.full(B, SUB_FLAT, dtype=np.int32)
         sub_eps = np.asarray(seawater_permittivity_klein76(freq_b, water_temperature, water_salinity), dtype=np.complex128)
@@ -689,10 +709,10 @@ def pack_sea_ice_ensemble(frequency, thickness, temperature, salinity, porosity,
         sub_kind, sub_eps, sub_T = np.zeros(B, dtype=np.int32), np.zeros(B, dtype=np.complex128), np.zeros(B)
     return ProblemBatch(
         mode=MODE_PASSIVE, frequency=freq_b, nlayer=np.full(B, L, dtype=np.int32), thickness=tile(thickness),
-        temperature=temp_b, frac_volume=tile(porosity), eps_bg=np.asarray(eps_bg, dtype=np.complex128),
-        eps_sc=np.ones((B, L), dtype=np.complex128), emmodel=np.full((B, L), emmodel_code("iba"), dtype=np.int32),
+        temperature=temp_b, frac_volume=frac, eps_bg=np.asarray(eps_bg, dtype=np.complex128),
+        eps_sc=eps_sc, emmodel=np.full((B, L), emmodel_code("iba"), dtype=np.int32),
         ms_kind=np.full((B, L), MS_EXPONENTIAL, dtype=np.int32), ms_p0=tile(corr_length), ms_p1=np.zeros((B, L)),
         interface=np.zeros((B, L), dtype=np.int32), substrate_kind=sub_kind, substrate_eps=sub_eps,
         substrate_temperature=sub_T, theta=np.radians(np.atleast_1d(np.asarray(theta_deg, dtype=float))),
-        theta_inc=np.zeros(0), phi=0.0, dense_snow_correction=np.zeros((B, L), dtype=np.int32),
+        theta_inc=np.zeros(0), phi=0.0, dense_snow_correction=np.zeros((B, L), dtype=np.int32), inclusion=inclusion,
     )

@@ -320,3 +320,31 @@ def test_high_azimuthal_mode_counts_run_like_the_reference_schur_test():
     assert abs(s16.sigmaVV_dB() - s2.sigmaVV_dB()) < 0.5  # small grains: the modes beyond 2 carry almost nothing
     with pytest.raises(SMRTError):
         make_model("iba", "dort", rtsolver_options=dict(m_max=17))
+
+
+def test_first_year_sea_ice_ensemble_packer_matches_the_reference_inputs():
+    """pack_sea_ice_ensemble(ice_type="firstyear") against what the reference's make_ice_column produced: the 9-layer
+    column of test/test_iba_sea_ice.py (spheres) and the needle / mixed brine columns of
+    tests/golden/inclusion_shapes_passive.npz"""
+    from smrt_b200 import pack_sea_ice_ensemble
+
+    d, ref, _ = load_golden("ref_sea_ice_128streams")  # member 0 = first-year ice, 1.4 GHz, 40 degrees
+    L = 9
+    b = pack_sea_ice_ensemble(1.4e9, [[1.5 / L] * L], np.linspace(273.15 - 20.0, 273.15 - 1.8, L)[None],
+                              np.linspace(2.0, 10.0, L)[None] * 1e-3, 0.0, 500e-6, theta_deg=40.0, ice_type="firstyear")
+    for name in ("thickness", "temperature", "ms_p0", "substrate_temperature", "theta"):
+        np.testing.assert_allclose(getattr(b, name)[0], getattr(ref, name)[0], rtol=1e-15, err_msg=name)
+    for name in ("frac_volume", "eps_bg", "eps_sc", "substrate_eps"):
+        np.testing.assert_allclose(getattr(b, name)[0], getattr(ref, name)[0], rtol=1e-13, err_msg=name)
+    d, ref, _ = load_golden("inclusion_shapes_passive")  # members 0 / 1: needles / 30 % spheres + 70 % needles; 3 frequencies
+    for member, shape in ((0, "random_needles"), (1, {"spheres": 0.3, "random_needles": 0.7})):
+        b = pack_sea_ice_ensemble([1.4e9, 6.925e9, 18.7e9], [[0.25, 0.35, 0.4]], [[258.0, 264.0, 269.0]],
+                                  np.array([[5.0, 7.0, 9.0]]) * 1e-3, 0.0, [[2e-4, 3e-4, 4e-4]], theta_deg=[40, 55],
+                                  ice_type="firstyear", brine_inclusion_shape=shape)
+        rows = [f * 3 + member for f in range(3)]  # frequency-major order, three snowpacks per frequency
+        for name in ("frac_volume", "eps_bg", "eps_sc", "substrate_eps"):
+            got, want = getattr(b, name), getattr(ref, name)[rows]
+            np.testing.assert_allclose(got, want[:, :3] if want.ndim == 2 else want, rtol=1e-13, err_msg=name)
+        np.testing.assert_allclose(b.inclusion, ref.inclusion[rows][:, :3], rtol=1e-15)
+    with pytest.raises(SMRTError):
+        pack_sea_ice_ensemble(1.4e9, [[1.0]], [[260.0]], [[5e-3]], 0.05, 5e-4, ice_type="firstyear")
