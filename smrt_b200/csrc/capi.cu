@@ -4,6 +4,7 @@
 // per-layer aux values, work counters, optional per-CTA global scratch) so that the eigen kernel of chunk c+1 overlaps
 // the boundary kernel of chunk c, pinned host staging buffers for the *_host entry point, and CUDA events for timing.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges around pack / H2D / kernels / D2H
 
 #include <algorithm>
 #include <cstdarg>
@@ -76,10 +77,19 @@ struct smrtb200_plan {
   float last_total_ms = 0.f, last_eigen_ms = 0.f, last_boundary_ms = 0.f;  // sums over the chunks of the last solve
   int last_chunks = 0;
   std::vector<cudaEvent_t> chunk_events;  // 3 per chunk: before eigen, after eigen, after boundary
-  // device-side staging for the *_host entry point
-  std::vector<void*> dev_bufs;
-  std::vector<void*> pinned_bufs;
-  smrtb200_batch dev_batch;
+  cudaEvent_t ev_dep = nullptr;  // orders the plan's two slot streams after the caller's stream
+  // *_host entry point: a ring of kRing fixed-size staging slots (pinned host block + device block + three events per
+  // slot); H2D of host chunk k+1 and D2H of host chunk k-1 run under the kernels of host chunk k
+  struct RingSlot {
+    std::vector<void*> dev, pinned;  // one buffer per field of field_table()
+    smrtb200_batch dev_batch;
+    cudaEvent_t h2d_done = nullptr, solve_done = nullptr, d2h_done = nullptr;
+    int b0 = 0, nb = 0;  // host chunk in flight (nb == 0: none)
+  };
+  std::vector<RingSlot> ring;
+  std::vector<void*> shared_dev;  // theta / theta_inc (shared by every problem)
+  int host_chunk = 0;
+  cudaStream_t host_stream = nullptr, h2d_stream = nullptr, d2h_stream = nullptr;
   bool staging_ready = false;
 };
 
@@ -115,8 +125,18 @@ extern "C" int smrtb200_plan_destroy(smrtb200_plan* p) {
     if (s.stream) cudaStreamDestroy(s.stream);
   }
   for (cudaEvent_t e : p->chunk_events) cudaEventDestroy(e);
-  for (void* d : p->dev_bufs) cudaFree(d);
-  for (void* h : p->pinned_bufs) cudaFreeHost(h);
+  for (auto& r : p->ring) {
+    for (void* d : r.dev) cudaFree(d);
+    for (void* h : r.pinned) cudaFreeHost(h);
+    if (r.h2d_done) cudaEventDestroy(r.h2d_done);
+    if (r.solve_done) cudaEventDestroy(r.solve_done);
+    if (r.d2h_done) cudaEventDestroy(r.d2h_done);
+  }
+  for (void* d : p->shared_dev) cudaFree(d);
+  if (p->host_stream) cudaStreamDestroy(p->host_stream);
+  if (p->h2d_stream) cudaStreamDestroy(p->h2d_stream);
+  if (p->d2h_stream) cudaStreamDestroy(p->d2h_stream);
+  if (p->ev_dep) cudaEventDestroy(p->ev_dep);
   if (p->prof) {
     unsigned long long c[16];
     if (cudaMemcpy(c, p->prof, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess) {
@@ -155,7 +175,6 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
   p->sm_count = prop.multiProcessorCount;
   p->layout = smrt_host::make_layout(*options);
   const smrt_host::Layout& L = p->layout;
-  std::memset(&p->dev_batch, 0, sizeof(p->dev_batch));
 
   // shared-memory path if both kernels fit into the opt-in limit, else matrices in an L2-resident global scratch
   p->use_global_scratch = (L.eigen_smem_bytes > kMaxSmemOptin) || (L.boundary_smem_bytes > kMaxSmemOptin);
@@ -280,6 +299,7 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
   }
   PLAN_CUDA(cudaEventCreate(&p->ev_begin));
   PLAN_CUDA(cudaEventCreate(&p->ev_end));
+  PLAN_CUDA(cudaEventCreateWithFlags(&p->ev_dep, cudaEventDisableTiming));
   *out = p;
   return 0;
 }
@@ -320,19 +340,17 @@ static int check_batch(const smrtb200_plan* p, const smrtb200_batch* b) {
   return 0;
 }
 
-extern "C" int smrtb200_solve_batch_device(smrtb200_plan* p, const smrtb200_batch* batch, void* cuda_stream) {
-  int rc = check_batch(p, batch);
-  if (rc) return rc;
-  if (batch->B == 0) return 0;
-  CUDA_TRY(cudaSetDevice(p->device));
-  cudaStream_t user = (cudaStream_t)cuda_stream;
+// Queue the kernels of one batch (device pointers).  The plan's two slot streams are ordered after `user` on entry and
+// `user` after them on exit.  ev_base: index of the first per-chunk event triple to use (the host entry point queues
+// several batches per call and keeps all their events); returns the number of chunks in *nchunks_out.
+static int solve_device_impl(smrtb200_plan* p, const smrtb200_batch* batch, cudaStream_t user, int ev_base,
+                             int* nchunks_out) {
   const smrt_host::Layout& L = p->layout;
   const int B = batch->B;
-
   CUDA_TRY(cudaMemsetAsync(batch->status, 0, sizeof(int) * (size_t)B, user));
-  CUDA_TRY(cudaEventRecord(p->ev_begin, user));
+  CUDA_TRY(cudaEventRecord(p->ev_dep, user));
   for (auto& s : p->slots) {
-    CUDA_TRY(cudaStreamWaitEvent(s.stream, p->ev_begin, 0));
+    CUDA_TRY(cudaStreamWaitEvent(s.stream, p->ev_dep, 0));
     s.used = false;
   }
   int nchunks = 0;
@@ -354,12 +372,12 @@ extern "C" int smrtb200_solve_batch_device(smrtb200_plan* p, const smrtb200_batc
     CUDA_TRY(cudaMemsetAsync(s.counters, 0, 2 * sizeof(int), s.stream));
     const int nthreads_opt = 128;
     const int items = nb * p->opt.max_layers;
-    while (p->chunk_events.size() < 3 * (size_t)(nchunks + 1)) {
+    while (p->chunk_events.size() < 3 * (size_t)(ev_base + nchunks + 1)) {
       cudaEvent_t e;
       CUDA_TRY(cudaEventCreate(&e));
       p->chunk_events.push_back(e);
     }
-    cudaEvent_t* ev = &p->chunk_events[3 * (size_t)nchunks];
+    cudaEvent_t* ev = &p->chunk_events[3 * (size_t)(ev_base + nchunks)];
     optics_kernel<<<(items + nthreads_opt - 1) / nthreads_opt, nthreads_opt, 0, s.stream>>>(A);
     CUDA_TRY(cudaEventRecord(ev[0], s.stream));
     p->eigen_fn<<<std::min(p->eigen_grid, items), p->eigen_threads, p->eigen_smem, s.stream>>>(A);
@@ -375,6 +393,22 @@ extern "C" int smrtb200_solve_batch_device(smrtb200_plan* p, const smrtb200_batc
     CUDA_TRY(cudaEventRecord(s.done, s.stream));
     CUDA_TRY(cudaStreamWaitEvent(user, s.done, 0));
   }
+  if (nchunks_out) *nchunks_out = nchunks;
+  return 0;
+}
+
+extern "C" int smrtb200_solve_batch_device(smrtb200_plan* p, const smrtb200_batch* batch, void* cuda_stream) {
+  int rc = check_batch(p, batch);
+  if (rc) return rc;
+  if (batch->B == 0) return 0;
+  CUDA_TRY(cudaSetDevice(p->device));
+  cudaStream_t user = (cudaStream_t)cuda_stream;
+  nvtxRangePushA("smrtb200 solve_batch_device (queue optics / eigen / boundary kernels)");
+  CUDA_TRY(cudaEventRecord(p->ev_begin, user));
+  int nchunks = 0;
+  rc = solve_device_impl(p, batch, user, 0, &nchunks);
+  nvtxRangePop();
+  if (rc) return rc;
   CUDA_TRY(cudaEventRecord(p->ev_end, user));
   p->last_chunks = nchunks;
   return 0;
@@ -442,22 +476,67 @@ static const void* field_cptr(const smrtb200_batch* b, size_t off) {
   return *reinterpret_cast<void* const*>(reinterpret_cast<const char*>(b) + off);
 }
 
+constexpr int kRing = 3;
+
 static int ensure_staging(smrtb200_plan* p) {
   if (p->staging_ready) return 0;
   auto tab = field_table(p);
-  const size_t Bm = (size_t)p->opt.max_batch;
-  for (const auto& f : tab) {
-    size_t bytes = f.per_problem ? f.elem * Bm : f.elem;
-    void* d = nullptr;
-    void* h = nullptr;
-    CUDA_TRY(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
-    CUDA_TRY(cudaMallocHost(&h, std::max<size_t>(bytes, 16)));
-    p->dev_bufs.push_back(d);
-    p->pinned_bufs.push_back(h);
-    p->workspace_bytes += bytes;
-    field_ptr(&p->dev_batch, f.offset) = d;
+  // host chunk: several kernel waves, so that the two-slot kernel pipeline of a chunk reaches its steady state, yet
+  // small enough for the pinned ring to stay at tens of MB whatever the batch size
+  long long hc = 8LL * p->chunk;
+  if (const char* e = std::getenv("SMRT_B200_HOST_CHUNK")) {
+    long long v = std::atoll(e);
+    if (v > 0) hc = v;
+  }
+  p->host_chunk = (int)std::max<long long>(1, std::min<long long>(hc, p->opt.max_batch));
+  CUDA_TRY(cudaStreamCreateWithFlags(&p->host_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&p->h2d_stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&p->d2h_stream, cudaStreamNonBlocking));
+  p->ring.resize(kRing);
+  p->shared_dev.assign(tab.size(), nullptr);
+  for (size_t k = 0; k < tab.size(); ++k) {
+    if (tab[k].per_problem) continue;
+    CUDA_TRY(cudaMalloc(&p->shared_dev[k], std::max<size_t>(tab[k].elem, 16)));
+    p->workspace_bytes += tab[k].elem;
+  }
+  for (auto& r : p->ring) {
+    std::memset(&r.dev_batch, 0, sizeof(r.dev_batch));
+    CUDA_TRY(cudaEventCreateWithFlags(&r.h2d_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&r.solve_done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&r.d2h_done, cudaEventDisableTiming));
+    r.dev.assign(tab.size(), nullptr);
+    r.pinned.assign(tab.size(), nullptr);
+    for (size_t k = 0; k < tab.size(); ++k) {
+      const auto& f = tab[k];
+      if (!f.per_problem) {
+        field_ptr(&r.dev_batch, f.offset) = p->shared_dev[k];
+        continue;
+      }
+      const size_t bytes = std::max<size_t>(f.elem * (size_t)p->host_chunk, 16);
+      CUDA_TRY(cudaMalloc(&r.dev[k], bytes));
+      CUDA_TRY(cudaMallocHost(&r.pinned[k], bytes));
+      p->workspace_bytes += bytes;
+      field_ptr(&r.dev_batch, f.offset) = r.dev[k];
+    }
   }
   p->staging_ready = true;
+  return 0;
+}
+
+// results of the host chunk in flight in ring slot `r` -> the caller's arrays
+static int ring_drain(smrtb200_plan* p, smrtb200_plan::RingSlot& r, const smrtb200_batch* batch,
+                      const std::vector<FieldDesc>& tab) {
+  if (r.nb == 0) return 0;
+  CUDA_TRY(cudaEventSynchronize(r.d2h_done));
+  nvtxRangePushA("smrtb200 unpack results (pinned -> caller)");
+  for (size_t k = 0; k < tab.size(); ++k) {
+    const auto& f = tab[k];
+    if (!f.is_output) continue;
+    char* dst = static_cast<char*>(const_cast<void*>(field_cptr(batch, f.offset)));
+    std::memcpy(dst + f.elem * (size_t)r.b0, r.pinned[k], f.elem * (size_t)r.nb);
+  }
+  nvtxRangePop();
+  r.nb = 0;
   return 0;
 }
 
@@ -469,38 +548,65 @@ extern "C" int smrtb200_solve_batch_host(smrtb200_plan* p, const smrtb200_batch*
   rc = ensure_staging(p);
   if (rc) return rc;
   auto tab = field_table(p);
-  const size_t B = (size_t)batch->B;
-  cudaStream_t st = p->slots[0].stream;
-  // H2D through the pinned staging buffers
+  const int B = batch->B;
+  // arrays shared by every problem (viewing / incidence angles): pageable copy, ordered before the first kernels
   for (size_t k = 0; k < tab.size(); ++k) {
     const auto& f = tab[k];
-    if (f.is_output) continue;
+    if (f.per_problem) continue;
     const void* src = field_cptr(batch, f.offset);
-    if (!src) continue;  // theta / theta_inc of the unused mode
-    size_t bytes = f.per_problem ? f.elem * B : f.elem;
-    std::memcpy(p->pinned_bufs[k], src, bytes);
-    CUDA_TRY(cudaMemcpyAsync(p->dev_bufs[k], p->pinned_bufs[k], bytes, cudaMemcpyHostToDevice, st));
+    if (src) CUDA_TRY(cudaMemcpyAsync(p->shared_dev[k], src, f.elem, cudaMemcpyHostToDevice, p->host_stream));
   }
-  p->dev_batch.B = batch->B;
-  p->dev_batch.phi = batch->phi;
-  smrtb200_batch db = p->dev_batch;  // optional inputs the caller did not give stay NULL on the device side
-  if (!batch->substrate_params) db.substrate_params = nullptr;
-  if (!batch->atmosphere) db.atmosphere = nullptr;
-  if (!batch->inclusion) db.inclusion = nullptr;
-  rc = smrtb200_solve_batch_device(p, &db, st);
-  if (rc) return rc;
-  for (size_t k = 0; k < tab.size(); ++k) {
-    const auto& f = tab[k];
-    if (!f.is_output) continue;
-    CUDA_TRY(cudaMemcpyAsync(p->pinned_bufs[k], p->dev_bufs[k], f.elem * B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaEventRecord(p->ev_begin, p->host_stream));
+  int ev_base = 0, chunk_no = 0;
+  for (int b0 = 0; b0 < B; b0 += p->host_chunk, ++chunk_no) {
+    const int nb = std::min(p->host_chunk, B - b0);
+    auto& r = p->ring[chunk_no % kRing];
+    rc = ring_drain(p, r, batch, tab);  // the slot's previous chunk: wait for its D2H, hand the results over
+    if (rc) return rc;
+    nvtxRangePushA("smrtb200 pack chunk (caller -> pinned) + H2D");
+    for (size_t k = 0; k < tab.size(); ++k) {
+      const auto& f = tab[k];
+      if (f.is_output || !f.per_problem) continue;
+      const char* src = static_cast<const char*>(field_cptr(batch, f.offset));
+      if (!src) continue;  // optional input not given
+      const size_t bytes = f.elem * (size_t)nb;
+      std::memcpy(r.pinned[k], src + f.elem * (size_t)b0, bytes);
+      CUDA_TRY(cudaMemcpyAsync(r.dev[k], r.pinned[k], bytes, cudaMemcpyHostToDevice, p->h2d_stream));
+    }
+    CUDA_TRY(cudaEventRecord(r.h2d_done, p->h2d_stream));
+    nvtxRangePop();
+    smrtb200_batch db = r.dev_batch;  // optional inputs the caller did not give stay NULL on the device side
+    db.B = nb;
+    db.phi = batch->phi;
+    if (!batch->substrate_params) db.substrate_params = nullptr;
+    if (!batch->atmosphere) db.atmosphere = nullptr;
+    if (!batch->inclusion) db.inclusion = nullptr;
+    CUDA_TRY(cudaStreamWaitEvent(p->host_stream, r.h2d_done, 0));
+    int nchunks = 0;
+    nvtxRangePushA("smrtb200 queue kernels of a host chunk");
+    rc = solve_device_impl(p, &db, p->host_stream, ev_base, &nchunks);
+    nvtxRangePop();
+    if (rc) return rc;
+    ev_base += nchunks;
+    CUDA_TRY(cudaEventRecord(r.solve_done, p->host_stream));
+    CUDA_TRY(cudaStreamWaitEvent(p->d2h_stream, r.solve_done, 0));
+    for (size_t k = 0; k < tab.size(); ++k) {
+      const auto& f = tab[k];
+      if (!f.is_output) continue;
+      CUDA_TRY(cudaMemcpyAsync(r.pinned[k], r.dev[k], f.elem * (size_t)nb, cudaMemcpyDeviceToHost, p->d2h_stream));
+    }
+    CUDA_TRY(cudaEventRecord(r.d2h_done, p->d2h_stream));
+    r.b0 = b0;
+    r.nb = nb;
   }
-  CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaEventRecord(p->ev_end, p->host_stream));
+  for (int k = 0; k < kRing; ++k) {  // oldest first
+    rc = ring_drain(p, p->ring[(chunk_no + k) % kRing], batch, tab);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaStreamSynchronize(p->host_stream));
+  p->last_chunks = ev_base;
   collect_timing(p);
-  for (size_t k = 0; k < tab.size(); ++k) {
-    const auto& f = tab[k];
-    if (!f.is_output) continue;
-    std::memcpy(const_cast<void*>(field_cptr(batch, f.offset)), p->pinned_bufs[k], f.elem * B);
-  }
   return 0;
 }
 

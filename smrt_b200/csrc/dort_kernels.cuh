@@ -72,6 +72,20 @@ SMRT_HD long long smrt_even(long long x) { return (x + 1) & ~1LL; }
 #define SMRT_DYN_SMEM(ptr) double* ptr = reinterpret_cast<double*>(simt::dynamic_smem(0))
 #endif
 
+// Re sqrt(eps_star / eps_medium): the refraction index ratio that maps the most refringent layer's nodes to a medium
+SMRT_DEV double real_index_of(cplx eps_star, cplx eps_medium) { return c_sqrt(c_div(eps_star, eps_medium)).re; }
+
+SMRT_DEV void set_error(int* status, int b, int code) {
+  // the error codes are enumerated values, not bits: the FIRST error wins (compare-and-swap on the low 4 bits; CTAs of
+  // different layers of one problem run concurrently); warnings are OR-ed separately into the high bits
+  int old = status[b];
+  while ((old & 15) == 0) {
+    const int seen = atomicCAS(&status[b], old, old | code);
+    if (seen == old) break;
+    old = seen;
+  }
+}
+
 // --------------------------------------------------------------------------------------------------------------------
 // kernel 1: layer optics
 // --------------------------------------------------------------------------------------------------------------------
@@ -95,16 +109,7 @@ SMRT_GLOBAL void __launch_bounds__(128) optics_kernel(KArgs A) {
   aux[1] = o.kk;
   aux[2] = o.f;
   aux[3] = 0.0;
-  if (o.status != ST_OK) atomicOr(&A.status[b], o.status);
-}
-
-// Re sqrt(eps_star / eps_medium): the refraction index ratio that maps the most refringent layer's nodes to a medium
-SMRT_DEV double real_index_of(cplx eps_star, cplx eps_medium) { return c_sqrt(c_div(eps_star, eps_medium)).re; }
-
-SMRT_DEV void set_error(int* status, int b, int code) {
-  // keep the first error code (low 4 bits); warnings are OR-ed separately
-  int old = status[b];
-  if ((old & 15) == 0) atomicOr(&status[b], code);
+  if (o.status != ST_OK) set_error(A.status, b, o.status);
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -366,6 +371,11 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
         if (tid == 0 && A.diag) {
           atomicAdd(&A.diag[0], sw);
           atomicAdd(&A.diag[1], 1);
+        }
+        if (sw >= SMRT_JACOBI_MAX_SWEEPS) {  // not converged (never seen): report it instead of using the vectors
+          if (tid == 0) set_error(A.status, b, ST_EIGEN);
+          failed = true;
+          break;
         }
       }
       __syncthreads();

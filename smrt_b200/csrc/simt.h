@@ -192,6 +192,10 @@ inline T __shfl_down_sync(unsigned m, T v, unsigned delta, int width = 32) {
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 inline int atomicOr(int* p, int v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicCAS(int* p, int compare, int v) {
+  __atomic_compare_exchange_n(p, &compare, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return compare;  // the value seen (== compare on success)
+}
 inline int atomicMax(int* p, int v) {
   int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
   while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {

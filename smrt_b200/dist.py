@@ -36,14 +36,14 @@ def solve_sharded(batch: ProblemBatch, rtsolver_options: Optional[dict] = None, 
     import torch
     import torch.distributed as dist
 
+    import os
+
     rank, world = dist.get_rank(), dist.get_world_size()
     shard = shard_batch(batch, world, rank)
+    device = int(os.environ.get("LOCAL_RANK", rank))  # the GPU this rank solves on AND stages the gather on
     if solve_fn is None:
-        import os
-
         from .model import solve_batch
 
-        device = int(os.environ.get("LOCAL_RANK", rank))
         out = solve_batch(shard, rtsolver_options, device=device)
     else:
         out = solve_fn(shard, rtsolver_options)
@@ -54,7 +54,9 @@ def solve_sharded(batch: ProblemBatch, rtsolver_options: Optional[dict] = None, 
     nmax = max(hi - lo for lo, hi in sizes)
     tail = out.values.shape[1:]
     use_cuda = dist.get_backend() == "nccl"
-    dev = torch.device("cuda", torch.cuda.current_device()) if use_cuda else torch.device("cpu")
+    dev = torch.device("cuda", device) if use_cuda else torch.device("cpu")
+    if use_cuda:
+        torch.cuda.set_device(device)  # NCCL picks the current device: one GPU per rank
     buf = torch.zeros((nmax,) + tail, dtype=torch.float64, device=dev)
     buf[:out.values.shape[0]] = torch.from_numpy(out.values).to(dev)
     st = torch.zeros(nmax, dtype=torch.int32, device=dev)

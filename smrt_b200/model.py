@@ -77,10 +77,14 @@ def check_dort_options(options: Optional[dict]) -> dict:
 
 
 class _PlanCache:
-    """One plan per (device, option set); plans own GBs of workspace, so they are reused across run() calls."""
+    """One plan per (device, option set); plans own GBs of workspace, so they are reused across run() calls and the
+    cache is bounded: least recently used plans are closed once the total workspace exceeds `budget_bytes` (or more
+    than `max_plans` are alive)."""
 
-    def __init__(self):
-        self._plans = {}
+    def __init__(self, budget_bytes: float = 48e9, max_plans: int = 8):
+        self._plans = {}  # key -> plan, in order of last use (dicts keep insertion order)
+        self.budget_bytes = budget_bytes
+        self.max_plans = max_plans
 
     def get(self, batch: ProblemBatch, opts: dict, device: int) -> capi.Plan:
         o = capi.make_options(batch, n_max_stream=opts["n_max_stream"], m_max=opts["m_max"],
@@ -89,14 +93,24 @@ class _PlanCache:
                               rayleigh_jeans_approximation=opts["rayleigh_jeans_approximation"], device=device)
         key = (device, o.mode, o.n_max_stream, o.m_max, o.max_layers, o.n_theta, o.n_inc, o.normalization,
                o.rayleigh_jeans, o.prune_deep_snowpack)
-        plan = self._plans.get(key)
-        if plan is None or plan.options.max_batch < batch.B:
-            if plan is not None:
-                plan.close()
+        plan = self._plans.pop(key, None)
+        if plan is not None and plan.options.max_batch < batch.B:
+            plan.close()
+            plan = None
+        if plan is None:
             o.max_batch = max(batch.B, 1)
             plan = capi.Plan(o)
-            self._plans[key] = plan
+        self._plans[key] = plan  # most recently used: last
+        self._evict(keep=key)
         return plan
+
+    def _evict(self, keep):
+        def total():
+            return sum(p.workspace_bytes for p in self._plans.values())
+
+        while len(self._plans) > 1 and (len(self._plans) > self.max_plans or total() > self.budget_bytes):
+            oldest = next(k for k in self._plans if k != keep)
+            self._plans.pop(oldest).close()
 
     def clear(self):
         for p in self._plans.values():
@@ -352,9 +366,22 @@ class DORT:
         self.options = check_dort_options(rtsolver_options)
         self.device = device
 
+    @staticmethod
+    def _instance_options(em, layer):
+        """Options the reference has already applied to an emmodel INSTANCE (``smrt/core/model.py:529-582`` builds
+        them with the model-level emmodel_options, which this seam never sees).  The one the device path implements is
+        dense_snow_correction="auto": IBA and the DMRT models then hold the inverted medium of a layer with
+        frac_volume > 0.5 (``iba.py:95-106``, ``dmrt_qca_shortrange.py:68-69``, ``core/layer.py:186-201``), which shows
+        in the instance's own frac_volume."""
+        f_em = getattr(em, "frac_volume", None)
+        f_layer = float(layer.frac_volume)
+        inverted = f_em is not None and f_layer > 0.5 and not np.isclose(float(f_em), f_layer)
+        return dict(dense_snow_correction="auto" if inverted else None)
+
     def solve(self, snowpack, emmodels, sensor, atmosphere=None, parallel_computation=None):
         ems = [type(em) for em in emmodels]
-        batch = pack_simulations([(sensor, snowpack)], ems, atmospheres=[atmosphere])
+        em_opts = [self._instance_options(em, layer) for em, layer in zip(emmodels, snowpack.layers)]
+        batch = pack_simulations([(sensor, snowpack)], ems, em_opts, atmospheres=[atmosphere])
         plan = _PLANS.get(batch, self.options, self.device)
         out = plan.solve_host(batch)
         _raise_or_nan(out, self.options)

@@ -17,8 +17,8 @@ from .labelled import DataArray, concat
 
 
 def dB(x):
-    """reference ``smrt/utils/__init__.py:13``"""
-    return 10 * np.log10(x)
+    """Ratio in dB; anything below 1e-20 reads -200 dB (reference ``smrt/utils/__init__.py:13-22``)."""
+    return 10 * np.log(np.maximum(x, 1e-20)) / np.log(10.0)
 
 
 def _is_sequence(x):
@@ -63,49 +63,57 @@ class Result:
         raise NotImplementedError("must be implemented in a subclass")
 
     # ------------------------------------------------------------------------------------------------- dataframes
+    # Behaviour pinned by the reference's smrt/core/test_result.py (run on the xarray stand-in) and by
+    # tests/test_host_api.py; written against labelled.DataArray.
+    @staticmethod
+    def _table(selection, label) -> pd.DataFrame:
+        """A selection as a pandas frame whose value column is `label` (coordinates that lost their dimension stay as
+        extra columns, like xarray's to_dataframe; a fully selected scalar becomes a one-row frame)."""
+        if selection.dims:
+            return selection.to_dataframe(name=label)
+        return pd.DataFrame({label: [float(selection)]})
+
+    def _channel_table(self, **kwargs) -> pd.DataFrame:
+        """One value column per channel of the channel map, rows = the coordinates common to every channel."""
+        if not self.channel_map:
+            raise SMRTError("No channel information is given in the result. Unable to index the result by channel.")
+        tables = [self._table(self.sel_data(channel=ch, **kwargs), ch) for ch in self.channel_map]
+        return pd.concat(tables, axis=1, join="inner")
+
+    def _with_mother_columns(self, table: pd.DataFrame, wide: bool) -> pd.DataFrame:
+        """Append the columns of the snowpack DataFrame given to Model.run (mother_df)."""
+        mother = self.mother_df
+        if wide:  # one row per snowpack, in the order of the mother frame: positional
+            out = pd.concat([table.reset_index(drop=True), mother.reset_index(drop=True)], axis=1)
+            out.index = mother.index
+            return out
+        if not mother.index.is_unique:
+            raise SMRTError("The index of the snowpack DataFrame in input of Model.run must be unique for "
+                            "calling to_dataframe. The index is used to join the result and original DataFrame.")
+        key = mother.index.names
+        if key[0] is None:  # unnamed index: it is the first level of the result's index
+            key = table.index.names[0]
+            if key in table.columns:
+                raise SMRTError("The index of the snowpack DataFrame in input of Model.run shall be named to "
+                                "avoid naming conflict in to_dataframe.")
+            mother = mother.rename_axis(key)
+        levels = table.index.names
+        return table.reset_index().join(mother, on=key).set_index(levels)
+
     def return_as_dataframe(self, name, channel_axis=None, **kwargs):
-        def to_df(x, nm):
-            return x.to_dataframe(name=nm) if x.dims else pd.DataFrame([float(x)], columns=[nm])
-
-        if channel_axis in ("column", "index"):
-            if not self.channel_map:
-                raise SMRTError("No channel information is given in the result. Unable to index the result by channel.")
-            df = pd.concat([to_df(self.sel_data(channel=ch, **kwargs), ch) for ch in self.channel_map], axis=1,
-                           join="inner")
-            if channel_axis == "index":
-                droplevel = not df.index.name and len(df.index) == 1 and df.index[0] == 0
-                df = df.stack()
-                if isinstance(df, pd.Series):
-                    df = pd.DataFrame(df, columns=[name])
-                df.index.set_names("channel", level=-1)
-                if droplevel:
-                    df = df.droplevel(0)
-        elif channel_axis is None:
-            df = to_df(self.sel_data(**kwargs), name)
-        else:
-            raise SMRTError('channel_axis argument must be None, "column" or "index"')
-
-        if self.mother_df is not None:
-            if channel_axis == "column":
-                df = df.reset_index(drop=True).join(self.mother_df.reset_index(drop=True))
-                df.index = self.mother_df.index
-            elif channel_axis is None:
-                if not self.mother_df.index.is_unique:
-                    raise SMRTError("The index of the snowpack DataFrame in input of Model.run must be unique for "
-                                    "calling to_dataframe. The index is used to join the result and original DataFrame.")
-                names = self.mother_df.index.names
-                if names[0] is None:
-                    nm = df.index.names[0]
-                    if nm in df.columns:
-                        raise SMRTError("The index of the snowpack DataFrame in input of Model.run shall be named to "
-                                        "avoid naming conflict in to_dataframe.")
-                    mother = self.mother_df.copy()
-                    mother.index.name = nm
-                    names = nm
-                else:
-                    mother = self.mother_df
-                df = df.reset_index().join(mother, on=names).set_index(df.index.names)
-        return df
+        if channel_axis is None:
+            table = self._table(self.sel_data(**kwargs), name)
+            return table if self.mother_df is None else self._with_mother_columns(table, wide=False)
+        if channel_axis == "column":
+            table = self._channel_table(**kwargs)
+            return table if self.mother_df is None else self._with_mother_columns(table, wide=True)
+        if channel_axis == "index":
+            wide = self._channel_table(**kwargs)
+            trivial = wide.index.name is None and wide.index.nlevels == 1 and list(wide.index) == [0]
+            long = wide.stack()  # the channel becomes the innermost (unnamed) index level
+            long = long.to_frame(name) if isinstance(long, pd.Series) else long
+            return long.droplevel(0) if trivial else long
+        raise SMRTError('channel_axis argument must be None, "column" or "index"')
 
     def to_series(self, **kwargs):
         return self.return_as_dataframe("out", channel_axis="column", **kwargs).iloc[0]
@@ -187,32 +195,33 @@ class ActiveResult(Result):
     mode = "A"
 
     def sel_data(self, channel=None, return_backscatter=False, **kwargs):
+        """Select by channel and / or coordinates; with return_backscatter ("natural" or "dB") the intensity at
+        theta == theta_inc is converted to sigma0 = 4 pi cos(theta) I."""
+        selectors = dict(kwargs)
         if channel is not None:
-            kwargs.update({k: v for k, v in self.channel_map[channel].items() if k in self.data.dims})
-        if return_backscatter:
-            theta = kwargs.pop("theta", None)
-            theta_inc = kwargs.pop("theta_inc", None)
-            if theta is not None and theta_inc is not None and not np.all(theta_inc == theta):
-                raise SMRTError("theta and theta_inc must be the same when returning backscatter")
-            if theta is None:
-                theta = theta_inc
-            if theta is None:
-                theta = self.data.theta_inc
+            selectors.update((k, v) for k, v in self.channel_map[channel].items() if k in self.data.dims)
+        if not return_backscatter:
+            return self.data.sel(drop=True, **selectors)
 
-            def select_theta(x, th, **kw):
-                if "theta" in x.coords:
-                    return x.sel(theta=th, theta_inc=th, **kw)
-                return x.sel(theta_inc=th, **kw)
+        # the backscatter direction: one angle for both theta and theta_inc
+        requested = [selectors.pop(k) for k in ("theta", "theta_inc") if k in selectors]
+        requested = [a for a in requested if a is not None]
+        if len(requested) == 2 and not np.all(requested[0] == requested[1]):
+            raise SMRTError("theta and theta_inc must be the same when returning backscatter")
+        angle = requested[0] if requested else self.data.theta_inc
+        bistatic = "theta" in self.data.coords  # the solver kept a separate viewing-angle axis
 
-            if _is_sequence(theta):
-                x = concat([select_theta(self.data, t, drop=True, **kwargs) for t in theta],
-                           pd.Index(theta, name="theta_inc"))
-            else:
-                x = select_theta(self.data, theta, drop=True, **kwargs)
-            th = theta.values if hasattr(theta, "values") else theta
-            x = (4 * np.pi * np.cos(np.deg2rad(th))) * x  # sigma0 = 4 pi cos(theta) I  (result.py:485)
-            return dB(x) if return_backscatter == "dB" else x
-        return self.data.sel(drop=True, **kwargs)
+        def at(a):
+            both = dict(theta=a, theta_inc=a) if bistatic else dict(theta_inc=a)
+            return self.data.sel(drop=True, **both, **selectors)
+
+        if _is_sequence(angle):
+            intensity = concat([at(a) for a in angle], pd.Index(list(angle), name="theta_inc"))
+        else:  # a number, or the theta_inc coordinate itself (point-wise selection of the diagonal theta == theta_inc)
+            intensity = at(angle)
+        cos_angle = np.cos(np.deg2rad(np.asarray(angle, dtype=float)))
+        sigma0 = (4 * np.pi * cos_angle) * intensity
+        return dB(sigma0) if return_backscatter == "dB" else sigma0
 
     def sigma(self, channel=None, name="sigma", **kwargs):
         return _strongsqueeze(self.sel_data(channel=channel, return_backscatter="natural", **kwargs).rename(name))
@@ -277,25 +286,30 @@ def make_result(sensor, *args, **kwargs):
 
 
 def concat_results(result_list, coord):
-    """Stack results along a new dimension (reference ``result.py:768-817``)."""
-    if isinstance(coord, tuple):
-        dim_name, dim_value = coord
-        index = pd.Index(dim_value, name=dim_name)
-    elif isinstance(coord, pd.Index):
-        index = coord
-        if index.name is None:
-            index.name = "snowpack_index"
+    """Stack results of one type along a new leading dimension; ragged inner dimensions (layers, streams) are padded
+    with NaN (the reference's ``concat_results``, ``smrt/core/result.py:768-817``, does an outer-join ``xr.concat``).
+
+    `coord`: ``(name, values)`` or a ``pandas.Index`` (an unnamed one is called "snowpack_index").
+    """
+    results = list(result_list)
+    if isinstance(coord, pd.Index):
+        index = coord if coord.name is not None else coord.rename("snowpack_index")
+    elif isinstance(coord, tuple):
+        index = pd.Index(coord[1], name=coord[0])
     else:
         raise SMRTError("unknown type for the coord argument")
-    cls = type(result_list[0])
-    if not all(type(r) is cls for r in result_list):
+    kind = type(results[0])
+    if any(type(r) is not kind for r in results):
         raise SMRTError("The results are not all of the same type")
-    if any(r.channel_map != result_list[0].channel_map for r in result_list):
-        channel_map = {ch: dict(**r.channel_map[ch], dim_name=dv) for r, dv in zip(result_list, dim_value)
-                       for ch in r.channel_map}
-    else:
-        channel_map = result_list[0].channel_map
-    data = concat([r.data for r in result_list], index, join="outer")
-    other = {v: concat([r.other_data[v] for r in result_list], index, join="outer")
-             for v in result_list[0].other_data}
-    return cls(data, channel_map=channel_map, other_data=other)
+
+    def stack(arrays):
+        return concat(list(arrays), index, join="outer")
+
+    channel_map = results[0].channel_map
+    if any(r.channel_map != channel_map for r in results):
+        # results of different sensors: every channel remembers where it came from.  The reference stores that value
+        # under the literal key "dim_name" (result.py:795-800), which no selection ever uses; kept for parity.
+        channel_map = {ch: {**r.channel_map[ch], "dim_name": value}
+                       for r, value in zip(results, index) for ch in r.channel_map}
+    other = {key: stack(r.other_data[key] for r in results) for key in results[0].other_data}
+    return kind(stack(r.data for r in results), channel_map=channel_map, other_data=other)

@@ -72,3 +72,27 @@ def test_rtsolver_plugin_seam_matches_the_reference(smrt_ref):
     np.testing.assert_allclose(ours.sigmaVV(), ref.sigmaVV(), rtol=1e-6)
     np.testing.assert_allclose(ours.sigmaHH(), ref.sigmaHH(), rtol=1e-6)
     np.testing.assert_allclose(ours.sigmaHV(), ref.sigmaHV(), rtol=1e-6)
+
+
+def test_rtsolver_plugin_seam_keeps_the_dense_snow_correction(smrt_ref):
+    """Model-level emmodel options are applied by the reference to its emmodel INSTANCES before the rtsolver sees
+    them (smrt/core/model.py:529-582): with dense_snow_correction="auto" a layer denser than 458 kg m-3 is solved as
+    the inverted medium (iba.py:95-106); the plugin must recover that from the instances."""
+    import smrt_b200
+
+    smrt = smrt_ref
+    sp = smrt.make_snowpack([0.3, 0.5, 100], "exponential", density=[300, 700, 850], temperature=[255.0, 260.0, 265.0],
+                            corr_length=[1e-4, 2e-4, 3e-4])
+    sensor = smrt.sensor_list.passive(36.5e9, 55)
+    for em_opts in (dict(dense_snow_correction="auto"), {}):
+        kw = dict(emmodel_options=em_opts, rtsolver_options=dict(n_max_stream=8))
+        ref = smrt.make_model("iba", "dort", **kw).run(sensor, sp, parallel_computation="none")
+        ours = smrt.make_model("iba", smrt_b200.DORT, **kw).run(sensor, sp, parallel_computation="none")
+        np.testing.assert_allclose(ours.TbV(), ref.TbV(), rtol=1e-9)
+        np.testing.assert_allclose(ours.TbH(), ref.TbH(), rtol=1e-9)
+    # the two settings differ by kelvins: the test would catch a dropped option
+    a = smrt.make_model("iba", "dort", emmodel_options=dict(dense_snow_correction="auto"),
+                        rtsolver_options=dict(n_max_stream=8)).run(sensor, sp, parallel_computation="none").TbV()
+    b = smrt.make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8)).run(sensor, sp,
+                                                                                 parallel_computation="none").TbV()
+    assert abs(a - b) > 0.1

@@ -11,7 +11,7 @@ if len(sys.argv) > 3:  # child: one configuration
     from smrt_b200 import capi
 
     streams, S = int(sys.argv[1]), int(sys.argv[2])
-    batch = bench.make_batch(S, seed=2)
+    batch = bench.make_batch("cfg2", S)
     plan = capi.Plan(capi.make_options(batch, n_max_stream=streams, serialize=True))
     for _ in range(3):
         out = plan.solve_host(batch)
