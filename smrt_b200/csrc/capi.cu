@@ -60,7 +60,9 @@ struct smrtb200_plan {
   int device = 0;
   int sm_count = 0;
   int chunk = 0;
-  bool use_global_scratch = false;
+  bool use_global_scratch = false;  // the BOUNDARY kernel keeps its matrices in the per-CTA global scratch
+  int eigen_variant = 0;            // 0: shared memory (h <= 64), 1: global scratch, 2: shared memory, 64 < h <= 128
+  bool boundary_mid = false;        // boundary kernel for 64 < h <= 128: one resident matrix + L2-resident scratch
   int eigen_grid = 0, boundary_grid = 0;
   int boundary_threads = SMRT_NT_B;
   int eigen_threads = SMRT_NT;
@@ -177,9 +179,22 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
   const smrt_host::Layout& L = p->layout;
 
   // shared-memory path if both kernels fit into the opt-in limit, else matrices in an L2-resident global scratch
-  p->use_global_scratch = (L.eigen_smem_bytes > kMaxSmemOptin) || (L.boundary_smem_bytes > kMaxSmemOptin);
-  p->eigen_smem = p->use_global_scratch ? L.eigen_vec_bytes : L.eigen_smem_bytes;
+  p->use_global_scratch = L.boundary_smem_bytes > kMaxSmemOptin;
+  if (L.hmax <= 64 && L.eigen_smem_bytes <= kMaxSmemOptin)
+    p->eigen_variant = 0;
+  else if (L.eigen_mid_smem_bytes > 0 && L.eigen_mid_smem_bytes <= kMaxSmemOptin && !std::getenv("SMRT_B200_NO_MID"))
+    p->eigen_variant = 2;
+  else
+    p->eigen_variant = 1;
+  p->eigen_smem = p->eigen_variant == 0 ? L.eigen_smem_bytes
+                  : p->eigen_variant == 2 ? L.eigen_mid_smem_bytes : L.eigen_vec_bytes;
   p->boundary_smem = p->use_global_scratch ? L.boundary_vec_bytes : L.boundary_smem_bytes;
+  if (p->use_global_scratch && L.boundary_mid_smem_bytes > 0 && L.boundary_mid_smem_bytes <= kMaxSmemOptin &&
+      !std::getenv("SMRT_B200_NO_MID")) {
+    p->boundary_mid = true;
+    p->use_global_scratch = false;
+    p->boundary_smem = L.boundary_mid_smem_bytes;
+  }
   int rc = 0;
   auto bail = [&](int code) {
     smrtb200_plan_destroy(p);
@@ -196,10 +211,11 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
     if (_e != cudaSuccess) return bail(fail(-2, "%s failed: %s", #expr, cudaGetErrorString(_e)));     \
   } while (0)
 
-  p->eigen_fn = p->use_global_scratch ? eigen_kernel<true> : eigen_kernel<false>;
+  p->eigen_fn = p->eigen_variant == 0 ? eigen_kernel<0> : p->eigen_variant == 2 ? eigen_kernel<2> : eigen_kernel<1>;
   // boundary kernel: 512 threads (128 registers) or 256 threads (255 registers: no spills in the register-tiled
   // eliminations); the block size is a plan parameter
   if (!p->use_global_scratch) p->boundary_threads = 256;  // measured: 14.9 ms per launch vs 17.9 ms with 512 (cfg 2)
+  if (p->boundary_mid) p->boundary_threads = 512;         // the tile maps of the mid instantiation are written for 512
   if (const char* e = std::getenv("SMRT_B200_BOUNDARY_THREADS")) {
     int v = std::atoi(e);
     if (v >= 64 && v <= SMRT_NT_B && (v % 64) == 0) p->boundary_threads = v;
@@ -208,7 +224,7 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
   // registers allow it too), or the instantiation that stages F and G into [T | R] does (h <= 64, <= 113 KB per CTA)
   const size_t two_per_sm = (size_t)(228 * 1024) / 2 - 1024 - 256;
   bool stream_fg = false;
-  if (!p->use_global_scratch && !std::getenv("SMRT_B200_BOUNDARY_THREADS")) {
+  if (!p->use_global_scratch && !p->boundary_mid && !std::getenv("SMRT_B200_BOUNDARY_THREADS")) {
     if (L.boundary_smem_bytes <= two_per_sm) {
       p->boundary_threads = 128;
     } else if (L.boundary_stream_smem_bytes > 0 && L.boundary_stream_smem_bytes <= two_per_sm) {
@@ -221,13 +237,15 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
     if (!want) {
       if (stream_fg) p->boundary_threads = 256;
       stream_fg = false;
-    } else if (!p->use_global_scratch && L.boundary_stream_smem_bytes > 0) {
+    } else if (!p->use_global_scratch && !p->boundary_mid && L.boundary_stream_smem_bytes > 0) {
       stream_fg = true;
       p->boundary_threads = 128;
     }
   }
   if (stream_fg) p->boundary_smem = L.boundary_stream_smem_bytes;
-  if (p->use_global_scratch)
+  if (p->boundary_mid)
+    p->boundary_fn = boundary_kernel<false, 512, false, true>;
+  else if (p->use_global_scratch)
     p->boundary_fn = boundary_kernel<true, SMRT_NT_B>;
   else if (stream_fg)
     p->boundary_fn = boundary_kernel<false, 128, true>;
@@ -249,19 +267,22 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
                                    optin - (int)fa.sharedSizeBytes));
   }
   int occ_e = 0, occ_b = 0;
-  p->eigen_threads = p->use_global_scratch ? SMRT_NT : SMRT_NT_SMEM;
+  p->eigen_threads = p->eigen_variant == 0 ? SMRT_NT_SMEM : p->eigen_variant == 2 ? SMRT_NT_MID : SMRT_NT;
   PLAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, p->eigen_fn, p->eigen_threads, p->eigen_smem));
   PLAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, p->boundary_fn, p->boundary_threads, p->boundary_smem));
   if (occ_e < 1 || occ_b < 1) return bail(fail(-2, "kernels do not fit on an SM (occupancy %d / %d)", occ_e, occ_b));
-  if (p->use_global_scratch) {  // keep the scratch L2-resident: at most 2 CTAs per SM
-    occ_e = std::min(occ_e, 2);
-    occ_b = std::min(occ_b, 2);
-  }
+  // keep the scratch L2-resident: at most 2 CTAs per SM
+  if (p->eigen_variant == 1) occ_e = std::min(occ_e, 2);
+  if (p->use_global_scratch) occ_b = std::min(occ_b, 2);
   p->eigen_grid = p->sm_count * occ_e;
   p->boundary_grid = p->sm_count * occ_b;
   // stride in doubles, a multiple of 16 (128 B): the kernels use 16-byte vector accesses on the per-CTA scratch
-  p->scratch_stride =
-      p->use_global_scratch ? ((std::max(L.eigen_scratch_doubles, L.boundary_scratch_doubles) + 31) & ~15LL) : 0;
+  const bool any_scratch = p->use_global_scratch || p->eigen_variant == 1 || p->boundary_mid;
+  long long need = 0;
+  if (p->eigen_variant == 1) need = std::max(need, L.eigen_scratch_doubles);
+  if (p->use_global_scratch) need = std::max(need, L.boundary_scratch_doubles);
+  if (p->boundary_mid) need = std::max(need, L.boundary_mid_scratch_doubles);
+  p->scratch_stride = any_scratch ? ((need + 31) & ~15LL) : 0;
 
   // chunk: enough problems to fill the machine several times, bounded by a workspace budget of ~6 GB per slot
   {
@@ -293,7 +314,7 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
     PLAN_TRY(dev_alloc(p, &s.kmin, CL * SMRT_MAX_MODES));
     PLAN_TRY(dev_alloc(p, &s.scat_flag, CL));
     PLAN_TRY(dev_alloc(p, &s.counters, 2));
-    if (p->use_global_scratch)
+    if (any_scratch)
       PLAN_TRY(dev_alloc(p, &s.scratch, (size_t)std::max(p->eigen_grid, p->boundary_grid) * (size_t)p->scratch_stride));
     PLAN_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
   }

@@ -41,6 +41,9 @@ struct Layout {
   long long eig_stride;            // doubles per (problem, layer)
   int eig_off[SMRT_MAX_MODES];
   size_t eigen_smem_bytes, boundary_smem_bytes;            // dynamic shared memory of the shared-memory path
+  size_t eigen_mid_smem_bytes;                              // ... of the eigen instantiation for 64 < h <= 128 (0: n/a)
+  size_t boundary_mid_smem_bytes;                           // ... of the boundary instantiation for 64 < h <= 128 (0: n/a)
+  long long boundary_mid_scratch_doubles;                   // its per-CTA global scratch
   size_t boundary_stream_smem_bytes;                        // ... of the boundary instantiation that stages F and G (0: n/a)
   size_t eigen_vec_bytes, boundary_vec_bytes;              // vector region only (global-scratch path)
   long long eigen_scratch_doubles, boundary_scratch_doubles;  // per-CTA matrix scratch
@@ -78,9 +81,15 @@ inline Layout make_layout(const smrtb200_options& o) {
   L.eigen_vec_bytes = eigen_vec_doubles(L.n, L.hmax, L.K) * sizeof(double);
   L.eigen_scratch_doubles = (long long)eigen_mat_doubles(L.hmax);
   L.eigen_smem_bytes = L.eigen_vec_bytes + (size_t)L.eigen_scratch_doubles * sizeof(double);
+  L.eigen_mid_smem_bytes =
+      (L.hmax > 64 && L.hmax <= 128) ? L.eigen_vec_bytes + eigen_mat_doubles(L.hmax, true) * sizeof(double) : 0;
   L.boundary_vec_bytes = boundary_vec_doubles(L.n, L.hmax, L.mode) * sizeof(double);
   L.boundary_scratch_doubles = (long long)boundary_mat_doubles(L.hmax, L.nrhs_max);
   L.boundary_smem_bytes = L.boundary_vec_bytes + (size_t)L.boundary_scratch_doubles * sizeof(double);
+  const bool mid = L.hmax > 64 && L.hmax <= 128;
+  L.boundary_mid_smem_bytes =
+      mid ? L.boundary_vec_bytes + boundary_mid_smem_doubles(L.hmax, L.nrhs_max) * sizeof(double) : 0;
+  L.boundary_mid_scratch_doubles = mid ? (long long)boundary_mid_scratch_doubles(L.hmax) : 0;
   // F / G staged into [T | R] (deferred-store products): blocks of <= 64 unknowns only
   L.boundary_stream_smem_bytes =
       (L.hmax <= 64) ? L.boundary_vec_bytes + boundary_mat_doubles(L.hmax, L.nrhs_max, true) * sizeof(double) : 0;

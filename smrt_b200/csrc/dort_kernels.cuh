@@ -19,6 +19,7 @@
 #define SMRT_AUX_STRIDE 4     // per (problem, layer): iba_coeff, kk, f_eff, spare
 #define SMRT_NT 256           // threads per CTA of the eigen kernel, global-scratch instantiation (large stream counts)
 #define SMRT_NT_SMEM 128      // ... shared-memory instantiation (h <= 64): 16 Jacobi groups of 8 lanes, 3 CTAs per SM
+#define SMRT_NT_MID 512       // ... shared-memory instantiation for 64 < h <= 128: 32 Jacobi groups of 16 lanes, 1 CTA per SM
 #define SMRT_NT_B 512         // max threads per CTA of the boundary kernel
 
 struct KArgs {
@@ -120,14 +121,26 @@ SMRT_GLOBAL void __launch_bounds__(128) optics_kernel(KArgs A) {
 // matrix region: A1 (X- -> L -> M -> W -> E~+, hmax x (hmax + 3)), A2 (X+ -> C, hmax x (hmax + 1)): 68 KB at 32
 // streams, so that three CTAs fit on an SM
 #define SMRT_PANEL 8  // columns of L staged per step of the in-place product M = C^T L
+// the column of zeros standing for missing Jacobi columns: 8 lanes x 8 rows, or 16 lanes x 8 rows beyond 64 unknowns
+SMRT_HD int eigen_zcol_doubles(int hmax) { return hmax > 64 ? 128 : 64; }
 SMRT_HD size_t eigen_vec_doubles(int n, int hmax, int K) {
-  return ((size_t)64 + 4 * n + 6 * hmax + 4 * K + (size_t)SMRT_PANEL * hmax + 12 + 1) & ~(size_t)1;
+  return ((size_t)eigen_zcol_doubles(hmax) + 4 * n + 6 * hmax + 4 * K + (size_t)SMRT_PANEL * hmax + 12 + 1) & ~(size_t)1;
 }
 SMRT_HD size_t eigen_mat1_doubles(int hmax) { return (size_t)hmax * jacobi_ld(hmax); }  // even: A2 16-byte aligned
-SMRT_HD size_t eigen_mat_doubles(int hmax) { return eigen_mat1_doubles(hmax) + (size_t)hmax * (hmax + 1); }
+// packed: the second matrix (X+ -> C) holds its lower triangle only, packed by columns
+SMRT_HD size_t eigen_mat_doubles(int hmax, bool packed = false) {
+  return eigen_mat1_doubles(hmax) + (packed ? ((size_t)hmax * (hmax + 1) / 2 + 1) & ~(size_t)1 : (size_t)hmax * (hmax + 1));
+}
 
-template <bool kGlobalScratch>
-SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlobalScratch ? 1 : 3) eigen_kernel(KArgs A) {
+// kVariant 0: matrices in shared memory, h <= 64, 128 threads, three CTAs per SM
+//          1: matrices in a per-CTA global (L2-resident) scratch, any h, 256 threads
+//          2: matrices in shared memory, 64 < h <= 128, 512 threads, one CTA per SM: X+ / C packed (lower triangle),
+//             Jacobi groups of 16 lanes with 6 or 8 rows per lane
+template <int kVariant>
+SMRT_GLOBAL void __launch_bounds__(kVariant == 1 ? SMRT_NT : (kVariant == 2 ? SMRT_NT_MID : SMRT_NT_SMEM),
+                                   kVariant == 0 ? 3 : 1) eigen_kernel(KArgs A) {
+  constexpr bool kGlobalScratch = kVariant == 1;
+  constexpr bool kPacked = kVariant == 2;
   SMRT_DYN_SMEM(smem);
   SMRT_SHARED int s_item;
   SMRT_SHARED int s_ctrl[8];
@@ -139,7 +152,8 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
   const int K = A.K;
 
   double* zcol = smem;  // a column of zeros: stands for the missing columns of the register-blocked Jacobi
-  double* mu = zcol + 64;
+  const int nz = eigen_zcol_doubles(hmax);
+  double* mu = zcol + nz;
   double* w = mu + n;
   double* norm0 = w + n;
   double* gvec = norm0 + 2 * n;
@@ -157,7 +171,7 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
   double* A1 = mats;
   double* A2 = mats + eigen_mat1_doubles(hmax);
 
-  for (int j = tid; j < 64; j += NT) zcol[j] = 0.0;
+  for (int j = tid; j < nz; j += NT) zcol[j] = 0.0;
   for (int j = tid; j < 2 * K; j += NT) {
     double s, c;
     sincospi((double)j / (double)K, &s, &c);
@@ -224,6 +238,10 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
       const int ld = (h & 1) ? h : h + 1;
       const int ld1 = jacobi_ld(h);
       const double coef = (m == 0) ? 0.5 : 0.25;
+      LowerMat<kPacked> C2;  // X+ -> C: full (ld) or packed lower triangle
+      C2.p = A2;
+      C2.ld = ld;
+      C2.h = h;
 
       // phase matrix Fourier mode m on (mu_s > 0) x (mu_i > 0 | mu_i < 0): A1 <- P++, A2 <- (P+-) D.
       // Only the stream pairs js <= ji are evaluated: the phase matrix is reciprocal, P_ab(i, s) = P_ba(s, i) q_a / q_b
@@ -246,17 +264,22 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
         } else {
           rayleigh_phase_mode(m, mu[js], mui, ks, pv);
         }
-        double* dst = backward ? A2 : A1;
-        const int ldd = backward ? ld : ld1;
         for (int ps = 0; ps < npol; ++ps)
           for (int pi = 0; pi < npol; ++pi) {
             const int a = js * npol + ps, c = ji * npol + pi;
             double v = pv[ps * npol + pi];
             if (backward && pi == 2) v = -v;
-            SMRT_AT(dst, ldd, a, c) = v;
-            if (js != ji) {  // mirrored block: row (ji, pi), column (js, ps)
-              const double qr = ((pi == 2) ? 2.0 : 1.0) / ((ps == 2) ? 2.0 : 1.0);
-              SMRT_AT(dst, ldd, c, a) = v * qr;
+            // mirrored block: row (ji, pi), column (js, ps)
+            const double qr = ((pi == 2) ? 2.0 : 1.0) / ((ps == 2) ? 2.0 : 1.0);
+            if (!backward) {
+              SMRT_AT(A1, ld1, a, c) = v;
+              if (js != ji) SMRT_AT(A1, ld1, c, a) = v * qr;
+            } else if (!kPacked) {
+              SMRT_AT(A2, ld, a, c) = v;
+              if (js != ji) SMRT_AT(A2, ld, c, a) = v * qr;
+            } else {  // lower triangle only
+              if (a >= c) C2.at(a, c) = v;
+              if (js != ji) C2.at(c, a) = v * qr;
             }
           }
       }
@@ -270,7 +293,18 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
         if (A.normalization != 0) {
           if (m == 0) {
             double rs = 0.0;
-            for (int c = 0; c < h; ++c) rs += (SMRT_AT(A1, ld1, a, c) + SMRT_AT(A2, ld, a, c)) * w[c / npol];
+            if (!kPacked) {
+              for (int c = 0; c < h; ++c) rs += (SMRT_AT(A1, ld1, a, c) + SMRT_AT(A2, ld, a, c)) * w[c / npol];
+            } else {
+              // the part of the backward half above the diagonal follows from reciprocity:
+              // P(a, c) = P(c, a) q_a / q_c with q = (1, 1, 2) for (V, H, U)
+              const double qa = (p == 2) ? 2.0 : 1.0;
+              for (int c = 0; c <= a; ++c) rs += (SMRT_AT(A1, ld1, a, c) + C2.at(a, c)) * w[c / npol];
+              for (int c = a + 1; c < h; ++c) {
+                const double qc = (c % npol == 2) ? 2.0 : 1.0;
+                rs += (SMRT_AT(A1, ld1, a, c) + C2.at(c, a) * (qa / qc)) * w[c / npol];
+              }
+            }
             // A row sum = -coef * rs ; norm_0 = -ks / rowsum
             norm = ks / (coef * rs);
             norm0[a] = norm;
@@ -296,12 +330,24 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
       }
       // X- = diag(ke/mu) - g Ps++ g + g Ps+-' g   (A1),   X+ = diag(ke/mu) - g Ps++ g - g Ps+-' g   (A2)
       // (gq = g / q: the reciprocity weight of the row is folded into the row scale)
-      SMRT_FOR_2D(a, c, h, h) {
-        double sc = gq[a] * gvec[c];
-        double x1 = sc * SMRT_AT(A1, ld1, a, c), x2 = sc * SMRT_AT(A2, ld, a, c);
-        double d = (a == c) ? dk[a] : 0.0;
-        SMRT_AT(A1, ld1, a, c) = d - x1 + x2;
-        SMRT_AT(A2, ld, a, c) = d - x1 - x2;
+      if (!kPacked) {
+        SMRT_FOR_2D(a, c, h, h) {
+          double sc = gq[a] * gvec[c];
+          double x1 = sc * SMRT_AT(A1, ld1, a, c), x2 = sc * SMRT_AT(A2, ld, a, c);
+          double d = (a == c) ? dk[a] : 0.0;
+          SMRT_AT(A1, ld1, a, c) = d - x1 + x2;
+          SMRT_AT(A2, ld, a, c) = d - x1 - x2;
+        }
+      } else {  // both matrices are symmetric and only their lower triangles are read from here on
+        SMRT_FOR_2D(a, c, h, h) {
+          if (a >= c) {
+            double sc = gq[a] * gvec[c];
+            double x1 = sc * SMRT_AT(A1, ld1, a, c), x2 = sc * C2.at(a, c);
+            double d = (a == c) ? dk[a] : 0.0;
+            SMRT_AT(A1, ld1, a, c) = d - x1 + x2;
+            C2.at(a, c) = d - x1 - x2;
+          }
+        }
       }
       __syncthreads();
 
@@ -313,7 +359,16 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
         int which = tid / half;
         tm.rank = tid % half;
         tm.bar_id = 1 + which;
-        int bad = team_cholesky_fast(tm, which == 0 ? A1 : A2, which == 0 ? ld1 : ld, h, which == 0 ? sigma : nrm);
+        int bad;
+        if (which == 0) {
+          LowerMat<false> X1;
+          X1.p = A1;
+          X1.ld = ld1;
+          X1.h = h;
+          bad = team_cholesky_fast(tm, X1, h, sigma);
+        } else {
+          bad = team_cholesky_fast(tm, C2, h, nrm);
+        }
         if (tm.rank == 0) s_ctrl[4 + which] = bad;
       }
       __syncthreads();
@@ -336,7 +391,7 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
         // columns are zero above their diagonal, so a common lower summation bound is exact)
         for (int e = tid; e < h * ((pw + 3) >> 2); e += NT) {
           const int i = e % h, jq = (e / h) << 2;
-          const double* cc = A2 + (size_t)i * ld;
+          const double* cc = C2.col(i);
           const double* p0 = panel + (size_t)jq * h;
           const int nj = (pw - jq < 4) ? (pw - jq) : 4;
           const double* p1 = p0 + ((nj > 1) ? h : 0);
@@ -361,13 +416,14 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
 
       // singular values / right rotations by one-sided Jacobi: A1 <- W = U Sigma
       {
-        const bool fastj = h <= 64;
+        const bool fastj = kPacked ? (h <= 128) : (h <= 64);
         if (fastj) {  // zero pad rows of the register-blocked Jacobi operand: rows [h, ld1 - 2)
           const int npad = ld1 - 2 - h;
           for (int e = tid; e < npad * h; e += NT) SMRT_AT(A1, ld1, h + e % npad, e / npad) = 0.0;
           __syncthreads();
         }
-        int sw = fastj ? block_jacobi_svd_fast(A1, ld1, h, nrm, zcol) : block_jacobi_svd(A1, ld1, h, s_ctrl);
+        int sw = fastj ? block_jacobi_svd_fast(A1, ld1, h, nrm, zcol, kPacked ? 16 : 8)
+                       : block_jacobi_svd(A1, ld1, h, s_ctrl);
         if (tid == 0 && A.diag) {
           atomicAdd(&A.diag[0], sw);
           atomicAdd(&A.diag[1], 1);
@@ -393,7 +449,7 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
       {
         Team tm = block_team();
         team_gemm(
-            tm, h, h, h, [&](int i, int k) { return (k <= i) ? SMRT_AT(A2, ld, i, k) : 0.0; },
+            tm, h, h, h, [&](int i, int k) { return (k <= i) ? C2.at(i, k) : 0.0; },
             [&](int k, int j) { return SMRT_AT(A1, ld1, k, j); },
             [&](int i, int j, double acc) { rG[(size_t)j * h + i] = -acc / sigma[j]; });
       }
@@ -401,9 +457,9 @@ SMRT_GLOBAL void __launch_bounds__(kGlobalScratch ? SMRT_NT : SMRT_NT_SMEM, kGlo
 
       // E~+ = C^-T W: back substitution with the upper-triangular C^T, in place on the columns of A1 (two lanes per
       // column, blocks of 8 unknowns in registers); gq is dead since the formation of X+-: reciprocal diagonal of C
-      for (int j = tid; j < h; j += NT) gq[j] = 1.0 / SMRT_AT(A2, ld, j, j);
+      for (int j = tid; j < h; j += NT) gq[j] = 1.0 / C2.at(j, j);
       __syncthreads();
-      block_backsolve_lt(A2, ld, A1, ld1, h, gq);
+      block_backsolve_lt(C2, A1, ld1, h, gq);
       __syncthreads();
 
       // store k, F = s (E~+ - E~-) / 2, G = s (E~+ + E~-) / 2
@@ -454,6 +510,21 @@ SMRT_HD size_t boundary_mat_doubles(int hmax, int nrhs_max, bool stream = false)
          (size_t)hmax * (hmax + 1) + (size_t)(hmax + 1) * (2 * hmax + nrhs_max) + 4 * (size_t)hmax * nrhs_max + 16;
 }
 
+// kMid instantiation (64 < h <= 128, 512 threads, one CTA per SM): shared memory holds ONE h x h matrix (the block being
+// factorised in product form, then the B operand of the products), the staging panels of the GEMMs, the pivot-row
+// exchange buffer and the right-hand sides; the other h x h blocks live in an L2-resident per-CTA global scratch.
+SMRT_HD int boundary_mid_ld(int h) { return (h + 7) & ~7; }
+SMRT_HD size_t boundary_mid_smem_doubles(int hmax, int nrhs_max) {
+  const size_t ldm = boundary_mid_ld(hmax);
+  return (size_t)1024 + ldm /* matvec scratch, reciprocal pivots */ + (size_t)hmax * ldm /* M1 */ +
+         4096 /* GEMM staging */ + 2 * SMRT_GJ_NB * 32 /* pivot-row exchange */ + ldm * nrhs_max /* rhs block */ +
+         4 * (size_t)hmax * nrhs_max + 16;
+}
+// global scratch: gA (A22 -> S), gB (Y~ -> R of the stack), gC (K), gF / gG (generated operands of non-scattering layers)
+SMRT_HD size_t boundary_mid_scratch_doubles(int hmax) {
+  return 3 * (size_t)hmax * boundary_mid_ld(hmax) + 2 * (size_t)hmax * hmax + 16;
+}
+
 struct BoundaryCtx {
   // per problem
   int b, nl, n_air, n_incs, npol_out;
@@ -478,7 +549,7 @@ struct BoundaryCtx {
     prof_t0 = now_;                                                \
   }
 #endif
-template <bool kGlobalScratch, int kMaxThreads, bool kStreamFG = false>
+template <bool kGlobalScratch, int kMaxThreads, bool kStreamFG = false, bool kMid = false>
 SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kernel(KArgs A) {
   SMRT_DYN_SMEM(smem);
   SMRT_SHARED int s_item;
@@ -535,6 +606,31 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
   double* svec = btop + szr;
   double* ytr = svec + szr;
   double* vvec = ytr + szr;
+  // kMid: one resident matrix, the rest in the global scratch
+  const int ldm_max = boundary_mid_ld(hmax);
+  double* M1 = nullptr;
+  double* stage = nullptr;
+  double* xch = nullptr;
+  double* rhsM = nullptr;
+  double *gA = nullptr, *gB = nullptr, *gC = nullptr, *gF = nullptr, *gG = nullptr;
+  if (kMid) {
+    GJV = mats;  // scratch of the block matrix-vector products (1024 doubles)
+    pivinv = GJV + 1024;
+    M1 = pivinv + ldm_max;
+    stage = M1 + (size_t)hmax * ldm_max;
+    xch = stage + 4096;
+    rhsM = xch + 2 * SMRT_GJ_NB * 32;
+    btop = rhsM + (size_t)ldm_max * nrhs_max;
+    svec = btop + szr;
+    ytr = svec + szr;
+    vvec = ytr + szr;
+    gA = A.scratch + (size_t)blockIdx.x * A.scratch_stride;
+    gB = gA + (size_t)hmax * ldm_max;
+    gC = gB + (size_t)hmax * ldm_max;
+    gF = gC + (size_t)hmax * ldm_max;
+    gG = gF + (size_t)hmax * hmax;
+    BR = gB;
+  }
 
   long long prof_t0 = 0;
 #ifndef SMRT_SIMT_EMULATION
@@ -728,7 +824,22 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
           return false;
         };
         bool waitF = false, waitG = false;
-        if (kStreamFG) {
+        if (kMid) {
+          // the operands stay where they are (layer record in global memory, L2 after the first touch); a non-scattering
+          // layer gets F = I, G = 0 generated in the global scratch
+          if (scat) {
+            BF = const_cast<double*>(rF_l);
+            BG = const_cast<double*>(rG_l);
+          } else {
+            BF = gF;
+            BG = gG;
+            SMRT_FOR_2D(i, j, h, h) {
+              gF[(size_t)j * h + i] = (i == j) ? 1.0 : 0.0;
+              gG[(size_t)j * h + i] = 0.0;
+            }
+            for (int a = tid; a < h; a += NT) kvec[a] = ke / mu[a / npol];
+          }
+        } else if (kStreamFG) {
           // formation phase: F in the left block of T, G in the right block (compact, ld = h)
           BF = TT;
           BG = TT + (size_t)h * ldp;
@@ -844,7 +955,9 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
 
         // right-hand sides ---------------------------------------------------------------------- dort.py:375-441
         const int r = have_prev ? (h < h_prev ? h : h_prev) : 0;
-        double* Trhs = TT + (size_t)(2 * h) * ldp;  // b_bot lives in the augmented columns of T
+        const int ldm = boundary_mid_ld(h);            // kMid: leading dimension of the resident matrix and of the rhs block
+        const int ldt = kMid ? ldm : ldp;
+        double* Trhs = kMid ? rhsM : TT + (size_t)(2 * h) * ldp;  // b_bot lives in the augmented columns of T
         if (nr > 0) {
           const double Tl = A.temperature[bL + l];
           const double Bl = (thermal && Tl > 0.0) ? planck_function(freq, Tl, A.rayleigh_jeans) : 0.0;
@@ -871,7 +984,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
             }
             if (l < l_end && a < r && src_prev) vb += Ttprev[a] * SMRT_AT(svec, h_prev, a, c);
             SMRT_AT(btop, h, a, c) = vt;
-            SMRT_AT(Trhs, ldp, a, c) = vb;
+            SMRT_AT(Trhs, ldt, a, c) = vb;
           }
         }
         __syncthreads();
@@ -896,6 +1009,133 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
             }
           }
         }
+        if constexpr (kMid) {
+          // ------------------------------------------------------------------------------------------------------------
+          // 64 < h <= 128: one resident h x h matrix (M1), product-form eliminations, every other block in the L2-resident
+          // global scratch; same algebra as the resident path below
+          // ------------------------------------------------------------------------------------------------------------
+          const double* Fo = BF;
+          const double* Go = BG;
+          int* kof = rowstep;  // inverse of the pivot order: kof[rowof[k]] = k
+          // coupling operator of the stack below: R' = T_top(l+1) R(l+1) T_bottom(l) D on the common streams
+          SMRT_FOR_2D(i, k, r, r) { SMRT_AT(gB, ldr_prev, i, k) *= Ttprev[i] * (Tb[k] * Dsg[k]); }
+          __syncthreads();
+          // A21 = F - Rb D G - R' G -> M1 ;  A22 = (G - Rb D F - R' F) t -> gA
+          mid_gemm<false, false, 8>(h, r, h, 0, r, gB, nullptr, ldr_prev, Go, h, stage, [&](int i, int j, double acc, double) {
+            const size_t e = (size_t)j * h + i;
+            M1[(size_t)j * ldm + i] = Fo[e] - RbD[i] * Go[e] - acc;
+          });
+          mid_gemm<false, false, 8>(h, r, h, 0, r, gB, nullptr, ldr_prev, Fo, h, stage, [&](int i, int j, double acc, double) {
+            const size_t e = (size_t)j * h + i;
+            gA[(size_t)j * ldm + i] = (Go[e] - RbD[i] * Fo[e] - acc) * tvec[j];
+          });
+          __syncthreads();
+          SMRT_PHASE(3)  // right-hand sides, formation of [A21 | A22]
+          // A21 in product form (the right-hand sides ride along), then A22 in chunks of 32 columns
+          if (block_gj_factor(M1, ldm, Trhs, ldm, h, nr, rowof, pivinv, &s_ctrl[6])) {
+            failed = true;
+            break;
+          }
+          for (int k = tid; k < h; k += NT) {
+            ipiv[k] = tvec[k] * pivinv[k];
+            kof[rowof[k]] = k;
+          }
+          __syncthreads();
+          SMRT_FOR_2D(k, c, h, nr) { SMRT_AT(ytr, h, k, c) = SMRT_AT(Trhs, ldm, rowof[k], c) * ipiv[k]; }
+          // Y~ = diag(t) A21^-1 A22 -> gB (the operator of the stack below is dead)
+          for (int c0 = 0; c0 < h; c0 += 32) {
+            const int nc = (h - c0 < 32) ? (h - c0) : 32;
+            gj_apply_chunk(
+                M1, ldm, h, rowof, nc, xch, [&](int i, int c) { return gA[(size_t)(c0 + c) * ldm + i]; },
+                [&](int i, int c, double v) {
+                  const int k = kof[i];
+                  gB[(size_t)(c0 + c) * ldm + k] = v * ipiv[k];
+                });
+          }
+          __syncthreads();
+          SMRT_PHASE(4)  // first elimination
+          // Y~ becomes the resident B operand of  P = F - G Y~,  K = G - F Y~ ;  S = D P - Rt K -> gA,  K -> gC
+          // (l > 0: both TRANSPOSED, so that R_new = K S^-1 = (S^-T K^T)^T comes out of the same row elimination)
+          SMRT_FOR_2D(i, j, h, h) { M1[(size_t)j * ldm + i] = gB[(size_t)j * ldm + i]; }
+          __syncthreads();
+          const bool transposed = l > 0;
+          for (int n0 = 0; n0 < h; n0 += 64) {
+            mid_gemm<true, true, 4>(h, h, h, n0, h, Go, Fo, h, M1, ldm, stage, [&](int i, int j, double c1, double c2) {
+              const size_t e = (size_t)j * h + i;
+              const double pv = Fo[e] - c1;
+              const double kv = Go[e] - c2;
+              const double sv = Dsg[i] * pv - Rt[i] * kv;
+              const size_t o = transposed ? (size_t)i * ldm + j : (size_t)j * ldm + i;
+              gA[o] = sv;
+              gC[o] = kv;
+            });
+          }
+          // v = F y~r ;  b' = b_top - D (G y~r) + Rt v  (in the right-hand-side block)
+          if (nr == 1) {
+            block_matvec_dual(h, h, Go, Fo, h, ytr, GJV, [&](int i, double c1, double c2) {
+              vvec[i] = c2;
+              Trhs[i] = btop[i] - Dsg[i] * c1 + Rt[i] * c2;
+            });
+          } else {
+            if (nr > 0) {
+              block_gemm_dual(NT, h, nr, h, Go, Fo, h, ytr, h, [&](int i, int c, double c1, double c2) {
+                SMRT_AT(vvec, h, i, c) = c2;
+                SMRT_AT(Trhs, ldm, i, c) = SMRT_AT(btop, h, i, c) - Dsg[i] * c1 + Rt[i] * c2;
+              });
+            }
+            __syncthreads();
+          }
+          // S (or S^T) -> M1 (the products were stored by other threads, and M1 was their B operand)
+          __syncthreads();
+          SMRT_FOR_2D(i, j, h, h) { M1[(size_t)j * ldm + i] = gA[(size_t)j * ldm + i]; }
+          __syncthreads();
+          SMRT_PHASE(5)  // extraction, products P / K / S, b'
+          if (l > 0) {
+            // [S^T | K^T]: rows of S^-T K^T = columns of R_new; b' is not touched
+            if (block_gj_factor(M1, ldm, Trhs, ldm, h, 0, rowof, pivinv, &s_ctrl[6])) {
+              failed = true;
+              break;
+            }
+            for (int k = tid; k < h; k += NT) kof[rowof[k]] = k;
+            __syncthreads();
+            for (int c0 = 0; c0 < h; c0 += 32) {
+              const int nc = (h - c0 < 32) ? (h - c0) : 32;
+              gj_apply_chunk(
+                  M1, ldm, h, rowof, nc, xch, [&](int i, int c) { return gC[(size_t)(c0 + c) * ldm + i]; },
+                  [&](int i, int c, double v) {
+                    const int k = kof[i];
+                    gB[(size_t)k * ldm + c0 + c] = v * pivinv[k];  // R_new(c0 + c, k)
+                  });
+            }
+            __syncthreads();
+            SMRT_PHASE(6)  // second elimination
+            if (nr == 1) {  // s = v + R_new b'
+              block_matvec_dual(h, h, gB, (const double*)nullptr, ldm, Trhs, GJV,
+                                [&](int i, double acc, double) { svec[i] = vvec[i] + acc; });
+            } else if (nr > 0) {
+              block_gemm_ptr(NT, h, nr, h, gB, ldm, [&](int c) { return Trhs + (size_t)c * ldm; },
+                             [&](int i, int c, double acc) { SMRT_AT(svec, h, i, c) = SMRT_AT(vvec, h, i, c) + acc; });
+            }
+            for (int a = tid; a < h; a += NT) Ttprev[a] = Tt[a];
+            h_prev = h;
+            ldr_prev = ldm;
+            have_prev = true;
+            src_prev = (nr > 0);
+            __syncthreads();
+            SMRT_PHASE(7)  // R of the stack, source vector
+          } else {
+            // top layer: z = S^-1 b' by row elimination of [S | b'], then s = v + K z
+            if (block_gj_factor(M1, ldm, Trhs, ldm, h, nr, rowof, pivinv, &s_ctrl[6])) {
+              failed = true;
+              break;
+            }
+            SMRT_FOR_2D(k, c, h, nr) { SMRT_AT(ytr, h, k, c) = SMRT_AT(Trhs, ldm, rowof[k], c) * pivinv[k]; }
+            __syncthreads();
+            block_gemm_ptr(NT, h, nr, h, gC, ldm, [&](int c) { return ytr + (size_t)c * h; },
+                           [&](int i, int c, double acc) { SMRT_AT(svec, h, i, c) = SMRT_AT(vvec, h, i, c) + acc; });
+            __syncthreads();
+          }
+        } else {
         // T = [A21 | A22] without the coupling term:  A21 = F - Rb D G,  A22 = (G - Rb D F) t
         // (Dsg holds the sign D of the third Stokes component, RbD = Rb D)
         if (!kStreamFG) {
@@ -1120,6 +1360,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
                          [&](int i, int c, double acc) { SMRT_AT(svec, h, i, c) = SMRT_AT(vvec, h, i, c) + acc; });
           __syncthreads();
         }
+        }  // resident / staged-operand layouts
       }  // layers
       if (pf_layer >= 0) {  // left the loop early with a bulk copy in flight: drain it before BF / BG are reused
         smrt_mbar_wait(&s_mbar, pf_parity);

@@ -83,8 +83,23 @@ SMRT_DEV void team_gemm(const Team& tm, int M, int N, int K, FA a, FB b, FS stor
 }
 
 // ------------------------------------------------------------------------------------------------------------ Cholesky
-// In-place lower Cholesky A = L L^T of the h x h symmetric positive definite matrix whose LOWER triangle is stored in A
-// (column-major, leading dimension ld); the strict upper triangle is neither read nor written.
+// Lower-triangular operand (the factor C of X+ and, before it, the lower triangle of X+ itself), either inside a full
+// column-major array (leading dimension ld) or PACKED by columns (column k holds rows k .. h-1: h (h + 1) / 2 doubles,
+// half the shared memory; the 64 < h <= 128 instantiation of the eigen kernel could not hold two full matrices).
+// col(k)[i] = element (i, k) for i >= k in both layouts.
+template <bool kPacked>
+struct LowerMat {
+  double* p;
+  int ld, h;
+  SMRT_DEV double* col(int k) const {
+    return kPacked ? p + ((k * (2 * h - k - 1)) >> 1) : p + (size_t)k * ld;
+  }
+  SMRT_DEV int col_step(int k) const { return kPacked ? h - k - 1 : ld; }  // col(k + 1) - col(k)
+  SMRT_DEV double& at(int i, int k) const { return col(k)[i]; }
+};
+
+// In-place lower Cholesky A = L L^T of the h x h symmetric positive definite matrix whose LOWER triangle is stored in A;
+// the strict upper triangle is neither read nor written.
 // Left-looking with ONE team barrier per step (a right-looking version needs three per column and rewrites the
 // trailing matrix at every step).  Thread t owns the rows t, t + size, ... (NR of them); at step j it forms
 //   s_i = A(i, j) - sum_{k<j} L(i, k) L(j, k)      for its rows i > j
@@ -93,62 +108,65 @@ SMRT_DEV void team_gemm(const Team& tm, int M, int N, int K, FA a, FB b, FS stor
 // the factorisation; it is collected in dvec (team-shared double[h]) and copied into A at the end, which removes the
 // write-after-read race on A(j, j).  Only the lower triangle is read or written.  Returns 1 (to every thread of the
 // team) when a pivot is not positive.
-template <int NR>
-SMRT_DEV int team_cholesky_ll(const Team& tm, double* A, int ld, int h, double* dvec) {
+template <int NR, bool kPacked>
+SMRT_DEV int team_cholesky_ll(const Team& tm, const LowerMat<kPacked>& A, int h, double* dvec) {
   int failed = 0;
   // two columns (j, j + 1) per step: the three operands L(i, k), L(j, k), L(j + 1, k) feed five FMAs, and the team
   // synchronises once per pair of columns
   int j = 0;
   for (; j + 1 < h; j += 2) {
-    const double* SMRT_RESTRICT Lj = A + j;  // L(j, k) = Lj[k * ld], L(j + 1, k) = Lj[k * ld + 1]
     double p00[2] = {0.0, 0.0}, p10[2] = {0.0, 0.0}, p11[2] = {0.0, 0.0};
     double s0[NR][2], s1[NR][2];
-    const double* rowp[NR];
+    int row[NR];
     bool own[NR];
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       const int i = tm.rank + r * tm.size;
       own[r] = (i > j + 1) && (i < h);
-      rowp[r] = A + (own[r] ? i : j);
+      row[r] = own[r] ? i : j;
       s0[r][0] = s0[r][1] = s1[r][0] = s1[r][1] = 0.0;
     }
+    const double* SMRT_RESTRICT ck = A.col(0);  // column k: ck[i] = L(i, k)
     int k = 0;
     for (; k + 1 < j; k += 2) {
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const double l0 = Lj[(size_t)(k + u) * ld], l1 = Lj[(size_t)(k + u) * ld + 1];
+        const double l0 = ck[j], l1 = ck[j + 1];
         p00[u] = fma(l0, l0, p00[u]);
         p10[u] = fma(l1, l0, p10[u]);
         p11[u] = fma(l1, l1, p11[u]);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-          const double li = rowp[r][(size_t)(k + u) * ld];
+          const double li = ck[row[r]];
           s0[r][u] = fma(li, l0, s0[r][u]);
           s1[r][u] = fma(li, l1, s1[r][u]);
         }
+        ck += A.col_step(k + u);
       }
     }
     if (k < j) {
-      const double l0 = Lj[(size_t)k * ld], l1 = Lj[(size_t)k * ld + 1];
+      const double l0 = ck[j], l1 = ck[j + 1];
       p00[0] = fma(l0, l0, p00[0]);
       p10[0] = fma(l1, l0, p10[0]);
       p11[0] = fma(l1, l1, p11[0]);
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
-        const double li = rowp[r][(size_t)k * ld];
+        const double li = ck[row[r]];
         s0[r][0] = fma(li, l0, s0[r][0]);
         s1[r][0] = fma(li, l1, s1[r][0]);
       }
     }
+    double* cj = A.col(j);
+    double* cj1 = A.col(j + 1);
     // 2 x 2 diagonal block (identical values in every thread: uniform exits)
-    const double d0 = SMRT_AT(A, ld, j, j) - (p00[0] + p00[1]);
+    const double d0 = cj[j] - (p00[0] + p00[1]);
     if (!(d0 > 0.0)) {
       failed = 1;
       break;
     }
     const double r0 = rsqrt(d0);
-    const double l10 = (SMRT_AT(A, ld, j + 1, j) - (p10[0] + p10[1])) * r0;
-    const double d1 = SMRT_AT(A, ld, j + 1, j + 1) - (p11[0] + p11[1]) - l10 * l10;
+    const double l10 = (cj[j + 1] - (p10[0] + p10[1])) * r0;
+    const double d1 = cj1[j + 1] - (p11[0] + p11[1]) - l10 * l10;
     if (!(d1 > 0.0)) {
       failed = 1;
       break;
@@ -158,10 +176,10 @@ SMRT_DEV int team_cholesky_ll(const Team& tm, double* A, int ld, int h, double* 
     for (int r = 0; r < NR; ++r) {
       const int i = tm.rank + r * tm.size;
       if (own[r]) {
-        const double x0 = (SMRT_AT(A, ld, i, j) - (s0[r][0] + s0[r][1])) * r0;
-        const double x1 = (SMRT_AT(A, ld, i, j + 1) - (s1[r][0] + s1[r][1]) - x0 * l10) * r1;
-        SMRT_AT(A, ld, i, j) = x0;
-        SMRT_AT(A, ld, i, j + 1) = x1;
+        const double x0 = (cj[i] - (s0[r][0] + s0[r][1])) * r0;
+        const double x1 = (cj1[i] - (s1[r][0] + s1[r][1]) - x0 * l10) * r1;
+        cj[i] = x0;
+        cj1[i] = x1;
       }
       if (i == j) {
         dvec[j] = d0 * r0;
@@ -172,16 +190,17 @@ SMRT_DEV int team_cholesky_ll(const Team& tm, double* A, int ld, int h, double* 
     // L(j + 1, j) is read as an operand by the later steps but A(j + 1, j) was also an INPUT of this step for every
     // thread: written only after the barrier, by its owner, and published by the next step's barrier (the next step
     // reads column j only through rows >= j + 2)
-    if (tm.rank == (j + 1) % tm.size) SMRT_AT(A, ld, j + 1, j) = l10;
+    if (tm.rank == (j + 1) % tm.size) cj[j + 1] = l10;
   }
   if (!failed && j < h) {  // last column of an odd-sized matrix
-    const double* SMRT_RESTRICT Lj = A + j;
     double p[2] = {0.0, 0.0};
+    const double* SMRT_RESTRICT ck = A.col(0);
     for (int k = 0; k < j; ++k) {
-      const double lj = Lj[(size_t)k * ld];
+      const double lj = ck[j];
       p[k & 1] = fma(lj, lj, p[k & 1]);
+      ck += A.col_step(k);
     }
-    const double d = SMRT_AT(A, ld, j, j) - (p[0] + p[1]);
+    const double d = A.at(j, j) - (p[0] + p[1]);
     if (!(d > 0.0))
       failed = 1;
     else if (tm.rank == 0)
@@ -189,15 +208,16 @@ SMRT_DEV int team_cholesky_ll(const Team& tm, double* A, int ld, int h, double* 
   }
   tm.sync();
   if (failed) return 1;
-  for (int jj = tm.rank; jj < h; jj += tm.size) SMRT_AT(A, ld, jj, jj) = dvec[jj];
+  for (int jj = tm.rank; jj < h; jj += tm.size) A.at(jj, jj) = dvec[jj];
   tm.sync();
   return 0;
 }
-SMRT_DEV int team_cholesky_fast(const Team& tm, double* A, int ld, int h, double* dvec) {
-  if (h <= tm.size) return team_cholesky_ll<1>(tm, A, ld, h, dvec);
-  if (h <= 2 * tm.size) return team_cholesky_ll<2>(tm, A, ld, h, dvec);
-  if (h <= 4 * tm.size) return team_cholesky_ll<4>(tm, A, ld, h, dvec);
-  return team_cholesky_ll<8>(tm, A, ld, h, dvec);
+template <bool kPacked>
+SMRT_DEV int team_cholesky_fast(const Team& tm, const LowerMat<kPacked>& A, int h, double* dvec) {
+  if (h <= tm.size) return team_cholesky_ll<1, kPacked>(tm, A, h, dvec);
+  if (h <= 2 * tm.size) return team_cholesky_ll<2, kPacked>(tm, A, h, dvec);
+  if (h <= 4 * tm.size) return team_cholesky_ll<4, kPacked>(tm, A, h, dvec);
+  return team_cholesky_ll<8, kPacked>(tm, A, h, dvec);
 }
 
 // ------------------------------------------------------------------------------------------------- one-sided Jacobi SVD
@@ -373,6 +393,8 @@ SMRT_HD int jacobi_ld(int h) {
   if (hr <= 32) return 34;
   if (hr <= 48) return 50;
   if (hr <= 64) return 66;
+  if (hr <= 96) return 98;    // 16 lanes x 6 rows
+  if (hr <= 128) return 130;  // 16 lanes x 8 rows
   return ((hr & 3) == 2) ? hr : hr + 2;
 }
 
@@ -593,6 +615,7 @@ SMRT_DEV int block_jacobi_svd_reg(double* W, int ld, int h, double* nrm, const d
         int r00, r11, r01, r10;
         jreg_rotate2<JG, R>(lane, x0, y0, a0, b0, x1, y1, a1, b1, r00, r11);
         jreg_rotate2<JG, R>(lane, x0, y1, a0, b1, x1, y0, a1, b0, r01, r10);
+        __syncwarp();  // every lane of the group has read the tracked norms before lane 0 replaces them
         // a column that rotated is a real column (missing ones have zero norm): unpredicated stores
         if ((r00 | r01) & 2) {
           jreg_store<JG, R>(wp0, lane, x0);
@@ -626,7 +649,9 @@ SMRT_DEV int block_jacobi_svd_fast(double* W, int ld, int h, double* nrm, const 
     if (ld <= 18) return block_jacobi_svd_reg<16, 1>(W, ld, h, nrm, zcol);
     if (ld <= 34) return block_jacobi_svd_reg<16, 2>(W, ld, h, nrm, zcol);
     if (ld <= 50) return block_jacobi_svd_reg<16, 3>(W, ld, h, nrm, zcol);
-    return block_jacobi_svd_reg<16, 4>(W, ld, h, nrm, zcol);
+    if (ld <= 66) return block_jacobi_svd_reg<16, 4>(W, ld, h, nrm, zcol);
+    if (ld <= 98) return block_jacobi_svd_reg<16, 6>(W, ld, h, nrm, zcol);
+    return block_jacobi_svd_reg<16, 8>(W, ld, h, nrm, zcol);  // ld = 130: up to 128 rows (zcol holds 128 zeros)
   }
   if (ld <= 18) return block_jacobi_svd_reg<8, 2>(W, ld, h, nrm, zcol);
   if (ld <= 34) return block_jacobi_svd_reg<8, 4>(W, ld, h, nrm, zcol);
@@ -640,7 +665,8 @@ SMRT_DEV int block_jacobi_svd_fast(double* W, int ld, int h, double* nrm, const 
 // and walk it bottom-up in blocks of 8 unknowns held in registers (both lanes solve the 8 x 8 diagonal block
 // redundantly, then split the update of the rows above between them), so the only synchronisation is one __syncwarp
 // per block and all C operands are warp-wide broadcasts.  Called by every thread of the block.
-SMRT_DEV void block_backsolve_lt(const double* SMRT_RESTRICT C, int ldc, double* W, int ldw, int h,
+template <bool kPacked>
+SMRT_DEV void block_backsolve_lt(const LowerMat<kPacked>& C, double* W, int ldw, int h,
                                  const double* SMRT_RESTRICT rdiag) {
   const int NT = blockDim.x, tid = threadIdx.x;
   const int half = tid & 1;
@@ -661,7 +687,7 @@ SMRT_DEV void block_backsolve_lt(const double* SMRT_RESTRICT C, int ldc, double*
         if (jj < nv) {
           z[jj] *= rdiag[jb + jj];
 #pragma unroll
-          for (int ii = 0; ii < jj; ++ii) z[ii] = fma(-SMRT_AT(C, ldc, jb + jj, jb + ii), z[jj], z[ii]);
+          for (int ii = 0; ii < jj; ++ii) z[ii] = fma(-C.at(jb + jj, jb + ii), z[jj], z[ii]);
         }
       }
       if (act && half == 0) {
@@ -673,8 +699,8 @@ SMRT_DEV void block_backsolve_lt(const double* SMRT_RESTRICT C, int ldc, double*
       if (act) {
         int i = half;
         for (; i + 2 < jb; i += 4) {
-          const double* ca = C + (size_t)i * ldc + jb;
-          const double* cb = C + (size_t)(i + 2) * ldc + jb;
+          const double* ca = C.col(i) + jb;
+          const double* cb = C.col(i + 2) + jb;
           double xa = x[i], xb = x[i + 2];
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
@@ -687,7 +713,7 @@ SMRT_DEV void block_backsolve_lt(const double* SMRT_RESTRICT C, int ldc, double*
           x[i + 2] = xb;
         }
         if (i < jb) {
-          const double* ca = C + (size_t)i * ldc + jb;
+          const double* ca = C.col(i) + jb;
           double xa = x[i];
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj)
@@ -1259,8 +1285,8 @@ SMRT_DEV void gj_pivot_finish(unsigned mx, int bu, double mine, double myinv, in
 // soon as its column is up to date, ahead of the other updates of the current step (software pipelining of the only
 // loop-carried dependency).
 template <int RPL>
-SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int j0, int npc, unsigned& used, int lane,
-                            int* rowof, double* ipiv, double* SMRT_RESTRICT Vout, int* flag) {
+SMRT_DEV void gj_panel_warp(const double* Lb, int ldl, int h, int j0, int npc, unsigned& used, int lane,
+                            int* rowof, double* ipiv, double* Vout, int ldv, int* flag) {
   double pc[RPL][SMRT_GJ_NB], v[RPL][SMRT_GJ_NB];
 #pragma unroll
   for (int u = 0; u < RPL; ++u) {
@@ -1339,7 +1365,7 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
 #pragma unroll
       for (int c = 0; c < SMRT_GJ_NB; ++c) {
         const int kcol = npc - 1 - c;  // slot c holds the column created at step npc - 1 - c
-        if (kcol >= 0) Vout[(size_t)kcol * h + row] = v[u][c];
+        if (kcol >= 0) Vout[(size_t)kcol * ldv + row] = v[u][c];
       }
     }
   }
@@ -1353,7 +1379,7 @@ SMRT_DEV void gj_panel_warp(const double* SMRT_RESTRICT Lb, int ldl, int h, int 
 // on the panel index.
 template <int RT, bool kFull>
 SMRT_DEV void gj_update_cols_t(double* Lb, int ldl, double* Rb, int ldr, int h, int cbeg, int cend, int hw, int nhw,
-                               int lx, int npc, const double* SMRT_RESTRICT Vin, const int* SMRT_RESTRICT prow) {
+                               int lx, int npc, const double* Vin, int ldv, const int* SMRT_RESTRICT prow) {
   const int cw0 = cbeg + (hw & ~1);
   if (cw0 >= cend) return;  // warp uniform
   double Vr[RT][SMRT_GJ_NB];
@@ -1366,7 +1392,7 @@ SMRT_DEV void gj_update_cols_t(double* Lb, int ldl, double* Rb, int ldr, int h, 
     const int row = lx + 16 * u;
     rowok[u] = row < h;
 #pragma unroll
-    for (int k = 0; k < SMRT_GJ_NB; ++k) Vr[u][k] = (rowok[u] && (kFull || k < npc)) ? Vin[k * h + row] : 0.0;
+    for (int k = 0; k < SMRT_GJ_NB; ++k) Vr[u][k] = (rowok[u] && (kFull || k < npc)) ? Vin[k * ldv + row] : 0.0;
   }
   for (int cw = cw0; cw < cend; cw += nhw) {
     const int cc = cw + (hw & 1);
@@ -1389,16 +1415,21 @@ SMRT_DEV void gj_update_cols_t(double* Lb, int ldl, double* Rb, int ldr, int h, 
 }
 template <int RT>
 SMRT_DEV void gj_update_cols(double* Lb, int ldl, double* Rb, int ldr, int h, int cbeg, int cend, int hw, int nhw,
-                             int lx, int npc, const double* SMRT_RESTRICT Vin, const int* SMRT_RESTRICT prow) {
+                             int lx, int npc, const double* Vin, int ldv, const int* SMRT_RESTRICT prow) {
   if (npc == SMRT_GJ_NB)
-    gj_update_cols_t<RT, true>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, prow);
+    gj_update_cols_t<RT, true>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, ldv, prow);
   else
-    gj_update_cols_t<RT, false>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, prow);
+    gj_update_cols_t<RT, false>(Lb, ldl, Rb, ldr, h, cbeg, cend, hw, nhw, lx, npc, Vin, ldv, prow);
 }
 
 // one instance per (rows per lane of the panel warp, rows per lane of the update tiles); NOT inlined: the boundary
 // kernel calls it from three places and the straight-line panel code is large (instruction-cache footprint)
-template <int RPL, int RT, bool kShared>
+// kKeepV: PRODUCT FORM.  The V of a panel is stored into the panel's own (dead) columns of the left block instead of
+// the double buffer, so that after the call the left block holds the whole transformation: applying the panels in
+// order, x <- x + V_p x[P_p] (P_p = rowof[4p .. 4p+3], old values), maps ANY further column b to the unscaled solution
+// of the system (gj_apply_chunk): right-hand blocks that do not fit next to the left block in shared memory are
+// eliminated afterwards, chunk by chunk.
+template <int RPL, int RT, bool kShared, bool kKeepV = false>
 SMRT_DEV_NOINLINE int block_gj_rows_blocked_t(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowof,
                                               double* ipiv, double* Vbuf, int* flag) {
   if (kShared) {  // every operand lives in the block's shared memory
@@ -1423,7 +1454,8 @@ SMRT_DEV_NOINLINE int block_gj_rows_blocked_t(double* Lb, int ldl, double* Rb, i
     const bool cur = j0 >= 0;
     const int npc = cur ? ((h - j0 < SMRT_GJ_NB) ? (h - j0) : SMRT_GJ_NB) : 0;
     const int cstart = cur ? j0 + npc : 0;
-    const double* Vin = Vbuf + (size_t)buf * h * SMRT_GJ_NB;
+    const double* Vin = kKeepV ? Lb + (size_t)(cur ? j0 : 0) * ldl : Vbuf + (size_t)buf * h * SMRT_GJ_NB;
+    const int ldv = kKeepV ? ldl : h;
     const bool more = cstart < h;
     const int npn = more ? ((h - cstart < SMRT_GJ_NB) ? (h - cstart) : SMRT_GJ_NB) : 0;  // width of the next panel
     if (cur) {
@@ -1433,20 +1465,21 @@ SMRT_DEV_NOINLINE int block_gj_rows_blocked_t(double* Lb, int ldl, double* Rb, i
       if (more) {
         if (nwarp > 2) {
           if (warp < 2) {
-            gj_update_cols<RT>(Lb, ldl, Rb, ldr, h, cstart, cstart + npn, tid >> 4, 4, lx, npc, Vin, rowof + j0);
+            gj_update_cols<RT>(Lb, ldl, Rb, ldr, h, cstart, cstart + npn, tid >> 4, 4, lx, npc, Vin, ldv, rowof + j0);
             smrt_named_barrier(1, 64);
           }
         } else if (warp == 0) {
-          gj_update_cols<RT>(Lb, ldl, Rb, ldr, h, cstart, cstart + npn, (tid >> 4) & 1, 2, lx, npc, Vin, rowof + j0);
+          gj_update_cols<RT>(Lb, ldl, Rb, ldr, h, cstart, cstart + npn, (tid >> 4) & 1, 2, lx, npc, Vin, ldv, rowof + j0);
         }
       }
       if (warp > 0)
-        gj_update_cols<RT>(Lb, ldl, Rb, ldr, h, cstart + npn, W, (tid >> 4) - 2, 2 * (nwarp - 1), lx, npc, Vin,
+        gj_update_cols<RT>(Lb, ldl, Rb, ldr, h, cstart + npn, W, (tid >> 4) - 2, 2 * (nwarp - 1), lx, npc, Vin, ldv,
                            rowof + j0);
     }
     if (warp == 0 && more) {
       __syncwarp();
-      gj_panel_warp<RPL>(Lb, ldl, h, cstart, npn, used, lane, rowof, ipiv, Vbuf + (size_t)(buf ^ 1) * h * SMRT_GJ_NB, flag);
+      gj_panel_warp<RPL>(Lb, ldl, h, cstart, npn, used, lane, rowof, ipiv,
+                         kKeepV ? Lb + (size_t)cstart * ldl : Vbuf + (size_t)(buf ^ 1) * h * SMRT_GJ_NB, ldv, flag);
     }
     __syncthreads();
     if (*flag) return 1;
@@ -1462,4 +1495,185 @@ SMRT_DEV int block_gj_rows_blocked(double* Lb, int ldl, double* Rb, int ldr, int
   if (h <= 32) return block_gj_rows_blocked_t<1, 2, kShared>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
   if (h <= 48) return block_gj_rows_blocked_t<2, 3, kShared>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
   return block_gj_rows_blocked_t<2, 4, kShared>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
+}
+
+// =====================================================================================================================
+// Blocks of 64 < h <= 128 unknowns (boundary kernel, one CTA of 512 threads per SM).  [A | B] with two h x h blocks no
+// longer fits in shared memory, so the elimination is split: (1) the LEFT block is factorised in shared memory in
+// product form (block_gj_factor: the blocked Gauss-Jordan above, every panel's V kept in the panel's columns), with the
+// few right-hand-side columns riding along as before; (2) the RIGHT block is streamed through afterwards in chunks of
+// 32 columns (gj_apply_chunk), each thread holding 8 rows of one column in registers for the whole pass.
+// =====================================================================================================================
+SMRT_DEV int block_gj_factor(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowof, double* ipiv, int* flag) {
+  // (the V buffer argument is unused in product form: any shared-memory pointer)
+  if (h <= 32) return block_gj_rows_blocked_t<1, 2, true, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Lb, flag);
+  if (h <= 64) return block_gj_rows_blocked_t<2, 4, true, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Lb, flag);
+  if (h <= 96) return block_gj_rows_blocked_t<3, 6, true, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Lb, flag);
+  return block_gj_rows_blocked_t<4, 8, true, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Lb, flag);
+}
+
+// Apply the product-form factorisation held in M (h x h, leading dimension ldm, a multiple of 2; panels of SMRT_GJ_NB
+// columns, pivot rows rowof[]) to ncols <= 32 columns.  Warp w owns the rows 8 w .. 8 w + 7, lane c the column c: a
+// thread keeps its 8 entries in registers through all the panels; per panel the owners of the pivot rows publish their
+// entries (xch: block-shared double[2 * SMRT_GJ_NB * 32], double buffered: ONE block barrier per panel), every thread
+// reads the SMRT_GJ_NB pivot entries of its column, and the V operands are warp-wide broadcasts (16-byte loads).
+// load(i, c) gives the initial entry (i < h, c < ncols); store(i, c, v) receives the transformed entry of row i
+// (the unscaled solution: row rowof[k] holds piv_k * x_k).  Every thread of the block must call; blockDim.x >= 32 *
+// ceil(h / 8).
+template <typename FLoad, typename FStore>
+SMRT_DEV void gj_apply_chunk(const double* M, int ldm, int h, const int* rowof, int ncols, double* xch, FLoad load,
+                             FStore store) {
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int r0 = 8 * w;
+  const bool mine = (r0 < h) && (lane < ncols);  // (r0 < h is warp-uniform)
+  double x[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) x[u] = (mine && r0 + u < h) ? load(r0 + u, lane) : 0.0;
+  int buf = 0;
+  for (int j0 = 0; j0 < h; j0 += SMRT_GJ_NB, buf ^= 1) {
+    const int npc = (h - j0 < SMRT_GJ_NB) ? (h - j0) : SMRT_GJ_NB;
+    double* xb = xch + buf * (SMRT_GJ_NB * 32);
+#pragma unroll
+    for (int k = 0; k < SMRT_GJ_NB; ++k) {
+      if (k < npc) {
+        const int pr = rowof[j0 + k];
+        if ((pr >> 3) == w) {  // warp-uniform: this warp owns the pivot row
+          double val = x[0];
+#pragma unroll
+          for (int u = 1; u < 8; ++u) val = ((pr & 7) == u) ? x[u] : val;
+          xb[k * 32 + lane] = val;
+        }
+      }
+    }
+    __syncthreads();
+    if (r0 < h) {
+#pragma unroll
+      for (int k = 0; k < SMRT_GJ_NB; ++k) {
+        if (k < npc) {
+          const double tp = xb[k * 32 + lane];
+          const double2* vc = reinterpret_cast<const double2*>(M + (size_t)(j0 + k) * ldm + r0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const double2 v = vc[q];
+            x[2 * q] = fma(v.x, tp, x[2 * q]);
+            x[2 * q + 1] = fma(v.y, tp, x[2 * q + 1]);
+          }
+        }
+      }
+    }
+  }
+  if (mine) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (r0 + u < h) store(r0 + u, lane, x[u]);
+  }
+  __syncthreads();  // the exchange buffers are free again (the next chunk starts with buffer 0 whatever the panel count)
+}
+
+// C1 = A1 B (and C2 = A2 B when kDual) for M x N results with inner dimension K, M <= 128 rows, the columns
+// [n0, n0 + 64) of the result per call... see the tile map below.  A1 / A2: column-major in GLOBAL memory (lda), streamed
+// through shared-memory panels of SMRT_MG_KP columns (double buffered, the next panel is fetched into registers while the
+// current one is multiplied: ONE block barrier per panel); B: column-major (ldb) in global memory (kBShared = false:
+// its row panels are staged too) or in shared memory (kBShared = true: read in place).  512 threads: tx = tid % 32 owns
+// the rows tx + 32 u (u < 4), ty = tid / 32 the columns n0 + ty + 16 v (v < NV).  epi(i, j, c1, c2) is called for i < M,
+// j < n0 + 16 NV, j < N.  Rows of A beyond Ma (the product has only Ma <= M non-zero rows) read as zero.
+// stage: block-shared double[2 * SMRT_MG_KP * (128 * (kDual ? 2 : 1) + (kBShared ? 0 : 16 * NV))].
+#define SMRT_MG_KP 8
+template <bool kDual, bool kBShared, int NV, typename FE>
+SMRT_DEV void mid_gemm(int M, int Ma, int N, int n0, int K, const double* SMRT_RESTRICT A1, const double* SMRT_RESTRICT A2,
+                       int lda, const double* Bm, int ldb, double* stage, FE epi) {
+  constexpr int KP = SMRT_MG_KP;
+  constexpr int NA = kDual ? 2 : 1;
+  constexpr int BW = 16 * NV;                           // columns of the result handled by this call
+  constexpr int SA = 128;                               // row stride of a staged A panel
+  constexpr int BUF = KP * (SA * NA + (kBShared ? 0 : BW));
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int tx = tid & 31, ty = tid >> 5;
+  double c1[4][NV], c2[4][NV];  // (c2 is dead code unless kDual)
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) c1[u][v] = c2[u][v] = 0.0;
+  // staged element e of a panel: A part, e in [0, KP * SA * NA): (which = e / (KP * SA), kk = (e / SA) % KP, i = e % SA);
+  // B part: (kk = e / BW, jj = e % BW) -> B(k0 + kk, n0 + jj); per thread EA / EB elements
+  constexpr int EA = (KP * SA * NA + 511) / 512, EB = kBShared ? 1 : (KP * BW + 511) / 512;
+  double ra[EA], rb[EB];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < EA; ++q) {
+      const int e = tid + q * NT;
+      const int i = e % SA, kk = (e / SA) % KP, which = e / (KP * SA);
+      const double* Ap = (kDual && which == 1) ? A2 : A1;
+      ra[q] = (e < KP * SA * NA && i < Ma && k0 + kk < K) ? Ap[(size_t)(k0 + kk) * lda + i] : 0.0;
+    }
+    if (!kBShared) {
+#pragma unroll
+      for (int q = 0; q < EB; ++q) {
+        const int e = tid + q * NT;
+        const int kk = e % KP, jj = e / KP;  // consecutive threads walk down a column of B: contiguous in memory
+        rb[q] = (e < KP * BW && k0 + kk < K && n0 + jj < N) ? Bm[(size_t)(n0 + jj) * ldb + k0 + kk] : 0.0;
+      }
+    }
+  };
+  auto put = [&](double* buf) {
+#pragma unroll
+    for (int q = 0; q < EA; ++q) {
+      const int e = tid + q * NT;
+      if (e < KP * SA * NA) buf[e] = ra[q];
+    }
+    if (!kBShared) {
+#pragma unroll
+      for (int q = 0; q < EB; ++q) {
+        const int e = tid + q * NT;
+        const int kk = e % KP, jj = e / KP;
+        if (e < KP * BW) buf[KP * SA * NA + kk * BW + jj] = rb[q];
+      }
+    }
+  };
+  if (K > 0) {
+    fetch(0);
+    put(stage);
+  }
+  __syncthreads();
+  int cur = 0;
+  for (int k0 = 0; k0 < K; k0 += KP, cur ^= 1) {
+    const bool more = k0 + KP < K;
+    if (more) fetch(k0 + KP);
+    const double* buf = stage + cur * BUF;
+    const int kn = (K - k0 < KP) ? (K - k0) : KP;
+#pragma unroll 2
+    for (int kk = 0; kk < kn; ++kk) {
+      double a1[4], a2[4], bv[NV];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        a1[u] = buf[kk * SA + tx + 32 * u];
+        a2[u] = kDual ? buf[KP * SA + kk * SA + tx + 32 * u] : 0.0;
+      }
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        if (kBShared) {
+          const int j = n0 + ty + 16 * v;
+          bv[v] = Bm[(size_t)(j < N ? j : N - 1) * ldb + k0 + kk];
+        } else {
+          bv[v] = buf[KP * SA * NA + kk * BW + ty + 16 * v];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          c1[u][v] = fma(a1[u], bv[v], c1[u][v]);
+          if (kDual) c2[u][v] = fma(a2[u], bv[v], c2[u][v]);  // compile-time condition
+        }
+    }
+    if (more) put(stage + (cur ^ 1) * BUF);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int i = tx + 32 * u, j = n0 + ty + 16 * v;
+      if (i < M && j < N) epi(i, j, c1[u][v], kDual ? c2[u][v] : 0.0);
+    }
 }

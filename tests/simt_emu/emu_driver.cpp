@@ -28,7 +28,8 @@ int emu_solve_batch(const smrtb200_options* opt, const smrtb200_batch* batch, in
   std::vector<double> gl(L.n), aux(BL * SMRT_AUX_STRIDE), eig(BL * (size_t)L.eig_stride), kmin(BL * SMRT_MAX_MODES);
   std::vector<int> scat(BL, 0), counters(2, 0);
   smrt_host::gauss_legendre_positive_nodes(L.n, gl.data());
-  std::vector<double> scratch((size_t)std::max(L.eigen_scratch_doubles, L.boundary_scratch_doubles) + 64);
+  std::vector<double> scratch((size_t)std::max(std::max(L.eigen_scratch_doubles, L.boundary_scratch_doubles),
+                                               L.boundary_mid_scratch_doubles) + 64);
 
   KArgs A = smrt_host::make_kargs(*opt, L, *batch, 0, B);
   A.gl_mu = gl.data();
@@ -45,10 +46,19 @@ int emu_solve_batch(const smrtb200_options* opt, const smrtb200_batch* batch, in
   for (int b = 0; b < B; ++b) batch->status[b] = 0;
 
   simt::launch((unsigned)((BL + 127) / 128), 128, [&]() { optics_kernel(A); });
-  simt::launch(1, (unsigned)threads, [&]() { eigen_kernel<true>(A); });
+  // SMRT_EMU_EIGEN_MID=1: the shared-memory instantiation for 64 < h <= 128 (packed C, Jacobi groups of 16 lanes)
+  const char* em = std::getenv("SMRT_EMU_EIGEN_MID");
+  if (em && em[0] == '1' && L.eigen_mid_smem_bytes > 0)
+    simt::launch(1, (unsigned)threads, [&]() { eigen_kernel<2>(A); });
+  else
+    simt::launch(1, (unsigned)threads, [&]() { eigen_kernel<1>(A); });
   // SMRT_EMU_STREAM_FG=1: the boundary instantiation that stages F and G into [T | R] (h <= 64)
   const char* sf = std::getenv("SMRT_EMU_STREAM_FG");
-  if (sf && sf[0] == '1' && L.hmax <= 64)
+  // SMRT_EMU_BOUNDARY_MID=1: the boundary instantiation for 64 < h <= 128 (its tile maps need 512 threads)
+  const char* bm = std::getenv("SMRT_EMU_BOUNDARY_MID");
+  if (bm && bm[0] == '1' && L.boundary_mid_smem_bytes > 0)
+    simt::launch(1, 512u, [&]() { boundary_kernel<false, 512, false, true>(A); });
+  else if (sf && sf[0] == '1' && L.hmax <= 64)
     simt::launch(1, (unsigned)threads, [&]() { boundary_kernel<true, 512, true>(A); });
   else
     simt::launch(1, (unsigned)threads, [&]() { boundary_kernel<true, 512>(A); });
@@ -107,9 +117,9 @@ int emu_jacobi(double* W, int h, int threads) {
 int emu_jacobi_ld(int h) { return jacobi_ld(h); }
 int emu_jacobi_fast(double* W, int h, int ld, int threads) {
   int sweeps = 0;
-  std::vector<double> nrm(h + 8, 0.0), zcol(64, 0.0);
+  std::vector<double> nrm(h + 8, 0.0), zcol(128, 0.0);
   simt::launch(1, (unsigned)threads, [&]() {
-    int s = block_jacobi_svd_fast(W, ld, h, nrm.data(), zcol.data());
+    int s = block_jacobi_svd_fast(W, ld, h, nrm.data(), zcol.data(), h > 64 ? 16 : 8);
     if (threadIdx.x == 0) sweeps = s;
   });
   return sweeps;
@@ -142,7 +152,11 @@ int emu_cholesky_pair(double* A, double* A2, int h, int threads) {
     tm.size = half;
     tm.rank = (int)threadIdx.x % half;
     tm.bar_id = 1 + which;
-    int b = team_cholesky_fast(tm, which == 0 ? A : A2, h, h, which == 0 ? d0.data() : d1.data());
+    LowerMat<false> X;
+    X.p = which == 0 ? A : A2;
+    X.ld = h;
+    X.h = h;
+    int b = team_cholesky_fast(tm, X, h, which == 0 ? d0.data() : d1.data());
     if (tm.rank == 0) bad[which] = b;
   });
   return bad[0] | (bad[1] << 1);
@@ -152,7 +166,11 @@ int emu_cholesky_pair(double* A, double* A2, int h, int threads) {
 int emu_backsolve_lt(const double* Cm, double* W, int h, int ldw, int threads) {
   std::vector<double> rdiag(h);
   for (int j = 0; j < h; ++j) rdiag[j] = 1.0 / Cm[(size_t)j * h + j];
-  simt::launch(1, (unsigned)threads, [&]() { block_backsolve_lt(Cm, h, W, ldw, h, rdiag.data()); });
+  LowerMat<false> Cl;
+  Cl.p = const_cast<double*>(Cm);
+  Cl.ld = h;
+  Cl.h = h;
+  simt::launch(1, (unsigned)threads, [&]() { block_backsolve_lt(Cl, W, ldw, h, rdiag.data()); });
   return 0;
 }
 
