@@ -517,7 +517,7 @@ SMRT_HD int boundary_mid_ld(int h) { return (h + 7) & ~7; }
 SMRT_HD size_t boundary_mid_smem_doubles(int hmax, int nrhs_max) {
   const size_t ldm = boundary_mid_ld(hmax);
   return (size_t)1024 + ldm /* matvec scratch, reciprocal pivots */ + (size_t)hmax * ldm /* M1 */ +
-         4096 /* GEMM staging */ + 2 * SMRT_GJ_NB * 32 /* pivot-row exchange */ + ldm * nrhs_max /* rhs block */ +
+         4096 /* GEMM staging */ + 2 * 8 * 32 * 4 /* pivot-row exchange */ + ldm * nrhs_max /* rhs block */ +
          4 * (size_t)hmax * nrhs_max + 16;
 }
 // global scratch: gA (A22 -> S), gB (Y~ -> R of the stack), gC (K), gF / gG (generated operands of non-scattering layers)
@@ -619,7 +619,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
     M1 = pivinv + ldm_max;
     stage = M1 + (size_t)hmax * ldm_max;
     xch = stage + 4096;
-    rhsM = xch + 2 * SMRT_GJ_NB * 32;
+    rhsM = xch + 2 * 8 * 32 * 4;
     btop = rhsM + (size_t)ldm_max * nrhs_max;
     svec = btop + szr;
     ytr = svec + szr;
@@ -1043,15 +1043,12 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
           __syncthreads();
           SMRT_FOR_2D(k, c, h, nr) { SMRT_AT(ytr, h, k, c) = SMRT_AT(Trhs, ldm, rowof[k], c) * ipiv[k]; }
           // Y~ = diag(t) A21^-1 A22 -> gB (the operator of the stack below is dead)
-          for (int c0 = 0; c0 < h; c0 += 32) {
-            const int nc = (h - c0 < 32) ? (h - c0) : 32;
-            gj_apply_chunk(
-                M1, ldm, h, rowof, nc, xch, [&](int i, int c) { return gA[(size_t)(c0 + c) * ldm + i]; },
-                [&](int i, int c, double v) {
-                  const int k = kof[i];
-                  gB[(size_t)(c0 + c) * ldm + k] = v * ipiv[k];
-                });
-          }
+          gj_apply_all(
+              M1, ldm, h, rowof, xch, [&](int i, int c) { return gA[(size_t)c * ldm + i]; },
+              [&](int i, int c, double v) {
+                const int k = kof[i];
+                gB[(size_t)c * ldm + k] = v * ipiv[k];
+              });
           __syncthreads();
           SMRT_PHASE(4)  // first elimination
           // Y~ becomes the resident B operand of  P = F - G Y~,  K = G - F Y~ ;  S = D P - Rt K -> gA,  K -> gC
@@ -1098,15 +1095,12 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
             }
             for (int k = tid; k < h; k += NT) kof[rowof[k]] = k;
             __syncthreads();
-            for (int c0 = 0; c0 < h; c0 += 32) {
-              const int nc = (h - c0 < 32) ? (h - c0) : 32;
-              gj_apply_chunk(
-                  M1, ldm, h, rowof, nc, xch, [&](int i, int c) { return gC[(size_t)(c0 + c) * ldm + i]; },
-                  [&](int i, int c, double v) {
-                    const int k = kof[i];
-                    gB[(size_t)k * ldm + c0 + c] = v * pivinv[k];  // R_new(c0 + c, k)
-                  });
-            }
+            gj_apply_all(
+                M1, ldm, h, rowof, xch, [&](int i, int c) { return gC[(size_t)c * ldm + i]; },
+                [&](int i, int c, double v) {
+                  const int k = kof[i];
+                  gB[(size_t)k * ldm + c] = v * pivinv[k];  // R_new(c, k)
+                });
             __syncthreads();
             SMRT_PHASE(6)  // second elimination
             if (nr == 1) {  // s = v + R_new b'

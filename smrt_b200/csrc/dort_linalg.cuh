@@ -1427,7 +1427,7 @@ SMRT_DEV void gj_update_cols(double* Lb, int ldl, double* Rb, int ldr, int h, in
 // kKeepV: PRODUCT FORM.  The V of a panel is stored into the panel's own (dead) columns of the left block instead of
 // the double buffer, so that after the call the left block holds the whole transformation: applying the panels in
 // order, x <- x + V_p x[P_p] (P_p = rowof[4p .. 4p+3], old values), maps ANY further column b to the unscaled solution
-// of the system (gj_apply_chunk): right-hand blocks that do not fit next to the left block in shared memory are
+// of the system (gj_apply_block): right-hand blocks that do not fit next to the left block in shared memory are
 // eliminated afterwards, chunk by chunk.
 template <int RPL, int RT, bool kShared, bool kKeepV = false>
 SMRT_DEV_NOINLINE int block_gj_rows_blocked_t(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowof,
@@ -1502,7 +1502,7 @@ SMRT_DEV int block_gj_rows_blocked(double* Lb, int ldl, double* Rb, int ldr, int
 // longer fits in shared memory, so the elimination is split: (1) the LEFT block is factorised in shared memory in
 // product form (block_gj_factor: the blocked Gauss-Jordan above, every panel's V kept in the panel's columns), with the
 // few right-hand-side columns riding along as before; (2) the RIGHT block is streamed through afterwards in chunks of
-// 32 columns (gj_apply_chunk), each thread holding 8 rows of one column in registers for the whole pass.
+// up to 96 columns (gj_apply_block), each thread holding 8 rows of up to 3 columns in registers for the whole pass.
 // =====================================================================================================================
 SMRT_DEV int block_gj_factor(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowof, double* ipiv, int* flag) {
   // (the V buffer argument is unused in product form: any shared-memory pointer)
@@ -1512,62 +1512,126 @@ SMRT_DEV int block_gj_factor(double* Lb, int ldl, double* Rb, int ldr, int h, in
   return block_gj_rows_blocked_t<4, 8, true, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Lb, flag);
 }
 
-// Apply the product-form factorisation held in M (h x h, leading dimension ldm, a multiple of 2; panels of SMRT_GJ_NB
-// columns, pivot rows rowof[]) to ncols <= 32 columns.  Warp w owns the rows 8 w .. 8 w + 7, lane c the column c: a
-// thread keeps its 8 entries in registers through all the panels; per panel the owners of the pivot rows publish their
-// entries (xch: block-shared double[2 * SMRT_GJ_NB * 32], double buffered: ONE block barrier per panel), every thread
-// reads the SMRT_GJ_NB pivot entries of its column, and the V operands are warp-wide broadcasts (16-byte loads).
-// load(i, c) gives the initial entry (i < h, c < ncols); store(i, c, v) receives the transformed entry of row i
-// (the unscaled solution: row rowof[k] holds piv_k * x_k).  Every thread of the block must call; blockDim.x >= 32 *
-// ceil(h / 8).
-template <typename FLoad, typename FStore>
-SMRT_DEV void gj_apply_chunk(const double* M, int ldm, int h, const int* rowof, int ncols, double* xch, FLoad load,
+// Apply the product-form factorisation held in M (h x h, leading dimension ldm, a multiple of 2; panels of SMRT_GJ_NB = 4
+// columns, pivot rows rowof[]) to ncols <= 32 NC columns at once.  Warp w owns the rows 8 w .. 8 w + 7, lane c the
+// columns c, c + 32, ... (NC of them): a thread keeps its 8 x NC entries in registers through all the panels and every
+// 16-byte V operand (a warp-wide broadcast) feeds 2 NC FMAs.  TWO panels per block barrier: the owners of the 8 pivot
+// rows of a panel pair publish their entries as they are before the pair (xch: block-shared double[2 * 8 * 32 * NC],
+// double buffered); every thread derives the entries the second panel meets from them,
+//     z1 = x[P1] + V0[P1, :] z0,   z0 = x[P0]          (16 FMAs per column, V0[P1, :] are broadcast loads),
+// and applies both panels,  x <- x + V0 z0 + V1 z1.
+// load(i, c) gives the initial entry (i < h, c < ncols); store(i, c, v) receives the transformed entry of row i (the
+// unscaled solution: row rowof[k] holds piv_k * x_k).  Every thread of the block must call; blockDim.x >= 32 ceil(h / 8).
+template <int NC, typename FLoad, typename FStore>
+SMRT_DEV_NOINLINE void gj_apply_block(const double* M, int ldm, int h, const int* rowof, int ncols, double* xch, FLoad load,
                              FStore store) {
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int r0 = 8 * w;
-  const bool mine = (r0 < h) && (lane < ncols);  // (r0 < h is warp-uniform)
-  double x[8];
+  const bool active = r0 < h;  // warp-uniform
+  double x[NC][8];
 #pragma unroll
-  for (int u = 0; u < 8; ++u) x[u] = (mine && r0 + u < h) ? load(r0 + u, lane) : 0.0;
+  for (int q = 0; q < NC; ++q)
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      x[q][u] = (active && r0 + u < h && lane + 32 * q < ncols) ? load(r0 + u, lane + 32 * q) : 0.0;
   int buf = 0;
-  for (int j0 = 0; j0 < h; j0 += SMRT_GJ_NB, buf ^= 1) {
-    const int npc = (h - j0 < SMRT_GJ_NB) ? (h - j0) : SMRT_GJ_NB;
-    double* xb = xch + buf * (SMRT_GJ_NB * 32);
+  for (int j0 = 0; j0 < h; j0 += 2 * SMRT_GJ_NB, buf ^= 1) {
+    const int npc = (h - j0 < 2 * SMRT_GJ_NB) ? (h - j0) : 2 * SMRT_GJ_NB;  // pivot rows of this pair of panels
+    double* xb = xch + buf * (8 * 32 * NC);
+    int pr[8];
 #pragma unroll
-    for (int k = 0; k < SMRT_GJ_NB; ++k) {
-      if (k < npc) {
-        const int pr = rowof[j0 + k];
-        if ((pr >> 3) == w) {  // warp-uniform: this warp owns the pivot row
-          double val = x[0];
+    for (int k = 0; k < 8; ++k) pr[k] = (k < npc) ? rowof[j0 + k] : -8;
 #pragma unroll
-          for (int u = 1; u < 8; ++u) val = ((pr & 7) == u) ? x[u] : val;
-          xb[k * 32 + lane] = val;
+    for (int k = 0; k < 8; ++k) {
+      if ((pr[k] >> 3) == w) {  // warp-uniform: this warp owns the pivot row
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+          // (an opaque select chain: written as a conditional expression the compiler turns it back into a dynamically
+          // indexed array and moves x[][] to local memory)
+          double val = x[q][0];
+#pragma unroll
+          for (int u = 1; u < 8; ++u) val = smrt_select_eq(pr[k] & 7, u, x[q][u], val);
+          xb[(k * NC + q) * 32 + lane] = val;
         }
       }
     }
     __syncthreads();
-    if (r0 < h) {
+    if (active) {
+      // (register budget: the 4 x NC pivot values of the first panel stay live, those of the second panel are formed
+      // and consumed one column at a time; the two updates commute)
+      double z0[NC][4];
 #pragma unroll
-      for (int k = 0; k < SMRT_GJ_NB; ++k) {
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int q = 0; q < NC; ++q) z0[q][k] = (k < npc) ? xb[(k * NC + q) * 32 + lane] : 0.0;
+      const double* vcol = M + (size_t)j0 * ldm + r0;
+#pragma unroll
+      for (int k = 4; k < 8; ++k) {
         if (k < npc) {
-          const double tp = xb[k * 32 + lane];
-          const double2* vc = reinterpret_cast<const double2*>(M + (size_t)(j0 + k) * ldm + r0);
+          // the second panel meets its pivot row after the first one has been applied
+          double zk[NC];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const double2 v = vc[q];
-            x[2 * q] = fma(v.x, tp, x[2 * q]);
-            x[2 * q + 1] = fma(v.y, tp, x[2 * q + 1]);
+          for (int q = 0; q < NC; ++q) zk[q] = xb[(k * NC + q) * 32 + lane];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const double wv = M[(size_t)(j0 + kk) * ldm + pr[k]];
+#pragma unroll
+            for (int q = 0; q < NC; ++q) zk[q] = fma(wv, z0[q][kk], zk[q]);
+          }
+          const double2* vc = reinterpret_cast<const double2*>(vcol + (size_t)k * ldm);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const double2 v = vc[t];
+#pragma unroll
+            for (int q = 0; q < NC; ++q) {
+              x[q][2 * t] = fma(v.x, zk[q], x[q][2 * t]);
+              x[q][2 * t + 1] = fma(v.y, zk[q], x[q][2 * t + 1]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k < npc) {
+          const double2* vc = reinterpret_cast<const double2*>(vcol + (size_t)k * ldm);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const double2 v = vc[t];
+#pragma unroll
+            for (int q = 0; q < NC; ++q) {
+              x[q][2 * t] = fma(v.x, z0[q][k], x[q][2 * t]);
+              x[q][2 * t + 1] = fma(v.y, z0[q][k], x[q][2 * t + 1]);
+            }
           }
         }
       }
     }
   }
-  if (mine) {
+  if (active) {
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
-      if (r0 + u < h) store(r0 + u, lane, x[u]);
+    for (int q = 0; q < NC; ++q)
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (r0 + u < h && lane + 32 * q < ncols) store(r0 + u, lane + 32 * q, x[q][u]);
   }
-  __syncthreads();  // the exchange buffers are free again (the next chunk starts with buffer 0 whatever the panel count)
+  __syncthreads();  // the exchange buffers are free again
+}
+// all the h columns of an h x h right block (h <= 128): one pass of up to 96 columns (3 per thread: 8 x 3 entries and
+// 8 x 3 pivot values per thread fit the 128-register budget of a 512-thread block), or two passes of 64
+template <typename FLoad, typename FStore>
+SMRT_DEV void gj_apply_all(const double* M, int ldm, int h, const int* rowof, double* xch, FLoad load, FStore store) {
+  if (h <= 32) {
+    gj_apply_block<1>(M, ldm, h, rowof, h, xch, load, store);
+  } else if (h <= 64) {
+    gj_apply_block<2>(M, ldm, h, rowof, h, xch, load, store);
+  } else if (h <= 96) {
+    gj_apply_block<3>(M, ldm, h, rowof, h, xch, load, store);
+  } else {
+    gj_apply_block<2>(M, ldm, h, rowof, 64, xch, load, store);
+    gj_apply_block<2>(
+        M, ldm, h, rowof, h - 64, xch, [&](int i, int c) { return load(i, c + 64); },
+        [&](int i, int c, double v) { store(i, c + 64, v); });
+  }
 }
 
 // C1 = A1 B (and C2 = A2 B when kDual) for M x N results with inner dimension K, M <= 128 rows, the columns

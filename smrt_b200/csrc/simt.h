@@ -27,6 +27,14 @@ SMRT_DEV void smrt_named_barrier(int id, int nthreads) {
 // an opaque identity: the value must be kept (register or spill), it cannot be re-derived inside a loop
 #define SMRT_KEEP_INT(x) asm volatile("" : "+r"(x))
 
+// a == b ? x : y as ONE predicated select the optimiser cannot rewrite (it would turn a chain of them over the elements
+// of a register array into a dynamically indexed, i.e. local-memory, array)
+SMRT_DEV double smrt_select_eq(int a, int b, double x, double y) {
+  double r;
+  asm("{\n .reg .pred p;\n setp.eq.s32 p, %3, %4;\n selp.f64 %0, %1, %2, p;\n}\n" : "=d"(r) : "d"(x), "d"(y), "r"(a), "r"(b));
+  return r;
+}
+
 // ---- single-instruction fp64 approximations (MUFU.RCP64H / MUFU.RSQ64H, ~2^-20 relative error): seeds that the
 // callers refine with Newton steps where they need more
 SMRT_DEV double smrt_rcp_approx(double x) {
@@ -216,6 +224,7 @@ inline void smrt_bulk_load1(smrt_mbar_t*, void* dst, const void* src, unsigned b
 inline void smrt_prefetch_l2(const void*, unsigned) {}
 inline void smrt_mbar_wait(smrt_mbar_t*, unsigned) {}
 
+inline double smrt_select_eq(int a, int b, double x, double y) { return a == b ? x : y; }
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 // the device versions are ~20-bit seeds: keep only a float mantissa so that the emulation tests the same tolerance
 inline double smrt_approx_round(double v) {
