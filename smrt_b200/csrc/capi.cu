@@ -181,13 +181,15 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
   // shared-memory path if both kernels fit into the opt-in limit, else matrices in an L2-resident global scratch
   p->use_global_scratch = L.boundary_smem_bytes > kMaxSmemOptin;
   if (L.hmax <= 64 && L.eigen_smem_bytes <= kMaxSmemOptin)
-    p->eigen_variant = 0;
+    p->eigen_variant = std::getenv("SMRT_B200_EIGEN4") ? 3 : 0;  // experiment: four CTAs per SM (packed C, 128 registers)
   else if (L.eigen_mid_smem_bytes > 0 && L.eigen_mid_smem_bytes <= kMaxSmemOptin && !std::getenv("SMRT_B200_NO_MID"))
     p->eigen_variant = 2;
   else
     p->eigen_variant = 1;
-  p->eigen_smem = p->eigen_variant == 0 ? L.eigen_smem_bytes
-                  : p->eigen_variant == 2 ? L.eigen_mid_smem_bytes : L.eigen_vec_bytes;
+  p->eigen_smem = p->eigen_variant == 0   ? L.eigen_smem_bytes
+                  : p->eigen_variant == 2 ? L.eigen_mid_smem_bytes
+                  : p->eigen_variant == 3 ? L.eigen_small_packed_smem_bytes
+                                          : L.eigen_vec_bytes;
   p->boundary_smem = p->use_global_scratch ? L.boundary_vec_bytes : L.boundary_smem_bytes;
   if (p->use_global_scratch && L.boundary_mid_smem_bytes > 0 && L.boundary_mid_smem_bytes <= kMaxSmemOptin &&
       !std::getenv("SMRT_B200_NO_MID")) {
@@ -211,7 +213,10 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
     if (_e != cudaSuccess) return bail(fail(-2, "%s failed: %s", #expr, cudaGetErrorString(_e)));     \
   } while (0)
 
-  p->eigen_fn = p->eigen_variant == 0 ? eigen_kernel<0> : p->eigen_variant == 2 ? eigen_kernel<2> : eigen_kernel<1>;
+  p->eigen_fn = p->eigen_variant == 0   ? eigen_kernel<0>
+                : p->eigen_variant == 2 ? eigen_kernel<2>
+                : p->eigen_variant == 3 ? eigen_kernel<3>
+                                        : eigen_kernel<1>;
   // boundary kernel: 512 threads (128 registers) or 256 threads (255 registers: no spills in the register-tiled
   // eliminations); the block size is a plan parameter
   if (!p->use_global_scratch) p->boundary_threads = 256;  // measured: 14.9 ms per launch vs 17.9 ms with 512 (cfg 2)
@@ -267,7 +272,9 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
                                    optin - (int)fa.sharedSizeBytes));
   }
   int occ_e = 0, occ_b = 0;
-  p->eigen_threads = p->eigen_variant == 0 ? SMRT_NT_SMEM : p->eigen_variant == 2 ? SMRT_NT_MID : SMRT_NT;
+  p->eigen_threads = (p->eigen_variant == 0 || p->eigen_variant == 3) ? SMRT_NT_SMEM
+                     : p->eigen_variant == 2                          ? SMRT_NT_MID
+                                                                      : SMRT_NT;
   PLAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_e, p->eigen_fn, p->eigen_threads, p->eigen_smem));
   PLAN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_b, p->boundary_fn, p->boundary_threads, p->boundary_smem));
   if (occ_e < 1 || occ_b < 1) return bail(fail(-2, "kernels do not fit on an SM (occupancy %d / %d)", occ_e, occ_b));

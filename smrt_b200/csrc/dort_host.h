@@ -42,6 +42,7 @@ struct Layout {
   int eig_off[SMRT_MAX_MODES];
   size_t eigen_smem_bytes, boundary_smem_bytes;            // dynamic shared memory of the shared-memory path
   size_t eigen_mid_smem_bytes;                              // ... of the eigen instantiation for 64 < h <= 128 (0: n/a)
+  size_t eigen_small_packed_smem_bytes;                     // ... of the 4-CTAs-per-SM eigen instantiation (h <= 64; 0: n/a)
   size_t boundary_mid_smem_bytes;                           // ... of the boundary instantiation for 64 < h <= 128 (0: n/a)
   long long boundary_mid_scratch_doubles;                   // its per-CTA global scratch
   size_t boundary_stream_smem_bytes;                        // ... of the boundary instantiation that stages F and G (0: n/a)
@@ -86,6 +87,9 @@ inline Layout make_layout(const smrtb200_options& o) {
   L.boundary_vec_bytes = boundary_vec_doubles(L.n, L.hmax, L.mode) * sizeof(double);
   L.boundary_scratch_doubles = (long long)boundary_mat_doubles(L.hmax, L.nrhs_max);
   L.boundary_smem_bytes = L.boundary_vec_bytes + (size_t)L.boundary_scratch_doubles * sizeof(double);
+  L.eigen_small_packed_smem_bytes =
+      (L.hmax <= 64) ? (eigen_vec_doubles(L.n, L.hmax, L.K, SMRT_PANEL_SMALL) + eigen_mat_doubles(L.hmax, true)) * sizeof(double)
+                     : 0;
   const bool mid = L.hmax > 64 && L.hmax <= 128;
   L.boundary_mid_smem_bytes =
       mid ? L.boundary_vec_bytes + boundary_mid_smem_doubles(L.hmax, L.nrhs_max) * sizeof(double) : 0;

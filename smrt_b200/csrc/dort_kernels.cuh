@@ -117,14 +117,15 @@ SMRT_GLOBAL void __launch_bounds__(128) optics_kernel(KArgs A) {
 // kernel 2: per-layer eigenproblem
 // --------------------------------------------------------------------------------------------------------------------
 // shared-memory vector region (doubles): mu[n] w[n] norm0[2n] g[hmax] sdiag[hmax] dk[hmax] sigma[hmax] ctab[2K] stab[2K]
-//                                        panel[SMRT_PANEL * hmax] gq[hmax] nrm[hmax + 4]; in front: zcol[64] (zeros)
+//                                        gq[hmax] nrm[hmax + 12] | g[hmax] dk[hmax] = panel[kPanel * hmax]; in front: zcol (zeros)
 // matrix region: A1 (X- -> L -> M -> W -> E~+, hmax x (hmax + 3)), A2 (X+ -> C, hmax x (hmax + 1)): 68 KB at 32
 // streams, so that three CTAs fit on an SM
 #define SMRT_PANEL 8  // columns of L staged per step of the in-place product M = C^T L
 // the column of zeros standing for missing Jacobi columns: 8 lanes x 8 rows, or 16 lanes x 8 rows beyond 64 unknowns
 SMRT_HD int eigen_zcol_doubles(int hmax) { return hmax > 64 ? 128 : 64; }
-SMRT_HD size_t eigen_vec_doubles(int n, int hmax, int K) {
-  return ((size_t)eigen_zcol_doubles(hmax) + 4 * n + 6 * hmax + 4 * K + (size_t)SMRT_PANEL * hmax + 12 + 1) & ~(size_t)1;
+// (the staging panel of M = C^T L lies over the scales g and ke / mu, which are dead by then; `panel` = its column count)
+SMRT_HD size_t eigen_vec_doubles(int n, int hmax, int K, int panel = SMRT_PANEL) {
+  return ((size_t)eigen_zcol_doubles(hmax) + 4 * n + 4 * hmax + 4 * K + (size_t)panel * hmax + 12 + 1) & ~(size_t)1;
 }
 SMRT_HD size_t eigen_mat1_doubles(int hmax) { return (size_t)hmax * jacobi_ld(hmax); }  // even: A2 16-byte aligned
 // packed: the second matrix (X+ -> C) holds its lower triangle only, packed by columns
@@ -136,11 +137,14 @@ SMRT_HD size_t eigen_mat_doubles(int hmax, bool packed = false) {
 //          1: matrices in a per-CTA global (L2-resident) scratch, any h, 256 threads
 //          2: matrices in shared memory, 64 < h <= 128, 512 threads, one CTA per SM: X+ / C packed (lower triangle),
 //             Jacobi groups of 16 lanes with 6 or 8 rows per lane
+//          3: as 0 with X+ / C packed and a 4-column staging panel: 56 KB and 128 registers, FOUR CTAs per SM
+#define SMRT_PANEL_SMALL 4
 template <int kVariant>
 SMRT_GLOBAL void __launch_bounds__(kVariant == 1 ? SMRT_NT : (kVariant == 2 ? SMRT_NT_MID : SMRT_NT_SMEM),
-                                   kVariant == 0 ? 3 : 1) eigen_kernel(KArgs A) {
+                                   kVariant == 0 ? 3 : (kVariant == 3 ? 4 : 1)) eigen_kernel(KArgs A) {
   constexpr bool kGlobalScratch = kVariant == 1;
-  constexpr bool kPacked = kVariant == 2;
+  constexpr bool kPacked = kVariant == 2 || kVariant == 3;
+  constexpr int kPanel = kVariant == 3 ? SMRT_PANEL_SMALL : SMRT_PANEL;
   SMRT_DYN_SMEM(smem);
   SMRT_SHARED int s_item;
   SMRT_SHARED int s_ctrl[8];
@@ -156,18 +160,18 @@ SMRT_GLOBAL void __launch_bounds__(kVariant == 1 ? SMRT_NT : (kVariant == 2 ? SM
   double* mu = zcol + nz;
   double* w = mu + n;
   double* norm0 = w + n;
-  double* gvec = norm0 + 2 * n;
-  double* sdiag = gvec + hmax;
-  double* dk = sdiag + hmax;
-  double* sigma = dk + hmax;
+  double* sdiag = norm0 + 2 * n;
+  double* sigma = sdiag + hmax;
   double* ctab = sigma + hmax;
   double* stab = ctab + 2 * K;
-  double* panel = stab + 2 * K;
-  double* gq = panel + (size_t)SMRT_PANEL * hmax;
+  double* gq = stab + 2 * K;
   double* nrm = gq + hmax;  // tracked squared column norms of the Jacobi sweeps
+  double* gvec = nrm + hmax + 12;
+  double* dk = gvec + hmax;
+  double* panel = gvec;  // kPanel * hmax doubles over [gvec | dk | ...]: the scales are dead when M = C^T L is formed
   // compile-time choice so that the shared-memory instantiation addresses its matrices with LDS/STS, not generic LD/ST
   double* mats = kGlobalScratch ? (A.scratch + (size_t)blockIdx.x * A.scratch_stride)
-                                : (smem + eigen_vec_doubles(n, hmax, K));
+                                : (smem + eigen_vec_doubles(n, hmax, K, kPanel));
   double* A1 = mats;
   double* A2 = mats + eigen_mat1_doubles(hmax);
 
@@ -379,9 +383,9 @@ SMRT_GLOBAL void __launch_bounds__(kVariant == 1 ? SMRT_NT : (kVariant == 2 ? SM
       }
 
       // M = C^T L in place over L (A1): M(i, j) = sum_{k >= max(i, j)} C(k, i) L(k, j) needs only column j of L,
-      // staged SMRT_PANEL columns at a time
-      for (int jp = 0; jp < h; jp += SMRT_PANEL) {
-        const int pw = (h - jp < SMRT_PANEL) ? (h - jp) : SMRT_PANEL;
+      // staged kPanel columns at a time
+      for (int jp = 0; jp < h; jp += kPanel) {
+        const int pw = (h - jp < kPanel) ? (h - jp) : kPanel;
         for (int e = tid; e < h * pw; e += NT) {
           int k = e % h, jj = e / h;
           panel[jj * h + k] = (k >= jp + jj) ? SMRT_AT(A1, ld1, k, jp + jj) : 0.0;
@@ -416,13 +420,13 @@ SMRT_GLOBAL void __launch_bounds__(kVariant == 1 ? SMRT_NT : (kVariant == 2 ? SM
 
       // singular values / right rotations by one-sided Jacobi: A1 <- W = U Sigma
       {
-        const bool fastj = kPacked ? (h <= 128) : (h <= 64);
+        const bool fastj = (kVariant == 2) ? (h <= 128) : (h <= 64);
         if (fastj) {  // zero pad rows of the register-blocked Jacobi operand: rows [h, ld1 - 2)
           const int npad = ld1 - 2 - h;
           for (int e = tid; e < npad * h; e += NT) SMRT_AT(A1, ld1, h + e % npad, e / npad) = 0.0;
           __syncthreads();
         }
-        int sw = fastj ? block_jacobi_svd_fast(A1, ld1, h, nrm, zcol, kPacked ? 16 : 8)
+        int sw = fastj ? block_jacobi_svd_fast(A1, ld1, h, nrm, zcol, (kVariant == 2) ? 16 : 8)
                        : block_jacobi_svd(A1, ld1, h, s_ctrl);
         if (tid == 0 && A.diag) {
           atomicAdd(&A.diag[0], sw);
