@@ -20,6 +20,8 @@ from __future__ import annotations
 import itertools
 import warnings
 from collections.abc import Mapping
+from concurrent.futures import ThreadPoolExecutor
+from types import SimpleNamespace
 from typing import Optional, Sequence
 
 import numpy as np
@@ -165,13 +167,71 @@ def _simulation_result(mode, sensor, batch: ProblemBatch, out: capi.HostOutputs,
     return ActiveResult(out.values[b].copy(), coords, channel_map=sensor.channel_map, other_data=other)
 
 
+def _merged_channel_map(maps, dimensions):
+    """The channel map the reference ends up with after stacking per-simulation results dimension by dimension
+    (``concat_results``: unchanged when every result of a group has the same map, else every channel is tagged with
+    the coordinate it came from, under the literal key "dim_name")."""
+    for name, values in reversed(dimensions):
+        n = len(values)
+        merged = []
+        for g in range(0, len(maps), n):
+            group = maps[g:g + n]
+            first = group[0]
+            if all(m is first or m == first for m in group):
+                merged.append(first)
+            else:
+                merged.append({ch: {**m[ch], "dim_name": v} for m, v in zip(group, values) for ch in m})
+        maps = merged
+    return maps[0]
+
+
+def _nd_result(mode, sims, rows, out, dimensions) -> Result:
+    """The N-d Result of a whole run in ONE shot (the reference stacks one Result per simulation with an outer-join
+    ``xr.concat`` per dimension, ``smrt/core/model.py:401-404``, ``result.py:768-817``): simulations are enumerated with
+    the first dimension outermost, so the output block only needs reshaping; ragged layer / stream axes are padded
+    with NaN like the outer join does."""
+    sensor = sims[0][0]
+    lead = [(name, list(values)) for name, values in dimensions]
+    shape = tuple(len(v) for _, v in lead)
+    B = len(sims)
+    nl = np.asarray(rows.nlayer[:B])
+    Lmax = max(int(nl.max()) if B else 0, 0)
+    lay = np.arange(max(Lmax, 1))[None, :] < nl[:, None]
+
+    def per_layer(a, name=None, dtype=float):
+        block = np.where(lay[:, :Lmax], np.asarray(a)[:B, :Lmax], np.nan).astype(dtype)
+        return DataArray(block.reshape(shape + (Lmax,)), coords=lead + [("layer", range(Lmax))], name=name)
+
+    ns = np.asarray(out.n_streams[:B])
+    smax = int(ns.max()) if B else 0
+    angles = np.where(np.arange(smax)[None, :] < ns[:, None], out.stream_angles[:B, :smax], np.nan)
+    other = {
+        "stream_angles": DataArray(angles.reshape(shape + (smax,)), coords=lead + [("dim_0", range(smax))]),
+        "effective_permittivity": per_layer(out.eps_eff, dtype=np.complex128),
+        "ks": per_layer(out.ks, "ks"),
+        "ke": per_layer(np.asarray(out.ks) + np.asarray(out.ka), "ke"),
+        "ka": per_layer(out.ka, "ka"),
+        "thickness": per_layer(rows.thickness, "thickness"),
+    }
+    channel_map = _merged_channel_map([s.channel_map for s, _ in sims], dimensions)
+    if mode == "P":
+        coords = lead + [("polarization", ["V", "H"]), ("theta", sensor.theta_deg)]
+        return PassiveResult(np.asarray(out.values[:B]).reshape(shape + out.values.shape[1:]), coords,
+                             channel_map=channel_map, other_data=other)
+    pola = ["V", "H", "U"]
+    coords = lead + [("polarization_inc", pola), ("polarization", pola), ("theta_inc", sensor.theta_inc_deg)]
+    return ActiveResult(np.asarray(out.values[:B]).reshape(shape + out.values.shape[1:]), coords,
+                        channel_map=channel_map, other_data=other)
+
+
 class Model:
     """Batched B200 counterpart of ``smrt.core.model.Model`` for emmodel in {iba, dmrt_qca_shortrange,
     dmrt_qcacp_shortrange, nonscattering} and rtsolver "dort"."""
 
     _broadcast_capability = {"theta_inc", "polarization_inc", "theta", "phi", "polarization"}  # dort.py:140-146
 
-    def __init__(self, emmodel, rtsolver="dort", emmodel_options=None, rtsolver_options=None, device: int = 0):
+    def __init__(self, emmodel, rtsolver="dort", emmodel_options=None, rtsolver_options=None, device: int = 0,
+                 devices: Optional[Sequence[int]] = None):
         if rtsolver is not None and not (rtsolver == "dort" or getattr(rtsolver, "__name__", "") == "DORT"):
             raise SMRTError(f"rtsolver {rtsolver!r} is not implemented on the B200 path (only 'dort')")
         self.emmodel = emmodel
@@ -183,6 +243,7 @@ class Model:
         self.emmodel_options = list(emmodel_options) if _is_sequence(emmodel_options) else dict(emmodel_options or {})
         self.rtsolver_options = dict(rtsolver_options or {})
         self.device = device
+        self.devices = list(devices) if devices else [device]  # GPUs that share the simulations of one run() call
         check_dort_options(self.rtsolver_options)
 
     def set_rtsolver_options(self, options=None, **kwargs):
@@ -266,15 +327,96 @@ class Model:
         sims, dimensions = self.prepare_simulations(sensor, snowpack, snowpack_dimension, snowpack_column)
         if not sims:
             raise SMRTError("nothing to simulate")
-        results = self._run_simulations(sims, opts)
-        for dimension in reversed(dimensions):
-            n = len(dimension[1])
-            results = [concat_results(results[i:i + n], dimension) for i in range(0, len(results), n)]
-        assert len(results) == 1, f"Results size is {len(results)=}"
-        result = results[0]
+        modes = {s.mode for s, _ in sims}
+        if dimensions and len(modes) == 1 and len(sims) == int(np.prod([len(d[1]) for d in dimensions])):
+            # the usual case: ONE N-d block built directly from the output arrays of the batched solve
+            mode = modes.pop()
+            rows, out = self._solve_simulations(sims, list(range(len(sims))), opts)
+            result = _nd_result(mode, sims, rows, out, dimensions)
+        else:  # sensors of both modes in one call, or no dimension at all: per-simulation results, stacked
+            results = self._run_simulations(sims, opts)
+            for dimension in reversed(dimensions):
+                n = len(dimension[1])
+                results = [concat_results(results[i:i + n], dimension) for i in range(0, len(results), n)]
+            assert len(results) == 1, f"Results size is {len(results)=}"
+            result = results[0]
         if isinstance(snowpack, pd.DataFrame):
             result.mother_df = snowpack.drop(snowpack_column, axis=1)
         return result
+
+    # simulations per pack / solve chunk of a large run: packing (Python) of chunk k+1 overlaps the GPU call of chunk k
+    CHUNK_SIMULATIONS = 12288
+
+    def _solve_simulations(self, sims, idx, opts, atmospheres=None):
+        """Pack and solve the simulations sims[i], i in idx (one sensor mode).  Returns (rows, out): per-simulation
+        arrays in the order of idx — rows.nlayer / rows.thickness from the packed batch, out = the solver's output block.
+
+        Large runs are cut into chunks of whole snowpacks (a snowpack's simulations, one per frequency, stay together
+        so that it is walked once): a packing thread prepares chunk k+1 while chunk k is on the GPU (the C call
+        releases the GIL), and with several ``devices`` the chunks go round-robin to one worker thread per GPU."""
+        group = [sims[i] for i in idx]
+        atm = [atmospheres[i] for i in idx] if atmospheres is not None else None
+
+        def pack(sel):
+            batch = pack_simulations([group[k] for k in sel], self.emmodel, self.emmodel_options,
+                                     atmospheres=[atm[k] for k in sel] if atm is not None else None)
+            if batch.mode == MODE_ACTIVE and not np.array_equal(batch.theta, batch.theta_inc):
+                raise SMRTError("only backscatter (theta == theta_inc) is implemented on the B200 path")
+            return batch
+
+        n = len(group)
+        if n <= self.CHUNK_SIMULATIONS and len(self.devices) == 1:
+            batch = pack(range(n))
+            out = _PLANS.get(batch, opts, self.devices[0]).solve_host(batch)
+            _raise_or_nan(out, opts)
+            return SimpleNamespace(nlayer=batch.nlayer, thickness=batch.thickness), out
+
+        # chunks of whole snowpacks, in order of first appearance
+        first_seen, sp_of = {}, np.empty(n, dtype=np.int64)
+        for k, (_, sp) in enumerate(group):
+            sp_of[k] = first_seen.setdefault(id(sp), len(first_seen))
+        per_sp = max(1, n // max(len(first_seen), 1))
+        sp_per_chunk = max(1, self.CHUNK_SIMULATIONS // per_sp)
+        if len(self.devices) > 1:  # at least two chunks per device
+            sp_per_chunk = max(1, min(sp_per_chunk, -(-len(first_seen) // (2 * len(self.devices)))))
+        chunk_of = sp_of // sp_per_chunk
+        selections = [np.flatnonzero(chunk_of == c) for c in range(int(chunk_of.max()) + 1)]
+
+        def solve(batch, device):
+            return _PLANS.get(batch, opts, device).solve_host(batch)
+
+        packer = ThreadPoolExecutor(1)
+        workers = [ThreadPoolExecutor(1) for _ in self.devices]  # one thread per GPU: a plan is used by one thread
+        try:
+            pending = packer.submit(pack, selections[0])
+            jobs = []
+            for c, sel in enumerate(selections):
+                batch = pending.result()
+                if c + 1 < len(selections):
+                    pending = packer.submit(pack, selections[c + 1])
+                d = c % len(self.devices)
+                jobs.append((sel, batch, workers[d].submit(solve, batch, self.devices[d])))
+            L = max(b.L for _, b, _ in jobs)
+            first = jobs[0][2].result()
+            out = SimpleNamespace(
+                values=np.empty((n,) + first.values.shape[1:]), ks=np.zeros((n, L)), ka=np.zeros((n, L)),
+                eps_eff=np.zeros((n, L), dtype=np.complex128), n_streams=np.zeros(n, dtype=np.int32),
+                stream_angles=np.full((n, first.stream_angles.shape[1]), np.nan), optical_depth=np.zeros(n),
+                status=np.zeros(n, dtype=np.int32))
+            rows = SimpleNamespace(nlayer=np.zeros(n, dtype=np.int32), thickness=np.zeros((n, L)))
+            for sel, batch, job in jobs:
+                o = job.result()
+                out.values[sel] = o.values
+                out.ks[sel, :batch.L], out.ka[sel, :batch.L], out.eps_eff[sel, :batch.L] = o.ks, o.ka, o.eps_eff
+                out.n_streams[sel], out.stream_angles[sel] = o.n_streams, o.stream_angles
+                out.optical_depth[sel], out.status[sel] = o.optical_depth, o.status
+                rows.nlayer[sel], rows.thickness[sel, :batch.L] = batch.nlayer, batch.thickness
+        finally:
+            packer.shutdown(wait=False)
+            for w in workers:
+                w.shutdown(wait=False)
+        _raise_or_nan(out, opts)
+        return rows, out
 
     def _run_simulations(self, sims, opts, atmospheres=None):
         """Pack, solve in one batched GPU call per sensor mode, unpack into per-simulation Results."""
@@ -285,27 +427,21 @@ class Model:
             groups.setdefault(s.mode, []).append(i)
         results = [None] * len(sims)
         for mode, idx in groups.items():
-            group = [sims[i] for i in idx]
-            batch = pack_simulations(group, self.emmodel, self.emmodel_options,
-                                     atmospheres=[atmospheres[i] for i in idx] if atmospheres is not None else None)
-            if batch.mode == MODE_ACTIVE and not np.array_equal(batch.theta, batch.theta_inc):
-                raise SMRTError("only backscatter (theta == theta_inc) is implemented on the B200 path")
-            plan = _PLANS.get(batch, opts, self.device)
-            out = plan.solve_host(batch)
-            _raise_or_nan(out, opts)
+            rows, out = self._solve_simulations(sims, idx, opts, atmospheres)
             for k, i in enumerate(idx):
-                results[i] = _simulation_result(mode, sims[i][0], batch, out, k)
+                results[i] = _simulation_result(mode, sims[i][0], rows, out, k)
         return results
 
 
 def make_model(emmodel=None, rtsolver="dort", emmodel_options=None, rtsolver_options=None, emmodel_kwargs=None,
-               rtsolver_kwargs=None, device: int = 0) -> Model:
+               rtsolver_kwargs=None, device: int = 0, devices: Optional[Sequence[int]] = None) -> Model:
     """Same signature as reference ``smrt.core.model.make_model`` (``model.py:120-177``)."""
     if emmodel_kwargs is not None:
         raise DeprecationWarning("Use emmodel_options instead of emmodel_kwargs")
     if rtsolver_kwargs is not None:
         raise DeprecationWarning("Use rtsolver_options instead of rtsolver_kwargs")
-    return Model(emmodel, rtsolver, emmodel_options=emmodel_options, rtsolver_options=rtsolver_options, device=device)
+    return Model(emmodel, rtsolver, emmodel_options=emmodel_options, rtsolver_options=rtsolver_options, device=device,
+                 devices=devices)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

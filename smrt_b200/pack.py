@@ -354,12 +354,128 @@ def _inclusion_params(layer, code):
     return ws, wn, float(depol[0]), float(depol[1]), float(depol[2])
 
 
+_PERM_CONST, _PERM_ICE, _PERM_WETICE, _PERM_CALL = 0, 1, 2, 3
+_KNOWN_ICE_MODELS = {"ice_permittivity_maetzler06": _PERM_ICE, "wetice_permittivity_bohren83": _PERM_WETICE}
+
+
+def _classify_permittivity(model):
+    """How the permittivity of one medium of a layer can be evaluated for a whole block at once: a constant, one of the
+    two default ice models of the reference (recognised by name and module: ``smrt/permittivity/ice.py:24``,
+    ``wetice.py:13``, or this package's restatements), or an arbitrary callable that has to be called layer by layer."""
+    if not callable(model):
+        return _PERM_CONST, complex(model)
+    kind = _KNOWN_ICE_MODELS.get(getattr(model, "__name__", ""))
+    module = getattr(model, "__module__", "") or ""
+    if kind is not None and (module.startswith("smrt.permittivity") or module.startswith("smrt_b200")):
+        return kind, 0j
+    return _PERM_CALL, 0j
+
+
+def _layer_rows(sp, emmodel, emmodel_options, L):
+    """Frequency-independent rows of one snowpack (every quantity the device needs but the permittivities), plus how to
+    evaluate the permittivities: (kind, constant) per medium and layer.  One pass over the layers."""
+    layers = sp.layers
+    n = len(layers)
+    if len(sp.interfaces) != n:
+        raise SMRTError("the snowpack must have one interface per layer")
+    f8 = np.zeros((6, L))  # thickness, temperature, frac_volume, ms_p0, ms_p1, liquid_water
+    i4 = np.zeros((6, L), dtype=np.int32)  # emmodel, ms_kind, interface, dense_snow_correction, perm kind bg, perm kind sc
+    incl = np.empty((L, 5))
+    incl[:] = SPHERICAL_INCLUSIONS
+    const = np.zeros((2, L), dtype=np.complex128)
+    list_em = isinstance(emmodel, (list, tuple))
+    map_em = isinstance(emmodel, Mapping)
+    if list_em and len(emmodel) != n:
+        raise SMRTError("the list of emmodels must have one entry per layer of the snowpack")
+    list_opts = isinstance(emmodel_options, (list, tuple))
+    if list_opts and len(emmodel_options) != n:
+        raise SMRTError("the list of emmodel options must have one entry per layer of the snowpack")
+    map_opts = map_em and emmodel_options and all(isinstance(o, Mapping) for o in emmodel_options.values())
+    for l, layer in enumerate(layers):
+        # smrt/core/model.py:536-571: a list gives one emmodel per layer, a dict one per medium (layer.medium), else the
+        # layer's own emmodel attribute wins over the model's; the options follow the same three shapes
+        if list_em:
+            em = emmodel[l]
+        elif map_em:
+            medium = getattr(layer, "medium", None)
+            if medium not in emmodel:
+                raise SMRTError(f"no emmodel is given for the medium {medium!r} of layer {l}")
+            em = emmodel[medium]
+        else:
+            em = getattr(layer, "emmodel", None) or emmodel
+        code = emmodel_code(em)
+        opts = getattr(em, "_smrt_options", None)  # class_specializer stand-in
+        opts = dict(opts) if opts else {}
+        if list_opts:
+            opts.update(emmodel_options[l] or {})
+        elif map_opts:
+            opts.update(emmodel_options[getattr(layer, "medium", None)])
+        else:
+            opts.update(getattr(layer, "emmodel_options", None) or emmodel_options)
+        if opts:
+            unknown = set(opts) - {"dense_snow_correction"}
+            if unknown:
+                raise SMRTError(f"emmodel options {sorted(unknown)} are not implemented on the B200 path")
+        dsc = opts.get("dense_snow_correction", "auto" if code in _DMRT_CODES else None)
+        if dsc not in (None, "auto"):
+            raise SMRTError(f"dense_snow_correction={dsc!r} is not implemented")
+        i4[0, l] = code
+        i4[3, l] = 1 if dsc == "auto" else 0
+        i4[2, l] = _interface_code(sp.interfaces[l])
+        f8[0, l] = layer.thickness
+        f8[1, l] = layer.temperature
+        if code == EM_PRESCRIBED_KSKAEPS:  # emmodel/prescribed_kskaeps.py:20-27: everything is given on the layer
+            i4[1, l] = MS_HOMOGENEOUS
+            f8[2, l] = layer.frac_volume
+            f8[3, l], f8[4, l] = float(layer.ks), float(layer.ka)
+            const[0, l] = const[1, l] = complex(layer.effective_permittivity)
+            if _needs_inclusion_params(layer):
+                incl[l] = _inclusion_params(layer, code)
+            continue
+        f8[2, l] = layer.frac_volume
+        kind, p0, p1 = _microstructure_params(layer)
+        if code in _DMRT_CODES and kind != MS_SHS:
+            raise SMRTError("DMRT short range models are only compatible with SHS microstructure model")
+        if code in _IBA_CODES and kind == MS_HOMOGENEOUS:
+            raise SMRTError("IBA needs a microstructure with a Fourier transform (exponential, sticky hard spheres)")
+        if code == EM_RAYLEIGH:  # emmodel/rayleigh.py:41-47
+            if not hasattr(layer.microstructure, "radius"):
+                raise SMRTError("Only microstructure_model which defined a `radius` can be used with Rayleigh "
+                                "scattering")
+            kind, p0, p1 = MS_HOMOGENEOUS, float(layer.microstructure.radius), 0.0
+        i4[1, l], f8[3, l], f8[4, l] = kind, p0, p1
+        if code == EM_IBA_MAXWELL_GARNETT or _needs_inclusion_params(layer):
+            incl[l] = _inclusion_params(layer, code)
+        models = getattr(layer, "permittivity_model", None)
+        if models is None:  # stand-in dry-snow layer of smrt_b200.inputs: ice (Maetzler 2006) in air
+            i4[4, l], i4[5, l] = _PERM_CONST, _PERM_ICE
+            const[0, l] = 1.0
+        else:
+            i4[4, l], const[0, l] = _classify_permittivity(models[0])
+            i4[5, l], const[1, l] = _classify_permittivity(models[1])
+        if i4[4, l] == _PERM_WETICE or i4[5, l] == _PERM_WETICE:
+            f8[5, l] = getattr(layer, "liquid_water", 0.0) or 0.0
+    return n, f8, i4, incl, const
+
+
+def _needs_inclusion_params(layer):
+    """False for the default layer (spherical inclusions, depolarisation factors 1/3): the common case is not charged
+    the shape / depolarisation logic"""
+    d = layer.__dict__ if hasattr(layer, "__dict__") else {}
+    return (d.get("inclusion_shape") not in (None, "spheres") or d.get("depolarization_factors") is not None
+            or d.get("length_ratio") not in (None, 1, 1.0) or d.get("mixing_ratio") is not None)
+
+
 def pack_simulations(simulations, emmodel, emmodel_options=None, atmospheres=None) -> ProblemBatch:
     """Pack a flat list of (sensor, snowpack) pairs (reference ``Model.prepare_simulations`` order,
     ``smrt/core/model.py:485-502``) into one ProblemBatch.
 
     ``sensor`` must have a scalar frequency (DORT broadcasts every sensor axis but frequency,
     ``smrt/rtsolver/dort.py:140-146``); every sensor of the batch must share mode and angles.
+
+    A snowpack that appears in several simulations (one per frequency of the sensor) is walked ONCE; the permittivities
+    are evaluated for whole (snowpack, layer) blocks per frequency when the layer uses a constant or one of the
+    reference's default ice models, and through ``layer.permittivity(i, f)`` otherwise (any user-defined model works).
     """
     simulations = list(simulations)
     if not simulations:
@@ -367,103 +483,89 @@ def pack_simulations(simulations, emmodel, emmodel_options=None, atmospheres=Non
     emmodel_options = emmodel_options or {}
     sensor0 = simulations[0][0]
     mode = MODE_PASSIVE if sensor0.mode == "P" else MODE_ACTIVE
-
-    B = len(simulations)
-    L = max(max(len(sp.layers) for _, sp in simulations), 1)
-    z = lambda dt=np.float64: np.zeros((B, L), dtype=dt)  # noqa: E731
-    batch = ProblemBatch(
-        mode=mode, frequency=np.zeros(B), nlayer=np.zeros(B, dtype=np.int32), thickness=z(), temperature=z(),
-        frac_volume=z(), eps_bg=z(np.complex128), eps_sc=z(np.complex128), emmodel=z(np.int32), ms_kind=z(np.int32),
-        ms_p0=z(), ms_p1=z(), interface=z(np.int32), substrate_kind=np.zeros(B, dtype=np.int32),
-        substrate_eps=np.zeros(B, dtype=np.complex128), substrate_temperature=np.zeros(B),
-        theta=np.atleast_1d(np.asarray(sensor0.theta, dtype=float)).copy(),
-        theta_inc=(np.atleast_1d(np.asarray(sensor0.theta_inc, dtype=float)).copy() if mode == MODE_ACTIVE
-                   else np.zeros(0)),
-        phi=float(np.atleast_1d(getattr(sensor0, "phi", 0.0))[0]),
-        dense_snow_correction=z(np.int32),
-    )
+    theta0 = np.atleast_1d(np.asarray(sensor0.theta, dtype=float)).copy()
     phi = np.atleast_1d(getattr(sensor0, "phi", 0.0))
     if len(phi) > 1:
         raise SMRTError("phi as an array must be implemented")  # same as reference dort.py:180-187
 
+    B = len(simulations)
+    freq = np.empty(B)
+    sp_index = np.empty(B, dtype=np.int64)
+    unique, position = [], {}
+    checked_sensors = {}
     for b, (sensor, sp) in enumerate(simulations):
-        if sensor.mode != sensor0.mode:
-            raise SMRTError("all the sensors of a batch must have the same mode")
-        f = np.atleast_1d(sensor.frequency)
-        if len(f) != 1:
-            raise SMRTError("internal error: the frequency axis must be split before packing")
-        f = float(f[0])
-        batch.frequency[b] = f
-        th = np.atleast_1d(np.asarray(sensor.theta, dtype=float))
-        if th.shape != batch.theta.shape or not np.array_equal(th, batch.theta):
-            raise SMRTError("all the sensors of a batch must have the same viewing angles")
+        sid = id(sensor)
+        f = checked_sensors.get(sid)
+        if f is None:
+            if sensor.mode != sensor0.mode:
+                raise SMRTError("all the sensors of a batch must have the same mode")
+            fa = np.atleast_1d(sensor.frequency)
+            if len(fa) != 1:
+                raise SMRTError("internal error: the frequency axis must be split before packing")
+            th = np.atleast_1d(np.asarray(sensor.theta, dtype=float))
+            if th.shape != theta0.shape or not np.array_equal(th, theta0):
+                raise SMRTError("all the sensors of a batch must have the same viewing angles")
+            f = checked_sensors[sid] = float(fa[0])
+        freq[b] = f
+        key = id(sp)
+        u = position.get(key)
+        if u is None:
+            u = position[key] = len(unique)
+            unique.append(sp)
+        sp_index[b] = u
+
+    U = len(unique)
+    L = max(max(len(sp.layers) for sp in unique), 1)
+    nlayer_u = np.zeros(U, dtype=np.int32)
+    F8 = np.zeros((U, 6, L))
+    I4 = np.zeros((U, 6, L), dtype=np.int32)
+    INCL = np.empty((U, L, 5))
+    CONST = np.zeros((U, 2, L), dtype=np.complex128)
+    for u, sp in enumerate(unique):
+        nlayer_u[u], F8[u], I4[u], INCL[u], CONST[u] = _layer_rows(sp, emmodel, emmodel_options, L)
+
+    take = lambda a: np.ascontiguousarray(a[sp_index])  # noqa: E731
+    temperature = take(F8[:, 1])
+    batch = ProblemBatch(
+        mode=mode, frequency=freq, nlayer=take(nlayer_u), thickness=take(F8[:, 0]), temperature=temperature,
+        frac_volume=take(F8[:, 2]), eps_bg=np.zeros((B, L), dtype=np.complex128),
+        eps_sc=np.zeros((B, L), dtype=np.complex128), emmodel=take(I4[:, 0]), ms_kind=take(I4[:, 1]),
+        ms_p0=take(F8[:, 3]), ms_p1=take(F8[:, 4]), interface=take(I4[:, 2]),
+        substrate_kind=np.zeros(B, dtype=np.int32), substrate_eps=np.zeros(B, dtype=np.complex128),
+        substrate_temperature=np.zeros(B), theta=theta0,
+        theta_inc=(np.atleast_1d(np.asarray(sensor0.theta_inc, dtype=float)).copy() if mode == MODE_ACTIVE
+                   else np.zeros(0)),
+        phi=float(phi[0]), dense_snow_correction=take(I4[:, 3]), inclusion=take(INCL),
+    )
+
+    # permittivities: whole blocks per medium for constants and the default ice models, layer by layer otherwise
+    liquid_water = take(F8[:, 5])
+    for medium, target in ((0, batch.eps_bg), (1, batch.eps_sc)):
+        kind = take(I4[:, 4 + medium])
+        target[...] = take(CONST[:, medium])
+        ice = kind == _PERM_ICE
+        wet = kind == _PERM_WETICE
+        if ice.any() or wet.any():
+            fb = np.broadcast_to(freq[:, None], kind.shape)
+            if ice.any():
+                target[ice] = ice_permittivity_maetzler06(fb[ice], temperature[ice])
+            if wet.any():
+                target[wet] = wetice_permittivity_bohren83(fb[wet], temperature[wet], liquid_water[wet])
+        call = np.argwhere(kind == _PERM_CALL)
+        for b, l in call:
+            target[b, l] = complex(unique[sp_index[b]].layers[l].permittivity(medium, float(freq[b])))
+
+    # substrate and atmosphere (frequency dependent): only the simulations that have one
+    for b, (sensor, sp) in enumerate(simulations):
+        substrate = sp.substrate
+        if substrate is not None:
+            kind, eps, temp, par = _substrate(substrate, float(freq[b]), mode)
+            batch.substrate_kind[b], batch.substrate_eps[b], batch.substrate_temperature[b] = kind, eps, temp
+            batch.substrate_params[b] = par
         # smrt/core/model.py:615: snowpack.atmosphere or the (deprecated) atmosphere argument of the run
         atmos = getattr(sp, "atmosphere", None) or (atmospheres[b] if atmospheres is not None else None)
         if atmos is not None and mode == MODE_PASSIVE:  # active mode ignores it (rtsolver_utils.py:109-147, 302-305)
-            batch.atmosphere[b] = _atmosphere(atmos, f, mode)
-        n = len(sp.layers)
-        batch.nlayer[b] = n
-        if len(sp.interfaces) != n:
-            raise SMRTError("the snowpack must have one interface per layer")
-        for l, layer in enumerate(sp.layers):
-            batch.thickness[b, l] = layer.thickness
-            batch.temperature[b, l] = layer.temperature
-            # smrt/core/model.py:536-571: a list gives one emmodel per layer, a dict one per medium (layer.medium),
-            # else the layer's own emmodel attribute wins over the model's; the options follow the same three shapes
-            if isinstance(emmodel, (list, tuple)):
-                if len(emmodel) != len(sp.layers):
-                    raise SMRTError("the list of emmodels must have one entry per layer of the snowpack")
-                em = emmodel[l]
-            elif isinstance(emmodel, Mapping):
-                medium = getattr(layer, "medium", None)
-                if medium not in emmodel:
-                    raise SMRTError(f"no emmodel is given for the medium {medium!r} of layer {l}")
-                em = emmodel[medium]
-            else:
-                em = getattr(layer, "emmodel", None) or emmodel
-            code = emmodel_code(em)
-            opts = dict(getattr(em, "_smrt_options", {}) or {})  # class_specializer stand-in
-            if isinstance(emmodel_options, (list, tuple)):
-                if len(emmodel_options) != len(sp.layers):
-                    raise SMRTError("the list of emmodel options must have one entry per layer of the snowpack")
-                opts.update(emmodel_options[l] or {})
-            elif isinstance(emmodel, Mapping) and emmodel_options and \
-                    all(isinstance(o, Mapping) for o in emmodel_options.values()):
-                opts.update(emmodel_options[getattr(layer, "medium", None)])
-            else:
-                opts.update(getattr(layer, "emmodel_options", None) or emmodel_options)
-            unknown = set(opts) - {"dense_snow_correction"}
-            if unknown:
-                raise SMRTError(f"emmodel options {sorted(unknown)} are not implemented on the B200 path")
-            dsc = opts.get("dense_snow_correction", "auto" if code in _DMRT_CODES else None)
-            if dsc not in (None, "auto"):
-                raise SMRTError(f"dense_snow_correction={dsc!r} is not implemented")
-            batch.dense_snow_correction[b, l] = 1 if dsc == "auto" else 0
-            batch.emmodel[b, l] = code
-            batch.frac_volume[b, l] = layer.frac_volume
-            kind, p0, p1 = (MS_HOMOGENEOUS, 0.0, 0.0) if code == EM_PRESCRIBED_KSKAEPS else _microstructure_params(layer)
-            if code in _DMRT_CODES and kind != MS_SHS:
-                raise SMRTError("DMRT short range models are only compatible with SHS microstructure model")
-            if code in _IBA_CODES and kind == MS_HOMOGENEOUS:
-                raise SMRTError("IBA needs a microstructure with a Fourier transform (exponential, sticky hard spheres)")
-            if code == EM_RAYLEIGH:  # emmodel/rayleigh.py:41-47
-                if not hasattr(layer.microstructure, "radius"):
-                    raise SMRTError("Only microstructure_model which defined a `radius` can be used with Rayleigh "
-                                    "scattering")
-                kind, p0, p1 = MS_HOMOGENEOUS, float(layer.microstructure.radius), 0.0
-            batch.ms_kind[b, l], batch.ms_p0[b, l], batch.ms_p1[b, l] = kind, p0, p1
-            batch.inclusion[b, l] = _inclusion_params(layer, code)
-            if code == EM_PRESCRIBED_KSKAEPS:  # emmodel/prescribed_kskaeps.py:20-27: everything is given on the layer
-                batch.ms_kind[b, l], batch.ms_p0[b, l], batch.ms_p1[b, l] = MS_HOMOGENEOUS, float(layer.ks), float(layer.ka)
-                batch.eps_bg[b, l] = batch.eps_sc[b, l] = complex(layer.effective_permittivity)
-                batch.interface[b, l] = _interface_code(sp.interfaces[l])
-                continue
-            batch.eps_bg[b, l] = complex(layer.permittivity(0, f))
-            batch.eps_sc[b, l] = complex(layer.permittivity(1, f))
-            batch.interface[b, l] = _interface_code(sp.interfaces[l])
-        kind, eps, temp, par = _substrate(sp.substrate, f, mode)
-        batch.substrate_kind[b], batch.substrate_eps[b], batch.substrate_temperature[b] = kind, eps, temp
-        batch.substrate_params[b] = par
+            batch.atmosphere[b] = _atmosphere(atmos, float(freq[b]), mode)
     return batch
 
 
@@ -492,15 +594,75 @@ def ice_permittivity_maetzler06(frequency, temperature):
     return Ereal + 1j * (alpha / freqGHz + beta * freqGHz)
 
 
+def water_permittivity_maetzler87(frequency, temperature):
+    """Pure water, Mätzler & Wegmüller 1987 — reference ``smrt/permittivity/water.py:12-47`` (vectorised)."""
+    frequency = np.asarray(frequency, dtype=float)
+    temperature = np.asarray(temperature, dtype=float)
+    if np.any(temperature < 273.15):
+        raise SMRTError("The water temperature must be higher or equal to 273.15K")
+    fghz = frequency / 1e9
+    theta = 1 - 300.0 / temperature
+    e0 = 77.66 - 103.3 * theta
+    e1 = 0.0671 * e0
+    f1 = 20.2 + 146.4 * theta + 316 * theta**2
+    e2 = 3.52 + 7.52 * theta
+    f2 = 39.8 * f1
+    return e2 + (e1 - e2) / (1 - 1j * fghz / f2) + (e0 - e1) / (1 - 1j * fghz / f1)
+
+
+def wetice_permittivity_bohren83(frequency, temperature, liquid_water):
+    """Wet ice particles: Maxwell Garnett mixing with water as the background and ice as the inclusions — reference
+    ``smrt/permittivity/wetice.py:13-41`` with ``maxwell_garnett_for_spheres``
+    (``generic_mixing_formula.py:360-380``); dry ice where liquid_water <= 0 (vectorised)."""
+    frequency, temperature, liquid_water = np.broadcast_arrays(np.asarray(frequency, dtype=float),
+                                                              np.asarray(temperature, dtype=float),
+                                                              np.asarray(liquid_water, dtype=float))
+    eps = np.asarray(ice_permittivity_maetzler06(frequency, temperature), dtype=np.complex128).copy()
+    wet = liquid_water > 0.0
+    if np.any(wet):
+        e0 = water_permittivity_maetzler87(frequency[wet], temperature[wet])
+        ei = eps[wet]
+        cplus = ei + 2 * e0
+        cminus = (ei - e0) * (1 - liquid_water[wet])
+        eps[wet] = (cplus + 2 * cminus) / (cplus - cminus) * e0
+    return eps
+
+
+def snow_frac_volumes(density, volumetric_liquid_water=None, liquid_water=None):
+    """(frac_volume of ice + water, liquid_water = water / (ice + water)) of snow layers — reference
+    ``SnowLayer.compute_frac_volumes``, ``smrt/inputs/make_medium.py:390-434`` (vectorised)."""
+    density = np.asarray(density, dtype=float)
+    rho_ice, rho_water = 916.7, 1000.0
+    if volumetric_liquid_water is not None:
+        if liquid_water is not None:
+            raise SMRTError("Setting both liquid_water and volumetric_liquid_water is ambiguous")
+        vlw = np.asarray(volumetric_liquid_water, dtype=float)
+        frac_volume = (density - (rho_water - rho_ice) * vlw) / rho_ice
+        liquid_water = vlw / frac_volume
+    else:
+        liquid_water = np.zeros_like(density) if liquid_water is None else np.asarray(liquid_water, dtype=float)
+        frac_volume = density / (rho_ice * (1 - liquid_water) + rho_water * liquid_water)
+    if not (np.all(frac_volume >= 0) and np.all(frac_volume <= 1.01)):
+        raise SMRTError("the frac_volume of ice+water in snow must be between 0 and 1")
+    if not (np.all(liquid_water >= 0) and np.all(liquid_water <= 1)):
+        raise SMRTError("liquid_water must be between 0 and 1")
+    return np.minimum(frac_volume, 1.0), np.broadcast_to(liquid_water, frac_volume.shape)
+
+
 def pack_snow_ensemble(frequency, thickness, density, temperature, *, microstructure="exponential",
                        corr_length=None, radius=None, stickiness=None, emmodel="iba", mode="P", theta_deg=55.0,
-                       theta_inc_deg=None, phi_deg=180.0) -> ProblemBatch:
+                       theta_inc_deg=None, phi_deg=180.0, volumetric_liquid_water=None,
+                       liquid_water=None) -> ProblemBatch:
     """Dry-snow ensemble given directly as arrays: ``(S, L)`` profiles x ``(F,)`` frequencies -> ``F*S`` problems in the
     reference's simulation order (frequency outermost, snowpack innermost; ``smrt/core/model.py:485-502``).
 
     Equivalent to ``make_snowpack(thickness[s], microstructure, density=density[s], temperature=temperature[s], ...)``
     for every member (``smrt/inputs/make_medium.py:158-232``: frac_volume = density / 916.7, background air eps = 1,
     scatterers = pure ice, flat interfaces, no substrate) without building any Python object.
+
+    Wet snow: ``volumetric_liquid_water`` (or ``liquid_water``) as ``(S, L)`` arrays, like the reference's
+    ``make_snowpack(..., volumetric_liquid_water=...)``: the fractional volumes follow
+    ``SnowLayer.compute_frac_volumes`` and the scatterers are wet ice (``wetice_permittivity_bohren83``).
     """
     thickness = np.atleast_2d(np.asarray(thickness, dtype=float))
     S, L = thickness.shape
@@ -525,7 +687,13 @@ def pack_snow_ensemble(frequency, thickness, density, temperature, *, microstruc
         raise SMRTError("the microstructure parameter (corr_length or radius) is required")
     freq_b = np.repeat(freqs, S)
     temp_b = tile(temperature)
-    eps_sc = ice_permittivity_maetzler06(freq_b[:, None], temp_b)
+    if volumetric_liquid_water is None and liquid_water is None:
+        frac_volume = density / 916.7
+        eps_sc = ice_permittivity_maetzler06(freq_b[:, None], temp_b)
+    else:
+        bc = lambda a: None if a is None else np.broadcast_to(np.asarray(a, dtype=float), (S, L))  # noqa: E731
+        frac_volume, lw = snow_frac_volumes(density, bc(volumetric_liquid_water), bc(liquid_water))
+        eps_sc = wetice_permittivity_bohren83(freq_b[:, None], temp_b, tile(lw))
     theta = np.radians(np.atleast_1d(np.asarray(theta_deg, dtype=float)))
     if mode == "A":
         theta_inc = np.radians(np.atleast_1d(np.asarray(theta_deg if theta_inc_deg is None else theta_inc_deg,
@@ -535,7 +703,7 @@ def pack_snow_ensemble(frequency, thickness, density, temperature, *, microstruc
     return ProblemBatch(
         mode=MODE_PASSIVE if mode == "P" else MODE_ACTIVE,
         frequency=freq_b, nlayer=np.full(B, L, dtype=np.int32), thickness=tile(thickness), temperature=temp_b,
-        frac_volume=tile(density / 916.7), eps_bg=np.ones((B, L), dtype=np.complex128), eps_sc=eps_sc,
+        frac_volume=tile(frac_volume), eps_bg=np.ones((B, L), dtype=np.complex128), eps_sc=eps_sc,
         emmodel=np.full((B, L), code, dtype=np.int32), ms_kind=np.full((B, L), kind, dtype=np.int32),
         ms_p0=tile(p0), ms_p1=tile(p1), interface=np.zeros((B, L), dtype=np.int32),
         substrate_kind=np.zeros(B, dtype=np.int32), substrate_eps=np.zeros(B, dtype=np.complex128),

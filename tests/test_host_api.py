@@ -2,6 +2,7 @@
 
 The batched solve is stood in by the SIMT-emulated kernels (tests/simt_emu) so that the host code is exercised end to
 end without a GPU; the `-m gpu` twin (tests/test_gpu_api.py) runs the same calls through the CUDA library."""
+import threading
 import warnings
 
 import numpy as np
@@ -14,13 +15,17 @@ from smrt_b200 import capi, make_model, make_snowpack, model as model_mod, senso
 from smrt_b200.error import SMRTError, SMRTWarning
 
 
+_EMU_LOCK = threading.Lock()  # the SIMT emulator runs one launch at a time (the real plans are one per device)
+
+
 class EmuPlan:
     def __init__(self, opts):
         self.opts = opts
         self.options = type("O", (), dict(max_batch=10 ** 9, n_max_stream=opts["n_max_stream"]))()
 
     def solve_host(self, batch):
-        return emu_solve(batch, self.opts, threads=64)
+        with _EMU_LOCK:
+            return emu_solve(batch, self.opts, threads=64)
 
 
 @pytest.fixture(autouse=True)
@@ -348,3 +353,102 @@ def test_first_year_sea_ice_ensemble_packer_matches_the_reference_inputs():
         np.testing.assert_allclose(b.inclusion, ref.inclusion[rows][:, :3], rtol=1e-15)
     with pytest.raises(SMRTError):
         pack_sea_ice_ensemble(1.4e9, [[1.0]], [[260.0]], [[5e-3]], 0.05, 5e-4, ice_type="firstyear")
+
+
+def _ragged_snowpacks():
+    rng = np.random.default_rng(3)
+    sps = []
+    for n in (1, 3, 2, 4, 2):
+        sps.append(make_snowpack(list(rng.uniform(0.1, 0.5, n - 1)) + [20.0], "exponential",
+                                 density=rng.uniform(200, 420, n), temperature=rng.uniform(245, 270, n),
+                                 corr_length=rng.uniform(5e-5, 3e-4, n)))
+    return sps
+
+
+def _assert_same_result(a, b):
+    assert a.data.dims == b.data.dims and type(a) is type(b)
+    np.testing.assert_array_equal(np.asarray(a.data.values), np.asarray(b.data.values))
+    for d in a.data.dims:
+        assert list(a.data.coords[d].values) == list(b.data.coords[d].values)
+    assert a.channel_map == b.channel_map
+    assert set(a.other_data) == set(b.other_data)
+    for k in a.other_data:
+        assert a.other_data[k].dims == b.other_data[k].dims, k
+        np.testing.assert_array_equal(np.asarray(a.other_data[k].values), np.asarray(b.other_data[k].values))
+
+
+def test_one_shot_result_equals_the_stacked_per_simulation_results():
+    """Model.run builds the N-d Result directly from the output block; the reference stacks one Result per simulation
+    (core/model.py:401-404).  Ragged layer counts and ragged numbers of air streams are NaN padded the same way."""
+    from smrt_b200.result import concat_results
+
+    sps = _ragged_snowpacks()
+    sensor = sensor_list.amsre(["19", "37", "89"])
+    m = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8))
+    fast = m.run(sensor, sps)
+    assert fast.data.dims == ("frequency", "snowpack", "polarization", "theta") and fast.data.shape == (3, 5, 2, 1)
+    assert fast.other_data["ks"].shape == (3, 5, 4) and np.isnan(fast.other_data["ks"].values[0, 0, 1:]).all()
+    sims, dimensions = m.prepare_simulations(sensor, sps, None, "snowpack")
+    from smrt_b200.model import check_dort_options
+    results = m._run_simulations(sims, check_dort_options(m.rtsolver_options))
+    for dimension in reversed(dimensions):
+        n = len(dimension[1])
+        results = [concat_results(results[i:i + n], dimension) for i in range(0, len(results), n)]
+    _assert_same_result(fast, results[0])
+    assert fast.Tb(channel="37V", snowpack=3) == fast.data.values[1, 3, 0, 0]
+    # chunked pack / solve pipeline (and the same through two "devices"): identical block
+    m2 = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8), devices=[0, 1])
+    m2.CHUNK_SIMULATIONS = 4
+    _assert_same_result(fast, m2.run(sensor, sps))
+    # active mode
+    radar = sensor_list.active([13e9, 17e9], 40)
+    fa = m.run(radar, sps[1:4])
+    assert fa.data.dims == ("frequency", "snowpack", "polarization_inc", "polarization", "theta_inc")
+    one = m.run(sensor_list.active(17e9, 40), sps[2])
+    np.testing.assert_array_equal(fa.data.values[1, 1], one.data.values)
+
+
+def test_wet_snow_packers_agree_and_follow_the_reference_formulas():
+    """Wet snow: the array packer, the object packer (reference wetice model recognised by name) and the scalar
+    formulas of smrt/permittivity/wetice.py:13-41, water.py:12-47, make_medium.py:390-434."""
+    from smrt_b200 import pack
+
+    f, T, lw = 18.7e9, 273.15, 0.06
+    theta = 1 - 300.0 / T
+    e0 = 77.66 - 103.3 * theta
+    e1 = 0.0671 * e0
+    f1 = 20.2 + 146.4 * theta + 316 * theta**2
+    e2 = 3.52 + 7.52 * theta
+    ew = e2 + (e1 - e2) / complex(1, -f / 1e9 / (39.8 * f1)) + (e0 - e1) / complex(1, -f / 1e9 / f1)
+    assert complex(pack.water_permittivity_maetzler87(f, T)) == pytest.approx(ew, rel=1e-15)
+    ei = complex(pack.ice_permittivity_maetzler06(f, T))
+    cplus, cminus = ei + 2 * ew, (ei - ew) * (1 - lw)
+    assert complex(pack.wetice_permittivity_bohren83(f, T, lw)) == pytest.approx((cplus + 2 * cminus) / (cplus - cminus) * ew,
+                                                                               rel=1e-15)
+    assert complex(pack.wetice_permittivity_bohren83(f, 260.0, 0.0)) == complex(pack.ice_permittivity_maetzler06(f, 260.0))
+    fv, lwf = pack.snow_frac_volumes(np.array([300.0, 400.0]), volumetric_liquid_water=np.array([0.0, 0.03]))
+    np.testing.assert_allclose(fv, [300 / 916.7, (400 - 83.3 * 0.03) / 916.7], rtol=1e-15)
+    np.testing.assert_allclose(lwf, [0.0, 0.03 / fv[1]], rtol=1e-15)
+
+    # object packer on layers that carry the reference's default permittivity model (by name) and a liquid_water attribute
+    def wetice_permittivity_bohren83(frequency, temperature=None, liquid_water=None, _properties_to_inject=None):
+        p = _properties_to_inject
+        return complex(pack.wetice_permittivity_bohren83(frequency, p.temperature, p.liquid_water))
+
+    wetice_permittivity_bohren83.__module__ = "smrt.permittivity.wetice"
+    th = np.array([[0.2, 0.4, 10.0]]); rho = np.array([[250.0, 320.0, 400.0]]); T3 = np.array([[273.15] * 3])
+    vlw = np.array([[0.02, 0.0, 0.05]]); pc = np.array([[1e-4, 2e-4, 3e-4]])
+    arr = pack.pack_snow_ensemble([18.7e9, 36.5e9], th, rho, T3, corr_length=pc, volumetric_liquid_water=vlw)
+    fvol, lwat = pack.snow_frac_volumes(rho[0], vlw[0])
+    sp = make_snowpack(th[0], "exponential", density=rho[0], temperature=T3[0], corr_length=pc[0])
+    for l, layer in enumerate(sp.layers):
+        layer.microstructure.frac_volume = float(fvol[l])
+        layer.liquid_water = float(lwat[l])
+        layer.permittivity_model = (1.0, wetice_permittivity_bohren83)
+        layer.permittivity = (lambda lay: lambda i, fr: lay.permittivity_model[i](fr, _properties_to_inject=lay)
+                              if callable(lay.permittivity_model[i]) else lay.permittivity_model[i])(layer)
+    sims = [(s, sp) for s in sensor_list.passive([18.7e9, 36.5e9], 55).iterate("frequency")]
+    obj = pack.pack_simulations(sims, "iba")
+    np.testing.assert_allclose(obj.eps_sc, arr.eps_sc, rtol=1e-15)
+    np.testing.assert_allclose(obj.frac_volume, arr.frac_volume, rtol=1e-15)
+    assert abs(arr.eps_sc[0, 0].imag) > 10 * abs(arr.eps_sc[0, 1].imag)  # the wet layers absorb far more
