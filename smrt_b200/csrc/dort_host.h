@@ -1,6 +1,7 @@
 // dort_host.h — host-side planning shared by the CUDA library (capi.cu) and the CPU emulation driver used by the test
 // suite: Gauss-Legendre nodes, workspace layout, kernel-argument assembly.  Plain C++ (no CUDA runtime calls).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstddef>
 #include <cstring>
@@ -45,6 +46,7 @@ struct Layout {
   size_t eigen_small_packed_smem_bytes;                     // ... of the 4-CTAs-per-SM eigen instantiation (h <= 64; 0: n/a)
   size_t boundary_mid_smem_bytes;                           // ... of the boundary instantiation for 64 < h <= 128 (0: n/a)
   long long boundary_mid_scratch_doubles;                   // its per-CTA global scratch
+  long long boundary_mid_arena;                             // doubles of its shared-memory matrix arena
   size_t boundary_stream_smem_bytes;                        // ... of the boundary instantiation that stages F and G (0: n/a)
   size_t eigen_vec_bytes, boundary_vec_bytes;              // vector region only (global-scratch path)
   long long eigen_scratch_doubles, boundary_scratch_doubles;  // per-CTA matrix scratch
@@ -91,8 +93,16 @@ inline Layout make_layout(const smrtb200_options& o) {
       (L.hmax <= 64) ? (eigen_vec_doubles(L.n, L.hmax, L.K, SMRT_PANEL_SMALL) + eigen_mat_doubles(L.hmax, true)) * sizeof(double)
                      : 0;
   const bool mid = L.hmax > 64 && L.hmax <= 128;
+  // the matrix arena takes whatever the 227 KB opt-in limit leaves (at least the one resident matrix)
+  {
+    const long long limit = (227 * 1024 - 256) / 8;
+    const long long fixed = (long long)(L.boundary_vec_bytes / 8 + boundary_mid_fixed_doubles(L.hmax, L.nrhs_max));
+    const long long m1 = (long long)L.hmax * boundary_mid_ld(L.hmax) + SMRT_MID_STAGE;
+    L.boundary_mid_arena = mid ? std::max(m1, (limit - fixed) & ~1LL) : 0;
+  }
   L.boundary_mid_smem_bytes =
-      mid ? L.boundary_vec_bytes + boundary_mid_smem_doubles(L.hmax, L.nrhs_max) * sizeof(double) : 0;
+      mid ? L.boundary_vec_bytes + boundary_mid_smem_doubles(L.hmax, L.nrhs_max, (size_t)L.boundary_mid_arena) * sizeof(double)
+          : 0;
   L.boundary_mid_scratch_doubles = mid ? (long long)boundary_mid_scratch_doubles(L.hmax) : 0;
   // F / G staged into [T | R] (deferred-store products): blocks of <= 64 unknowns only
   L.boundary_stream_smem_bytes =
@@ -148,6 +158,7 @@ inline KArgs make_kargs(const smrtb200_options& o, const Layout& L, const smrtb2
   A.optical_depth = bt.optical_depth + b0;
   A.status = bt.status + b0;
   A.eig_stride = L.eig_stride;
+  A.mid_arena = L.boundary_mid_arena;
   for (int m = 0; m < SMRT_MAX_MODES; ++m) A.eig_off[m] = L.eig_off[m];
   return A;
 }

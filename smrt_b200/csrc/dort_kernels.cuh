@@ -52,6 +52,7 @@ struct KArgs {
   unsigned long long* prof;  // optional [16] cycle counters of the boundary kernel phases (SMRT_B200_PROFILE; may be NULL)
   double* scratch;      // [gridDim.x, scratch_stride] when use_global_scratch
   long long eig_stride, scratch_stride;
+  long long mid_arena;  // boundary kernel for 64 < h <= 128: doubles of the shared-memory matrix arena
   int use_global_scratch;
   int eig_off[SMRT_MAX_MODES];  // offset of mode m inside one (problem, layer) eigen record
 };
@@ -518,11 +519,19 @@ SMRT_HD size_t boundary_mat_doubles(int hmax, int nrhs_max, bool stream = false)
 // factorised in product form, then the B operand of the products), the staging panels of the GEMMs, the pivot-row
 // exchange buffer and the right-hand sides; the other h x h blocks live in an L2-resident per-CTA global scratch.
 SMRT_HD int boundary_mid_ld(int h) { return (h + 7) & ~7; }
-SMRT_HD size_t boundary_mid_smem_doubles(int hmax, int nrhs_max) {
+#define SMRT_MID_STAGE 6144  // doubles of the GEMM staging ring (3 panels; inside the arena, placed per layer)
+// `arena`: doubles of the matrix arena (>= hmax * ld + SMRT_MID_STAGE: the resident matrix M1 and the staging panels of
+// the GEMMs; whatever shared memory is left goes to it,
+// so that layers whose TWO blocks [A21 | A22 | rhs] fit — most layers keep fewer streams than n_max_stream — are
+// eliminated in shared memory like the h <= 64 instantiations, with the right block riding along)
+SMRT_HD size_t boundary_mid_fixed_doubles(int hmax, int nrhs_max) {
   const size_t ldm = boundary_mid_ld(hmax);
-  return (size_t)1024 + ldm /* matvec scratch, reciprocal pivots */ + (size_t)hmax * ldm /* M1 */ +
-         4096 /* GEMM staging */ + 2 * 8 * 32 * 4 /* pivot-row exchange */ + ldm * nrhs_max /* rhs block */ +
+  return (size_t)1024 + ldm /* matvec scratch, reciprocal pivots */ +
+         2 * 8 * 32 * 4 /* pivot-row exchange / V buffer */ + ldm * nrhs_max /* rhs block */ +
          4 * (size_t)hmax * nrhs_max + 16;
+}
+SMRT_HD size_t boundary_mid_smem_doubles(int hmax, int nrhs_max, size_t arena) {
+  return boundary_mid_fixed_doubles(hmax, nrhs_max) + arena;
 }
 // global scratch: gA (A22 -> S), gB (Y~ -> R of the stack), gC (K), gF / gG (generated operands of non-scattering layers)
 SMRT_HD size_t boundary_mid_scratch_doubles(int hmax) {
@@ -620,14 +629,13 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
   if (kMid) {
     GJV = mats;  // scratch of the block matrix-vector products (1024 doubles)
     pivinv = GJV + 1024;
-    M1 = pivinv + ldm_max;
-    stage = M1 + (size_t)hmax * ldm_max;
-    xch = stage + 4096;
-    rhsM = xch + 2 * 8 * 32 * 4;
+    rhsM = pivinv + ldm_max;
     btop = rhsM + (size_t)ldm_max * nrhs_max;
     svec = btop + szr;
     ytr = svec + szr;
     vvec = ytr + szr;
+    M1 = vvec + szr;  // the matrix arena: [M1 | staging] or [M1 | right block | rhs] (A.mid_arena doubles)
+    xch = M1 + A.mid_arena;
     gA = A.scratch + (size_t)blockIdx.x * A.scratch_stride;
     gB = gA + (size_t)hmax * ldm_max;
     gC = gB + (size_t)hmax * ldm_max;
@@ -961,7 +969,16 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
         const int r = have_prev ? (h < h_prev ? h : h_prev) : 0;
         const int ldm = boundary_mid_ld(h);            // kMid: leading dimension of the resident matrix and of the rhs block
         const int ldt = kMid ? ldm : ldp;
-        double* Trhs = kMid ? rhsM : TT + (size_t)(2 * h) * ldp;  // b_bot lives in the augmented columns of T
+        // kMid: both blocks and the right-hand sides fit in the arena -> the right block rides along (resident path)
+        // (the staging panels of the GEMMs then lie over the right block, which is dead or not yet formed whenever a GEMM
+        // streams its operands; blocks so small that the panels would reach the right-hand sides get them behind)
+        const long long need2 = (long long)(2 * h + nr) * ldm;
+        const bool stage_behind = (long long)h * ldm < SMRT_MID_STAGE;
+        const bool resident = kMid && need2 + (stage_behind ? SMRT_MID_STAGE : 0) <= A.mid_arena;
+        double* R2 = kMid ? M1 + (size_t)h * ldm : nullptr;
+        if (kMid) stage = (resident && stage_behind) ? M1 + ((need2 + 1) & ~1LL) : R2;
+        double* Trhs = kMid ? (resident ? R2 + (size_t)h * ldm : rhsM)
+                            : TT + (size_t)(2 * h) * ldp;  // b_bot lives in the augmented columns of T
         if (nr > 0) {
           const double Tl = A.temperature[bL + l];
           const double Bl = (thermal && Tl > 0.0) ? planck_function(freq, Tl, A.rayleigh_jeans) : 0.0;
@@ -1025,51 +1042,95 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
           SMRT_FOR_2D(i, k, r, r) { SMRT_AT(gB, ldr_prev, i, k) *= Ttprev[i] * (Tb[k] * Dsg[k]); }
           __syncthreads();
           // A21 = F - Rb D G - R' G -> M1 ;  A22 = (G - Rb D F - R' F) t -> gA
-          mid_gemm<false, false, 8>(h, r, h, 0, r, gB, nullptr, ldr_prev, Go, h, stage, [&](int i, int j, double acc, double) {
+          // (tile maps by block size: 32-row slabs x 16-column groups without padding)
+          auto form21 = [&](int i, int j, double acc, double) {
             const size_t e = (size_t)j * h + i;
             M1[(size_t)j * ldm + i] = Fo[e] - RbD[i] * Go[e] - acc;
-          });
-          mid_gemm<false, false, 8>(h, r, h, 0, r, gB, nullptr, ldr_prev, Fo, h, stage, [&](int i, int j, double acc, double) {
+          };
+          auto form22 = [&](int i, int j, double acc, double) {
             const size_t e = (size_t)j * h + i;
-            gA[(size_t)j * ldm + i] = (Go[e] - RbD[i] * Fo[e] - acc) * tvec[j];
-          });
+            (resident ? R2 : gA)[(size_t)j * ldm + i] = (Go[e] - RbD[i] * Fo[e] - acc) * tvec[j];
+          };
+          if (h <= 64) {
+            mid_gemm<false, false, 4, 2>(h, r, h, 0, r, gB, nullptr, ldr_prev, Go, h, stage, form21);
+            mid_gemm<false, false, 4, 2>(h, r, h, 0, r, gB, nullptr, ldr_prev, Fo, h, stage, form22);
+          } else if (h <= 96) {
+            mid_gemm<false, false, 6, 3>(h, r, h, 0, r, gB, nullptr, ldr_prev, Go, h, stage, form21);
+            mid_gemm<false, false, 6, 3>(h, r, h, 0, r, gB, nullptr, ldr_prev, Fo, h, stage, form22);
+          } else {
+            mid_gemm<false, false, 8, 4>(h, r, h, 0, r, gB, nullptr, ldr_prev, Go, h, stage, form21);
+            mid_gemm<false, false, 8, 4>(h, r, h, 0, r, gB, nullptr, ldr_prev, Fo, h, stage, form22);
+          }
           __syncthreads();
           SMRT_PHASE(3)  // right-hand sides, formation of [A21 | A22]
-          // A21 in product form (the right-hand sides ride along), then A22 in chunks of 32 columns
-          if (block_gj_factor(M1, ldm, Trhs, ldm, h, nr, rowof, pivinv, &s_ctrl[6])) {
-            failed = true;
-            break;
+          if (resident) {
+            // [A21 | A22 | b_bot] in shared memory: the blocked elimination of the h <= 64 instantiations, whose look-ahead
+            // hides the serial panel chain behind the updates of the right block; Y~ goes straight into M1
+            if (block_gj_rows_blocked_mid(M1, ldm, R2, ldm, h, h + nr, rowof, pivinv, xch, &s_ctrl[6])) {
+              failed = true;
+              break;
+            }
+            for (int k = tid; k < h; k += NT) ipiv[k] = tvec[k] * pivinv[k];
+            __syncthreads();
+            SMRT_FOR_2D(k, c, h, nr) { SMRT_AT(ytr, h, k, c) = SMRT_AT(Trhs, ldm, rowof[k], c) * ipiv[k]; }
+            SMRT_FOR_2D(k, c, h, h) { M1[(size_t)c * ldm + k] = R2[(size_t)c * ldm + rowof[k]] * ipiv[k]; }
+          } else {
+            // A21 in product form (the right-hand sides ride along), then A22 in one register-resident pass
+            if (block_gj_factor(M1, ldm, Trhs, ldm, h, nr, rowof, pivinv, &s_ctrl[6])) {
+              failed = true;
+              break;
+            }
+            for (int k = tid; k < h; k += NT) {
+              ipiv[k] = tvec[k] * pivinv[k];
+              kof[rowof[k]] = k;
+            }
+            __syncthreads();
+            SMRT_FOR_2D(k, c, h, nr) { SMRT_AT(ytr, h, k, c) = SMRT_AT(Trhs, ldm, rowof[k], c) * ipiv[k]; }
+            // Y~ = diag(t) A21^-1 A22 -> gB (the operator of the stack below is dead)
+            gj_apply_all(
+                M1, ldm, h, rowof, xch, [&](int i, int c) { return gA[(size_t)c * ldm + i]; },
+                [&](int i, int c, double v) {
+                  const int k = kof[i];
+                  gB[(size_t)c * ldm + k] = v * ipiv[k];
+                });
+            // Y~ -> M1 by ONE bulk copy of the TMA engine (the threads' own loop exposed the L2 latency)
+            smrt_fence_async_global();
+            __syncthreads();
+            if (tid == 0) smrt_bulk_load1(&s_mbar, M1, gB, (unsigned)((size_t)h * ldm * sizeof(double)));
+            smrt_mbar_wait(&s_mbar, pf_parity);
+            pf_parity ^= 1u;
           }
-          for (int k = tid; k < h; k += NT) {
-            ipiv[k] = tvec[k] * pivinv[k];
-            kof[rowof[k]] = k;
-          }
-          __syncthreads();
-          SMRT_FOR_2D(k, c, h, nr) { SMRT_AT(ytr, h, k, c) = SMRT_AT(Trhs, ldm, rowof[k], c) * ipiv[k]; }
-          // Y~ = diag(t) A21^-1 A22 -> gB (the operator of the stack below is dead)
-          gj_apply_all(
-              M1, ldm, h, rowof, xch, [&](int i, int c) { return gA[(size_t)c * ldm + i]; },
-              [&](int i, int c, double v) {
-                const int k = kof[i];
-                gB[(size_t)c * ldm + k] = v * ipiv[k];
-              });
           __syncthreads();
           SMRT_PHASE(4)  // first elimination
           // Y~ becomes the resident B operand of  P = F - G Y~,  K = G - F Y~ ;  S = D P - Rt K -> gA,  K -> gC
           // (l > 0: both TRANSPOSED, so that R_new = K S^-1 = (S^-T K^T)^T comes out of the same row elimination)
-          SMRT_FOR_2D(i, j, h, h) { M1[(size_t)j * ldm + i] = gB[(size_t)j * ldm + i]; }
-          __syncthreads();
           const bool transposed = l > 0;
-          for (int n0 = 0; n0 < h; n0 += 64) {
-            mid_gemm<true, true, 4>(h, h, h, n0, h, Go, Fo, h, M1, ldm, stage, [&](int i, int j, double c1, double c2) {
-              const size_t e = (size_t)j * h + i;
-              const double pv = Fo[e] - c1;
-              const double kv = Go[e] - c2;
-              const double sv = Dsg[i] * pv - Rt[i] * kv;
-              const size_t o = transposed ? (size_t)i * ldm + j : (size_t)j * ldm + i;
-              gA[o] = sv;
-              gC[o] = kv;
-            });
+          auto prod = [&](int i, int j, double c1, double c2) {
+            const size_t e = (size_t)j * h + i;
+            const double pv = Fo[e] - c1;
+            const double kv = Go[e] - c2;
+            const double sv = Dsg[i] * pv - Rt[i] * kv;
+            const size_t o = transposed ? (size_t)i * ldm + j : (size_t)j * ldm + i;
+            gA[o] = sv;
+            gC[o] = kv;
+          };
+          if (h <= 64) {
+            for (int n0 = 0; n0 < h; n0 += 32) mid_gemm<true, true, 2, 2>(h, h, h, n0, h, Go, Fo, h, M1, ldm, stage, prod);
+          } else if (h <= 96) {
+            for (int n0 = 0; n0 < h; n0 += 48) mid_gemm<true, true, 3, 3>(h, h, h, n0, h, Go, Fo, h, M1, ldm, stage, prod);
+          } else {
+            for (int n0 = 0; n0 < h; n0 += 64) mid_gemm<true, true, 4, 4>(h, h, h, n0, h, Go, Fo, h, M1, ldm, stage, prod);
+          }
+          // S (or S^T) -> M1 and, on the resident path, K^T -> the right block: bulk copies by the TMA engine (the products
+          // were stored by other threads: proxy fence + barrier first; M1 was their B operand), in flight under b'
+          smrt_fence_async_global();
+          __syncthreads();
+          if (tid == 0) {
+            const unsigned bytes = (unsigned)((size_t)h * ldm * sizeof(double));
+            if (resident && l > 0)
+              smrt_bulk_load2(&s_mbar, M1, gA, R2, gC, bytes);
+            else
+              smrt_bulk_load1(&s_mbar, M1, gA, bytes);
           }
           // v = F y~r ;  b' = b_top - D (G y~r) + Rt v  (in the right-hand-side block)
           if (nr == 1) {
@@ -1084,27 +1145,33 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
                 SMRT_AT(Trhs, ldm, i, c) = SMRT_AT(btop, h, i, c) - Dsg[i] * c1 + Rt[i] * c2;
               });
             }
-            __syncthreads();
           }
-          // S (or S^T) -> M1 (the products were stored by other threads, and M1 was their B operand)
-          __syncthreads();
-          SMRT_FOR_2D(i, j, h, h) { M1[(size_t)j * ldm + i] = gA[(size_t)j * ldm + i]; }
+          smrt_mbar_wait(&s_mbar, pf_parity);
+          pf_parity ^= 1u;
           __syncthreads();
           SMRT_PHASE(5)  // extraction, products P / K / S, b'
           if (l > 0) {
             // [S^T | K^T]: rows of S^-T K^T = columns of R_new; b' is not touched
-            if (block_gj_factor(M1, ldm, Trhs, ldm, h, 0, rowof, pivinv, &s_ctrl[6])) {
-              failed = true;
-              break;
+            if (resident) {
+              if (block_gj_rows_blocked_mid(M1, ldm, R2, ldm, h, h, rowof, pivinv, xch, &s_ctrl[6])) {
+                failed = true;
+                break;
+              }
+              SMRT_FOR_2D(i, k, h, h) { gB[(size_t)k * ldm + i] = R2[(size_t)i * ldm + rowof[k]] * pivinv[k]; }
+            } else {
+              if (block_gj_factor(M1, ldm, Trhs, ldm, h, 0, rowof, pivinv, &s_ctrl[6])) {
+                failed = true;
+                break;
+              }
+              for (int k = tid; k < h; k += NT) kof[rowof[k]] = k;
+              __syncthreads();
+              gj_apply_all(
+                  M1, ldm, h, rowof, xch, [&](int i, int c) { return gC[(size_t)c * ldm + i]; },
+                  [&](int i, int c, double v) {
+                    const int k = kof[i];
+                    gB[(size_t)k * ldm + c] = v * pivinv[k];  // R_new(c, k)
+                  });
             }
-            for (int k = tid; k < h; k += NT) kof[rowof[k]] = k;
-            __syncthreads();
-            gj_apply_all(
-                M1, ldm, h, rowof, xch, [&](int i, int c) { return gC[(size_t)c * ldm + i]; },
-                [&](int i, int c, double v) {
-                  const int k = kof[i];
-                  gB[(size_t)k * ldm + c] = v * pivinv[k];  // R_new(c, k)
-                });
             __syncthreads();
             SMRT_PHASE(6)  // second elimination
             if (nr == 1) {  // s = v + R_new b'
@@ -1123,7 +1190,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
             SMRT_PHASE(7)  // R of the stack, source vector
           } else {
             // top layer: z = S^-1 b' by row elimination of [S | b'], then s = v + K z
-            if (block_gj_factor(M1, ldm, Trhs, ldm, h, nr, rowof, pivinv, &s_ctrl[6])) {
+            if (block_gj_rows_blocked_mid(M1, ldm, Trhs, ldm, h, nr, rowof, pivinv, xch, &s_ctrl[6])) {
               failed = true;
               break;
             }

@@ -1429,7 +1429,9 @@ SMRT_DEV void gj_update_cols(double* Lb, int ldl, double* Rb, int ldr, int h, in
 // order, x <- x + V_p x[P_p] (P_p = rowof[4p .. 4p+3], old values), maps ANY further column b to the unscaled solution
 // of the system (gj_apply_block): right-hand blocks that do not fit next to the left block in shared memory are
 // eliminated afterwards, chunk by chunk.
-template <int RPL, int RT, bool kShared, bool kKeepV = false>
+// kSpare (blocks of 16 warps): the warps that share the panel warp's scheduler (warp % 4 == 0) take no part in the
+// updates of the remaining columns: the serial panel chain is the critical path and runs faster alone on its scheduler
+template <int RPL, int RT, bool kShared, bool kKeepV = false, bool kSpare = false>
 SMRT_DEV_NOINLINE int block_gj_rows_blocked_t(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowof,
                                               double* ipiv, double* Vbuf, int* flag) {
   if (kShared) {  // every operand lives in the block's shared memory
@@ -1472,7 +1474,11 @@ SMRT_DEV_NOINLINE int block_gj_rows_blocked_t(double* Lb, int ldl, double* Rb, i
           gj_update_cols<RT>(Lb, ldl, Rb, ldr, h, cstart, cstart + npn, (tid >> 4) & 1, 2, lx, npc, Vin, ldv, rowof + j0);
         }
       }
-      if (warp > 0)
+      if (kSpare) {
+        if ((warp & 3) != 0)  // 3 update warps per scheduler group of 4: index warp - 1 - warp / 4 among 3 nwarp / 4
+          gj_update_cols<RT>(Lb, ldl, Rb, ldr, h, cstart + npn, W, 2 * (warp - 1 - (warp >> 2)) + ((tid >> 4) & 1),
+                             2 * (nwarp - (nwarp >> 2)), lx, npc, Vin, ldv, rowof + j0);
+      } else if (warp > 0)
         gj_update_cols<RT>(Lb, ldl, Rb, ldr, h, cstart + npn, W, (tid >> 4) - 2, 2 * (nwarp - 1), lx, npc, Vin, ldv,
                            rowof + j0);
     }
@@ -1506,10 +1512,19 @@ SMRT_DEV int block_gj_rows_blocked(double* Lb, int ldl, double* Rb, int ldr, int
 // =====================================================================================================================
 SMRT_DEV int block_gj_factor(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowof, double* ipiv, int* flag) {
   // (the V buffer argument is unused in product form: any shared-memory pointer)
-  if (h <= 32) return block_gj_rows_blocked_t<1, 2, true, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Lb, flag);
-  if (h <= 64) return block_gj_rows_blocked_t<2, 4, true, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Lb, flag);
-  if (h <= 96) return block_gj_rows_blocked_t<3, 6, true, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Lb, flag);
-  return block_gj_rows_blocked_t<4, 8, true, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Lb, flag);
+  if (h <= 32) return block_gj_rows_blocked_t<1, 2, true, true, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Lb, flag);
+  if (h <= 64) return block_gj_rows_blocked_t<2, 4, true, true, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Lb, flag);
+  if (h <= 96) return block_gj_rows_blocked_t<3, 6, true, true, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Lb, flag);
+  return block_gj_rows_blocked_t<4, 8, true, true, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Lb, flag);
+}
+
+// the plain (two resident blocks) elimination for up to 128 unknowns: Vbuf double[>= 8 h]
+SMRT_DEV int block_gj_rows_blocked_mid(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowof, double* ipiv,
+                                       double* Vbuf, int* flag) {
+  if (h <= 32) return block_gj_rows_blocked_t<1, 2, true, false, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
+  if (h <= 64) return block_gj_rows_blocked_t<2, 4, true, false, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
+  if (h <= 96) return block_gj_rows_blocked_t<3, 6, true, false, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
+  return block_gj_rows_blocked_t<4, 8, true, false, true>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
 }
 
 // Apply the product-form factorisation held in M (h x h, leading dimension ldm, a multiple of 2; panels of SMRT_GJ_NB = 4
@@ -1641,75 +1656,72 @@ SMRT_DEV void gj_apply_all(const double* M, int ldm, int h, const int* rowof, do
 // its row panels are staged too) or in shared memory (kBShared = true: read in place).  512 threads: tx = tid % 32 owns
 // the rows tx + 32 u (u < 4), ty = tid / 32 the columns n0 + ty + 16 v (v < NV).  epi(i, j, c1, c2) is called for i < M,
 // j < n0 + 16 NV, j < N.  Rows of A beyond Ma (the product has only Ma <= M non-zero rows) read as zero.
-// stage: block-shared double[2 * SMRT_MG_KP * (128 * (kDual ? 2 : 1) + (kBShared ? 0 : 16 * NV))].
+// stage: block-shared double[SMRT_MG_STAGES * SMRT_MG_KP * (32 MU (kDual ? 2 : 1) + (kBShared ? 0 : 16 NV))] <= 6144.
 #define SMRT_MG_KP 8
-template <bool kDual, bool kBShared, int NV, typename FE>
+#define SMRT_MG_STAGES 3
+// MU: row slabs of 32 (M <= 32 MU), NV: columns per thread (the call covers the columns [n0, n0 + 16 NV)): the caller picks
+// both from the block size, so that the inner loop carries no guards and no padded tiles (guards inside the loop were
+// measured: 2x slower)
+template <bool kDual, bool kBShared, int NV, int MU, typename FE>
 SMRT_DEV void mid_gemm(int M, int Ma, int N, int n0, int K, const double* SMRT_RESTRICT A1, const double* SMRT_RESTRICT A2,
                        int lda, const double* Bm, int ldb, double* stage, FE epi) {
   constexpr int KP = SMRT_MG_KP;
   constexpr int NA = kDual ? 2 : 1;
   constexpr int BW = 16 * NV;                           // columns of the result handled by this call
-  constexpr int SA = 128;                               // row stride of a staged A panel
+  constexpr int SA = 32 * MU;                           // row stride of a staged A panel
   constexpr int BUF = KP * (SA * NA + (kBShared ? 0 : BW));
   const int tid = threadIdx.x, NT = blockDim.x;
   const int tx = tid & 31, ty = tid >> 5;
-  double c1[4][NV], c2[4][NV];  // (c2 is dead code unless kDual)
+  double c1[MU][NV], c2[MU][NV];  // (c2 is dead code unless kDual)
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int u = 0; u < MU; ++u)
 #pragma unroll
     for (int v = 0; v < NV; ++v) c1[u][v] = c2[u][v] = 0.0;
   // staged element e of a panel: A part, e in [0, KP * SA * NA): (which = e / (KP * SA), kk = (e / SA) % KP, i = e % SA);
-  // B part: (kk = e / BW, jj = e % BW) -> B(k0 + kk, n0 + jj); per thread EA / EB elements
-  constexpr int EA = (KP * SA * NA + 511) / 512, EB = kBShared ? 1 : (KP * BW + 511) / 512;
-  double ra[EA], rb[EB];
-  auto fetch = [&](int k0) {
+  // B part: (kk = e % KP, jj = e / KP) -> B(k0 + kk, n0 + jj).  The panels travel by asynchronous 8-byte copies (LDGSTS)
+  // through a ring of SMRT_MG_STAGES buffers: the operands come from L2 / HBM (microseconds under load), one panel of
+  // look-ahead in registers left the loop latency bound (profiles/r04_notes.txt)
+  constexpr int NS = SMRT_MG_STAGES;
+  constexpr int EA = (KP * SA * NA + 511) / 512, EB = kBShared ? 0 : (KP * BW + 511) / 512;
+  auto issue = [&](int k0, double* buf) {
 #pragma unroll
     for (int q = 0; q < EA; ++q) {
       const int e = tid + q * NT;
-      const int i = e % SA, kk = (e / SA) % KP, which = e / (KP * SA);
-      const double* Ap = (kDual && which == 1) ? A2 : A1;
-      ra[q] = (e < KP * SA * NA && i < Ma && k0 + kk < K) ? Ap[(size_t)(k0 + kk) * lda + i] : 0.0;
+      if (e < KP * SA * NA) {
+        const int i = e % SA, kk = (e / SA) % KP, which = e / (KP * SA);
+        const double* Ap = (kDual && which == 1) ? A2 : A1;
+        const bool ok = i < Ma && k0 + kk < K;
+        smrt_cp_async8(buf + e, ok ? Ap + (size_t)(k0 + kk) * lda + i : Ap, ok);
+      }
     }
-    if (!kBShared) {
 #pragma unroll
-      for (int q = 0; q < EB; ++q) {
-        const int e = tid + q * NT;
+    for (int q = 0; q < EB; ++q) {
+      const int e = tid + q * NT;
+      if (e < KP * BW) {
         const int kk = e % KP, jj = e / KP;  // consecutive threads walk down a column of B: contiguous in memory
-        rb[q] = (e < KP * BW && k0 + kk < K && n0 + jj < N) ? Bm[(size_t)(n0 + jj) * ldb + k0 + kk] : 0.0;
+        const bool ok = k0 + kk < K && n0 + jj < N;
+        smrt_cp_async8(buf + KP * SA * NA + kk * BW + jj, ok ? Bm + (size_t)(n0 + jj) * ldb + k0 + kk : Bm, ok);
       }
     }
   };
-  auto put = [&](double* buf) {
 #pragma unroll
-    for (int q = 0; q < EA; ++q) {
-      const int e = tid + q * NT;
-      if (e < KP * SA * NA) buf[e] = ra[q];
-    }
-    if (!kBShared) {
-#pragma unroll
-      for (int q = 0; q < EB; ++q) {
-        const int e = tid + q * NT;
-        const int kk = e % KP, jj = e / KP;
-        if (e < KP * BW) buf[KP * SA * NA + kk * BW + jj] = rb[q];
-      }
-    }
-  };
-  if (K > 0) {
-    fetch(0);
-    put(stage);
+  for (int st = 0; st < NS - 1; ++st) {
+    if (st * KP < K) issue(st * KP, stage + st * BUF);
+    smrt_cp_async_commit();
   }
-  __syncthreads();
-  int cur = 0;
-  for (int k0 = 0; k0 < K; k0 += KP, cur ^= 1) {
-    const bool more = k0 + KP < K;
-    if (more) fetch(k0 + KP);
+  int cur = 0, nxt = NS - 1;
+  for (int k0 = 0; k0 < K; k0 += KP) {
+    smrt_cp_async_wait<NS - 2>();  // this thread's copies of the current panel have landed ...
+    __syncthreads();               // ... and everybody's; the buffer computed last is free again
+    if (k0 + (NS - 1) * KP < K) issue(k0 + (NS - 1) * KP, stage + nxt * BUF);
+    smrt_cp_async_commit();
     const double* buf = stage + cur * BUF;
     const int kn = (K - k0 < KP) ? (K - k0) : KP;
 #pragma unroll 2
     for (int kk = 0; kk < kn; ++kk) {
-      double a1[4], a2[4], bv[NV];
+      double a1[MU], a2[MU], bv[NV];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < MU; ++u) {
         a1[u] = buf[kk * SA + tx + 32 * u];
         a2[u] = kDual ? buf[KP * SA + kk * SA + tx + 32 * u] : 0.0;
       }
@@ -1723,18 +1735,20 @@ SMRT_DEV void mid_gemm(int M, int Ma, int N, int n0, int K, const double* SMRT_R
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < MU; ++u)
 #pragma unroll
         for (int v = 0; v < NV; ++v) {
           c1[u][v] = fma(a1[u], bv[v], c1[u][v]);
           if (kDual) c2[u][v] = fma(a2[u], bv[v], c2[u][v]);  // compile-time condition
         }
     }
-    if (more) put(stage + (cur ^ 1) * BUF);
-    __syncthreads();
+    cur = (cur + 1 == NS) ? 0 : cur + 1;
+    nxt = (nxt + 1 == NS) ? 0 : nxt + 1;
   }
+  smrt_cp_async_wait<0>();
+  __syncthreads();  // the staging ring is free (the caller may overwrite it)
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int u = 0; u < MU; ++u)
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const int i = tx + 32 * u, j = n0 + ty + 16 * v;

@@ -48,6 +48,18 @@ SMRT_DEV double smrt_rsqrt_approx(double x) {
   return r;
 }
 
+// ---- asynchronous 8-byte copies global -> shared (LDGSTS), grouped; `valid` = false writes zeros without reading
+SMRT_DEV void smrt_cp_async8(double* dst_smem, const double* src, bool valid) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src),
+               "r"(valid ? 8 : 0)
+               : "memory");
+}
+SMRT_DEV void smrt_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+SMRT_DEV void smrt_cp_async_wait() {  // at most N of this thread's groups still in flight
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---- TMA bulk copy (cp.async.bulk, 1-D, global -> shared) completed on an mbarrier --------------------------------
 typedef unsigned long long smrt_mbar_t;
 SMRT_DEV unsigned smrt_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -80,6 +92,9 @@ SMRT_DEV void smrt_bulk_load1(smrt_mbar_t* bar, void* dst, const void* src, unsi
                "l"(src), "r"(bytes), "r"(smrt_smem_u32(bar))
                : "memory");
 }
+// every thread that wrote global memory a later bulk copy of this CTA will read: order its (generic-proxy) stores before the
+// async-proxy reads; followed by a block barrier, then the issuing thread
+SMRT_DEV void smrt_fence_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 // hint: bring [src, src + bytes) into L2 (bytes a multiple of 16)
 SMRT_DEV void smrt_prefetch_l2(const void* src, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
@@ -222,9 +237,15 @@ inline void smrt_bulk_load2(smrt_mbar_t*, void* dst0, const void* src0, void* ds
 }
 inline void smrt_bulk_load1(smrt_mbar_t*, void* dst, const void* src, unsigned bytes) { std::memcpy(dst, src, bytes); }
 inline void smrt_prefetch_l2(const void*, unsigned) {}
+inline void smrt_fence_async_global() {}
 inline void smrt_mbar_wait(smrt_mbar_t*, unsigned) {}
 
 inline double smrt_select_eq(int a, int b, double x, double y) { return a == b ? x : y; }
+// emulation of the asynchronous copies: done at once
+inline void smrt_cp_async8(double* dst, const double* src, bool valid) { *dst = valid ? *src : 0.0; }
+inline void smrt_cp_async_commit() {}
+template <int N>
+inline void smrt_cp_async_wait() {}
 inline double rsqrt(double x) { return 1.0 / std::sqrt(x); }
 // the device versions are ~20-bit seeds: keep only a float mantissa so that the emulation tests the same tolerance
 inline double smrt_approx_round(double v) {
