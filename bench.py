@@ -55,6 +55,13 @@ WORKLOADS = {
                  desc="DMRT-QCA-shortrange(SHS)+DORT active, 10 layers, 16 streams, C/X/Ku backscatter at 40deg, m_max=2",
                  layers=10, streams=16, freqs=(5.4e9, 9.6e9, 13.5e9), seed=3, mode="A", m_max=2, snowpacks=50_000,
                  full=50_000),
+    # the reference's DEFAULT radar configuration (DORT n_max_stream = 32, m_max = 2: blocks of 96 unknowns) on the cfg-3
+    # snowpacks: not a BASELINE config, kept as a line of record for the 64 < h <= 128 kernels
+    "active32": dict(metric="snowpack-frequency DORT solves/sec (10-layer, 32-stream, active)",
+                     desc="DMRT-QCA-shortrange(SHS)+DORT active, 10 layers, 32 streams (reference default), C/X/Ku "
+                          "backscatter at 40deg, m_max=2",
+                     layers=10, streams=32, freqs=(5.4e9, 9.6e9, 13.5e9), seed=3, mode="A", m_max=2, snowpacks=5_000,
+                     full=50_000),
     "cfg4": dict(metric="snowpack-frequency DORT solves/sec (50-layer, 64-stream)",
                  desc="IBA(exponential)+DORT passive, 50 layers, 64 streams, 12 frequencies, theta=55deg",
                  layers=50, streams=64, freqs=CFG4_FREQS, seed=4, mode="P", m_max=0, snowpacks=500, full=200_000),
@@ -101,7 +108,7 @@ def make_batch(workload, S, seed=None, lo=0, hi=None):
     if workload == "cfg5":
         th, T, sal, por, pc = sea_ice_members(S, seed, w["layers"])
         return pack_sea_ice_ensemble(w["freqs"][0], th[sl], T[sl], sal[sl], por[sl], pc[sl], theta_deg=40.0)
-    if workload == "cfg3":
+    if workload in ("cfg3", "active32"):
         th, rho, T, a = snow_members(S, seed, w["layers"], "shs")
         return pack_snow_ensemble(w["freqs"], th[sl], rho[sl], T[sl], microstructure="sticky_hard_spheres", radius=a[sl],
                                   stickiness=0.2, emmodel="dmrt_qca_shortrange", mode="A", theta_deg=40.0,
@@ -305,7 +312,7 @@ def sample_problems(workload, n_snow):
 def cpu_sample_size(workload, cores, budget_s):
     """Snowpacks of the bounded CPU sample: >= 8 solves per core, <= 200 snowpacks, sized for
     `budget_s` seconds at the per-core rates of BASELINE.md §2."""
-    per_core = {"cfg2": 4.6, "cfg3": 7.1, "cfg4": 0.52, "cfg5": 4.8}[workload]
+    per_core = {"cfg2": 4.6, "cfg3": 7.1, "cfg4": 0.52, "cfg5": 4.8, "active32": 2.0}[workload]
     F = len(WORKLOADS[workload]["freqs"])
     by_budget = int(per_core * cores * budget_s / F)
     floor = -(-8 * cores // F)

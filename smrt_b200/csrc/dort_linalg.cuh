@@ -1121,7 +1121,7 @@ SMRT_DEV_NOINLINE int block_gj_rows(double* T, int ld, int h, int W, int* rowste
     int bi = 0x7fffffff;
     for (int i = lane; i < h; i += 32) {
       int st = rowstep[i];
-      if (st < 0 || st == j) {
+      if (st < 0) {
         double v = fabs(colj[i]);
         if (v > best) {
           best = v;
@@ -1132,10 +1132,6 @@ SMRT_DEV_NOINLINE int block_gj_rows(double* T, int ld, int h, int W, int* rowste
     warp_argmax(best, bi);
     if (!(best > 0.0) || !(best < 1e300)) return 1;  // identical decision in every warp
     const int p = bi;
-    if (tid == 0) {
-      rowstep[p] = j;
-      rowof[j] = p;
-    }
     const double inv = 1.0 / colj[p];
     // columns still to update: (j, h) of the left block and the whole right block
     if (h <= 64)
@@ -1144,6 +1140,12 @@ SMRT_DEV_NOINLINE int block_gj_rows(double* T, int ld, int h, int W, int* rowste
       gj_rows_update<4>(T, ld, h, W, j, p, inv, lane, warp, nwarp);
     else
       gj_rows_update<8>(T, ld, h, W, j, p, inv, lane, warp, nwarp);
+    __syncthreads();
+    // the row is marked only now: slower warps were still scanning rowstep[] for this step's pivot (racecheck)
+    if (tid == 0) {
+      rowstep[p] = j;
+      rowof[j] = p;
+    }
     __syncthreads();
   }
   return 0;
@@ -1161,7 +1163,7 @@ SMRT_DEV_NOINLINE int block_gj_cols(double* S, int lds, double* Km, int ldk, int
     int bi = 0x7fffffff;
     for (int c = lane; c < h; c += 32) {
       int st = colstep[c];
-      if (st < 0 || st == j) {
+      if (st < 0) {
         double v = fabs(SMRT_AT(S, lds, j, c));
         if (v > best) {
           best = v;
@@ -1172,10 +1174,6 @@ SMRT_DEV_NOINLINE int block_gj_cols(double* S, int lds, double* Km, int ldk, int
     warp_argmax(best, bi);
     if (!(best > 0.0) || !(best < 1e300)) return 1;
     const int p = bi;
-    if (tid == 0) {
-      colstep[p] = j;
-      colof[j] = p;
-    }
     const double inv = 1.0 / SMRT_AT(S, lds, j, p);
     const double* sp = S + (size_t)p * lds;
     const double* kp = Km + (size_t)p * ldk;
@@ -1209,6 +1207,11 @@ SMRT_DEV_NOINLINE int block_gj_cols(double* S, int lds, double* Km, int ldk, int
       }
       // S(j, c) is mathematically zero now; it is never read again, and must NOT be written here: slower warps may
       // still be scanning row j for the pivot of this step
+    }
+    __syncthreads();
+    if (tid == 0) {  // marked only now (slower warps were still scanning colstep[] for this step's pivot)
+      colstep[p] = j;
+      colof[j] = p;
     }
     __syncthreads();
   }
