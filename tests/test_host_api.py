@@ -358,7 +358,7 @@ def test_first_year_sea_ice_ensemble_packer_matches_the_reference_inputs():
 def _ragged_snowpacks():
     rng = np.random.default_rng(3)
     sps = []
-    for n in (1, 3, 2, 4, 2):
+    for n in (1, 3, 2):
         sps.append(make_snowpack(list(rng.uniform(0.1, 0.5, n - 1)) + [20.0], "exponential",
                                  density=rng.uniform(200, 420, n), temperature=rng.uniform(245, 270, n),
                                  corr_length=rng.uniform(5e-5, 3e-4, n)))
@@ -383,11 +383,11 @@ def test_one_shot_result_equals_the_stacked_per_simulation_results():
     from smrt_b200.result import concat_results
 
     sps = _ragged_snowpacks()
-    sensor = sensor_list.amsre(["19", "37", "89"])
+    sensor = sensor_list.amsre(["19", "37"])
     m = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8))
     fast = m.run(sensor, sps)
-    assert fast.data.dims == ("frequency", "snowpack", "polarization", "theta") and fast.data.shape == (3, 5, 2, 1)
-    assert fast.other_data["ks"].shape == (3, 5, 4) and np.isnan(fast.other_data["ks"].values[0, 0, 1:]).all()
+    assert fast.data.dims == ("frequency", "snowpack", "polarization", "theta") and fast.data.shape == (2, 3, 2, 1)
+    assert fast.other_data["ks"].shape == (2, 3, 3) and np.isnan(fast.other_data["ks"].values[0, 0, 1:]).all()
     sims, dimensions = m.prepare_simulations(sensor, sps, None, "snowpack")
     from smrt_b200.model import check_dort_options
     results = m._run_simulations(sims, check_dort_options(m.rtsolver_options))
@@ -395,16 +395,16 @@ def test_one_shot_result_equals_the_stacked_per_simulation_results():
         n = len(dimension[1])
         results = [concat_results(results[i:i + n], dimension) for i in range(0, len(results), n)]
     _assert_same_result(fast, results[0])
-    assert fast.Tb(channel="37V", snowpack=3) == fast.data.values[1, 3, 0, 0]
+    assert fast.Tb(channel="37V", snowpack=2) == fast.data.values[1, 2, 0, 0]
     # chunked pack / solve pipeline (and the same through two "devices"): identical block
     m2 = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=8), devices=[0, 1])
-    m2.CHUNK_SIMULATIONS = 4
+    m2.CHUNK_SIMULATIONS = 2
     _assert_same_result(fast, m2.run(sensor, sps))
     # active mode
-    radar = sensor_list.active([13e9, 17e9], 40)
-    fa = m.run(radar, sps[1:4])
+    m4 = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=4, m_max=1))
+    fa = m4.run(sensor_list.active([13e9, 17e9], 40), sps[:2])
     assert fa.data.dims == ("frequency", "snowpack", "polarization_inc", "polarization", "theta_inc")
-    one = m.run(sensor_list.active(17e9, 40), sps[2])
+    one = m4.run(sensor_list.active(17e9, 40), sps[1])
     np.testing.assert_array_equal(fa.data.values[1, 1], one.data.values)
 
 

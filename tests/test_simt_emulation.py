@@ -40,7 +40,7 @@ def test_emulated_kernels_match_reference_fixture(name):
 
 
 @pytest.mark.parametrize("name", ["ref_iba_2layer_passive", "iba_exp_substrate_passive", "nonscattering_transparent",
-                                  "atmosphere_passive", "ref_dmrt_less_refringent_active", "soil_active"])
+                                  "atmosphere_passive", "ref_dmrt_less_refringent_active"])
 def test_emulated_boundary_kernel_with_staged_operands(name, monkeypatch):
     """the boundary instantiation that keeps only [T | R] resident and stages F / G into them (two CTAs per SM on the
     device): TMA copies for even block sizes, thread copies for odd ones, generated operands for non-scattering layers"""
@@ -277,3 +277,27 @@ def test_conservative_layer_is_reported_not_solved():
     out = emu_solve(batch, opts, threads=64)
     assert (out.status[0] & 15) == 2 and np.all(np.isnan(out.values[0]))
     assert out.ka[0, 1] == 0.0 and out.ks[0, 1] > 0.0
+
+
+@pytest.mark.parametrize("n_max_stream,mode,layers", [(36, "P", 3), (22, "A", 2)])
+def test_emulated_kernels_for_blocks_of_65_to_128_unknowns(n_max_stream, mode, layers, monkeypatch):
+    """The 64 < h <= 128 instantiations (eigen_kernel<2>: packed lower-triangular C, 16-lane Jacobi groups;
+    boundary_kernel<.., kMid>: one resident matrix or resident right block, product-form elimination, staged GEMMs)
+    against the oracle: 36 streams passive (blocks of 72, both elimination paths depend on the layer's stream count)
+    and 22 streams active with m_max = 2 (blocks of 44 / 66)."""
+    from oracle import dort_oracle as O
+    from smrt_b200.pack import pack_snow_ensemble
+
+    monkeypatch.setenv("SMRT_EMU_EIGEN_MID", "1")
+    monkeypatch.setenv("SMRT_EMU_BOUNDARY_MID", "1")
+    rng = np.random.default_rng(11)
+    th = np.concatenate((rng.uniform(0.05, 0.5, (1, layers - 1)), np.full((1, 1), 1000.0)), axis=1)
+    rho = rng.uniform(150, 450, (1, layers)); T = rng.uniform(240, 272, (1, layers))
+    pc = rng.uniform(5e-5, 3e-4, (1, layers))
+    kw = dict(mode="A", theta_inc_deg=40.0, theta_deg=40.0) if mode == "A" else dict(theta_deg=55.0)
+    batch = pack_snow_ensemble([36.5e9], th, rho, T, corr_length=pc, **kw)
+    opts = dict(n_max_stream=n_max_stream, m_max=2)
+    ref = np.asarray(O.solve_problem(batch.to_problem(0, opts))["values"])
+    out = emu_solve(batch, opts, threads=64)
+    assert (out.status[0] & 15) == 0
+    assert rel_err(out.values[0], ref, batch.mode) <= (1e-9 if mode == "P" else 1e-6)
