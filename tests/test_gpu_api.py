@@ -196,3 +196,27 @@ def test_iba_variants_and_per_medium_emmodels(setup_snowpack_2):
     np.testing.assert_allclose([res.TbV(), res.TbH()], [204.510189893163, 190.53692754287889], atol=1e-4)
     by_medium = make_model({"snow": "iba_original"}, "dort").run(sensor_list.amsre("37V"), setup_snowpack_2)
     np.testing.assert_allclose(by_medium.TbV(), 247.92662874568973, atol=1e-4)
+
+
+def test_one_shot_result_pipeline_and_devices():
+    """Model.run at a size where the pack / solve pipeline is used: identical to the single-call path, dims and
+    NaN-padded ragged layers like the reference's stacked result."""
+    rng = np.random.default_rng(5)
+    sps = []
+    for k in range(40):
+        n = 2 + k % 4
+        sps.append(make_snowpack(list(rng.uniform(0.05, 0.5, n - 1)) + [30.0], "exponential",
+                                 density=rng.uniform(150, 450, n), temperature=rng.uniform(240, 272, n),
+                                 corr_length=rng.uniform(5e-5, 3e-4, n)))
+    sensor = sensor_list.amsre(["19", "37", "89"])
+    m = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=16))
+    whole = m.run(sensor, sps)
+    assert whole.data.dims == ("frequency", "snowpack", "polarization", "theta") and whole.data.shape == (3, 40, 2, 1)
+    assert whole.other_data["ks"].shape == (3, 40, 5) and np.isnan(whole.other_data["ks"].values[0, 0, 2:]).all()
+    piped = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=16), devices=[0])
+    piped.CHUNK_SIMULATIONS = 21
+    res = piped.run(sensor, sps)
+    np.testing.assert_array_equal(res.data.values, whole.data.values)
+    np.testing.assert_array_equal(res.other_data["ke"].values, whole.other_data["ke"].values)
+    one = m.run(sensor_list.amsre("37"), sps[17])
+    np.testing.assert_allclose(whole.Tb(channel="37V", snowpack=17), one.TbV(), rtol=1e-12)
