@@ -220,3 +220,22 @@ def test_one_shot_result_pipeline_and_devices():
     np.testing.assert_array_equal(res.other_data["ke"].values, whole.other_data["ke"].values)
     one = m.run(sensor_list.amsre("37"), sps[17])
     np.testing.assert_allclose(whole.Tb(channel="37V", snowpack=17), one.TbV(), rtol=1e-12)
+
+
+def test_two_devices_in_one_process():
+    """make_model(..., devices=[0, 1]): the chunks of one run() go round-robin to one worker thread per GPU (needs a
+    box with two GPUs: `gpurun --gpus 2`); bit-identical to the single-device run."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(9)
+    sps = [make_snowpack(list(rng.uniform(0.05, 0.5, 5)) + [30.0], "exponential", density=rng.uniform(150, 450, 6),
+                         temperature=rng.uniform(240, 272, 6), corr_length=rng.uniform(5e-5, 3e-4, 6)) for _ in range(64)]
+    sensor = sensor_list.amsre()
+    one = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=16)).run(sensor, sps)
+    m2 = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=16), devices=[0, 1])
+    m2.CHUNK_SIMULATIONS = 48
+    two = m2.run(sensor, sps)
+    np.testing.assert_array_equal(two.data.values, one.data.values)
+    np.testing.assert_array_equal(two.other_data["ks"].values, one.other_data["ks"].values)
