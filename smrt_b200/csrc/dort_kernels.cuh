@@ -1039,27 +1039,32 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
           const double* Go = BG;
           int* kof = rowstep;  // inverse of the pivot order: kof[rowof[k]] = k
           // coupling operator of the stack below: R' = T_top(l+1) R(l+1) T_bottom(l) D on the common streams
-          SMRT_FOR_2D(i, k, r, r) { SMRT_AT(gB, ldr_prev, i, k) *= Ttprev[i] * (Tb[k] * Dsg[k]); }
+          for (int k = tid; k < r; k += NT) ipiv[k] = Tb[k] * Dsg[k];  // (ipiv is free until the elimination)
+          __syncthreads();
+          scale_block_global(gB, ldr_prev, r, Ttprev, ipiv);
           __syncthreads();
           // A21 = F - Rb D G - R' G -> M1 ;  A22 = (G - Rb D F - R' F) t -> gA
           // (tile maps by block size: 32-row slabs x 16-column groups without padding)
-          auto form21 = [&](int i, int j, double acc, double) {
+          auto fg = [&](int i, int j, double& f, double& g) {  // the layer's F and G at (i, j), from the record
             const size_t e = (size_t)j * h + i;
-            M1[(size_t)j * ldm + i] = Fo[e] - RbD[i] * Go[e] - acc;
+            f = Fo[e];
+            g = Go[e];
           };
-          auto form22 = [&](int i, int j, double acc, double) {
-            const size_t e = (size_t)j * h + i;
-            (resident ? R2 : gA)[(size_t)j * ldm + i] = (Go[e] - RbD[i] * Fo[e] - acc) * tvec[j];
+          auto form21 = [&](int i, int j, double acc, double, double f, double g) {
+            M1[(size_t)j * ldm + i] = f - RbD[i] * g - acc;
+          };
+          auto form22 = [&](int i, int j, double acc, double, double f, double g) {
+            (resident ? R2 : gA)[(size_t)j * ldm + i] = (g - RbD[i] * f - acc) * tvec[j];
           };
           if (h <= 64) {
-            mid_gemm<false, false, 4, 2>(h, r, h, 0, r, gB, nullptr, ldr_prev, Go, h, stage, form21);
-            mid_gemm<false, false, 4, 2>(h, r, h, 0, r, gB, nullptr, ldr_prev, Fo, h, stage, form22);
+            mid_gemm<false, false, 4, 2>(h, r, h, 0, r, gB, nullptr, ldr_prev, Go, h, stage, fg, form21);
+            mid_gemm<false, false, 4, 2>(h, r, h, 0, r, gB, nullptr, ldr_prev, Fo, h, stage, fg, form22);
           } else if (h <= 96) {
-            mid_gemm<false, false, 6, 3>(h, r, h, 0, r, gB, nullptr, ldr_prev, Go, h, stage, form21);
-            mid_gemm<false, false, 6, 3>(h, r, h, 0, r, gB, nullptr, ldr_prev, Fo, h, stage, form22);
+            mid_gemm<false, false, 6, 3>(h, r, h, 0, r, gB, nullptr, ldr_prev, Go, h, stage, fg, form21);
+            mid_gemm<false, false, 6, 3>(h, r, h, 0, r, gB, nullptr, ldr_prev, Fo, h, stage, fg, form22);
           } else {
-            mid_gemm<false, false, 8, 4>(h, r, h, 0, r, gB, nullptr, ldr_prev, Go, h, stage, form21);
-            mid_gemm<false, false, 8, 4>(h, r, h, 0, r, gB, nullptr, ldr_prev, Fo, h, stage, form22);
+            mid_gemm<false, false, 8, 4>(h, r, h, 0, r, gB, nullptr, ldr_prev, Go, h, stage, fg, form21);
+            mid_gemm<false, false, 8, 4>(h, r, h, 0, r, gB, nullptr, ldr_prev, Fo, h, stage, fg, form22);
           }
           __syncthreads();
           SMRT_PHASE(3)  // right-hand sides, formation of [A21 | A22]
@@ -1105,21 +1110,20 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
           // Y~ becomes the resident B operand of  P = F - G Y~,  K = G - F Y~ ;  S = D P - Rt K -> gA,  K -> gC
           // (l > 0: both TRANSPOSED, so that R_new = K S^-1 = (S^-T K^T)^T comes out of the same row elimination)
           const bool transposed = l > 0;
-          auto prod = [&](int i, int j, double c1, double c2) {
-            const size_t e = (size_t)j * h + i;
-            const double pv = Fo[e] - c1;
-            const double kv = Go[e] - c2;
+          auto prod = [&](int i, int j, double c1, double c2, double f, double g) {
+            const double pv = f - c1;
+            const double kv = g - c2;
             const double sv = Dsg[i] * pv - Rt[i] * kv;
             const size_t o = transposed ? (size_t)i * ldm + j : (size_t)j * ldm + i;
             gA[o] = sv;
             gC[o] = kv;
           };
           if (h <= 64) {
-            for (int n0 = 0; n0 < h; n0 += 32) mid_gemm<true, true, 2, 2>(h, h, h, n0, h, Go, Fo, h, M1, ldm, stage, prod);
+            for (int n0 = 0; n0 < h; n0 += 32) mid_gemm<true, true, 2, 2>(h, h, h, n0, h, Go, Fo, h, M1, ldm, stage, fg, prod);
           } else if (h <= 96) {
-            for (int n0 = 0; n0 < h; n0 += 48) mid_gemm<true, true, 3, 3>(h, h, h, n0, h, Go, Fo, h, M1, ldm, stage, prod);
+            for (int n0 = 0; n0 < h; n0 += 48) mid_gemm<true, true, 3, 3>(h, h, h, n0, h, Go, Fo, h, M1, ldm, stage, fg, prod);
           } else {
-            for (int n0 = 0; n0 < h; n0 += 64) mid_gemm<true, true, 4, 4>(h, h, h, n0, h, Go, Fo, h, M1, ldm, stage, prod);
+            for (int n0 = 0; n0 < h; n0 += 64) mid_gemm<true, true, 4, 4>(h, h, h, n0, h, Go, Fo, h, M1, ldm, stage, fg, prod);
           }
           // S (or S^T) -> M1 and, on the resident path, K^T -> the right block: bulk copies by the TMA engine (the products
           // were stored by other threads: proxy fence + barrier first; M1 was their B operand), in flight under b'

@@ -1665,9 +1665,13 @@ SMRT_DEV void gj_apply_all(const double* M, int ldm, int h, const int* rowof, do
 // MU: row slabs of 32 (M <= 32 MU), NV: columns per thread (the call covers the columns [n0, n0 + 16 NV)): the caller picks
 // both from the block size, so that the inner loop carries no guards and no padded tiles (guards inside the loop were
 // measured: 2x slower)
-template <bool kDual, bool kBShared, int NV, int MU, typename FE>
+// pre(i, j, f, g) loads the two values the epilogue needs besides the sums (from global memory): they are fetched for
+// a whole row slab before the first epi(i, j, c1, c2, f, g) of the slab stores anything, so that their L2 latency is
+// paid once per slab, not once per element (the stores of an element and the loads of the next cannot be reordered
+// by the compiler).
+template <bool kDual, bool kBShared, int NV, int MU, typename FP, typename FE>
 SMRT_DEV void mid_gemm(int M, int Ma, int N, int n0, int K, const double* SMRT_RESTRICT A1, const double* SMRT_RESTRICT A2,
-                       int lda, const double* Bm, int ldb, double* stage, FE epi) {
+                       int lda, const double* Bm, int ldb, double* stage, FP pre, FE epi) {
   constexpr int KP = SMRT_MG_KP;
   constexpr int NA = kDual ? 2 : 1;
   constexpr int BW = 16 * NV;                           // columns of the result handled by this call
@@ -1751,10 +1755,40 @@ SMRT_DEV void mid_gemm(int M, int Ma, int N, int n0, int K, const double* SMRT_R
   smrt_cp_async_wait<0>();
   __syncthreads();  // the staging ring is free (the caller may overwrite it)
 #pragma unroll
-  for (int u = 0; u < MU; ++u)
+  for (int u = 0; u < MU; ++u) {
+    const int i = tx + 32 * u;
+    double fv[NV], gv[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      const int i = tx + 32 * u, j = n0 + ty + 16 * v;
-      if (i < M && j < N) epi(i, j, c1[u][v], kDual ? c2[u][v] : 0.0);
+      const int j = n0 + ty + 16 * v;
+      fv[v] = gv[v] = 0.0;
+      if (i < M && j < N) pre(i, j, fv[v], gv[v]);
     }
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int j = n0 + ty + 16 * v;
+      if (i < M && j < N) epi(i, j, c1[u][v], kDual ? c2[u][v] : 0.0, fv[v], gv[v]);
+    }
+  }
+}
+
+// elementwise scaling of an r x r block in GLOBAL memory, A(i, k) *= rs[i] cs[k]: four independent elements per thread
+// and trip (a plain read-modify-write loop pays the L2 latency once per element)
+SMRT_DEV void scale_block_global(double* A, int ld, int r, const double* rs, const double* cs) {
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int total = r * r;
+  for (int e0 = tid; e0 < total; e0 += 4 * NT) {
+    double v[4];
+    int idx[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = e0 + q * NT;
+      const int k = e / r, i = e - k * r;
+      idx[q] = (e < total) ? k * ld + i : -1;
+      v[q] = (e < total) ? A[idx[q]] * (rs[i] * cs[k]) : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (idx[q] >= 0) A[idx[q]] = v[q];
+  }
 }
