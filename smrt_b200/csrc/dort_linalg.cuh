@@ -615,7 +615,9 @@ SMRT_DEV int block_jacobi_svd_reg(double* W, int ld, int h, double* nrm, const d
         int r00, r11, r01, r10;
         jreg_rotate2<JG, R>(lane, x0, y0, a0, b0, x1, y1, a1, b1, r00, r11);
         jreg_rotate2<JG, R>(lane, x0, y1, a0, b1, x1, y0, a1, b0, r01, r10);
+#ifndef SMRT_SIMT_EMULATION  // (the emulated shuffles above are warp barriers already; a pthread barrier per round is slow)
         __syncwarp();  // every lane of the group has read the tracked norms before lane 0 replaces them
+#endif
         // a column that rotated is a real column (missing ones have zero norm): unpredicated stores
         if ((r00 | r01) & 2) {
           jreg_store<JG, R>(wp0, lane, x0);

@@ -371,18 +371,19 @@ def _classify_permittivity(model):
     return _PERM_CALL, 0j
 
 
-def _layer_rows(sp, emmodel, emmodel_options, L):
+_MS_FAST = {"Exponential": (MS_EXPONENTIAL, "corr_length"), "IndependentSphere": (MS_INDEPENDENT_SPHERE, "radius")}
+_IF_FAST = {"Flat": IF_FLAT, "Transparent": IF_TRANSPARENT}
+_INCLUSION_KEYS = ("inclusion_shape", "depolarization_factors", "length_ratio", "mixing_ratio")
+
+
+def _layer_rows(sp, emmodel, emmodel_options, L, defaults=None):
     """Frequency-independent rows of one snowpack (every quantity the device needs but the permittivities), plus how to
-    evaluate the permittivities: (kind, constant) per medium and layer.  One pass over the layers."""
+    evaluate the permittivities: (kind, constant) per medium and layer.  One pass over the layers; the values are
+    collected in Python lists and converted once (element-wise writes into NumPy arrays cost more than the reads)."""
     layers = sp.layers
     n = len(layers)
     if len(sp.interfaces) != n:
         raise SMRTError("the snowpack must have one interface per layer")
-    f8 = np.zeros((6, L))  # thickness, temperature, frac_volume, ms_p0, ms_p1, liquid_water
-    i4 = np.zeros((6, L), dtype=np.int32)  # emmodel, ms_kind, interface, dense_snow_correction, perm kind bg, perm kind sc
-    incl = np.empty((L, 5))
-    incl[:] = SPHERICAL_INCLUSIONS
-    const = np.zeros((2, L), dtype=np.complex128)
     list_em = isinstance(emmodel, (list, tuple))
     map_em = isinstance(emmodel, Mapping)
     if list_em and len(emmodel) != n:
@@ -391,71 +392,107 @@ def _layer_rows(sp, emmodel, emmodel_options, L):
     if list_opts and len(emmodel_options) != n:
         raise SMRTError("the list of emmodel options must have one entry per layer of the snowpack")
     map_opts = map_em and emmodel_options and all(isinstance(o, Mapping) for o in emmodel_options.values())
+    plain = not (list_em or map_em or list_opts)  # one emmodel, one option dict: resolved once by the caller
+    thick, temp, fvol, p0s, p1s, lws = [], [], [], [], [], []
+    codes, kinds, ifaces, dscs, kbg, ksc = [], [], [], [], [], []
+    cbg, csc = [], []
+    incl = None
     for l, layer in enumerate(layers):
-        # smrt/core/model.py:536-571: a list gives one emmodel per layer, a dict one per medium (layer.medium), else the
-        # layer's own emmodel attribute wins over the model's; the options follow the same three shapes
-        if list_em:
-            em = emmodel[l]
-        elif map_em:
-            medium = getattr(layer, "medium", None)
-            if medium not in emmodel:
-                raise SMRTError(f"no emmodel is given for the medium {medium!r} of layer {l}")
-            em = emmodel[medium]
+        d = layer.__dict__
+        own_em = d.get("emmodel")
+        own_opts = d.get("emmodel_options")
+        if plain and own_em is None and not own_opts and defaults is not None:
+            code, dsc_flag = defaults
         else:
-            em = getattr(layer, "emmodel", None) or emmodel
-        code = emmodel_code(em)
-        opts = getattr(em, "_smrt_options", None)  # class_specializer stand-in
-        opts = dict(opts) if opts else {}
-        if list_opts:
-            opts.update(emmodel_options[l] or {})
-        elif map_opts:
-            opts.update(emmodel_options[getattr(layer, "medium", None)])
-        else:
-            opts.update(getattr(layer, "emmodel_options", None) or emmodel_options)
-        if opts:
-            unknown = set(opts) - {"dense_snow_correction"}
-            if unknown:
-                raise SMRTError(f"emmodel options {sorted(unknown)} are not implemented on the B200 path")
-        dsc = opts.get("dense_snow_correction", "auto" if code in _DMRT_CODES else None)
-        if dsc not in (None, "auto"):
-            raise SMRTError(f"dense_snow_correction={dsc!r} is not implemented")
-        i4[0, l] = code
-        i4[3, l] = 1 if dsc == "auto" else 0
-        i4[2, l] = _interface_code(sp.interfaces[l])
-        f8[0, l] = layer.thickness
-        f8[1, l] = layer.temperature
+            # smrt/core/model.py:536-571: a list gives one emmodel per layer, a dict one per medium (layer.medium), else
+            # the layer's own emmodel attribute wins over the model's; the options follow the same three shapes
+            if list_em:
+                em = emmodel[l]
+            elif map_em:
+                medium = getattr(layer, "medium", None)
+                if medium not in emmodel:
+                    raise SMRTError(f"no emmodel is given for the medium {medium!r} of layer {l}")
+                em = emmodel[medium]
+            else:
+                em = own_em or emmodel
+            code = emmodel_code(em)
+            opts = getattr(em, "_smrt_options", None)  # class_specializer stand-in
+            opts = dict(opts) if opts else {}
+            if list_opts:
+                opts.update(emmodel_options[l] or {})
+            elif map_opts:
+                opts.update(emmodel_options[getattr(layer, "medium", None)])
+            else:
+                opts.update(own_opts or emmodel_options)
+            dsc_flag = _dense_snow_flag(opts, code)
+        codes.append(code)
+        dscs.append(dsc_flag)
+        iface = sp.interfaces[l]
+        icode = _IF_FAST.get(type(iface).__name__)
+        ifaces.append(icode if icode is not None else _interface_code(iface))
+        thick.append(layer.thickness)
+        temp.append(layer.temperature)
+        fvol.append(layer.frac_volume)
         if code == EM_PRESCRIBED_KSKAEPS:  # emmodel/prescribed_kskaeps.py:20-27: everything is given on the layer
-            i4[1, l] = MS_HOMOGENEOUS
-            f8[2, l] = layer.frac_volume
-            f8[3, l], f8[4, l] = float(layer.ks), float(layer.ka)
-            const[0, l] = const[1, l] = complex(layer.effective_permittivity)
-            if _needs_inclusion_params(layer):
-                incl[l] = _inclusion_params(layer, code)
-            continue
-        f8[2, l] = layer.frac_volume
-        kind, p0, p1 = _microstructure_params(layer)
-        if code in _DMRT_CODES and kind != MS_SHS:
-            raise SMRTError("DMRT short range models are only compatible with SHS microstructure model")
-        if code in _IBA_CODES and kind == MS_HOMOGENEOUS:
-            raise SMRTError("IBA needs a microstructure with a Fourier transform (exponential, sticky hard spheres)")
-        if code == EM_RAYLEIGH:  # emmodel/rayleigh.py:41-47
-            if not hasattr(layer.microstructure, "radius"):
-                raise SMRTError("Only microstructure_model which defined a `radius` can be used with Rayleigh "
-                                "scattering")
-            kind, p0, p1 = MS_HOMOGENEOUS, float(layer.microstructure.radius), 0.0
-        i4[1, l], f8[3, l], f8[4, l] = kind, p0, p1
-        if code == EM_IBA_MAXWELL_GARNETT or _needs_inclusion_params(layer):
-            incl[l] = _inclusion_params(layer, code)
-        models = getattr(layer, "permittivity_model", None)
-        if models is None:  # stand-in dry-snow layer of smrt_b200.inputs: ice (Maetzler 2006) in air
-            i4[4, l], i4[5, l] = _PERM_CONST, _PERM_ICE
-            const[0, l] = 1.0
+            kinds.append(MS_HOMOGENEOUS)
+            p0s.append(float(layer.ks))
+            p1s.append(float(layer.ka))
+            eps = complex(layer.effective_permittivity)
+            kbg.append(_PERM_CONST); ksc.append(_PERM_CONST); cbg.append(eps); csc.append(eps); lws.append(0.0)
         else:
-            i4[4, l], const[0, l] = _classify_permittivity(models[0])
-            i4[5, l], const[1, l] = _classify_permittivity(models[1])
-        if i4[4, l] == _PERM_WETICE or i4[5, l] == _PERM_WETICE:
-            f8[5, l] = getattr(layer, "liquid_water", 0.0) or 0.0
-    return n, f8, i4, incl, const
+            ms = d.get("microstructure")
+            fast = _MS_FAST.get(type(ms).__name__) if ms is not None else None
+            if fast is not None:
+                kind, p0, p1 = fast[0], float(getattr(ms, fast[1])), 0.0
+            else:
+                kind, p0, p1 = _microstructure_params(layer)
+            if code in _DMRT_CODES and kind != MS_SHS:
+                raise SMRTError("DMRT short range models are only compatible with SHS microstructure model")
+            if code in _IBA_CODES and kind == MS_HOMOGENEOUS:
+                raise SMRTError("IBA needs a microstructure with a Fourier transform (exponential, sticky hard spheres)")
+            if code == EM_RAYLEIGH:  # emmodel/rayleigh.py:41-47
+                if not hasattr(layer.microstructure, "radius"):
+                    raise SMRTError("Only microstructure_model which defined a `radius` can be used with Rayleigh "
+                                    "scattering")
+                kind, p0, p1 = MS_HOMOGENEOUS, float(layer.microstructure.radius), 0.0
+            kinds.append(kind); p0s.append(p0); p1s.append(p1)
+            models = d.get("permittivity_model")
+            if models is None:  # stand-in dry-snow layer of smrt_b200.inputs: ice (Maetzler 2006) in air
+                kbg.append(_PERM_CONST); ksc.append(_PERM_ICE); cbg.append(1.0); csc.append(0j); lws.append(0.0)
+            else:
+                k0, c0 = _classify_permittivity(models[0])
+                k1, c1 = _classify_permittivity(models[1])
+                kbg.append(k0); ksc.append(k1); cbg.append(c0); csc.append(c1)
+                lws.append((getattr(layer, "liquid_water", 0.0) or 0.0) if _PERM_WETICE in (k0, k1) else 0.0)
+        # shape of the inclusions / depolarisation factors: only layers that say something about them
+        if code == EM_IBA_MAXWELL_GARNETT or any(d.get(k) is not None for k in _INCLUSION_KEYS):
+            if code == EM_IBA_MAXWELL_GARNETT or _needs_inclusion_params(layer):
+                if incl is None:
+                    incl = {}
+                incl[l] = _inclusion_params(layer, code)
+    f8 = np.zeros((6, L))
+    f8[0, :n], f8[1, :n], f8[2, :n], f8[3, :n], f8[4, :n], f8[5, :n] = thick, temp, fvol, p0s, p1s, lws
+    i4 = np.zeros((6, L), dtype=np.int32)
+    i4[0, :n], i4[1, :n], i4[2, :n], i4[3, :n], i4[4, :n], i4[5, :n] = codes, kinds, ifaces, dscs, kbg, ksc
+    const = np.zeros((2, L), dtype=np.complex128)
+    const[0, :n], const[1, :n] = cbg, csc
+    inclusion = np.empty((L, 5))
+    inclusion[:] = SPHERICAL_INCLUSIONS
+    if incl:
+        for l, v in incl.items():
+            inclusion[l] = v
+    return n, f8, i4, inclusion, const
+
+
+def _dense_snow_flag(opts, code):
+    if opts:
+        unknown = set(opts) - {"dense_snow_correction"}
+        if unknown:
+            raise SMRTError(f"emmodel options {sorted(unknown)} are not implemented on the B200 path")
+    dsc = opts.get("dense_snow_correction", "auto" if code in _DMRT_CODES else None)
+    if dsc not in (None, "auto"):
+        raise SMRTError(f"dense_snow_correction={dsc!r} is not implemented")
+    return 1 if dsc == "auto" else 0
 
 
 def _needs_inclusion_params(layer):
@@ -521,8 +558,16 @@ def pack_simulations(simulations, emmodel, emmodel_options=None, atmospheres=Non
     I4 = np.zeros((U, 6, L), dtype=np.int32)
     INCL = np.empty((U, L, 5))
     CONST = np.zeros((U, 2, L), dtype=np.complex128)
+    defaults = None
+    if not isinstance(emmodel, (list, tuple, Mapping)) and not isinstance(emmodel_options, (list, tuple)) \
+            and emmodel is not None:
+        # one emmodel and one option dict for every layer that has none of its own: resolved once
+        code0 = emmodel_code(emmodel)
+        opts0 = dict(getattr(emmodel, "_smrt_options", None) or {})
+        opts0.update(emmodel_options)
+        defaults = (code0, _dense_snow_flag(opts0, code0))
     for u, sp in enumerate(unique):
-        nlayer_u[u], F8[u], I4[u], INCL[u], CONST[u] = _layer_rows(sp, emmodel, emmodel_options, L)
+        nlayer_u[u], F8[u], I4[u], INCL[u], CONST[u] = _layer_rows(sp, emmodel, emmodel_options, L, defaults)
 
     take = lambda a: np.ascontiguousarray(a[sp_index])  # noqa: E731
     temperature = take(F8[:, 1])
