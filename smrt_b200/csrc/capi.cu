@@ -63,6 +63,7 @@ struct smrtb200_plan {
   bool use_global_scratch = false;  // the BOUNDARY kernel keeps its matrices in the per-CTA global scratch
   int eigen_variant = 0;            // 0: shared memory (h <= 64), 1: global scratch, 2: shared memory, 64 < h <= 128
   bool boundary_mid = false;        // boundary kernel for 64 < h <= 128: one resident matrix + L2-resident scratch
+  int gj_single = 1;                // one blocked Gauss-Jordan instantiation for every block of a plan (h <= 64 kernels)
   int eigen_grid = 0, boundary_grid = 0;
   int boundary_threads = SMRT_NT_B;
   int eigen_threads = SMRT_NT;
@@ -176,6 +177,8 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
   p->device = options->device;
   p->sm_count = prop.multiProcessorCount;
   p->layout = smrt_host::make_layout(*options);
+  // default on (measured: boundary kernel 8.50 -> 8.31 ms per cfg-2 launch); SMRT_B200_GJ_SINGLE=0 picks by block size
+  p->gj_single = std::getenv("SMRT_B200_GJ_SINGLE") ? std::atoi(std::getenv("SMRT_B200_GJ_SINGLE")) : 1;
   const smrt_host::Layout& L = p->layout;
 
   // shared-memory path if both kernels fit into the opt-in limit, else matrices in an L2-resident global scratch
@@ -397,6 +400,7 @@ static int solve_device_impl(smrtb200_plan* p, const smrtb200_batch* batch, cuda
     A.scratch = s.scratch;
     A.scratch_stride = p->scratch_stride;
     A.use_global_scratch = p->use_global_scratch ? 1 : 0;
+    A.gj_single = p->gj_single;
     CUDA_TRY(cudaMemsetAsync(s.counters, 0, 2 * sizeof(int), s.stream));
     const int nthreads_opt = 128;
     const int items = nb * p->opt.max_layers;

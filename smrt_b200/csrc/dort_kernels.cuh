@@ -54,6 +54,7 @@ struct KArgs {
   long long eig_stride, scratch_stride;
   long long mid_arena;  // boundary kernel for 64 < h <= 128: doubles of the shared-memory matrix arena
   int use_global_scratch;
+  int gj_single;  // one blocked Gauss-Jordan instantiation for every block of a plan (0: pick by block size)
   int eig_off[SMRT_MAX_MODES];  // offset of mode m inside one (problem, layer) eigen record
 };
 
@@ -1248,7 +1249,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
         // [A21 | A22 | b_bot] -> [I | Y22 | Yr] (implicit row permutation, unscaled rows)
         const bool blocked = h <= 64;  // panel-blocked elimination (register tiles); larger blocks: one step at a time
         if (blocked ? block_gj_rows_blocked<!kGlobalScratch>(TT, ldp, TT + (size_t)h * ldp, ldp, h, h + nr, rowof, pivinv, GJV,
-                                            &s_ctrl[6])
+                                            &s_ctrl[6], A.gj_single ? hmax : 0)
                     : block_gj_rows(TT, ldp, h, 2 * h + nr, rowstep, rowof)) {
           if (kStreamFG && waitG) {  // drain the copy of G in flight before leaving
             smrt_mbar_wait(&s_mbarG, pg_parity);
@@ -1379,7 +1380,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
           // R_new = K S^-1 by column elimination of [S; K]
           if (transposed) {
             // [S^T | K^T] -> rows of S^-T K^T = columns of R_new
-            if (block_gj_rows_blocked<!kGlobalScratch>(TS, ldp, BR, ldp, h, h, rowof, pivinv, GJV, &s_ctrl[6])) {
+            if (block_gj_rows_blocked<!kGlobalScratch>(TS, ldp, BR, ldp, h, h, rowof, pivinv, GJV, &s_ctrl[6], A.gj_single ? hmax : 0)) {
               failed = true;
               break;
             }
@@ -1416,7 +1417,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
           SMRT_PHASE(7)  // R of the stack, source vector
         } else {
           // top layer: z = S^-1 b' by row elimination of [S | b'], then s = v + K z
-          if (blocked ? block_gj_rows_blocked<!kGlobalScratch>(TS, ldp, Trhs, ldp, h, nr, rowof, pivinv, GJV, &s_ctrl[6])
+          if (blocked ? block_gj_rows_blocked<!kGlobalScratch>(TS, ldp, Trhs, ldp, h, nr, rowof, pivinv, GJV, &s_ctrl[6], A.gj_single ? hmax : 0)
                       : block_gj_rows(TS, ldp, h, h + nr, rowstep, rowof)) {
             failed = true;
             break;

@@ -1499,9 +1499,13 @@ SMRT_DEV_NOINLINE int block_gj_rows_blocked_t(double* Lb, int ldl, double* Rb, i
 }
 // blockDim.x >= 64 (warp 0 factorises, the others update).  kShared: Lb, Rb, ipiv, Vbuf are in shared memory (rowof and
 // flag always are)
+// hcode: the largest block of the plan (h_max): with 32 < h_max <= 64 every block above 32 unknowns uses the ONE
+// instantiation sized for 64 rows (layers of a snowpack keep different stream counts: alternating between the <2, 3> and
+// <2, 4> copies of the hot loop thrashed the instruction cache; a few masked rows cost less) — 0: pick by h alone
 template <bool kShared>
 SMRT_DEV int block_gj_rows_blocked(double* Lb, int ldl, double* Rb, int ldr, int h, int nR, int* rowof, double* ipiv,
-                                   double* Vbuf, int* flag) {
+                                   double* Vbuf, int* flag, int hcode = 0) {
+  if (hcode > 48 && h > 32) return block_gj_rows_blocked_t<2, 4, kShared>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
   if (h <= 16) return block_gj_rows_blocked_t<1, 1, kShared>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
   if (h <= 32) return block_gj_rows_blocked_t<1, 2, kShared>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);
   if (h <= 48) return block_gj_rows_blocked_t<2, 3, kShared>(Lb, ldl, Rb, ldr, h, nR, rowof, ipiv, Vbuf, flag);

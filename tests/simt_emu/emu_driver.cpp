@@ -41,6 +41,7 @@ int emu_solve_batch(const smrtb200_options* opt, const smrtb200_batch* batch, in
   A.scratch = scratch.data();
   A.scratch_stride = (long long)scratch.size();
   A.use_global_scratch = 1;  // the emulator's "shared memory" is 1 MiB: keep matrices in the scratch
+  A.gj_single = 1;           // like the plans of the library
   int diag[2] = {0, 0};
   A.diag = diag;
   for (int b = 0; b < B; ++b) batch->status[b] = 0;
