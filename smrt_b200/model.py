@@ -88,7 +88,7 @@ class _PlanCache:
         self.budget_bytes = budget_bytes
         self.max_plans = max_plans
 
-    def get(self, batch: ProblemBatch, opts: dict, device: int) -> capi.Plan:
+    def get(self, batch: ProblemBatch, opts: dict, device: int, max_batch: int = 0) -> capi.Plan:
         o = capi.make_options(batch, n_max_stream=opts["n_max_stream"], m_max=opts["m_max"],
                               phase_normalization=opts["phase_normalization"],
                               prune_deep_snowpack=opts["prune_deep_snowpack"],
@@ -96,11 +96,11 @@ class _PlanCache:
         key = (device, o.mode, o.n_max_stream, o.m_max, o.max_layers, o.n_theta, o.n_inc, o.normalization,
                o.rayleigh_jeans, o.prune_deep_snowpack)
         plan = self._plans.pop(key, None)
-        if plan is not None and plan.options.max_batch < batch.B:
+        if plan is not None and plan.options.max_batch < max(batch.B, max_batch):
             plan.close()
             plan = None
         if plan is None:
-            o.max_batch = max(batch.B, 1)
+            o.max_batch = max(batch.B, max_batch, 1)  # (max_batch: the largest batch the caller will bring)
             plan = capi.Plan(o)
         self._plans[key] = plan  # most recently used: last
         self._evict(keep=key)
@@ -379,11 +379,14 @@ class Model:
         sp_per_chunk = max(1, self.CHUNK_SIMULATIONS // per_sp)
         if len(self.devices) > 1:  # at least two chunks per device
             sp_per_chunk = max(1, min(sp_per_chunk, -(-len(first_seen) // (2 * len(self.devices)))))
-        chunk_of = sp_of // sp_per_chunk
+        # a short first chunk: nothing overlaps its packing
+        head = max(1, sp_per_chunk // 6)
+        chunk_of = np.where(sp_of < head, 0, 1 + (sp_of - head) // sp_per_chunk)
         selections = [np.flatnonzero(chunk_of == c) for c in range(int(chunk_of.max()) + 1)]
+        largest = max(len(sel) for sel in selections)
 
         def solve(batch, device):
-            return _PLANS.get(batch, opts, device).solve_host(batch)
+            return _PLANS.get(batch, opts, device, max_batch=largest).solve_host(batch)
 
         packer = ThreadPoolExecutor(1)
         workers = [ThreadPoolExecutor(1) for _ in self.devices]  # one thread per GPU: a plan is used by one thread

@@ -30,7 +30,7 @@ class EmuPlan:
 
 @pytest.fixture(autouse=True)
 def emulated_plans(monkeypatch):
-    monkeypatch.setattr(model_mod._PLANS, "get", lambda batch, opts, device: EmuPlan(opts))
+    monkeypatch.setattr(model_mod._PLANS, "get", lambda batch, opts, device, max_batch=0: EmuPlan(opts))
 
 
 def two_layer():

@@ -36,7 +36,7 @@ def emulated_plans(monkeypatch):
         def solve_host(self, batch):
             return emu_solve(batch, self.opts, threads=64)
 
-    monkeypatch.setattr(model_mod._PLANS, "get", lambda batch, opts, device: EmuPlan(opts))
+    monkeypatch.setattr(model_mod._PLANS, "get", lambda batch, opts, device, max_batch=0: EmuPlan(opts))
 
 
 def test_runner_seam_matches_the_reference(smrt_ref):
