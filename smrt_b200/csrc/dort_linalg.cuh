@@ -501,22 +501,28 @@ SMRT_DEV void jreg_rotate2(int lane, double (&x0)[R], double (&y0)[R], double& a
       q1 = fma(x1[u + 1], y1[u + 1], q1);
     }
   }
-  double g0 = p0 + p1, g1 = q0 + q1;
-#pragma unroll
-  for (int off = 1; off < JG; off <<= 1) {
-    const double o0 = __shfl_xor_sync(0xffffffffu, g0, off, 32);
-    const double o1 = __shfl_xor_sync(0xffffffffu, g1, off, 32);
-    g0 += o0;
-    g1 += o1;
-  }
-  const double g20 = g0 * g0, ab0 = a0 * b0, g21 = g1 * g1, ab1 = a1 * b1;
-  const bool rot0 = g20 > SMRT_JACOBI_TOL2 * ab0, rot1 = g21 > SMRT_JACOBI_TOL2 * ab1;
-  rc0 = rc1 = 0;
-  if (!__any_sync(0xffffffffu, rot0 || rot1)) return;
+  // the lower half of the group collects the inner product of the first pair, the upper half that of the second one:
+  // one exchange across the halves, then log2(JG / 2) butterfly stages on ONE value (half the shuffles of reducing
+  // both sums in every lane; each half computes the angle of its own pair anyway)
   const bool hi = (lane & (JG / 2)) != 0;
+  const double g0p = p0 + p1, g1p = q0 + q1;
+  double gm = (hi ? g1p : g0p) + __shfl_xor_sync(0xffffffffu, hi ? g0p : g1p, JG / 2, 32);
+#pragma unroll
+  for (int off = 1; off < JG / 2; off <<= 1) gm += __shfl_xor_sync(0xffffffffu, gm, off, 32);
+  const double am = hi ? a1 : a0, bm = hi ? b1 : b0;
+  const double g2m = gm * gm, abm = am * bm;
+  const bool rotm = g2m > SMRT_JACOBI_TOL2 * abm;
+  const bool quadm = g2m > SMRT_JACOBI_QUAD2 * abm;
+  // the flags of both pairs for every lane of the group: two warp votes, bit = first lane of the half
+  const unsigned vrot = __ballot_sync(0xffffffffu, rotm), vquad = __ballot_sync(0xffffffffu, quadm);
+  rc0 = rc1 = 0;
+  if (vrot == 0u) return;  // warp-uniform
+  const int g0lane = ((int)threadIdx.x & 31) & ~(JG - 1);
+  const bool rot0 = (vrot >> g0lane) & 1u, rot1 = (vrot >> (g0lane + JG / 2)) & 1u;
+  const bool quad0 = (vquad >> g0lane) & 1u, quad1 = (vquad >> (g0lane + JG / 2)) & 1u;
   double t, c, s;
-  jreg_angle(hi ? a1 : a0, hi ? b1 : b0, hi ? g1 : g0, hi ? rot1 : rot0, t, c, s);
-  const double tg = t * (hi ? g1 : g0);
+  jreg_angle(am, bm, gm, rotm, t, c, s);
+  const double tg = t * gm;
   const double co = __shfl_xor_sync(0xffffffffu, c, JG / 2, 32);
   const double so = __shfl_xor_sync(0xffffffffu, s, JG / 2, 32);
   const double tgo = __shfl_xor_sync(0xffffffffu, tg, JG / 2, 32);
@@ -528,14 +534,14 @@ SMRT_DEV void jreg_rotate2(int lane, double (&x0)[R], double (&y0)[R], double& a
     const double tg0 = hi ? tgo : tg;
     a0 -= tg0;
     b0 += tg0;
-    rc0 = rot0 ? ((g20 > SMRT_JACOBI_QUAD2 * ab0) ? 3 : 2) : 0;
+    rc0 = rot0 ? (quad0 ? 3 : 2) : 0;
   }
   {
     jreg_apply<R>(x1, y1, hi ? c : co, hi ? s : so);
     const double tg1 = hi ? tg : tgo;
     a1 -= tg1;
     b1 += tg1;
-    rc1 = rot1 ? ((g21 > SMRT_JACOBI_QUAD2 * ab1) ? 3 : 2) : 0;
+    rc1 = rot1 ? (quad1 ? 3 : 2) : 0;
   }
 }
 
