@@ -13,4 +13,10 @@ for lib in "$@"; do
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
 print('value', round(d['value']), 'e2e', round(d['e2e']['value']), 'ms', r['avg_launch_ms'], 'clk', d['clocks']['sm_mhz'])" | tee -a $OUT/${TAG}_variants.log
+  if [[ -n "$VARIANT_CFG4" ]]; then
+    timeout 300 python bench.py --workload cfg4 --steps 1 --warmup 1 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); r=d['roofline']
+print('cfg4 value', round(d['value']), 'ms', r['avg_launch_ms'], 'clk', d['clocks']['sm_mhz'])" | tee -a $OUT/${TAG}_variants.log
+  fi
 done
