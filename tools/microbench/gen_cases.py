@@ -30,7 +30,7 @@ def hook(P_half, mu, weight, ks, ke, m, norm_rows=None, normalization=True):
 A.layer_eigen_symmetric = hook
 nsnow = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 full = len(sys.argv) > 2 and sys.argv[2] == "full"
-batch = bench.make_batch(nsnow, 2)
+batch = bench.make_batch("cfg2", nsnow)
 for b in range(batch.B):
     A.solve_problem(batch.to_problem(b, dict(n_max_stream=32)))
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cases.bin")
