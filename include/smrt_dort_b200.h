@@ -70,6 +70,11 @@ extern "C" {
 #define SMRTB200_SUB_REFLECTOR 4       /* params = specular reflection V, H; passive only; substrate_eps unused
                                           smrt/substrate/reflector.py:51-111 (scalar / dict specifications) */
 #define SMRTB200_SUB_ROUGH_CHOUDHURY 5 /* params[0] = roughness_rms (m)          smrt/substrate/rough_choudhury79.py:19-79 */
+#define SMRTB200_SUB_REFLECTOR_BACKSCATTER 6 /* params = specular reflection V, H, backscattering coefficient VV, HH
+                                          (linear); passive and active: the backscatter enters every azimuth mode as a
+                                          DIAGONAL diffuse reflection +- sigma0 w / (2 mu (1 + 2 m_max)), absent from the
+                                          coherent pass     smrt/substrate/reflector_backscatter.py:66-135,
+                                          smrt/rtsolver/rtsolver_utils.py:690-709, 728-740 */
 
 /* phase_normalization option (smrt/rtsolver/dort.py:94-103, 782-819) */
 #define SMRTB200_NORM_OFF 0

@@ -72,6 +72,7 @@ MS_EXPONENTIAL, MS_SHS, MS_HOMOGENEOUS = 0, 1, 2
 MS_INDEPENDENT_SPHERE, MS_TEUBNER_STREY, MS_UNIFIED_TS_1, MS_UNIFIED_TS_2, MS_SHS_T = 3, 4, 5, 6, 7
 IF_FLAT, IF_TRANSPARENT = 0, 1
 SUB_NONE, SUB_FLAT, SUB_SOIL_WEGMULLER, SUB_SOIL_QNH, SUB_REFLECTOR, SUB_ROUGH_CHOUDHURY = 0, 1, 2, 3, 4, 5
+SUB_REFLECTOR_BACKSCATTER = 6
 
 # status codes shared with the C ABI (include/smrt_dort_b200.h)
 ST_OK = 0
@@ -471,6 +472,14 @@ def substrate_R_T(problem, eps_1, mu, npol):
         R[0] = par[0]
         R[1] = par[1]
         return R, 1 - R
+    if kind == SUB_REFLECTOR_BACKSCATTER:  # reflector_backscatter.py:72-88, 118-135: the third component stays zero
+        R = np.zeros((npol, len(mu)))
+        T = np.zeros((npol, len(mu)))
+        R[0] = par[0]
+        R[1] = par[1]
+        T[0] = 1 - par[0]
+        T[1] = 1 - par[1]
+        return R, T
     R, T = interface_R_T(IF_FLAT, eps_1, problem["substrate_eps"], mu, npol)
     if kind == SUB_FLAT:
         return R, T
@@ -506,6 +515,27 @@ def substrate_R_T(problem, eps_1, mu, npol):
     T[1] = 1 - rh
     T[0] = 1 - rv
     return R, T
+
+
+def substrate_diffuse_reflection(problem, streams, mode, m_max):
+    """Diagonal diffuse (backscatter) reflection of the substrate for azimuth mode `mode`, already multiplied by the
+    mode's integration coefficient and compressed like the coherent part (mu * npol + pol), or None: reference
+    smrt/substrate/reflector_backscatter.py:90-116 (the prescribed backscatter spread over the 1 + 2 m_max modes),
+    rtsolver_utils.py:728-740 (normalize_diffuse_matrix, 'diagonal5' with mu_i is mu_st: x weights) and 690-709
+    (combine_coherent_diffuse_matrix: 2 pi for mode 0, pi above)."""
+    if int(problem.get("substrate_kind", SUB_NONE)) != SUB_REFLECTOR_BACKSCATTER:
+        return None
+    par = np.asarray(problem.get("substrate_params", np.zeros(4)), dtype=float)
+    mu = np.asarray(streams["mu"][-1], dtype=float)
+    w = np.asarray(streams["weight"][-1], dtype=float)
+    npol = 2 if mode == 0 else 3
+    coef = 1.0 if mode == 0 else (-2.0 if mode % 2 == 1 else 2.0)
+    coef = coef / (1 + 2 * m_max) / (4 * np.pi * mu)
+    diff = np.zeros((npol, len(mu)))
+    diff[0] = coef * par[2]
+    diff[1] = coef * par[3]
+    diff *= w
+    return (2 * np.pi if mode == 0 else np.pi) * np.transpose(diff).reshape(-1)
 
 
 def compute_interfaces(problem, eps_eff, streams, npol):
@@ -875,6 +905,10 @@ def dort_modem_banded(problem, mode, streams, eigs, iface, intensity_down, planc
         Rbottom_l = cdiag(Rbot_, l)
         if Rbottom_l is None:
             Rbottom_l = np.zeros(nsl_npol)
+        if l == L - 1 and not coherent_only:  # diffuse part of a rough substrate (rtsolver_utils.py:656-659, 690-709)
+            Rdiff = substrate_diffuse_reflection(problem, streams, mode, int(problem.get("_m_max", 0)))
+            if Rdiff is not None:
+                Rbottom_l = Rbottom_l + Rdiff
         _todiag(bBC, il_bottom[l], jl[l], (Eu - Rbottom_l[:, None] * Ed) * transb[None, :])
         Ttop_lm1 = None
         if l > 0:
@@ -1004,6 +1038,7 @@ def solve_problem(problem, method="schur_forcedtriu", return_details=False):
         m_max = int(opts["m_max"]) if mode == "A" else 0
         npol = 2 if mode == "P" else 3
         iface = compute_interfaces(problem, eps_eff, streams, npol)
+        problem = dict(problem, _m_max=m_max)  # the mode count the diffuse substrate reflection is spread over
         norm = opts["phase_normalization"]
         if norm == "auto":
             norm = True  # IBA, DMRT: _respect_reciprocity_principle defaults to True (dort.py:240-242)

@@ -303,6 +303,33 @@ def reflector_passive():  # reference substrate/reflector.py: scalar, polarisati
 
 
 @case
+def reflector_backscatter_active():  # reference substrate/reflector_backscatter.py: prescribed sigma0 as a DIAGONAL
+    from smrt.substrate.reflector_backscatter import make_reflector  # diffuse reflection, active mode, m_max = 2 / 4
+
+    specs = [({"V": 0.3, "H": 0.4}, {"VV": 0.1, "HH": 0.05}), (0.2, {"VV": 0.03, "HH": 0.03}),
+             ({"V": 0.0, "H": 0.0}, {"VV": 0.3, "HH": 0.2})]
+    sps = _thin_snowpacks(27, 3, lambda i, rng: make_reflector(temperature=rng.uniform(255, 272),
+                                                               specular_reflection=specs[i][0],
+                                                               backscattering_coefficient=specs[i][1]))
+    run_case("reflector_backscatter_active", "iba", sensor_list.active([5.4e9, 13.5e9], [30, 40]), sps,
+             dict(n_max_stream=16, m_max=2))
+    run_case("reflector_backscatter_active_mmax4", "iba", sensor_list.active(13.5e9, 35), sps[:2],
+             dict(n_max_stream=12, m_max=4))
+
+
+@case
+def reflector_backscatter_passive():  # the same substrate under a radiometer: one mode, the backscatter adds to R
+    from smrt.substrate.reflector_backscatter import make_reflector
+
+    specs = [({"V": 0.3, "H": 0.4}, {"VV": 0.1, "HH": 0.05}), (0.6, None), (None, None)]
+    sps = _thin_snowpacks(28, 3, lambda i, rng: make_reflector(temperature=rng.uniform(255, 272),
+                                                               specular_reflection=specs[i][0],
+                                                               backscattering_coefficient=specs[i][1]))
+    run_case("reflector_backscatter_passive", "iba", sensor_list.passive([18.7e9, 36.5e9], 55), sps,
+             dict(n_max_stream=16))
+
+
+@case
 def choudhury_passive():  # reference substrate/rough_choudhury79.py (k sigma << 1)
     from smrt.substrate.rough_choudhury79 import ChoudhuryReflectivity
 

@@ -25,7 +25,15 @@ enum {
   MS_UNIFIED_TS_1 = 5, MS_UNIFIED_TS_2 = 6, MS_SHS_T = 7
 };
 enum { IF_FLAT = 0, IF_TRANSPARENT = 1 };
-enum { SUB_NONE = 0, SUB_FLAT = 1, SUB_SOIL_WEGMULLER = 2, SUB_SOIL_QNH = 3, SUB_REFLECTOR = 4, SUB_ROUGH_CHOUDHURY = 5 };
+enum {
+  SUB_NONE = 0,
+  SUB_FLAT = 1,
+  SUB_SOIL_WEGMULLER = 2,
+  SUB_SOIL_QNH = 3,
+  SUB_REFLECTOR = 4,
+  SUB_ROUGH_CHOUDHURY = 5,
+  SUB_REFLECTOR_BACKSCATTER = 6
+};
 enum { ST_OK = 0, ST_NORMALIZATION = 1, ST_EIGEN = 2, ST_SINGULAR = 3, ST_INPUT = 4, ST_SUBSTRATE = 5, ST_WARN_SHALLOW = 16 };
 
 // ---------------------------------------------------------------------------------------------------- complex numbers
@@ -518,7 +526,7 @@ SMRT_DEV_NOINLINE FresnelRT substrate_power(int kind, const double* par, double 
   FresnelRT o;
   const double zero4[4] = {0.0, 0.0, 0.0, 0.0};
   if (!par) par = zero4;
-  if (kind == SUB_REFLECTOR) {
+  if (kind == SUB_REFLECTOR || kind == SUB_REFLECTOR_BACKSCATTER) {  // (the diffuse part of kind 6: substrate_backscatter)
     o.R[0] = par[0];
     o.R[1] = par[1];
     o.R[2] = 0.0;
@@ -537,6 +545,15 @@ SMRT_DEV_NOINLINE FresnelRT substrate_power(int kind, const double* par, double 
   o.T[1] = 1.0 - rh;
   o.T[0] = 1.0 - rv;
   return o;
+}
+
+// Diagonal diffuse reflection of a substrate with a prescribed backscattering coefficient sigma0 (linear), azimuth mode
+// m of m_max, stream (mu, weight w) -- substrate/reflector_backscatter.py:90-116: the backscatter is spread over the
+// 1 + 2 m_max modes with signs (+1, -2, +2, ...) and converted to scattering by 1 / (4 pi mu); rtsolver_utils.py:735-737
+// multiplies by the weight and 690-709 by the mode integral (2 pi | pi): +- sigma0 w / (2 mu (1 + 2 m_max)).
+SMRT_DEV double substrate_backscatter(double sigma0, int m, int m_max, double mu, double w) {
+  const double sgn = (m & 1) ? -1.0 : 1.0;
+  return sgn * 0.5 * sigma0 * w / ((double)(1 + 2 * m_max) * mu);
 }
 
 // ---------------------------------------------------------------------------------------------------- phase matrix

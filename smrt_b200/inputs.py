@@ -304,7 +304,22 @@ class Reflector:
         self.specular_reflection = specular_reflection
 
 
-def make_reflector(temperature=None, specular_reflection=None):
+class ReflectorBackscatter:
+    """Prescribed specular reflection (scalar or {"V", "H"} dict) and backscattering coefficient ({"VV", "HH"} dict,
+    linear) — reference ``smrt/substrate/reflector_backscatter.py:54-135``; usable in active mode."""
+
+    def __init__(self, temperature=None, specular_reflection=None, backscattering_coefficient=None):
+        self.temperature = temperature
+        self.specular_reflection = specular_reflection
+        self.backscattering_coefficient = backscattering_coefficient
+
+
+def make_reflector(temperature=None, specular_reflection=None, backscattering_coefficient=None):
+    """``smrt.substrate.reflector.make_reflector``; with a backscattering_coefficient, the one of
+    ``smrt.substrate.reflector_backscatter``"""
+    if backscattering_coefficient is not None:
+        return ReflectorBackscatter(temperature=temperature, specular_reflection=specular_reflection,
+                                    backscattering_coefficient=backscattering_coefficient)
     return Reflector(temperature=temperature, specular_reflection=specular_reflection)
 
 
@@ -366,7 +381,7 @@ class Snowpack:
         return [lay.thickness for lay in self.layers]
 
     def __add__(self, other):
-        if isinstance(other, (FlatSubstrate, Reflector)):
+        if isinstance(other, (FlatSubstrate, Reflector, ReflectorBackscatter)):
             return Snowpack(self.layers, self.interfaces, other, self.atmosphere)
         raise SMRTError("only `snowpack + substrate` and `atmosphere + snowpack` are supported")
 

@@ -26,6 +26,7 @@ MS_EXPONENTIAL, MS_SHS, MS_HOMOGENEOUS = 0, 1, 2
 MS_INDEPENDENT_SPHERE, MS_TEUBNER_STREY, MS_UNIFIED_TS_1, MS_UNIFIED_TS_2, MS_SHS_T = 3, 4, 5, 6, 7
 IF_FLAT, IF_TRANSPARENT = 0, 1
 SUB_NONE, SUB_FLAT, SUB_SOIL_WEGMULLER, SUB_SOIL_QNH, SUB_REFLECTOR, SUB_ROUGH_CHOUDHURY = 0, 1, 2, 3, 4, 5
+SUB_REFLECTOR_BACKSCATTER = 6
 MODE_PASSIVE, MODE_ACTIVE = 0, 1
 
 _EMMODEL_NAMES = {
@@ -260,6 +261,22 @@ def _substrate(substrate, frequency, mode=MODE_PASSIVE):
         par[0] = _reflector_value(substrate, frequency, "V")
         par[1] = _reflector_value(substrate, frequency, "H")
         return SUB_REFLECTOR, 0j, temp, par
+    if name == "ReflectorBackscatter":  # reflector_backscatter.py:66-135: passive and active (third component zero)
+        spec, back = substrate.specular_reflection, substrate.backscattering_coefficient
+        if spec is None and back is None:
+            spec = 1  # reflector_backscatter.py:72-73
+        if back is not None and not (isinstance(back, dict) and "VV" in back and "HH" in back):
+            raise SMRTError("backscattering_coefficient must be a dictionary with keys VV and HH")
+        if spec is None:
+            raise SMRTError("a ReflectorBackscatter needs its specular_reflection next to the backscattering_coefficient "
+                            "(the reference turns a missing one into NaN reflectivities)")
+        vals = [spec["V"], spec["H"]] if isinstance(spec, dict) else [spec, spec]
+        vals += [back["VV"], back["HH"]] if back is not None else [0.0, 0.0]
+        if any(callable(v) for v in vals):
+            raise SMRTError("a reflector given as a function of theta is not implemented on the B200 path (the stream "
+                            "angles are computed on the device): give scalars")
+        par[:] = [float(v) for v in vals]
+        return SUB_REFLECTOR_BACKSCATTER, 0j, temp, par
     if name == "Flat":
         kind = SUB_FLAT
     elif name == "SoilWegmuller":
@@ -276,8 +293,8 @@ def _substrate(substrate, frequency, mode=MODE_PASSIVE):
                   N if np.isnan(Nh) else Nh]
     else:
         raise SMRTError(f"substrate '{name}' is not implemented on the B200 path (available: Flat, SoilWegmuller, "
-                        "SoilQNH, ChoudhuryReflectivity, Reflector; rough substrates with diffuse reflection make the "
-                        "boundary blocks dense)")
+                        "SoilQNH, ChoudhuryReflectivity, Reflector, ReflectorBackscatter; rough substrates with a dense "
+                        "diffuse reflection matrix are not: they make the boundary blocks dense)")
     return kind, complex(substrate.permittivity(frequency)), temp, par
 
 

@@ -203,6 +203,21 @@ def test_substrate_and_atmosphere_packing():
         pack.pack_simulations([(S.sensor_list.active(13e9, 40), sp(substrate=refl))], "iba")
     with pytest.raises(S.SMRTError):
         pack.pack_simulations([(sensor, sp(substrate=S.make_reflector(specular_reflection=np.cos)))], "iba")
+    # reflector with a prescribed backscattering coefficient (reference substrate/reflector_backscatter.py): passive and
+    # active, the four numbers travel as substrate parameters
+    rb = S.make_reflector(temperature=250, specular_reflection={"V": 0.3, "H": 0.4},
+                          backscattering_coefficient={"VV": 0.1, "HH": 0.05})
+    rb1 = S.make_reflector(specular_reflection=0.2, backscattering_coefficient={"VV": 0.03, "HH": 0.02})
+    radar = S.sensor_list.active(13e9, 40)
+    b3 = pack.pack_simulations([(radar, sp(substrate=rb)), (radar, sp(substrate=rb1))], "iba")
+    assert list(b3.substrate_kind) == [pack.SUB_REFLECTOR_BACKSCATTER] * 2
+    np.testing.assert_array_equal(b3.substrate_params, [[0.3, 0.4, 0.1, 0.05], [0.2, 0.2, 0.03, 0.02]])
+    assert pack.pack_simulations([(sensor, sp(substrate=rb))], "iba").substrate_kind[0] == pack.SUB_REFLECTOR_BACKSCATTER
+    for bad in (dict(specular_reflection=0.2, backscattering_coefficient=0.1),
+                dict(backscattering_coefficient={"VV": 0.1, "HH": 0.1}),
+                dict(specular_reflection=0.1, backscattering_coefficient={"VV": np.cos, "HH": 0.1})):
+        with pytest.raises(S.SMRTError):
+            pack.pack_simulations([(sensor, sp(substrate=S.make_reflector(**bad)))], "iba")
 
 
 def test_physics_laws_through_the_public_api():
