@@ -75,6 +75,13 @@ extern "C" {
                                           DIAGONAL diffuse reflection +- sigma0 w / (2 mu (1 + 2 m_max)), absent from the
                                           coherent pass     smrt/substrate/reflector_backscatter.py:66-135,
                                           smrt/rtsolver/rtsolver_utils.py:690-709, 728-740 */
+#define SMRTB200_SUB_IEM_FUNG92 7       /* params = roughness_rms (m), corr_length (m), autocorrelation (0 exponential /
+                                          1 gaussian), series_truncation; substrate_eps = soil permittivity.  Coherent
+                                          part under the Kirchhoff approximation (interface/interface_utils.py:21-64),
+                                          IEM backscatter of Fung et al. 1992 as a DIAGONAL diffuse reflection spread
+                                          over the azimuth modes       smrt/interface/iem_fung92.py:88-214 */
+#define SMRTB200_SUB_IEM_FUNG92_BRIOGONI10 8 /* same parameters; Fresnel coefficients at normal incidence when
+                                          ks kl > sqrt(eps_r)          smrt/interface/iem_fung92_brogioni10.py:31-54 */
 
 /* phase_normalization option (smrt/rtsolver/dort.py:94-103, 782-819) */
 #define SMRTB200_NORM_OFF 0

@@ -139,7 +139,8 @@ def solve_mode(problem, mode, streams, layers, iface, intensity_down, planck, co
         if Rb is None:
             Rb = np.zeros(h)
         if l == L - 1 and not coherent_only:  # diagonal diffuse (backscatter) reflection of the substrate
-            Rdiff = O.substrate_diffuse_reflection(problem, streams, mode, int(problem.get("_m_max", 0)))
+            Rdiff = O.substrate_diffuse_reflection(problem, streams, mode, int(problem.get("_m_max", 0)),
+                                                   problem.get("_eps_last"))
             if Rdiff is not None:
                 Rb = Rb + Rdiff
         Rbm = np.diag(Rb)  # effective bottom reflection: interface + (T R T) of the stack below
@@ -232,7 +233,7 @@ def solve_problem(problem, collect=None):
     m_max = int(opts["m_max"]) if mode == "A" else 0
     npol = 2 if mode == "P" else 3
     iface = O.compute_interfaces(problem, eps_eff, streams, npol)
-    problem = dict(problem, _m_max=m_max)
+    problem = dict(problem, _m_max=m_max, _eps_last=eps_eff[-1])
     norm = opts["phase_normalization"]
     if norm == "auto":
         norm = True

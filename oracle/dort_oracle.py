@@ -73,6 +73,7 @@ MS_INDEPENDENT_SPHERE, MS_TEUBNER_STREY, MS_UNIFIED_TS_1, MS_UNIFIED_TS_2, MS_SH
 IF_FLAT, IF_TRANSPARENT = 0, 1
 SUB_NONE, SUB_FLAT, SUB_SOIL_WEGMULLER, SUB_SOIL_QNH, SUB_REFLECTOR, SUB_ROUGH_CHOUDHURY = 0, 1, 2, 3, 4, 5
 SUB_REFLECTOR_BACKSCATTER = 6
+SUB_IEM_FUNG92, SUB_IEM_FUNG92_BRIOGONI10 = 7, 8
 
 # status codes shared with the C ABI (include/smrt_dort_b200.h)
 ST_OK = 0
@@ -484,6 +485,18 @@ def substrate_R_T(problem, eps_1, mu, npol):
     if kind == SUB_FLAT:
         return R, T
     freq = float(problem["frequency"])
+    if kind in (SUB_IEM_FUNG92, SUB_IEM_FUNG92_BRIOGONI10):
+        # coherent part under the Kirchhoff approximation, all components: interface/interface_utils.py:21-64 (the
+        # reference's k2 carries |eps_1|^2; kept); the emissivity of the substrate is the coherent transmission
+        # (core/interface.py:191-195)
+        eps_1c, eps_2c = complex(eps_1), complex(problem["substrate_eps"])
+        k0 = 2 * np.pi * freq / C_SPEED
+        k2 = k0**2 * abs2(eps_1c)
+        R = R * np.exp(-4 * k2 * par[0] ** 2 * mu**2)
+        k_iz = k0 * np.sqrt(eps_1c).real * mu
+        k_sz = k0 * np.sqrt(eps_2c - (1 - mu**2) * eps_1c).real
+        T = T * np.exp(-((k_sz - k_iz) ** 2) * par[0] ** 2)
+        return R, T
 
     def adjust(rh, rv):  # in place, like the reference
         if kind in (SUB_SOIL_WEGMULLER, SUB_ROUGH_CHOUDHURY):
@@ -517,13 +530,55 @@ def substrate_R_T(problem, eps_1, mu, npol):
     return R, T
 
 
-def substrate_diffuse_reflection(problem, streams, mode, m_max):
+def iem_fung92_backscatter(freq, eps_1, eps_2, mu, par, brogioni):
+    """sigma0_vv, sigma0_hh of the IEM of Fung et al. 1992 for backscatter on the streams mu of medium 1: reference
+    smrt/interface/iem_fung92.py:88-189 (Kirchhoff + complementary terms, series of `series_truncation` terms,
+    exponential or Gaussian surface spectrum); iem_fung92_brogioni10.py:45-54 switches the Fresnel coefficients to
+    normal incidence when ks kl > sqrt(eps_r).  par = roughness_rms, corr_length, autocorrelation (0 exponential,
+    1 gaussian), series_truncation.  The validity checks only warn in the reference (warning_handling='print')."""
+    rms, lc, acf, N = float(par[0]), float(par[1]), int(par[2]), int(par[3])
+    eps_1, eps_2 = complex(eps_1), complex(eps_2)
+    mu = np.asarray(mu, dtype=float)[None, :]
+    knorm = 2 * np.pi * freq / C_SPEED * np.sqrt(eps_1).real
+    kz, kx = knorm * mu, knorm * np.sqrt(1 - mu**2)
+    eps_r = eps_2 / eps_1
+    ks, kl = abs(knorm * rms), abs(knorm * lc)
+    sq = np.sqrt(eps_r)
+    at_nadir = brogioni and ((ks * kl, 0.0) > (sq.real, sq.imag))  # numpy orders complex numbers lexicographically
+    Rv, Rh, _ = fresnel_coefficients(eps_1, eps_2, np.ones(1) if at_nadir else mu[0])
+    fvv = 2 * Rv / mu
+    fhh = -2 * Rh / mu
+    n = np.arange(1, N + 1, dtype=np.float64)[:, None]
+    rms2 = rms**2
+    Iscalar_n = (2 * kz) ** n * np.exp(-rms2 * kz**2)
+    Ivv_n = Iscalar_n * fvv
+    Ihh_n = Iscalar_n * fhh
+    mu2 = mu**2
+    sin2 = 1 - mu2
+    tan2 = sin2 / mu2
+    Ivv_n = Ivv_n + kz**n * (sin2 / mu * (1 + Rv) ** 2 * (1 - 1 / eps_r) * (1 + tan2 / eps_r))
+    Ihh_n = Ihh_n - (kz**n) * (sin2 / mu * (1 + Rh) ** 2 * (eps_r - 1) / mu2)
+    rms2_over_factorial = np.cumprod(rms2 / n)[:, None]
+    kq = -2 * kx
+    if acf == 1:
+        W_n = (lc**2 / (2 * n)) * np.exp(-((kq * lc) ** 2) / (4 * n))
+    else:
+        W_n = (lc / n) ** 2 * (1 + (kq * lc / n) ** 2) ** (-1.5)
+    coef = knorm**2 / 2 * np.exp(-2 * rms2 * kz**2)
+    coef_n = rms2_over_factorial * W_n
+    sigma_vv = coef * np.sum(coef_n * abs2(Ivv_n), axis=0)
+    sigma_hh = coef * np.sum(coef_n * abs2(Ihh_n), axis=0)
+    return sigma_vv.reshape(-1), sigma_hh.reshape(-1)
+
+
+def substrate_diffuse_reflection(problem, streams, mode, m_max, eps_1=None):
     """Diagonal diffuse (backscatter) reflection of the substrate for azimuth mode `mode`, already multiplied by the
     mode's integration coefficient and compressed like the coherent part (mu * npol + pol), or None: reference
     smrt/substrate/reflector_backscatter.py:90-116 (the prescribed backscatter spread over the 1 + 2 m_max modes),
     rtsolver_utils.py:728-740 (normalize_diffuse_matrix, 'diagonal5' with mu_i is mu_st: x weights) and 690-709
     (combine_coherent_diffuse_matrix: 2 pi for mode 0, pi above)."""
-    if int(problem.get("substrate_kind", SUB_NONE)) != SUB_REFLECTOR_BACKSCATTER:
+    kind = int(problem.get("substrate_kind", SUB_NONE))
+    if kind not in (SUB_REFLECTOR_BACKSCATTER, SUB_IEM_FUNG92, SUB_IEM_FUNG92_BRIOGONI10):
         return None
     par = np.asarray(problem.get("substrate_params", np.zeros(4)), dtype=float)
     mu = np.asarray(streams["mu"][-1], dtype=float)
@@ -531,9 +586,14 @@ def substrate_diffuse_reflection(problem, streams, mode, m_max):
     npol = 2 if mode == 0 else 3
     coef = 1.0 if mode == 0 else (-2.0 if mode % 2 == 1 else 2.0)
     coef = coef / (1 + 2 * m_max) / (4 * np.pi * mu)
+    if kind == SUB_REFLECTOR_BACKSCATTER:
+        s_vv, s_hh = par[2], par[3]
+    else:  # iem_fung92.py:174-176, 191-214: the same spreading of the backscatter over the modes
+        s_vv, s_hh = iem_fung92_backscatter(float(problem["frequency"]), eps_1, problem["substrate_eps"], mu, par,
+                                            kind == SUB_IEM_FUNG92_BRIOGONI10)
     diff = np.zeros((npol, len(mu)))
-    diff[0] = coef * par[2]
-    diff[1] = coef * par[3]
+    diff[0] = coef * s_vv
+    diff[1] = coef * s_hh
     diff *= w
     return (2 * np.pi if mode == 0 else np.pi) * np.transpose(diff).reshape(-1)
 
@@ -906,7 +966,8 @@ def dort_modem_banded(problem, mode, streams, eigs, iface, intensity_down, planc
         if Rbottom_l is None:
             Rbottom_l = np.zeros(nsl_npol)
         if l == L - 1 and not coherent_only:  # diffuse part of a rough substrate (rtsolver_utils.py:656-659, 690-709)
-            Rdiff = substrate_diffuse_reflection(problem, streams, mode, int(problem.get("_m_max", 0)))
+            Rdiff = substrate_diffuse_reflection(problem, streams, mode, int(problem.get("_m_max", 0)),
+                                                 problem.get("_eps_last"))
             if Rdiff is not None:
                 Rbottom_l = Rbottom_l + Rdiff
         _todiag(bBC, il_bottom[l], jl[l], (Eu - Rbottom_l[:, None] * Ed) * transb[None, :])
@@ -1038,7 +1099,7 @@ def solve_problem(problem, method="schur_forcedtriu", return_details=False):
         m_max = int(opts["m_max"]) if mode == "A" else 0
         npol = 2 if mode == "P" else 3
         iface = compute_interfaces(problem, eps_eff, streams, npol)
-        problem = dict(problem, _m_max=m_max)  # the mode count the diffuse substrate reflection is spread over
+        problem = dict(problem, _m_max=m_max, _eps_last=eps_eff[-1])  # for the diffuse substrate reflection
         norm = opts["phase_normalization"]
         if norm == "auto":
             norm = True  # IBA, DMRT: _respect_reciprocity_principle defaults to True (dort.py:240-242)

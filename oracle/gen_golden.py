@@ -330,6 +330,34 @@ def reflector_backscatter_passive():  # the same substrate under a radiometer: o
 
 
 @case
+def iem_fung92_active():  # reference substrate/iem_fung92.py + iem_fung92_brogioni10.py: IEM backscatter of a rough soil
+    from smrt import make_soil  # as a DIAGONAL diffuse reflection, Kirchhoff coherent part; exponential / Gaussian spectra
+
+    args = [dict(roughness_rms=0.005, corr_length=0.05), dict(roughness_rms=0.012, corr_length=0.08,
+            autocorrelation_function="gaussian"), dict(roughness_rms=0.003, corr_length=0.02, series_truncation=6)]
+    sps = _thin_snowpacks(29, 3, lambda i, rng: make_soil(
+        "iem_fung92", permittivity_model=complex(rng.uniform(4, 20), rng.uniform(0.5, 5)),
+        temperature=rng.uniform(255, 272), **args[i]))
+    run_case("iem_fung92_active", "iba", sensor_list.active([5.4e9, 13.5e9], [25, 40]), sps,
+             dict(n_max_stream=16, m_max=2))
+    sps = _thin_snowpacks(30, 2, lambda i, rng: make_soil(
+        "iem_fung92_brogioni10", permittivity_model=complex(rng.uniform(4, 20), rng.uniform(0.5, 5)),
+        temperature=rng.uniform(255, 272), roughness_rms=[0.004, 0.02][i], corr_length=[0.03, 0.15][i]))
+    run_case("iem_fung92_brogioni10_active", "iba", sensor_list.active([5.4e9, 13.5e9], 35), sps,
+             dict(n_max_stream=16, m_max=2))
+
+
+@case
+def iem_fung92_passive():  # the same soil under a radiometer ("not suitable for emissivity calculations", but it runs)
+    from smrt import make_soil
+
+    sps = _thin_snowpacks(31, 2, lambda i, rng: make_soil(
+        "iem_fung92", permittivity_model=complex(rng.uniform(4, 20), rng.uniform(0.5, 5)),
+        temperature=rng.uniform(255, 272), roughness_rms=[0.002, 0.006][i], corr_length=[0.03, 0.06][i]))
+    run_case("iem_fung92_passive", "iba", sensor_list.passive([10.65e9, 18.7e9], 55), sps, dict(n_max_stream=16))
+
+
+@case
 def choudhury_passive():  # reference substrate/rough_choudhury79.py (k sigma << 1)
     from smrt.substrate.rough_choudhury79 import ChoudhuryReflectivity
 

@@ -32,7 +32,9 @@ enum {
   SUB_SOIL_QNH = 3,
   SUB_REFLECTOR = 4,
   SUB_ROUGH_CHOUDHURY = 5,
-  SUB_REFLECTOR_BACKSCATTER = 6
+  SUB_REFLECTOR_BACKSCATTER = 6,
+  SUB_IEM_FUNG92 = 7,
+  SUB_IEM_FUNG92_BRIOGONI10 = 8
 };
 enum { ST_OK = 0, ST_NORMALIZATION = 1, ST_EIGEN = 2, ST_SINGULAR = 3, ST_INPUT = 4, ST_SUBSTRATE = 5, ST_WARN_SHALLOW = 16 };
 
@@ -465,6 +467,18 @@ SMRT_DEV double stream_weight(const double* mu, int n, int j) {
 struct FresnelRT {
   double R[3], T[3];
 };
+// field reflection coefficients (rv, rh) and the cosine in medium 2: core/fresnel.py:99-146
+SMRT_DEV void fresnel_field(cplx eps_1, cplx eps_2, double mu, cplx& rv, cplx& rh, double& mu2) {
+  cplx n1 = c_sqrt(eps_1);
+  double kiz2 = n1.re * n1.re * (1.0 - mu * mu);
+  cplx kyi = c_scale(c_sqrt(c_make(eps_1.re - kiz2, eps_1.im)), -1.0);
+  cplx kyt = c_scale(c_sqrt(c_make(eps_2.re - kiz2, eps_2.im)), -1.0);
+  rh = c_div(c_sub(kyi, kyt), c_add(c_conj(kyi), kyt));
+  cplx num = c_mul(c_conj(n1), c_sub(c_mul(eps_2, kyi), c_mul(eps_1, kyt)));
+  cplx den = c_mul(n1, c_add(c_mul(eps_2, c_conj(kyi)), c_mul(c_conj(eps_1), kyt)));
+  rv = c_div(num, den);
+  mu2 = -kyt.re / c_sqrt(eps_2).re;
+}
 SMRT_DEV_NOINLINE FresnelRT fresnel_power(int kind, cplx eps_1, cplx eps_2, double mu) {
   FresnelRT o;
   if (kind == IF_TRANSPARENT) {  // interface/transparent.py:12-46
@@ -472,15 +486,9 @@ SMRT_DEV_NOINLINE FresnelRT fresnel_power(int kind, cplx eps_1, cplx eps_2, doub
     o.T[0] = o.T[1] = o.T[2] = 1.0;
     return o;
   }
-  cplx n1 = c_sqrt(eps_1);
-  double kiz2 = n1.re * n1.re * (1.0 - mu * mu);
-  cplx kyi = c_scale(c_sqrt(c_make(eps_1.re - kiz2, eps_1.im)), -1.0);
-  cplx kyt = c_scale(c_sqrt(c_make(eps_2.re - kiz2, eps_2.im)), -1.0);
-  cplx rh = c_div(c_sub(kyi, kyt), c_add(c_conj(kyi), kyt));
-  cplx num = c_mul(c_conj(n1), c_sub(c_mul(eps_2, kyi), c_mul(eps_1, kyt)));
-  cplx den = c_mul(n1, c_add(c_mul(eps_2, c_conj(kyi)), c_mul(c_conj(eps_1), kyt)));
-  cplx rv = c_div(num, den);
-  double mu2 = -kyt.re / c_sqrt(eps_2).re;
+  cplx rv, rh;
+  double mu2;
+  fresnel_field(eps_1, eps_2, mu, rv, rh, mu2);
   o.R[0] = c_abs2(rv);
   o.R[1] = c_abs2(rh);
   o.R[2] = c_mul(rv, c_conj(rh)).re;
@@ -519,10 +527,79 @@ SMRT_DEV void substrate_adjust(int kind, const double* par, double ksigma, doubl
     rv = trv;
   }
 }
+// Diagonal diffuse reflection of a substrate with a prescribed backscattering coefficient sigma0 (linear), azimuth mode
+// m of m_max, stream (mu, weight w) -- substrate/reflector_backscatter.py:90-116: the backscatter is spread over the
+// 1 + 2 m_max modes with signs (+1, -2, +2, ...) and converted to scattering by 1 / (4 pi mu); rtsolver_utils.py:735-737
+// multiplies by the weight and 690-709 by the mode integral (2 pi | pi): +- sigma0 w / (2 mu (1 + 2 m_max)).
+SMRT_DEV double substrate_backscatter(double sigma0, int m, int m_max, double mu, double w) {
+  const double sgn = (m & 1) ? -1.0 : 1.0;
+  return sgn * 0.5 * sigma0 * w / ((double)(1 + 2 * m_max) * mu);
+}
+
+// Backscattering coefficients (VV, HH) of a moderately rough surface by the IEM of Fung et al. 1992 on the stream mu of
+// medium 1 -- interface/iem_fung92.py:88-189: Kirchhoff and complementary terms, `series_truncation` terms of the series,
+// exponential or Gaussian surface spectrum; brogioni: Fresnel coefficients at normal incidence when
+// ks kl > sqrt(eps_r) (iem_fung92_brogioni10.py:45-54; complex numbers compare lexicographically in NumPy).
+// par = roughness_rms, corr_length, autocorrelation (0 exponential, 1 gaussian), series_truncation.
+SMRT_DEV_NOINLINE void iem_fung92_sigma0(double freq, cplx eps_1, cplx eps_2, double mu, const double* par,
+                                         bool brogioni, double& svv, double& shh) {
+  const double rms = par[0], lc = par[1];
+  const bool gauss = par[2] != 0.0;
+  const int N = (int)par[3];
+  const double knorm = 2.0 * SMRT_PI * freq / SMRT_C_SPEED * c_sqrt(eps_1).re;
+  const double mu2 = mu * mu, sin2 = 1.0 - mu2, tan2 = sin2 / mu2;
+  const double kz = knorm * mu, kx = knorm * sqrt(sin2);
+  const cplx eps_r = c_div(eps_2, eps_1);
+  const cplx sq = c_sqrt(eps_r);
+  const double kskl = fabs(knorm * rms) * fabs(knorm * lc);
+  const bool nadir = brogioni && (kskl > sq.re || (kskl == sq.re && 0.0 > sq.im));
+  cplx rv, rh;
+  double mut;
+  fresnel_field(eps_1, eps_2, nadir ? 1.0 : mu, rv, rh, mut);
+  const cplx one = c_make(1.0, 0.0);
+  const cplx fvv = c_scale(rv, 2.0 / mu), fhh = c_scale(rh, -2.0 / mu);
+  const cplx inv_er = c_div(one, eps_r);
+  const cplx opv = c_add(one, rv), oph = c_add(one, rh);
+  const cplx cv = c_scale(c_mul(c_mul(c_mul(opv, opv), c_sub(one, inv_er)), c_add(one, c_scale(inv_er, tan2))), sin2 / mu);
+  const cplx ch = c_scale(c_mul(c_mul(oph, oph), c_sub(eps_r, one)), sin2 / (mu * mu2));
+  const double rms2 = rms * rms, e1 = exp(-rms2 * kz * kz);
+  const double kql = -2.0 * kx * lc;
+  double p1 = 1.0, p2 = 1.0, fact = 1.0, sv = 0.0, sh = 0.0;
+  for (int n = 1; n <= N; ++n) {
+    p1 *= kz;
+    p2 *= 2.0 * kz;
+    fact *= rms2 / (double)n;
+    const cplx ivv = c_add(c_scale(fvv, p2 * e1), c_scale(cv, p1));
+    const cplx ihh = c_sub(c_scale(fhh, p2 * e1), c_scale(ch, p1));
+    const double ln = lc / (double)n;
+    const double W = gauss ? (lc * lc / (2.0 * n)) * exp(-(kql * kql) / (4.0 * n))
+                           : ln * ln * pow(1.0 + (kql / n) * (kql / n), -1.5);
+    sv = fma(fact * W, c_abs2(ivv), sv);
+    sh = fma(fact * W, c_abs2(ihh), sh);
+  }
+  const double coef = 0.5 * knorm * knorm * exp(-2.0 * rms2 * kz * kz);
+  svv = coef * sv;
+  shh = coef * sh;
+}
+
 // specular reflection and emissivity of the substrate under a layer of permittivity eps_1, on the stream mu:
 // substrate/flat.py:15-17, soil_wegmuller.py:45-81, soil_qnh.py:44-89, reflector.py:51-81, rough_choudhury79.py:39-79.
 // The third Stokes component keeps its Fresnel value (as in the reference).
-SMRT_DEV_NOINLINE FresnelRT substrate_power(int kind, const double* par, double freq, cplx eps_1, cplx eps_2, double mu) {
+// w, m_diff, m_max: weight of the stream, azimuth mode whose diffuse (backscatter) reflection is added to R for the
+// substrates that have one (kinds 6 - 8; m_diff < 0: none, the coherent pass), number of modes it is spread over.
+SMRT_DEV FresnelRT substrate_specular(int kind, const double* par, double freq, cplx eps_1, cplx eps_2, double mu);
+SMRT_DEV_NOINLINE FresnelRT substrate_power(int kind, const double* par, double freq, cplx eps_1, cplx eps_2, double mu,
+                                            double w = 0.0, int m_diff = -1, int m_max = 0) {
+  FresnelRT o = substrate_specular(kind, par, freq, eps_1, eps_2, mu);
+  if (m_diff >= 0 && par && kind >= SUB_REFLECTOR_BACKSCATTER && kind <= SUB_IEM_FUNG92_BRIOGONI10) {
+    double svv = par[2], shh = par[3];
+    if (kind != SUB_REFLECTOR_BACKSCATTER) iem_fung92_sigma0(freq, eps_1, eps_2, mu, par, kind == SUB_IEM_FUNG92_BRIOGONI10, svv, shh);
+    o.R[0] += substrate_backscatter(svv, m_diff, m_max, mu, w);
+    o.R[1] += substrate_backscatter(shh, m_diff, m_max, mu, w);
+  }
+  return o;
+}
+SMRT_DEV FresnelRT substrate_specular(int kind, const double* par, double freq, cplx eps_1, cplx eps_2, double mu) {
   FresnelRT o;
   const double zero4[4] = {0.0, 0.0, 0.0, 0.0};
   if (!par) par = zero4;
@@ -537,6 +614,21 @@ SMRT_DEV_NOINLINE FresnelRT substrate_power(int kind, const double* par, double 
   }
   o = fresnel_power(IF_FLAT, eps_1, eps_2, mu);
   if (kind == SUB_FLAT) return o;
+  if (kind == SUB_IEM_FUNG92 || kind == SUB_IEM_FUNG92_BRIOGONI10) {
+    // coherent part under the Kirchhoff approximation, every component: interface/interface_utils.py:21-64 (k2 carries
+    // |eps_1|^2 as in the reference); the emissivity of the substrate is the coherent transmission
+    const double k0 = 2.0 * SMRT_PI * freq / SMRT_C_SPEED, rms2 = par[0] * par[0];
+    const double fr = exp(-4.0 * (k0 * k0 * c_abs2(eps_1)) * rms2 * (mu * mu));
+    const double k_iz = k0 * c_sqrt(eps_1).re * mu;
+    const double s2 = 1.0 - mu * mu;
+    const double k_sz = k0 * c_sqrt(c_make(eps_2.re - s2 * eps_1.re, eps_2.im - s2 * eps_1.im)).re;
+    const double ft = exp(-((k_sz - k_iz) * (k_sz - k_iz)) * rms2);
+    for (int p = 0; p < 3; ++p) {
+      o.R[p] *= fr;
+      o.T[p] *= ft;
+    }
+    return o;
+  }
   const double ksigma =
       (kind == SUB_SOIL_WEGMULLER || kind == SUB_ROUGH_CHOUDHURY) ? substrate_ksigma(freq, eps_1, par[0]) : 0.0;
   substrate_adjust(kind, par, ksigma, mu, o.R[1], o.R[0]);
@@ -545,15 +637,6 @@ SMRT_DEV_NOINLINE FresnelRT substrate_power(int kind, const double* par, double 
   o.T[1] = 1.0 - rh;
   o.T[0] = 1.0 - rv;
   return o;
-}
-
-// Diagonal diffuse reflection of a substrate with a prescribed backscattering coefficient sigma0 (linear), azimuth mode
-// m of m_max, stream (mu, weight w) -- substrate/reflector_backscatter.py:90-116: the backscatter is spread over the
-// 1 + 2 m_max modes with signs (+1, -2, +2, ...) and converted to scattering by 1 / (4 pi mu); rtsolver_utils.py:735-737
-// multiplies by the weight and 690-709 by the mode integral (2 pi | pi): +- sigma0 w / (2 mu (1 + 2 m_max)).
-SMRT_DEV double substrate_backscatter(double sigma0, int m, int m_max, double mu, double w) {
-  const double sgn = (m & 1) ? -1.0 : 1.0;
-  return sgn * 0.5 * sigma0 * w / ((double)(1 + 2 * m_max) * mu);
 }
 
 // ---------------------------------------------------------------------------------------------------- phase matrix

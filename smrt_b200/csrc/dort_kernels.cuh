@@ -922,17 +922,12 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
               fb = fresnel_power(A.interface_kind[bL + l + 1], eps_l, c_make(eps_b[2 * (l + 1)], eps_b[2 * (l + 1) + 1]),
                                  mu[j]);
             } else if (A.substrate_kind[b] != SUB_NONE) {
+              // the diagonal diffuse (backscatter) reflection of the rough substrates joins the specular one in every
+              // pass but the coherent one (rtsolver_utils.py:690-709); the emissivity keeps the coherent value
               fb = substrate_power(A.substrate_kind[b], A.substrate_params ? A.substrate_params + 4 * (size_t)b : nullptr,
-                                   freq, eps_l, c_make(A.substrate_eps[2 * b], A.substrate_eps[2 * b + 1]), mu[j]);
-              // diagonal diffuse part of a reflector with prescribed backscatter; not in the coherent pass
-              // (rtsolver_utils.py:690-709).  The emissivity (fb.T) keeps the specular value.
-              if (A.substrate_kind[b] == SUB_REFLECTOR_BACKSCATTER && !coherent && A.substrate_params && n_l >= 2) {
-                const double* par = A.substrate_params + 4 * (size_t)b;
-                const int mm = (A.mode == 0) ? 0 : A.m_max;
-                const double wj = stream_weight(mu, n_l, j);
-                fb.R[0] += substrate_backscatter(par[2], m, mm, mu[j], wj);
-                fb.R[1] += substrate_backscatter(par[3], m, mm, mu[j], wj);
-              }
+                                   freq, eps_l, c_make(A.substrate_eps[2 * b], A.substrate_eps[2 * b + 1]), mu[j],
+                                   (n_l >= 2) ? stream_weight(mu, n_l, j) : 0.0, coherent ? -1 : m,
+                                   (A.mode == 0) ? 0 : A.m_max);
             } else {
               fb.R[0] = fb.R[1] = fb.R[2] = 0.0;
               fb.T[0] = fb.T[1] = fb.T[2] = 0.0;

@@ -295,6 +295,25 @@ class SoilQNH(FlatSubstrate):
         self.H, self.Q, self.N, self.Nv, self.Nh = H, Q, N, Nv, Nh
 
 
+class IEM_Fung92(FlatSubstrate):
+    """Moderately rough surface, backscatter by the IEM of Fung et al. 1992 — reference ``smrt/substrate/iem_fung92.py``
+    (``smrt/interface/iem_fung92.py:44-67``)."""
+
+    def __init__(self, temperature=None, permittivity_model=None, roughness_rms=None, corr_length=None,
+                 autocorrelation_function="exponential", warning_handling="print", series_truncation=10):
+        super().__init__(temperature, permittivity_model)
+        if roughness_rms is None or corr_length is None:
+            raise SMRTError("Parameters roughness_rms and corr_length must be specified")
+        self.roughness_rms, self.corr_length = roughness_rms, corr_length
+        self.autocorrelation_function = autocorrelation_function
+        self.warning_handling, self.series_truncation = warning_handling, series_truncation
+
+
+class IEM_Fung92_Briogoni10(IEM_Fung92):
+    """The same with the Fresnel coefficients taken at normal incidence for ks kl > sqrt(eps_r) — reference
+    ``smrt/interface/iem_fung92_brogioni10.py:31-54``."""
+
+
 class Reflector:
     """Prescribed specular reflection (scalar, or dict keyed by polarisation and / or frequency) — reference
     ``smrt/substrate/reflector.py:51-111``."""
@@ -324,7 +343,8 @@ def make_reflector(temperature=None, specular_reflection=None, backscattering_co
 
 
 _SOILS = {"flat": FlatSubstrate, "soil_wegmuller": SoilWegmuller, "soil_qnh": SoilQNH,
-          "rough_choudhury79": ChoudhuryReflectivity}
+          "rough_choudhury79": ChoudhuryReflectivity, "iem_fung92": IEM_Fung92,
+          "iem_fung92_brogioni10": IEM_Fung92_Briogoni10}
 
 
 def make_soil(substrate_model, permittivity_model=None, temperature=FREEZING_POINT, **kwargs):

@@ -27,6 +27,7 @@ MS_INDEPENDENT_SPHERE, MS_TEUBNER_STREY, MS_UNIFIED_TS_1, MS_UNIFIED_TS_2, MS_SH
 IF_FLAT, IF_TRANSPARENT = 0, 1
 SUB_NONE, SUB_FLAT, SUB_SOIL_WEGMULLER, SUB_SOIL_QNH, SUB_REFLECTOR, SUB_ROUGH_CHOUDHURY = 0, 1, 2, 3, 4, 5
 SUB_REFLECTOR_BACKSCATTER = 6
+SUB_IEM_FUNG92, SUB_IEM_FUNG92_BRIOGONI10 = 7, 8
 MODE_PASSIVE, MODE_ACTIVE = 0, 1
 
 _EMMODEL_NAMES = {
@@ -285,6 +286,18 @@ def _substrate(substrate, frequency, mode=MODE_PASSIVE):
     elif name == "ChoudhuryReflectivity":
         kind = SUB_ROUGH_CHOUDHURY
         par[0] = float(substrate.roughness_rms)
+    elif name in ("IEM_Fung92", "IEM_Fung92_Briogoni10"):  # substrate/iem_fung92.py, iem_fung92_brogioni10.py
+        kind = SUB_IEM_FUNG92 if name == "IEM_Fung92" else SUB_IEM_FUNG92_BRIOGONI10
+        acf = getattr(substrate, "autocorrelation_function", "exponential")
+        if acf not in ("exponential", "gaussian"):
+            raise SMRTError("The autocorrelation function must be exponential or gaussian")  # iem_fung92.py:189
+        if getattr(substrate, "warning_handling", "print") != "print":
+            raise SMRTError("IEM_Fung92 on the B200 path follows warning_handling='print' (outside the validity range "
+                            "the reference warns and goes on; no message is printed here)")
+        N = int(getattr(substrate, "series_truncation", 10))
+        if not 1 <= N <= 64:
+            raise SMRTError("series_truncation must be in 1..64")
+        par[:] = [float(substrate.roughness_rms), float(substrate.corr_length), 1.0 if acf == "gaussian" else 0.0, N]
     elif name == "SoilQNH":
         kind = SUB_SOIL_QNH
         N = float(getattr(substrate, "N", 0.0))
@@ -293,7 +306,7 @@ def _substrate(substrate, frequency, mode=MODE_PASSIVE):
                   N if np.isnan(Nh) else Nh]
     else:
         raise SMRTError(f"substrate '{name}' is not implemented on the B200 path (available: Flat, SoilWegmuller, "
-                        "SoilQNH, ChoudhuryReflectivity, Reflector, ReflectorBackscatter; rough substrates with a dense "
+                        "SoilQNH, ChoudhuryReflectivity, Reflector, ReflectorBackscatter, IEM_Fung92, IEM_Fung92_Briogoni10; rough substrates with a dense "
                         "diffuse reflection matrix are not: they make the boundary blocks dense)")
     return kind, complex(substrate.permittivity(frequency)), temp, par
 

@@ -213,6 +213,18 @@ def test_substrate_and_atmosphere_packing():
     assert list(b3.substrate_kind) == [pack.SUB_REFLECTOR_BACKSCATTER] * 2
     np.testing.assert_array_equal(b3.substrate_params, [[0.3, 0.4, 0.1, 0.05], [0.2, 0.2, 0.03, 0.02]])
     assert pack.pack_simulations([(sensor, sp(substrate=rb))], "iba").substrate_kind[0] == pack.SUB_REFLECTOR_BACKSCATTER
+    # rough soil with the IEM backscatter of Fung et al. 1992 (reference substrate/iem_fung92.py, iem_fung92_brogioni10.py)
+    iem = S.make_soil("iem_fung92", permittivity_model=complex(12, 2), roughness_rms=0.005, corr_length=0.05, temperature=265)
+    iemb = S.make_soil("iem_fung92_brogioni10", permittivity_model=complex(8, 1), roughness_rms=0.01, corr_length=0.1,
+                       autocorrelation_function="gaussian", series_truncation=6, temperature=265)
+    b4 = pack.pack_simulations([(radar, sp(substrate=iem)), (radar, sp(substrate=iemb))], "iba")
+    assert list(b4.substrate_kind) == [pack.SUB_IEM_FUNG92, pack.SUB_IEM_FUNG92_BRIOGONI10]
+    np.testing.assert_array_equal(b4.substrate_params, [[0.005, 0.05, 0, 10], [0.01, 0.1, 1, 6]])
+    np.testing.assert_array_equal(b4.substrate_eps, [12 + 2j, 8 + 1j])
+    with pytest.raises(S.SMRTError):
+        pack.pack_simulations([(radar, sp(substrate=S.make_soil(
+            "iem_fung92", permittivity_model=complex(12, 2), roughness_rms=0.005, corr_length=0.05,
+            autocorrelation_function="power")))], "iba")
     for bad in (dict(specular_reflection=0.2, backscattering_coefficient=0.1),
                 dict(backscattering_coefficient={"VV": 0.1, "HH": 0.1}),
                 dict(specular_reflection=0.1, backscattering_coefficient={"VV": np.cos, "HH": 0.1})):

@@ -15,10 +15,10 @@ SMALL = ["cfg1_iba_onelayer", "ref_iba_2layer_passive", "ref_dmrt_qcacp_2layer_p
          "iba_options_prune_rj", "iba_exp_substrate_passive", "soil_wegmuller_passive", "reflector_passive",
          "atmosphere_passive", "ref_physics_law", "iba_microstructures_passive", "prescribed_kskaeps_passive",
          "ref_iba_original_2layer_passive", "iba_maxwell_garnett_passive", "emmodel_per_medium_passive",
-         "inclusion_shapes_passive", "reflector_backscatter_passive"]
+         "inclusion_shapes_passive", "reflector_backscatter_passive", "iem_fung92_passive"]
 SMALL_ACTIVE = ["ref_dmrt_less_refringent_active", "nonscattering_active", "soil_active", "rayleigh_active",
                 "depolarization_active", "ref_rayleigh_mmax6_active", "reflector_backscatter_active",
-                "reflector_backscatter_active_mmax4"]
+                "reflector_backscatter_active_mmax4", "iem_fung92_active", "iem_fung92_brogioni10_active"]
 
 
 @pytest.mark.parametrize("name", SMALL + SMALL_ACTIVE)
