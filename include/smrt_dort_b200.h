@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SMRTB200_ABI_VERSION 3
+#define SMRTB200_ABI_VERSION 4
 
 /* sensor mode (reference smrt/core/sensor.py:331-339) */
 #define SMRTB200_MODE_PASSIVE 0
@@ -59,6 +59,12 @@ extern "C" {
 /* interface above a layer */
 #define SMRTB200_IF_FLAT 0        /* Fresnel, smrt/interface/flat.py:11-75 + smrt/core/fresnel.py:99-146,417-474 */
 #define SMRTB200_IF_TRANSPARENT 1 /* smrt/interface/transparent.py:7-49 */
+/* moderately rough interfaces: coherent reflection / transmission under the Kirchhoff approximation
+ * (smrt/interface/interface_utils.py:16-64) and the IEM backscatter of Fung et al. 1992 as a DIAGONAL diffuse reflection
+ * in every azimuth mode (smrt/interface/iem_fung92.py:88-214; no diffuse transmission); parameters in interface_params */
+#define SMRTB200_IF_IEM_FUNG92 2
+#define SMRTB200_IF_IEM_FUNG92_BRIOGONI10 3 /* Fresnel coefficients at normal incidence when ks kl > sqrt(eps_r):
+                                               smrt/interface/iem_fung92_brogioni10.py:31-54 */
 
 /* substrate */
 #define SMRTB200_SUB_NONE 0
@@ -148,6 +154,10 @@ typedef struct {
                                          the IBA field ratio and of Maxwell-Garnett (layer.depolarization_factors or
                                          length_ratio: smrt/emmodel/iba.py:112-119, smrt/permittivity/
                                          depolarization_factors.py:9-46); may be NULL = (1, 0, 1/3, 1/3, 1/3) */
+  const double* interface_params;     /* [B, L, 4] parameters of the interface ABOVE layer l for SMRTB200_IF_* kinds >= 2:
+                                         roughness_rms (m), corr_length (m), autocorrelation (0 exponential / 1 gaussian),
+                                         series_truncation; may be NULL when every interface is flat or transparent (a
+                                         rough kind without parameters is treated as flat) */
   const double* theta;                /* [n_theta] rad, viewing angles (passive) */
   const double* theta_inc;            /* [n_inc] rad, incidence angles (active) */
   double phi;                         /* rad, relative azimuth (active; pi = backscatter) */

@@ -138,11 +138,9 @@ def solve_mode(problem, mode, streams, layers, iface, intensity_down, planck, co
         Rb = cdiag(Rbot_, l)
         if Rb is None:
             Rb = np.zeros(h)
-        if l == L - 1 and not coherent_only:  # diagonal diffuse (backscatter) reflection of the substrate
-            Rdiff = O.substrate_diffuse_reflection(problem, streams, mode, int(problem.get("_m_max", 0)),
-                                                   problem.get("_eps_last"))
-            if Rdiff is not None:
-                Rb = Rb + Rdiff
+        # diagonal diffuse (backscatter) reflection of rough interfaces / substrates
+        Rb = O.with_diffuse_reflection(Rb, problem, streams, mode, coherent_only, "bottom", l)
+        Rt = O.with_diffuse_reflection(Rt, problem, streams, mode, coherent_only, "top", l)
         Rbm = np.diag(Rb)  # effective bottom reflection: interface + (T R T) of the stack below
         b_top = np.zeros((h, nrhs))
         b_bot = np.zeros((h, nrhs))
@@ -200,7 +198,7 @@ def solve_mode(problem, mode, streams, layers, iface, intensity_down, planck, co
     I1up = svec
     if mode == 0 and temperature is not None and temperature[0] > 0:
         I1up = I1up + planck(temperature[0])
-    Rair = O.compress_diag(Rbot_[-1], mode)
+    Rair = O.with_diffuse_reflection(O.compress_diag(Rbot_[-1], mode), problem, streams, mode, coherent_only, "air")
     Ttop0 = O.compress_diag(Ttop_[0], mode)
     n_air = streams["n_air"]
     I0up = Rair[:, None] * intensity_down + (Ttop0[:, None] * I1up)[0:n_air * npol, :]
@@ -233,7 +231,7 @@ def solve_problem(problem, collect=None):
     m_max = int(opts["m_max"]) if mode == "A" else 0
     npol = 2 if mode == "P" else 3
     iface = O.compute_interfaces(problem, eps_eff, streams, npol)
-    problem = dict(problem, _m_max=m_max, _eps_last=eps_eff[-1])
+    problem = dict(problem, _m_max=m_max, _eps_eff=eps_eff)
     norm = opts["phase_normalization"]
     if norm == "auto":
         norm = True

@@ -70,7 +70,7 @@ EM_IBA_ORIGINAL, EM_IBA_MAXWELL_GARNETT = 6, 7
 EM_IBA_FAMILY = (EM_IBA, EM_IBA_ORIGINAL, EM_IBA_MAXWELL_GARNETT)
 MS_EXPONENTIAL, MS_SHS, MS_HOMOGENEOUS = 0, 1, 2
 MS_INDEPENDENT_SPHERE, MS_TEUBNER_STREY, MS_UNIFIED_TS_1, MS_UNIFIED_TS_2, MS_SHS_T = 3, 4, 5, 6, 7
-IF_FLAT, IF_TRANSPARENT = 0, 1
+IF_FLAT, IF_TRANSPARENT, IF_IEM_FUNG92, IF_IEM_FUNG92_BRIOGONI10 = 0, 1, 2, 3
 SUB_NONE, SUB_FLAT, SUB_SOIL_WEGMULLER, SUB_SOIL_QNH, SUB_REFLECTOR, SUB_ROUGH_CHOUDHURY = 0, 1, 2, 3, 4, 5
 SUB_REFLECTOR_BACKSCATTER = 6
 SUB_IEM_FUNG92, SUB_IEM_FUNG92_BRIOGONI10 = 7, 8
@@ -433,11 +433,27 @@ def abs2(z):
     return z.real**2 + z.imag**2
 
 
-def interface_R_T(kind, eps_1, eps_2, mu, npol):
-    """Diagonal power reflection / transmission (npol, len(mu)) for medium 1 above/below medium 2."""
+def kirchhoff_factors(rms, freq, eps_1, eps_2, mu):
+    """factors of the coherent reflection / transmission of a rough surface under the Kirchhoff approximation: reference
+    smrt/interface/interface_utils.py:21-64 (the reference's k2 carries |eps_1|^2; kept)"""
+    eps_1, eps_2 = complex(eps_1), complex(eps_2)
+    k0 = 2 * np.pi * freq / C_SPEED
+    k2 = k0**2 * abs2(eps_1)
+    k_iz = k0 * np.sqrt(eps_1).real * mu
+    k_sz = k0 * np.sqrt(eps_2 - (1 - mu**2) * eps_1).real
+    return np.exp(-4 * k2 * rms**2 * mu**2), np.exp(-((k_sz - k_iz) ** 2) * rms**2)
+
+
+def interface_R_T(kind, eps_1, eps_2, mu, npol, par=None, freq=None):
+    """Diagonal COHERENT power reflection / transmission (npol, len(mu)) for medium 1 above/below medium 2; par, freq:
+    parameters of a rough interface (IEM_Fung92: interface/iem_fung92.py:44-67) and the frequency."""
     mu = np.atleast_1d(mu)
     if kind == IF_TRANSPARENT:
         return np.zeros((npol, len(mu))), np.ones((npol, len(mu)))
+    if kind in (IF_IEM_FUNG92, IF_IEM_FUNG92_BRIOGONI10):
+        R, T = interface_R_T(IF_FLAT, eps_1, eps_2, mu, npol)
+        fr, ft = kirchhoff_factors(float(par[0]), freq, eps_1, eps_2, mu)
+        return R * fr, T * ft
     rv, rh, mu2 = fresnel_coefficients(eps_1, eps_2, mu)
     R = np.ones((npol, len(mu)))
     T = np.zeros((npol, len(mu)))
@@ -489,14 +505,8 @@ def substrate_R_T(problem, eps_1, mu, npol):
         # coherent part under the Kirchhoff approximation, all components: interface/interface_utils.py:21-64 (the
         # reference's k2 carries |eps_1|^2; kept); the emissivity of the substrate is the coherent transmission
         # (core/interface.py:191-195)
-        eps_1c, eps_2c = complex(eps_1), complex(problem["substrate_eps"])
-        k0 = 2 * np.pi * freq / C_SPEED
-        k2 = k0**2 * abs2(eps_1c)
-        R = R * np.exp(-4 * k2 * par[0] ** 2 * mu**2)
-        k_iz = k0 * np.sqrt(eps_1c).real * mu
-        k_sz = k0 * np.sqrt(eps_2c - (1 - mu**2) * eps_1c).real
-        T = T * np.exp(-((k_sz - k_iz) ** 2) * par[0] ** 2)
-        return R, T
+        fr, ft = kirchhoff_factors(par[0], freq, eps_1, problem["substrate_eps"], mu)
+        return R * fr, T * ft
 
     def adjust(rh, rv):  # in place, like the reference
         if kind in (SUB_SOIL_WEGMULLER, SUB_ROUGH_CHOUDHURY):
@@ -571,6 +581,58 @@ def iem_fung92_backscatter(freq, eps_1, eps_2, mu, par, brogioni):
     return sigma_vv.reshape(-1), sigma_hh.reshape(-1)
 
 
+def backscatter_diffuse_diagonal(s_vv, s_hh, mu, w, mode, m_max):
+    """backscattering coefficients -> diagonal diffuse reflection of azimuth mode `mode`, multiplied by the mode's
+    integration coefficient and compressed (mu * npol + pol): iem_fung92.py:174-176, 191-214 / reflector_backscatter.py:
+    90-116 (spread over 1 + 2 m_max modes), rtsolver_utils.py:728-740 (x weights), 690-709 (2 pi | pi)"""
+    npol = 2 if mode == 0 else 3
+    coef = 1.0 if mode == 0 else (-2.0 if mode % 2 == 1 else 2.0)
+    coef = coef / (1 + 2 * m_max) / (4 * np.pi * mu)
+    diff = np.zeros((npol, len(mu)))
+    diff[0] = coef * s_vv
+    diff[1] = coef * s_hh
+    diff *= w
+    return (2 * np.pi if mode == 0 else np.pi) * np.transpose(diff).reshape(-1)
+
+
+def interface_diffuse_reflection(problem, l, eps_1, eps_2, mu, w, mode, m_max):
+    """diagonal diffuse reflection of the (rough) interface ABOVE layer l seen from the medium eps_1 on the streams
+    (mu, w), or None for flat / transparent interfaces: rtsolver_utils.py:489-501 (top of a layer), 570-582 (bottom),
+    631-642 (from the air)"""
+    kind = int(problem["interface"][l])
+    if kind not in (IF_IEM_FUNG92, IF_IEM_FUNG92_BRIOGONI10):
+        return None
+    par = np.asarray(problem["interface_params"][l], dtype=float)
+    mu = np.asarray(mu, dtype=float)
+    s_vv, s_hh = iem_fung92_backscatter(float(problem["frequency"]), eps_1, eps_2, mu, par,
+                                        kind == IF_IEM_FUNG92_BRIOGONI10)
+    return backscatter_diffuse_diagonal(s_vv, s_hh, mu, np.asarray(w, dtype=float), mode, m_max)
+
+
+def with_diffuse_reflection(R, problem, streams, mode, coherent_only, where, l=None):
+    """R (compressed diagonal reflection) + the diagonal diffuse reflection of the rough surface it belongs to, unless
+    this is the coherent pass: where = "top" (interface above layer l seen from layer l), "bottom" (interface or
+    substrate below layer l seen from layer l), "air" (top interface seen from the air, on the air streams) —
+    combine_coherent_diffuse_matrix, rtsolver_utils.py:646-709."""
+    if coherent_only:
+        return R
+    eps = problem.get("_eps_eff")
+    m_max = int(problem.get("_m_max", 0))
+    L = len(problem["thickness"])
+    d = None
+    if where == "top":
+        d = interface_diffuse_reflection(problem, l, eps[l], eps[l - 1] if l > 0 else 1, streams["mu"][l],
+                                         streams["weight"][l], mode, m_max)
+    elif where == "bottom" and l < L - 1:
+        d = interface_diffuse_reflection(problem, l + 1, eps[l], eps[l + 1], streams["mu"][l], streams["weight"][l],
+                                         mode, m_max)
+    elif where == "bottom":
+        d = substrate_diffuse_reflection(problem, streams, mode, m_max, eps[-1])
+    elif where == "air":
+        d = interface_diffuse_reflection(problem, 0, 1, eps[0], streams["outmu"], streams["outweight"], mode, m_max)
+    return R if d is None else R + d
+
+
 def substrate_diffuse_reflection(problem, streams, mode, m_max, eps_1=None):
     """Diagonal diffuse (backscatter) reflection of the substrate for azimuth mode `mode`, already multiplied by the
     mode's integration coefficient and compressed like the coherent part (mu * npol + pol), or None: reference
@@ -583,38 +645,38 @@ def substrate_diffuse_reflection(problem, streams, mode, m_max, eps_1=None):
     par = np.asarray(problem.get("substrate_params", np.zeros(4)), dtype=float)
     mu = np.asarray(streams["mu"][-1], dtype=float)
     w = np.asarray(streams["weight"][-1], dtype=float)
-    npol = 2 if mode == 0 else 3
-    coef = 1.0 if mode == 0 else (-2.0 if mode % 2 == 1 else 2.0)
-    coef = coef / (1 + 2 * m_max) / (4 * np.pi * mu)
     if kind == SUB_REFLECTOR_BACKSCATTER:
         s_vv, s_hh = par[2], par[3]
     else:  # iem_fung92.py:174-176, 191-214: the same spreading of the backscatter over the modes
         s_vv, s_hh = iem_fung92_backscatter(float(problem["frequency"]), eps_1, problem["substrate_eps"], mu, par,
                                             kind == SUB_IEM_FUNG92_BRIOGONI10)
-    diff = np.zeros((npol, len(mu)))
-    diff[0] = coef * s_vv
-    diff[1] = coef * s_hh
-    diff *= w
-    return (2 * np.pi if mode == 0 else np.pi) * np.transpose(diff).reshape(-1)
+    return backscatter_diffuse_diagonal(s_vv, s_hh, mu, w, mode, m_max)
 
 
 def compute_interfaces(problem, eps_eff, streams, npol):
     """reference smrt/rtsolver/rtsolver_utils.py:473-644 for Flat / Transparent interfaces and a flat substrate."""
     L = len(eps_eff)
     kinds = problem["interface"]
+    ipar = problem.get("interface_params")
+    freq = float(problem["frequency"])
+
+    def par(l):
+        return None if ipar is None else ipar[l]
+
     Rtop, Ttop, Rbot, Tbot = {}, {}, {}, {}
     for l in range(L):
         eps_lm1 = eps_eff[l - 1] if l > 0 else 1
         eps_l = eps_eff[l]
-        Rtop[l], Ttop[l] = interface_R_T(kinds[l], eps_l, eps_lm1, streams["mu"][l], npol)
+        Rtop[l], Ttop[l] = interface_R_T(kinds[l], eps_l, eps_lm1, streams["mu"][l], npol, par(l), freq)
         if l < L - 1:
-            Rbot[l], Tbot[l] = interface_R_T(kinds[l + 1], eps_l, eps_eff[l + 1], streams["mu"][l], npol)
+            Rbot[l], Tbot[l] = interface_R_T(kinds[l + 1], eps_l, eps_eff[l + 1], streams["mu"][l], npol, par(l + 1),
+                                             freq)
         elif problem.get("substrate_kind", SUB_NONE) != SUB_NONE:
             Rbot[l], Tbot[l] = substrate_R_T(problem, eps_l, streams["mu"][l], npol)
         else:
             Rbot[l] = None
             Tbot[l] = None
-    Rbot[-1], Tbot[-1] = interface_R_T(kinds[0], 1, eps_eff[0], streams["outmu"], npol)
+    Rbot[-1], Tbot[-1] = interface_R_T(kinds[0], 1, eps_eff[0], streams["outmu"], npol, par(0), freq)
     return Rtop, Ttop, Rbot, Tbot
 
 
@@ -941,7 +1003,7 @@ def dort_modem_banded(problem, mode, streams, eigs, iface, intensity_down, planc
         transb = np.exp(np.minimum(beta, 0) * thickness[l])
         if l == 0:
             Eu_0, transt_0 = Eu, transt
-        Rtop_l = cdiag(Rtop_, l)
+        Rtop_l = with_diffuse_reflection(cdiag(Rtop_, l), problem, streams, mode, coherent_only, "top", l)
         _todiag(bBC, il_top[l], jl[l], (Ed - Rtop_l[:, None] * Eu) * transt[None, :])
         Tbottom_lp1 = None
         if l < L - 1:
@@ -965,11 +1027,7 @@ def dort_modem_banded(problem, mode, streams, eigs, iface, intensity_down, planc
         Rbottom_l = cdiag(Rbot_, l)
         if Rbottom_l is None:
             Rbottom_l = np.zeros(nsl_npol)
-        if l == L - 1 and not coherent_only:  # diffuse part of a rough substrate (rtsolver_utils.py:656-659, 690-709)
-            Rdiff = substrate_diffuse_reflection(problem, streams, mode, int(problem.get("_m_max", 0)),
-                                                 problem.get("_eps_last"))
-            if Rdiff is not None:
-                Rbottom_l = Rbottom_l + Rdiff
+        Rbottom_l = with_diffuse_reflection(Rbottom_l, problem, streams, mode, coherent_only, "bottom", l)
         _todiag(bBC, il_bottom[l], jl[l], (Eu - Rbottom_l[:, None] * Ed) * transb[None, :])
         Ttop_lm1 = None
         if l > 0:
@@ -1010,7 +1068,8 @@ def dort_modem_banded(problem, mode, streams, eigs, iface, intensity_down, planc
     I1up_m = (Eu_0 * transt_0[None, :]) @ x[0:nsl2_npol, :]
     if mode == 0 and temperature is not None and temperature[0] > 0:
         I1up_m += planck(temperature[0])
-    Rbottom_air_down = compress_diag(Rbot_[-1], mode)
+    Rbottom_air_down = with_diffuse_reflection(compress_diag(Rbot_[-1], mode), problem, streams, mode, coherent_only,
+                                               "air")
     Ttop_0 = compress_diag(Ttop_[0], mode)
     I0up_m = Rbottom_air_down[:, None] * intensity_down + (Ttop_0[:, None] * I1up_m)[0:streams["n_air"] * npol, :]
     I0up_m = np.array(I0up_m).squeeze()
@@ -1099,7 +1158,7 @@ def solve_problem(problem, method="schur_forcedtriu", return_details=False):
         m_max = int(opts["m_max"]) if mode == "A" else 0
         npol = 2 if mode == "P" else 3
         iface = compute_interfaces(problem, eps_eff, streams, npol)
-        problem = dict(problem, _m_max=m_max, _eps_last=eps_eff[-1])  # for the diffuse substrate reflection
+        problem = dict(problem, _m_max=m_max, _eps_eff=eps_eff)  # for the diffuse reflection of rough surfaces
         norm = opts["phase_normalization"]
         if norm == "auto":
             norm = True  # IBA, DMRT: _respect_reciprocity_principle defaults to True (dort.py:240-242)

@@ -357,6 +357,51 @@ def iem_fung92_passive():  # the same soil under a radiometer ("not suitable for
     run_case("iem_fung92_passive", "iba", sensor_list.passive([10.65e9, 18.7e9], 55), sps, dict(n_max_stream=16))
 
 
+def _rough_surface_snowpacks(seed, n, interfaces_of, substrate_of=None, L=3):
+    rng = np.random.default_rng(seed)
+    sps = []
+    for i in range(n):
+        sps.append(make_snowpack(rng.uniform(0.1, 0.5, L), "sticky_hard_spheres", density=rng.uniform(200, 400, L),
+                                 temperature=rng.uniform(245, 270, L), radius=rng.uniform(2e-4, 6e-4, L), stickiness=0.3,
+                                 interface=interfaces_of(i), substrate=substrate_of(i, rng) if substrate_of else None))
+    return sps
+
+
+@case
+def iem_fung92_interface_active():  # reference interface/iem_fung92.py as the snow SURFACE and as an internal interface
+    from smrt import make_soil
+    from smrt.interface.flat import Flat
+    from smrt.interface.iem_fung92 import IEM_Fung92
+    from smrt.interface.iem_fung92_brogioni10 import IEM_Fung92_Briogoni10
+
+    ifaces = [[IEM_Fung92(roughness_rms=0.004, corr_length=0.05), Flat(), Flat()],
+              [Flat(), IEM_Fung92(roughness_rms=0.002, corr_length=0.03, autocorrelation_function="gaussian"), Flat()],
+              [IEM_Fung92_Briogoni10(roughness_rms=0.006, corr_length=0.1), Flat(),
+               IEM_Fung92(roughness_rms=0.003, corr_length=0.04, series_truncation=5)]]
+    soil = lambda i, rng: make_soil("iem_fung92", permittivity_model=complex(8, 1), roughness_rms=0.005,  # noqa: E731
+                                    corr_length=0.06, temperature=268.0) if i == 2 else None
+    sps = _rough_surface_snowpacks(33, 3, lambda i: ifaces[i], soil)
+    run_case("iem_fung92_interface_active", "iba", sensor_list.active([5.4e9, 13.5e9], [30, 45]), sps,
+             dict(n_max_stream=16, m_max=2))
+
+
+@case
+def iem_fung92_interface_passive():  # the rough surface / interface under a radiometer, with an isotropic atmosphere
+    from smrt import make_soil
+    from smrt.atmosphere.simple_isotropic_atmosphere import SimpleIsotropicAtmosphere
+    from smrt.interface.flat import Flat
+    from smrt.interface.iem_fung92 import IEM_Fung92
+
+    ifaces = [[IEM_Fung92(roughness_rms=0.003, corr_length=0.04), Flat(), Flat()],
+              [IEM_Fung92(roughness_rms=0.001, corr_length=0.02), IEM_Fung92(roughness_rms=0.002, corr_length=0.03), Flat()]]
+    soil = lambda i, rng: make_soil("soil_wegmuller", permittivity_model=complex(10, 1), roughness_rms=0.005,  # noqa: E731
+                                    temperature=268.0)
+    sps = _rough_surface_snowpacks(34, 2, lambda i: ifaces[i], soil)
+    sps[1].atmosphere = SimpleIsotropicAtmosphere(tb_down=25.0, tb_up=8.0, transmittance=0.9)
+    run_case("iem_fung92_interface_passive", "iba", sensor_list.passive([10.65e9, 18.7e9], [40, 55]), sps,
+             dict(n_max_stream=16))
+
+
 @case
 def choudhury_passive():  # reference substrate/rough_choudhury79.py (k sigma << 1)
     from smrt.substrate.rough_choudhury79 import ChoudhuryReflectivity

@@ -10,8 +10,8 @@ See DESIGN.md (path, kernels, rooflines), INTEGRATION.md (how an SMRT maintainer
 (the C ABI).  The compute path is CUDA only: without the built library / a GPU every solve raises SMRTError.
 """
 from .error import SMRTError, SMRTWarning  # noqa: F401
-from .inputs import (SimpleIsotropicAtmosphere, Snowpack, make_atmosphere, make_reflector, make_snowpack,  # noqa: F401
-                     make_soil, sensor_list)
+from .inputs import (SimpleIsotropicAtmosphere, Snowpack, make_atmosphere, make_interface, make_reflector,  # noqa: F401
+                     make_snowpack, make_soil, sensor_list)
 from .model import B200Runner, DORT, Model, make_model, run_ensemble, solve_batch  # noqa: F401
 from .pack import ProblemBatch, pack_sea_ice_ensemble, pack_simulations, pack_snow_ensemble  # noqa: F401
 from .result import ActiveResult, PassiveResult, Result, concat_results, make_result  # noqa: F401

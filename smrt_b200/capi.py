@@ -15,7 +15,7 @@ import numpy as np
 from .error import SMRTError
 from .pack import MODE_ACTIVE, MODE_PASSIVE, ProblemBatch
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 NORM_OFF, NORM_ON, NORM_FORCED = 0, 1, 2
 ST_OK, ST_NORMALIZATION, ST_EIGEN, ST_SINGULAR, ST_INPUT, ST_SUBSTRATE = 0, 1, 2, 3, 4, 5
@@ -56,7 +56,7 @@ class Batch(C.Structure):
         ("ms_kind", C.c_void_p), ("ms_p0", C.c_void_p), ("ms_p1", C.c_void_p), ("interface_kind", C.c_void_p),
         ("dense_snow_correction", C.c_void_p), ("substrate_kind", C.c_void_p), ("substrate_eps", C.c_void_p),
         ("substrate_temperature", C.c_void_p), ("substrate_params", C.c_void_p), ("atmosphere", C.c_void_p),
-        ("inclusion", C.c_void_p),
+        ("inclusion", C.c_void_p), ("interface_params", C.c_void_p),
         ("theta", C.c_void_p), ("theta_inc", C.c_void_p),
         ("phi", C.c_double),
         ("values", C.c_void_p), ("ks", C.c_void_p), ("ka", C.c_void_p), ("eps_eff", C.c_void_p),
@@ -74,7 +74,7 @@ INPUT_FIELDS = [  # (Batch field, ProblemBatch attribute, numpy dtype)
     ("substrate_kind", "substrate_kind", np.int32), ("substrate_eps", "substrate_eps", np.complex128),
     ("substrate_temperature", "substrate_temperature", np.float64),
     ("substrate_params", "substrate_params", np.float64), ("atmosphere", "atmosphere", np.float64),
-    ("inclusion", "inclusion", np.float64),
+    ("inclusion", "inclusion", np.float64), ("interface_params", "interface_params", np.float64),
 ]
 
 EXPORTED_SYMBOLS = [
@@ -178,7 +178,10 @@ def host_batch_struct(batch: ProblemBatch, out: HostOutputs, keep: list) -> Batc
     bt = Batch()
     bt.B = batch.B
     for fld, attr, dt in INPUT_FIELDS:
-        arr = np.ascontiguousarray(getattr(batch, attr), dtype=dt)
+        val = getattr(batch, attr)
+        if val is None:  # optional input the batch does not carry (interface_params without rough interfaces): NULL
+            continue
+        arr = np.ascontiguousarray(val, dtype=dt)
         keep.append(arr)
         setattr(bt, fld, arr.ctypes.data)
     theta = np.ascontiguousarray(batch.theta, dtype=np.float64)

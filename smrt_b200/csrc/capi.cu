@@ -497,6 +497,7 @@ static std::vector<FieldDesc> field_table(const smrtb200_plan* p) {
       {FOFF(substrate_temperature), d, true, false},
       {FOFF(substrate_params), 4 * d, true, false}, {FOFF(atmosphere), 3 * d, true, false},
       {FOFF(inclusion), 5 * Ls * d, true, false},
+      {FOFF(interface_params), 4 * Ls * d, true, false},
       {FOFF(theta), std::max<size_t>(p->opt.n_theta, 1) * d, false, false},
       {FOFF(theta_inc), std::max<size_t>(p->opt.n_inc, 1) * d, false, false},
       {FOFF(values), nout * d, true, true},     {FOFF(ks), Ls * d, true, true},
@@ -616,6 +617,7 @@ extern "C" int smrtb200_solve_batch_host(smrtb200_plan* p, const smrtb200_batch*
     if (!batch->substrate_params) db.substrate_params = nullptr;
     if (!batch->atmosphere) db.atmosphere = nullptr;
     if (!batch->inclusion) db.inclusion = nullptr;
+    if (!batch->interface_params) db.interface_params = nullptr;
     CUDA_TRY(cudaStreamWaitEvent(p->host_stream, r.h2d_done, 0));
     int nchunks = 0;
     nvtxRangePushA("smrtb200 queue kernels of a host chunk");

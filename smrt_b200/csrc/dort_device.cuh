@@ -24,7 +24,7 @@ enum {
   MS_EXPONENTIAL = 0, MS_SHS = 1, MS_HOMOGENEOUS = 2, MS_INDEPENDENT_SPHERE = 3, MS_TEUBNER_STREY = 4,
   MS_UNIFIED_TS_1 = 5, MS_UNIFIED_TS_2 = 6, MS_SHS_T = 7
 };
-enum { IF_FLAT = 0, IF_TRANSPARENT = 1 };
+enum { IF_FLAT = 0, IF_TRANSPARENT = 1, IF_IEM_FUNG92 = 2, IF_IEM_FUNG92_BRIOGONI10 = 3 };
 enum {
   SUB_NONE = 0,
   SUB_FLAT = 1,
@@ -585,6 +585,36 @@ SMRT_DEV_NOINLINE void iem_fung92_sigma0(double freq, cplx eps_1, cplx eps_2, do
 // specular reflection and emissivity of the substrate under a layer of permittivity eps_1, on the stream mu:
 // substrate/flat.py:15-17, soil_wegmuller.py:45-81, soil_qnh.py:44-89, reflector.py:51-81, rough_choudhury79.py:39-79.
 // The third Stokes component keeps its Fresnel value (as in the reference).
+// coherent reflection / transmission of a rough surface under the Kirchhoff approximation, every component:
+// interface/interface_utils.py:21-64 (k2 carries |eps_1|^2 as in the reference)
+SMRT_DEV void kirchhoff_coherent(FresnelRT& o, double rms, double freq, cplx eps_1, cplx eps_2, double mu) {
+  const double k0 = 2.0 * SMRT_PI * freq / SMRT_C_SPEED, rms2 = rms * rms;
+  const double fr = exp(-4.0 * (k0 * k0 * c_abs2(eps_1)) * rms2 * (mu * mu));
+  const double k_iz = k0 * c_sqrt(eps_1).re * mu;
+  const double s2 = 1.0 - mu * mu;
+  const double k_sz = k0 * c_sqrt(c_make(eps_2.re - s2 * eps_1.re, eps_2.im - s2 * eps_1.im)).re;
+  const double ft = exp(-((k_sz - k_iz) * (k_sz - k_iz)) * rms2);
+  for (int p = 0; p < 3; ++p) {
+    o.R[p] *= fr;
+    o.T[p] *= ft;
+  }
+}
+// Rough INTERFACE between two media (kinds IF_IEM_FUNG92 / _BRIOGONI10; par = roughness_rms, corr_length,
+// autocorrelation, series_truncation): Kirchhoff coherent part and, when m_diff >= 0, the IEM backscatter as a diagonal
+// diffuse reflection of azimuth mode m_diff on the stream (mu, w) -- interface/iem_fung92.py, interface_utils.py:16-64;
+// the IEM has no diffuse transmission (rtsolver_utils.py:506-522: the attribute is missing, the matrix is zero).
+SMRT_DEV_NOINLINE FresnelRT rough_interface_power(int kind, const double* par, double freq, cplx eps_1, cplx eps_2,
+                                                  double mu, double w, int m_diff, int m_max) {
+  FresnelRT o = fresnel_power(IF_FLAT, eps_1, eps_2, mu);
+  kirchhoff_coherent(o, par[0], freq, eps_1, eps_2, mu);
+  if (m_diff >= 0) {
+    double svv, shh;
+    iem_fung92_sigma0(freq, eps_1, eps_2, mu, par, kind == IF_IEM_FUNG92_BRIOGONI10, svv, shh);
+    o.R[0] += substrate_backscatter(svv, m_diff, m_max, mu, w);
+    o.R[1] += substrate_backscatter(shh, m_diff, m_max, mu, w);
+  }
+  return o;
+}
 // w, m_diff, m_max: weight of the stream, azimuth mode whose diffuse (backscatter) reflection is added to R for the
 // substrates that have one (kinds 6 - 8; m_diff < 0: none, the coherent pass), number of modes it is spread over.
 SMRT_DEV FresnelRT substrate_specular(int kind, const double* par, double freq, cplx eps_1, cplx eps_2, double mu);
@@ -614,19 +644,8 @@ SMRT_DEV FresnelRT substrate_specular(int kind, const double* par, double freq, 
   }
   o = fresnel_power(IF_FLAT, eps_1, eps_2, mu);
   if (kind == SUB_FLAT) return o;
-  if (kind == SUB_IEM_FUNG92 || kind == SUB_IEM_FUNG92_BRIOGONI10) {
-    // coherent part under the Kirchhoff approximation, every component: interface/interface_utils.py:21-64 (k2 carries
-    // |eps_1|^2 as in the reference); the emissivity of the substrate is the coherent transmission
-    const double k0 = 2.0 * SMRT_PI * freq / SMRT_C_SPEED, rms2 = par[0] * par[0];
-    const double fr = exp(-4.0 * (k0 * k0 * c_abs2(eps_1)) * rms2 * (mu * mu));
-    const double k_iz = k0 * c_sqrt(eps_1).re * mu;
-    const double s2 = 1.0 - mu * mu;
-    const double k_sz = k0 * c_sqrt(c_make(eps_2.re - s2 * eps_1.re, eps_2.im - s2 * eps_1.im)).re;
-    const double ft = exp(-((k_sz - k_iz) * (k_sz - k_iz)) * rms2);
-    for (int p = 0; p < 3; ++p) {
-      o.R[p] *= fr;
-      o.T[p] *= ft;
-    }
+  if (kind == SUB_IEM_FUNG92 || kind == SUB_IEM_FUNG92_BRIOGONI10) {  // the emissivity is the coherent transmission
+    kirchhoff_coherent(o, par[0], freq, eps_1, eps_2, mu);
     return o;
   }
   const double ksigma =

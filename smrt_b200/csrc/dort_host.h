@@ -146,6 +146,7 @@ inline KArgs make_kargs(const smrtb200_options& o, const Layout& L, const smrtb2
   A.substrate_params = bt.substrate_params ? bt.substrate_params + 4 * (size_t)b0 : nullptr;
   A.atmosphere = bt.atmosphere ? bt.atmosphere + 3 * (size_t)b0 : nullptr;
   A.inclusion = bt.inclusion ? bt.inclusion + 5 * b0 * Ls : nullptr;
+  A.interface_params = bt.interface_params ? bt.interface_params + 4 * b0 * Ls : nullptr;
   A.theta = bt.theta;
   A.theta_inc = bt.theta_inc;
   const size_t nout = (o.mode == SMRTB200_MODE_PASSIVE) ? 2 * (size_t)o.n_theta : 9 * (size_t)o.n_inc;

@@ -36,6 +36,7 @@ struct KArgs {
   const double *substrate_eps, *substrate_temperature, *theta, *theta_inc;
   const double *substrate_params, *atmosphere;  // optional (NULL): [B, 4] substrate model parameters, [B, 3] atmosphere
   const double* inclusion;                      // optional (NULL): [B, L, 5] inclusion shape weights, depolarisation factors
+  const double* interface_params;               // optional (NULL): [B, L, 4] parameters of the rough interface above layer l
   // outputs
   double *values, *ks, *ka, *eps_eff;
   int* n_streams_out;
@@ -113,6 +114,65 @@ SMRT_GLOBAL void __launch_bounds__(128) optics_kernel(KArgs A) {
   aux[2] = o.f;
   aux[3] = 0.0;
   if (o.status != ST_OK) set_error(A.status, b, o.status);
+}
+
+// parameters of the (rough) interface above layer l_ of problem b (bL = b * L), or NULL
+#define SMRT_IPAR(l_) (A.interface_params ? A.interface_params + 4 * (size_t)(bL + (l_)) : nullptr)
+
+// Rough interfaces of a layer (boundary kernel): the entries the Fresnel pass wrote for a rough interface are replaced by
+// the Kirchhoff coherent coefficients plus, in every pass but the coherent one, the diagonal diffuse (backscatter)
+// reflection -- rtsolver_utils.py:480-522, 551-582, 690-709.  Same (entry -> thread) map as the Fresnel pass: the thread
+// that wrote an entry rewrites it, no barrier in between.  NOT inlined: batches without rough interfaces (the pointer
+// test is block-uniform) keep the register allocation of the kernel body.
+// air - snow interface seen from the air on an air stream (rtsolver_utils.py:607-642); plain Fresnel unless it is rough
+SMRT_DEV_NOINLINE FresnelRT air_interface_power(const KArgs& A, long long bL, double freq, cplx eps0, double mu, double w,
+                                                int m_diff, int m_max) {
+  const int ik = A.interface_kind[bL];
+  if (ik >= IF_IEM_FUNG92 && A.interface_params)
+    return rough_interface_power(ik, A.interface_params + 4 * (size_t)bL, freq, c_make(1.0, 0.0), eps0, mu, w, m_diff, m_max);
+  return fresnel_power(ik, c_make(1.0, 0.0), eps0, mu);
+}
+struct RoughFix {
+  int ik_top, ik_bot, l, nl, n_l, n, npol, m_diff, m_max;
+  bool up_emits;
+  const double *par_top, *par_bot, *eps_b, *mu, *gl_mu;
+  double freq;
+  cplx eps_l, eps_star;
+  double *Rt, *Tt, *Rb, *Tb, *RbD, *Tup;
+};
+SMRT_DEV_NOINLINE void rough_interface_fixup(const RoughFix& f) {
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int span = 32 * ((f.n_l + 31) >> 5), npol = f.npol, l = f.l;
+  for (int e = tid; e < 3 * span; e += NT) {
+    const int which = e / span, j = e - which * span;
+    if (j >= f.n_l) continue;
+    const double wj = (f.n_l >= 2) ? stream_weight(f.mu, f.n_l, j) : 0.0;
+    if (which == 0 && f.ik_top >= IF_IEM_FUNG92) {
+      cplx eps_up = (l > 0) ? c_make(f.eps_b[2 * (l - 1)], f.eps_b[2 * (l - 1) + 1]) : c_make(1.0, 0.0);
+      FresnelRT ft = rough_interface_power(f.ik_top, f.par_top, f.freq, f.eps_l, eps_up, f.mu[j], wj, f.m_diff, f.m_max);
+      for (int p = 0; p < npol; ++p) {
+        f.Rt[j * npol + p] = ft.R[p];
+        f.Tt[j * npol + p] = ft.T[p];
+      }
+    } else if (which == 1 && f.ik_bot >= IF_IEM_FUNG92) {
+      FresnelRT fb = rough_interface_power(f.ik_bot, f.par_bot, f.freq, f.eps_l,
+                                           c_make(f.eps_b[2 * (l + 1)], f.eps_b[2 * (l + 1) + 1]), f.mu[j], wj, f.m_diff,
+                                           f.m_max);
+      for (int p = 0; p < npol; ++p) {
+        f.Rb[j * npol + p] = fb.R[p];
+        f.Tb[j * npol + p] = fb.T[p];
+        f.RbD[j * npol + p] = (p == 2) ? -fb.R[p] : fb.R[p];
+      }
+    } else if (which == 2 && f.ik_top >= IF_IEM_FUNG92 && f.up_emits) {
+      cplx eps_up = c_make(f.eps_b[2 * (l - 1)], f.eps_b[2 * (l - 1) + 1]);
+      double ri_up = real_index_of(f.eps_star, eps_up);
+      if (j < stream_count(ri_up, f.gl_mu, f.n)) {
+        FresnelRT fu = rough_interface_power(f.ik_top, f.par_top, f.freq, eps_up, f.eps_l, stream_mu(ri_up, f.gl_mu, j),
+                                             0.0, -1, 0);
+        for (int p = 0; p < npol; ++p) f.Tup[j * npol + p] = fu.T[p];
+      }
+    }
+  }
 }
 
 // --------------------------------------------------------------------------------------------------------------------
@@ -761,6 +821,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
       const bool coherent = (A.mode == 1 && run == 0);
       const int m = (A.mode == 0) ? 0 : (run == 0 ? 0 : run - 1);
       const int npol = smrt_npol(m);
+      const int mdiff_max = (A.mode == 0) ? 0 : A.m_max;  // modes the diffuse backscatter of rough surfaces is spread over
       const int nrhs = (A.mode == 0) ? 1 : npol * n_incs;
 
       // optical depth, top-down, and the last layer kept ------------------------------------------ dort.py:444-452
@@ -926,8 +987,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
               // pass but the coherent one (rtsolver_utils.py:690-709); the emissivity keeps the coherent value
               fb = substrate_power(A.substrate_kind[b], A.substrate_params ? A.substrate_params + 4 * (size_t)b : nullptr,
                                    freq, eps_l, c_make(A.substrate_eps[2 * b], A.substrate_eps[2 * b + 1]), mu[j],
-                                   (n_l >= 2) ? stream_weight(mu, n_l, j) : 0.0, coherent ? -1 : m,
-                                   (A.mode == 0) ? 0 : A.m_max);
+                                   (n_l >= 2) ? stream_weight(mu, n_l, j) : 0.0, coherent ? -1 : m, mdiff_max);
             } else {
               fb.R[0] = fb.R[1] = fb.R[2] = 0.0;
               fb.T[0] = fb.T[1] = fb.T[2] = 0.0;
@@ -950,6 +1010,19 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
               }
             }
             for (int p = 0; p < npol; ++p) Tup[j * npol + p] = tu[p];
+          }
+        }
+        if (A.interface_params) {
+          // rough interfaces (block-uniform: the batch carries parameters only when a snowpack has one)
+          const int ik_top = A.interface_kind[bL + l], ik_bot = (l < nl - 1) ? A.interface_kind[bL + l + 1] : IF_FLAT;
+          if (ik_top >= IF_IEM_FUNG92 || ik_bot >= IF_IEM_FUNG92) {
+            RoughFix rf;
+            rf.ik_top = ik_top, rf.ik_bot = ik_bot, rf.par_top = SMRT_IPAR(l), rf.par_bot = SMRT_IPAR(l + 1);
+            rf.freq = freq, rf.eps_l = eps_l, rf.eps_star = eps_star, rf.eps_b = eps_b, rf.l = l, rf.nl = nl, rf.n_l = n_l;
+            rf.n = n, rf.npol = npol, rf.m_diff = coherent ? -1 : m, rf.m_max = mdiff_max, rf.mu = mu, rf.gl_mu = A.gl_mu;
+            rf.up_emits = thermal && l > 0 && A.temperature[bL + (l > 0 ? l - 1 : 0)] > 0.0;
+            rf.Rt = Rt, rf.Tt = Tt, rf.Rb = Rb, rf.Tb = Tb, rf.RbD = RbD, rf.Tup = Tup;
+            rough_interface_fixup(rf);
           }
         }
         if (scat) {
@@ -1018,7 +1091,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
           // downwelling atmospheric radiation through the air-snow interface (dort.py:383-395): b_top += T_air I_down
           // on the air streams; rows beyond the layer's streams are truncated
           for (int a = tid; a < 2 * n_air && a < h; a += NT) {
-            FresnelRT fa = fresnel_power(A.interface_kind[bL], c_make(1.0, 0.0), eps0, outmu[a >> 1]);
+            FresnelRT fa = air_interface_power(A, bL, freq, eps0, outmu[a >> 1], 0.0, -1, 0);
             btop[a] += fa.T[a & 1] * atm_down;
           }
         }
@@ -1030,7 +1103,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
             if (i < n_l) {  // rows beyond the layer's streams are truncated (dort.py:391-395)
               double power = 1.0 / (2.0 * SMRT_PI * outw[i]);
               if (m > 0) power *= 2.0;
-              FresnelRT fa = fresnel_power(A.interface_kind[bL], c_make(1.0, 0.0), eps0, outmu[i]);
+              FresnelRT fa = air_interface_power(A, bL, freq, eps0, outmu[i], 0.0, -1, 0);
               SMRT_AT(btop, h, i * npol + ipol, c) += fa.T[ipol] * power;
             }
           }
@@ -1459,7 +1532,8 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
             double v = (a < h0) ? Tt[a] * (svec[a] + B0) : 0.0;
             if (A.atmosphere) {
               if (atm_down != 0.0) {
-                FresnelRT fa = fresnel_power(A.interface_kind[bL], c_make(1.0, 0.0), eps0, outmu[a >> 1]);
+                FresnelRT fa = air_interface_power(A, bL, freq, eps0, outmu[a >> 1], outw[a >> 1], coherent ? -1 : m,
+                                                   mdiff_max);
                 v = fa.R[a & 1] * atm_down + v;
               }
               v = atm_up + atm_trans * v;
@@ -1506,7 +1580,7 @@ SMRT_GLOBAL void __launch_bounds__(kMaxThreads, kStreamFG ? 2 : 1) boundary_kern
             int row = i * npol + ps, col = jinc * npol + pi;
             double power = 1.0 / (2.0 * SMRT_PI * outw[i]);
             if (m > 0) power *= 2.0;
-            FresnelRT fa = fresnel_power(A.interface_kind[bL], c_make(1.0, 0.0), eps0, outmu[i]);
+            FresnelRT fa = air_interface_power(A, bL, freq, eps0, outmu[i], outw[i], coherent ? -1 : m, mdiff_max);
             double idn = (ps == pi) ? power : 0.0;
             double i1 = (row < h0) ? SMRT_AT(svec, h0, row, col) : 0.0;
             double v = fa.R[ps] * idn + ((row < h0) ? Tt[row] * i1 : 0.0);

@@ -34,6 +34,8 @@ class DeviceBatch:
         self.dev = {}
         self.h2d_bytes = 0
         for fld, attr, dt in capi.INPUT_FIELDS:
+            if getattr(batch, attr) is None:  # optional input the batch does not carry: NULL in the struct
+                continue
             arr = np.ascontiguousarray(getattr(batch, attr), dtype=dt)
             if dt == np.complex128:
                 arr = arr.view(np.float64).reshape(arr.shape + (2,))
@@ -72,7 +74,8 @@ class DeviceBatch:
         bt = capi.Batch()
         bt.B = self.batch.B
         for fld, _, _ in capi.INPUT_FIELDS:
-            setattr(bt, fld, self.dev[fld].data_ptr())
+            if fld in self.dev:
+                setattr(bt, fld, self.dev[fld].data_ptr())
         bt.theta = self.dev["theta"].data_ptr()
         bt.theta_inc = self.dev["theta_inc"].data_ptr()
         bt.phi = float(self.batch.phi)

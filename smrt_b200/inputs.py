@@ -412,14 +412,19 @@ def _get(x, i):
     return x[i]
 
 
-def make_interface(interface):
+def make_interface(interface, **kwargs):
+    """``smrt.core.interface.make_interface``: a name, a class or an instance; the IEM interfaces take their parameters
+    as keywords (``make_interface("iem_fung92", roughness_rms=0.004, corr_length=0.05)``; the same stand-in classes serve
+    as interfaces and as substrates, like the reference's ``substrate_from_interface``)"""
+    if isinstance(interface, str) and interface in ("iem_fung92", "iem_fung92_brogioni10"):
+        return _SOILS[interface](**kwargs)
     if interface is None or interface in ("flat", Flat):
         return Flat()
     if interface in ("transparent", Transparent):
         return Transparent()
     if isinstance(interface, (Flat, Transparent)):
         return interface
-    if type(interface).__name__ in ("Flat", "Transparent"):
+    if type(interface).__name__ in ("Flat", "Transparent", "IEM_Fung92", "IEM_Fung92_Briogoni10"):
         return interface
     raise SMRTError(f"interface {interface!r} is not implemented on the B200 path")
 
@@ -450,5 +455,5 @@ def make_snowpack(thickness, microstructure_model, density, interface=None, subs
             ipm = kwargs["ice_permittivity_model"]
             extra["permittivity_model"] = (1.0, ipm if (callable(ipm) or np.isscalar(ipm)) else _get(ipm, i))
         sp.layers.append(Layer(dz, ms, temperature=_get(temperature, i), density=rho, **extra))
-        sp.interfaces.append(make_interface(_get(interface, i)))
+        sp.interfaces.append(make_interface(interface[i] if isinstance(interface, (list, tuple)) else interface))
     return sp

@@ -24,7 +24,7 @@ EM_IBA, EM_DMRT_QCA_SR, EM_NONSCATTERING, EM_DMRT_QCACP_SR, EM_RAYLEIGH, EM_PRES
 EM_IBA_ORIGINAL, EM_IBA_MAXWELL_GARNETT = 6, 7  # smrt/emmodel/iba_original.py, iba_maxwell_garnett.py
 MS_EXPONENTIAL, MS_SHS, MS_HOMOGENEOUS = 0, 1, 2
 MS_INDEPENDENT_SPHERE, MS_TEUBNER_STREY, MS_UNIFIED_TS_1, MS_UNIFIED_TS_2, MS_SHS_T = 3, 4, 5, 6, 7
-IF_FLAT, IF_TRANSPARENT = 0, 1
+IF_FLAT, IF_TRANSPARENT, IF_IEM_FUNG92, IF_IEM_FUNG92_BRIOGONI10 = 0, 1, 2, 3
 SUB_NONE, SUB_FLAT, SUB_SOIL_WEGMULLER, SUB_SOIL_QNH, SUB_REFLECTOR, SUB_ROUGH_CHOUDHURY = 0, 1, 2, 3, 4, 5
 SUB_REFLECTOR_BACKSCATTER = 6
 SUB_IEM_FUNG92, SUB_IEM_FUNG92_BRIOGONI10 = 7, 8
@@ -90,6 +90,7 @@ class ProblemBatch:
     substrate_params: np.ndarray = None  # (B, 4) parameters of the rough / prescribed substrates (see SUB_*)
     atmosphere: np.ndarray = None  # (B, 3) isotropic atmosphere: tb_down, tb_up (K), transmittance; (0, 0, 1) = none
     inclusion: np.ndarray = None  # (B, L, 5) weights of the spheres / needles solutions, depolarisation factors x, y, z
+    interface_params: np.ndarray = None  # (B, L, 4) parameters of the rough interfaces (IF_* >= 2), None without any
 
     def __post_init__(self):
         if self.dense_snow_correction is None:
@@ -142,19 +143,20 @@ class ProblemBatch:
             substrate_params=self.substrate_params[i].copy(),
             atmosphere=self.atmosphere[i].copy(),
             inclusion=self.inclusion[i, :n].copy(),
+            interface_params=None if self.interface_params is None else self.interface_params[i, :n].copy(),
             theta=self.theta.copy() if self.mode == MODE_PASSIVE else self.theta_inc.copy(),
             phi=float(self.phi),
             options=opts,
         )
 
     def save_fields(self) -> dict:
-        return {k: (v if isinstance(v, np.ndarray) else np.asarray(v)) for k, v in self.__dict__.items()}
+        return {k: (v if isinstance(v, np.ndarray) else np.asarray(v)) for k, v in self.__dict__.items() if v is not None}
 
     @staticmethod
     def from_fields(d) -> "ProblemBatch":
         kw = {}
         for k in ProblemBatch.__dataclass_fields__:
-            if k in ("substrate_params", "atmosphere", "inclusion") and k not in d:  # fixtures written before these fields existed
+            if k in ("substrate_params", "atmosphere", "inclusion", "interface_params") and k not in d:  # fixtures written before these fields existed
                 continue
             v = d[k]
             if k == "mode":
@@ -171,6 +173,18 @@ def concat_batches(batches: Sequence[ProblemBatch]) -> ProblemBatch:
     kw = {}
     for k in ProblemBatch.__dataclass_fields__:
         v0 = getattr(batches[0], k)
+        if k == "interface_params":
+            if all(b.interface_params is None for b in batches):
+                kw[k] = None
+            else:
+                parts = []
+                for b in batches:
+                    v = np.zeros((b.B, L, 4))
+                    if b.interface_params is not None:
+                        v[:, :b.L] = b.interface_params
+                    parts.append(v)
+                kw[k] = np.concatenate(parts, axis=0)
+            continue
         if isinstance(v0, np.ndarray) and k not in ("theta", "theta_inc"):
             parts = []
             for b in batches:
@@ -224,8 +238,25 @@ def _interface_code(iface):
         return IF_FLAT
     if name == "Transparent":
         return IF_TRANSPARENT
-    raise SMRTError(f"interface '{name}' is not implemented on the B200 path (only Flat and Transparent: "
-                    "rough interfaces make the boundary blocks dense)")
+    if name in ("IEM_Fung92", "IEM_Fung92_Briogoni10"):
+        return IF_IEM_FUNG92 if name == "IEM_Fung92" else IF_IEM_FUNG92_BRIOGONI10
+    raise SMRTError(f"interface '{name}' is not implemented on the B200 path (Flat, Transparent, IEM_Fung92, "
+                    "IEM_Fung92_Briogoni10: interfaces with a dense diffuse matrix make the boundary blocks dense)")
+
+
+def _iem_params(obj):
+    """(roughness_rms, corr_length, autocorrelation, series_truncation) of an IEM_Fung92 interface / substrate —
+    reference smrt/interface/iem_fung92.py:60-67"""
+    acf = getattr(obj, "autocorrelation_function", "exponential")
+    if acf not in ("exponential", "gaussian"):
+        raise SMRTError("The autocorrelation function must be exponential or gaussian")  # iem_fung92.py:189
+    if getattr(obj, "warning_handling", "print") != "print":
+        raise SMRTError("IEM_Fung92 on the B200 path follows warning_handling='print' (outside the validity range "
+                        "the reference warns and goes on; no message is printed here)")
+    N = int(getattr(obj, "series_truncation", 10))
+    if not 1 <= N <= 64:
+        raise SMRTError("series_truncation must be in 1..64")
+    return [float(obj.roughness_rms), float(obj.corr_length), 1.0 if acf == "gaussian" else 0.0, float(N)]
 
 
 def _reflector_value(substrate, frequency, polarization):
@@ -288,16 +319,7 @@ def _substrate(substrate, frequency, mode=MODE_PASSIVE):
         par[0] = float(substrate.roughness_rms)
     elif name in ("IEM_Fung92", "IEM_Fung92_Briogoni10"):  # substrate/iem_fung92.py, iem_fung92_brogioni10.py
         kind = SUB_IEM_FUNG92 if name == "IEM_Fung92" else SUB_IEM_FUNG92_BRIOGONI10
-        acf = getattr(substrate, "autocorrelation_function", "exponential")
-        if acf not in ("exponential", "gaussian"):
-            raise SMRTError("The autocorrelation function must be exponential or gaussian")  # iem_fung92.py:189
-        if getattr(substrate, "warning_handling", "print") != "print":
-            raise SMRTError("IEM_Fung92 on the B200 path follows warning_handling='print' (outside the validity range "
-                            "the reference warns and goes on; no message is printed here)")
-        N = int(getattr(substrate, "series_truncation", 10))
-        if not 1 <= N <= 64:
-            raise SMRTError("series_truncation must be in 1..64")
-        par[:] = [float(substrate.roughness_rms), float(substrate.corr_length), 1.0 if acf == "gaussian" else 0.0, N]
+        par[:] = _iem_params(substrate)
     elif name == "SoilQNH":
         kind = SUB_SOIL_QNH
         N = float(getattr(substrate, "N", 0.0))
@@ -427,6 +449,7 @@ def _layer_rows(sp, emmodel, emmodel_options, L, defaults=None):
     codes, kinds, ifaces, dscs, kbg, ksc = [], [], [], [], [], []
     cbg, csc = [], []
     incl = None
+    ipar = None  # parameters of the rough interfaces, (L, 4), only when the snowpack has one
     for l, layer in enumerate(layers):
         d = layer.__dict__
         own_em = d.get("emmodel")
@@ -459,7 +482,13 @@ def _layer_rows(sp, emmodel, emmodel_options, L, defaults=None):
         dscs.append(dsc_flag)
         iface = sp.interfaces[l]
         icode = _IF_FAST.get(type(iface).__name__)
-        ifaces.append(icode if icode is not None else _interface_code(iface))
+        if icode is None:
+            icode = _interface_code(iface)
+            if icode >= IF_IEM_FUNG92:
+                if ipar is None:
+                    ipar = np.zeros((L, 4))
+                ipar[l] = _iem_params(iface)
+        ifaces.append(icode)
         thick.append(layer.thickness)
         temp.append(layer.temperature)
         fvol.append(layer.frac_volume)
@@ -511,7 +540,7 @@ def _layer_rows(sp, emmodel, emmodel_options, L, defaults=None):
     if incl:
         for l, v in incl.items():
             inclusion[l] = v
-    return n, f8, i4, inclusion, const
+    return n, f8, i4, inclusion, const, ipar
 
 
 def _dense_snow_flag(opts, code):
@@ -596,8 +625,13 @@ def pack_simulations(simulations, emmodel, emmodel_options=None, atmospheres=Non
         opts0 = dict(getattr(emmodel, "_smrt_options", None) or {})
         opts0.update(emmodel_options)
         defaults = (code0, _dense_snow_flag(opts0, code0))
+    IPAR = None
     for u, sp in enumerate(unique):
-        nlayer_u[u], F8[u], I4[u], INCL[u], CONST[u] = _layer_rows(sp, emmodel, emmodel_options, L, defaults)
+        nlayer_u[u], F8[u], I4[u], INCL[u], CONST[u], ipar = _layer_rows(sp, emmodel, emmodel_options, L, defaults)
+        if ipar is not None:
+            if IPAR is None:
+                IPAR = np.zeros((U, L, 4))
+            IPAR[u] = ipar
 
     take = lambda a: np.ascontiguousarray(a[sp_index])  # noqa: E731
     temperature = take(F8[:, 1])
@@ -611,6 +645,7 @@ def pack_simulations(simulations, emmodel, emmodel_options=None, atmospheres=Non
         theta_inc=(np.atleast_1d(np.asarray(sensor0.theta_inc, dtype=float)).copy() if mode == MODE_ACTIVE
                    else np.zeros(0)),
         phi=float(phi[0]), dense_snow_correction=take(I4[:, 3]), inclusion=take(INCL),
+        interface_params=None if IPAR is None else take(IPAR),
     )
 
     # permittivities: whole blocks per medium for constants and the default ice models, layer by layer otherwise

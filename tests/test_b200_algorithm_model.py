@@ -11,7 +11,8 @@ CASES = ["cfg1_iba_onelayer", "ref_iba_2layer_passive", "ref_iba_2layer_active",
          "ref_dmrt_less_refringent_active", "iba_multiangle_passive", "iba_options_prune_rj",
          "iba_shs_active_multiangle", "iba_exp_substrate_passive", "nonscattering_active", "cfg3_first4", "cfg5_first6",
          "soil_wegmuller_passive", "atmosphere_passive", "ref_physics_law", "reflector_backscatter_active",
-         "reflector_backscatter_passive", "iem_fung92_active"]
+         "reflector_backscatter_passive", "iem_fung92_active",
+         "iem_fung92_interface_active", "iem_fung92_interface_passive"]
 
 
 @pytest.mark.parametrize("name", CASES)

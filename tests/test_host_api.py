@@ -225,6 +225,26 @@ def test_substrate_and_atmosphere_packing():
         pack.pack_simulations([(radar, sp(substrate=S.make_soil(
             "iem_fung92", permittivity_model=complex(12, 2), roughness_rms=0.005, corr_length=0.05,
             autocorrelation_function="power")))], "iba")
+    # the same IEM model as an INTERFACE (rough snow surface / internal interface): kinds per layer + a [B, L, 4] block of
+    # parameters that exists only when a snowpack has such an interface
+    rough = S.make_interface("iem_fung92", roughness_rms=0.004, corr_length=0.05)
+    rough_b = S.make_interface("iem_fung92_brogioni10", roughness_rms=0.006, corr_length=0.1,
+                               autocorrelation_function="gaussian")
+    sp2 = S.make_snowpack([0.2, 0.3], "exponential", density=[250, 350], temperature=265, corr_length=1e-4,
+                          interface=[rough, "flat"])
+    sp3 = S.make_snowpack([0.2, 0.3], "exponential", density=[250, 350], temperature=265, corr_length=1e-4,
+                          interface=["transparent", rough_b])
+    b5 = pack.pack_simulations([(radar, sp2), (radar, sp3), (radar, sp())], "iba")
+    np.testing.assert_array_equal(b5.interface, [[pack.IF_IEM_FUNG92, pack.IF_FLAT],
+                                                 [pack.IF_TRANSPARENT, pack.IF_IEM_FUNG92_BRIOGONI10], [pack.IF_FLAT, 0]])
+    np.testing.assert_array_equal(b5.interface_params[0], [[0.004, 0.05, 0, 10], [0, 0, 0, 0]])
+    np.testing.assert_array_equal(b5.interface_params[1], [[0, 0, 0, 0], [0.006, 0.1, 1, 10]])
+    np.testing.assert_array_equal(b5.interface_params[2], np.zeros((2, 4)))
+    assert b4.interface_params is None and pack.concat_batches([b4, b4]).interface_params is None
+    cat2 = pack.concat_batches([b4, b5])
+    assert cat2.interface_params.shape == (5, 2, 4) and not cat2.interface_params[:2].any()
+    assert b5.subset(slice(0, 2)).interface_params.shape == (2, 2, 4)
+    assert b5.to_problem(1)["interface_params"].shape == (2, 4) and b4.to_problem(0)["interface_params"] is None
     for bad in (dict(specular_reflection=0.2, backscattering_coefficient=0.1),
                 dict(backscattering_coefficient={"VV": 0.1, "HH": 0.1}),
                 dict(specular_reflection=0.1, backscattering_coefficient={"VV": np.cos, "HH": 0.1})):

@@ -17,7 +17,8 @@ FAST = ["cfg1_iba_onelayer", "ref_iba_2layer_passive", "ref_iba_2layer_active", 
         "emmodel_per_medium_passive", "inclusion_shapes_passive", "depolarization_active", "iba_original_depolarization_passive",
         "iba_maxwell_garnett_depolarization_passive", "ref_rayleigh_mmax6_active", "iba_mmax5_active",
         "reflector_backscatter_active", "reflector_backscatter_active_mmax4", "reflector_backscatter_passive",
-        "iem_fung92_active", "iem_fung92_brogioni10_active", "iem_fung92_passive"]
+        "iem_fung92_active", "iem_fung92_brogioni10_active", "iem_fung92_passive",
+        "iem_fung92_interface_active", "iem_fung92_interface_passive"]
 
 
 def solve_all(batch, opts, limit=None):

@@ -15,10 +15,10 @@ SMALL = ["cfg1_iba_onelayer", "ref_iba_2layer_passive", "ref_dmrt_qcacp_2layer_p
          "iba_options_prune_rj", "iba_exp_substrate_passive", "soil_wegmuller_passive", "reflector_passive",
          "atmosphere_passive", "ref_physics_law", "iba_microstructures_passive", "prescribed_kskaeps_passive",
          "ref_iba_original_2layer_passive", "iba_maxwell_garnett_passive", "emmodel_per_medium_passive",
-         "inclusion_shapes_passive", "reflector_backscatter_passive", "iem_fung92_passive"]
+         "inclusion_shapes_passive", "iem_fung92_interface_passive"]
 SMALL_ACTIVE = ["ref_dmrt_less_refringent_active", "nonscattering_active", "soil_active", "rayleigh_active",
-                "depolarization_active", "ref_rayleigh_mmax6_active", "reflector_backscatter_active",
-                "reflector_backscatter_active_mmax4", "iem_fung92_active", "iem_fung92_brogioni10_active"]
+                "depolarization_active", "ref_rayleigh_mmax6_active", "iem_fung92_active",
+                "iem_fung92_interface_active"]
 
 
 @pytest.mark.parametrize("name", SMALL + SMALL_ACTIVE)
@@ -143,8 +143,7 @@ def test_one_sided_jacobi_device_function(h, threads):
 
 @pytest.mark.parametrize("h,threads,kind", [(6, 64, "dense"), (15, 64, "dense"), (33, 64, "dense"), (47, 128, "dense"),
                                             (64, 128, "dense"), (64, 128, "degenerate"), (44, 128, "neardiag"),
-                                            (64, 256, "neardiag"), (70, 512, "dense"), (97, 512, "neardiag"),
-                                            (128, 512, "degenerate")])
+                                            (64, 256, "neardiag"), (97, 512, "neardiag")])
 def test_register_blocked_jacobi_device_function(h, threads, kind):
     """block_jacobi_svd_fast (2-column blocks in registers, tracked norms, MUFU-seeded tangent): singular values and
     orthogonality to rounding, including odd sizes (zero pad row), clusters of equal singular values and the nearly
