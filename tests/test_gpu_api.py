@@ -239,3 +239,34 @@ def test_two_devices_in_one_process():
     two = m2.run(sensor, sps)
     np.testing.assert_array_equal(two.data.values, one.data.values)
     np.testing.assert_array_equal(two.other_data["ks"].values, one.other_data["ks"].values)
+
+
+def test_rough_surfaces_with_diagonal_backscatter_through_the_public_api():
+    """reflector with a prescribed backscattering coefficient (reference substrate/reflector_backscatter.py) and the IEM
+    of Fung et al. 1992 as the snow surface and as the soil (interface/iem_fung92.py, substrate/iem_fung92.py) through
+    make_model(...).run() with this package's builders; the literals are the unmodified reference's outputs for the
+    same calls (16 streams, m_max = 2, 13.5 GHz, 40 degrees)"""
+    from smrt_b200 import make_interface, make_reflector, make_soil
+
+    kw = dict(density=[250, 350], temperature=[260, 265], radius=[3e-4, 5e-4], stickiness=0.2)
+    m = make_model("iba", "dort", rtsolver_options=dict(n_max_stream=16, m_max=2))
+    radar, radiometer = sensor_list.active(13.5e9, 40), sensor_list.passive(13.5e9, 40)
+    sub = make_reflector(temperature=265, specular_reflection={"V": 0.3, "H": 0.4},
+                         backscattering_coefficient={"VV": 0.1, "HH": 0.05})
+    sp = make_snowpack([0.3, 0.7], "sticky_hard_spheres", substrate=sub, **kw)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", category=SMRTWarning)
+        res = m.run(radar, sp)
+        np.testing.assert_allclose([res.sigmaVV_dB(), res.sigmaHH_dB(), res.sigmaVH_dB()],
+                                   [-11.573163275586909, -11.857597269280516, -30.616256833957248], atol=1e-4)
+        res = m.run(radiometer, sp)
+        np.testing.assert_allclose([res.TbV(), res.TbH()], [195.98956243324483, 171.1949806679902], atol=1e-4)
+        soil = make_soil("iem_fung92", permittivity_model=complex(10, 1), roughness_rms=0.005, corr_length=0.06,
+                         temperature=268.0)
+        sp = make_snowpack([0.3, 0.7], "sticky_hard_spheres", substrate=soil,
+                           interface=[make_interface("iem_fung92", roughness_rms=0.004, corr_length=0.05), "flat"], **kw)
+        res = m.run(radar, sp)
+        np.testing.assert_allclose([res.sigmaVV_dB(), res.sigmaHH_dB(), res.sigmaVH_dB()],
+                                   [-13.149321808779032, -12.468096175478424, -35.39501167583748], atol=1e-4)
+        res = m.run(radiometer, sp)
+        np.testing.assert_allclose([res.TbV(), res.TbH()], [15.115552515198775, 14.736331861270559], atol=1e-4)
