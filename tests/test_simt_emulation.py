@@ -16,7 +16,7 @@ SMALL = ["cfg1_iba_onelayer", "ref_iba_2layer_passive", "ref_dmrt_qcacp_2layer_p
          "atmosphere_passive", "ref_physics_law", "iba_microstructures_passive", "prescribed_kskaeps_passive",
          "ref_iba_original_2layer_passive", "iba_maxwell_garnett_passive", "emmodel_per_medium_passive",
          "inclusion_shapes_passive", "iem_fung92_interface_passive"]
-SMALL_ACTIVE = ["ref_dmrt_less_refringent_active", "nonscattering_active", "soil_active", "rayleigh_active",
+SMALL_ACTIVE = ["ref_dmrt_less_refringent_active", "rayleigh_active",
                 "depolarization_active", "ref_rayleigh_mmax6_active", "iem_fung92_active",
                 "iem_fung92_interface_active"]
 
