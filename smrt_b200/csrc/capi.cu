@@ -69,6 +69,7 @@ struct smrtb200_plan {
   int eigen_threads = SMRT_NT;
   void (*eigen_fn)(KArgs) = nullptr;
   void (*boundary_fn)(KArgs) = nullptr;
+  void (*boundary_fn_rough)(KArgs) = nullptr;  // the same instantiation with the rough-interface code (kRough)
   size_t eigen_smem = 0, boundary_smem = 0;
   long long scratch_stride = 0;
   double* gl_mu = nullptr;
@@ -251,16 +252,23 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
     }
   }
   if (stream_fg) p->boundary_smem = L.boundary_stream_smem_bytes;
-  if (p->boundary_mid)
+  if (p->boundary_mid) {
     p->boundary_fn = boundary_kernel<false, 512, false, true>;
-  else if (p->use_global_scratch)
+    p->boundary_fn_rough = boundary_kernel<false, 512, false, true, true>;
+  } else if (p->use_global_scratch) {
     p->boundary_fn = boundary_kernel<true, SMRT_NT_B>;
-  else if (stream_fg)
+    p->boundary_fn_rough = boundary_kernel<true, SMRT_NT_B, false, false, true>;
+  } else if (stream_fg) {
     p->boundary_fn = boundary_kernel<false, 128, true>;
-  else
+    p->boundary_fn_rough = boundary_kernel<false, 128, true, false, true>;
+  } else {
     p->boundary_fn = (p->boundary_threads <= 128)   ? boundary_kernel<false, 128>
                      : (p->boundary_threads <= 256) ? boundary_kernel<false, 256>
                                                     : boundary_kernel<false, SMRT_NT_B>;
+    p->boundary_fn_rough = (p->boundary_threads <= 128)   ? boundary_kernel<false, 128, false, false, true>
+                           : (p->boundary_threads <= 256) ? boundary_kernel<false, 256, false, false, true>
+                                                          : boundary_kernel<false, SMRT_NT_B, false, false, true>;
+  }
   // the attribute belongs to the FUNCTION, not to the plan: always raise it to the opt-in maximum so that plans with
   // different shared-memory footprints can coexist
   {
@@ -272,6 +280,9 @@ extern "C" int smrtb200_plan_create(const smrtb200_options* options, smrtb200_pl
                                    optin - (int)fa.sharedSizeBytes));
     PLAN_CUDA(cudaFuncGetAttributes(&fa, p->boundary_fn));
     PLAN_CUDA(cudaFuncSetAttribute(p->boundary_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   optin - (int)fa.sharedSizeBytes));
+    PLAN_CUDA(cudaFuncGetAttributes(&fa, p->boundary_fn_rough));
+    PLAN_CUDA(cudaFuncSetAttribute(p->boundary_fn_rough, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    optin - (int)fa.sharedSizeBytes));
   }
   int occ_e = 0, occ_b = 0;
@@ -417,7 +428,9 @@ static int solve_device_impl(smrtb200_plan* p, const smrtb200_batch* batch, cuda
     CUDA_TRY(cudaEventRecord(ev[0], s.stream));
     p->eigen_fn<<<std::min(p->eigen_grid, items), p->eigen_threads, p->eigen_smem, s.stream>>>(A);
     CUDA_TRY(cudaEventRecord(ev[1], s.stream));
-    p->boundary_fn<<<std::min(p->boundary_grid, nb), p->boundary_threads, p->boundary_smem, s.stream>>>(A);
+    // batches with rough interfaces run the instantiation that holds their code; the others the plain one
+    (A.interface_params ? p->boundary_fn_rough : p->boundary_fn)<<<std::min(p->boundary_grid, nb), p->boundary_threads,
+                                                                   p->boundary_smem, s.stream>>>(A);
     CUDA_TRY(cudaEventRecord(ev[2], s.stream));
     CUDA_TRY(cudaGetLastError());
     p->launches += 3;

@@ -57,12 +57,24 @@ int emu_solve_batch(const smrtb200_options* opt, const smrtb200_batch* batch, in
   const char* sf = std::getenv("SMRT_EMU_STREAM_FG");
   // SMRT_EMU_BOUNDARY_MID=1: the boundary instantiation for 64 < h <= 128 (its tile maps need 512 threads)
   const char* bm = std::getenv("SMRT_EMU_BOUNDARY_MID");
-  if (bm && bm[0] == '1' && L.boundary_mid_smem_bytes > 0)
-    simt::launch(1, 512u, [&]() { boundary_kernel<false, 512, false, true>(A); });
-  else if (sf && sf[0] == '1' && L.hmax <= 64)
-    simt::launch(1, (unsigned)threads, [&]() { boundary_kernel<true, 512, true>(A); });
-  else
-    simt::launch(1, (unsigned)threads, [&]() { boundary_kernel<true, 512>(A); });
+  // (batches with rough interfaces run the kRough instantiations, like the CUDA host code)
+  const bool rough = A.interface_params != nullptr;
+  if (bm && bm[0] == '1' && L.boundary_mid_smem_bytes > 0) {
+    if (rough)
+      simt::launch(1, 512u, [&]() { boundary_kernel<false, 512, false, true, true>(A); });
+    else
+      simt::launch(1, 512u, [&]() { boundary_kernel<false, 512, false, true>(A); });
+  } else if (sf && sf[0] == '1' && L.hmax <= 64) {
+    if (rough)
+      simt::launch(1, (unsigned)threads, [&]() { boundary_kernel<true, 512, true, false, true>(A); });
+    else
+      simt::launch(1, (unsigned)threads, [&]() { boundary_kernel<true, 512, true>(A); });
+  } else {
+    if (rough)
+      simt::launch(1, (unsigned)threads, [&]() { boundary_kernel<true, 512, false, false, true>(A); });
+    else
+      simt::launch(1, (unsigned)threads, [&]() { boundary_kernel<true, 512>(A); });
+  }
   if (sweeps_out) {
     sweeps_out[0] = diag[0];
     sweeps_out[1] = diag[1];
